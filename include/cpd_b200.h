@@ -1,0 +1,140 @@
+/*
+ * cpd_b200.h -- C ABI of libcpd_b200.so: the CPD EM hot path on one B200 (sm_100a).
+ *
+ * The reference (neka-nat/probreg v0.3.7) has no C/FFI boundary for this path: the seam
+ * is Python-level (probreg/cpd.py) plus one pybind11 module (probreg/_math).  Each entry
+ * point below names the reference interface it stands in for.  All host pointers are
+ * caller-owned, C-order, `double`; nothing is retained after a call returns.  One handle
+ * owns one CUDA device + one stream and is not re-entrant.  Every function returns 0 on
+ * success and a negative code on failure; cpd_last_error() then describes the failure.
+ * There is no CPU fallback: without a CUDA device cpd_create fails.
+ *
+ * Coordinates are D = 2 or 3; clouds are (count x D) row-major.
+ */
+#ifndef CPD_B200_H
+#define CPD_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct cpd_ctx cpd_ctx;
+
+enum { CPD_OK = 0, CPD_ERR_ARG = -1, CPD_ERR_CUDA = -2, CPD_ERR_STATE = -3, CPD_ERR_NCCL = -4 };
+
+/* transformation families: probreg/cpd.py:123 (RigidCPD), :195 (AffineCPD), :247 (NonRigidCPD) */
+enum { CPD_TF_RIGID = 0, CPD_TF_AFFINE = 1, CPD_TF_NONRIGID = 2 };
+
+/* Result of one M-step == probreg/cpd.py:18 MstepResult(transformation, sigma2, q) flattened.
+ * rigid : rot (D x D row-major in lin[0..D*D)), t, scale            (cpd.py:192)
+ * affine: b   (D x D row-major in lin),          t, scale == 1      (cpd.py:244)          */
+typedef struct cpd_params {
+    double lin[9];
+    double t[3];
+    double scale;
+    double sigma2;
+    double q;
+    double n_p;       /* EstepResult.n_p of the E-step that fed this M-step (cpd.py:88) */
+} cpd_params;
+
+const char* cpd_last_error(void);
+int cpd_version(void);
+
+/* Number of CUDA devices visible (0 => every other call fails). */
+int cpd_device_count(void);
+
+/* -- handle ---------------------------------------------------------------------------
+ * stream == NULL: the handle creates its own non-blocking stream.  Otherwise `stream` is a
+ * cudaStream_t the caller owns (e.g. torch.cuda.current_stream().cuda_stream).
+ * Replaces the backend selection of CoherentPointDrift.__init__ (cpd.py:42-59).        */
+int cpd_create(cpd_ctx** out, int device, int dim, void* stream);
+void cpd_destroy(cpd_ctx* h);
+
+/* CoherentPointDrift.set_source (cpd.py:61-62) / the `source` ctor argument.            */
+int cpd_set_source(cpd_ctx* h, const double* source, int64_t m);
+
+/* The `target` argument of registration()/expectation_step (cpd.py:71,106).
+ * `target` holds THIS handle's shard (n_local rows); n_global is the N of cpd.py:79.
+ * frame_origin (D doubles) is the common origin all ranks centre on; NULL => the shard mean
+ * (only valid when n_local == n_global).                                                */
+int cpd_set_target(cpd_ctx* h, const double* target, int64_t n_local, int64_t n_global,
+                   const double* frame_origin);
+
+/* math_utils.squared_kernel_sum (math_utils.py:28-29 -> _math.squared_kernel,
+ * cc/math_utils_py.cc:14) evaluated in closed form, FP64, on the device, over the handle's
+ * source and (all ranks') target.  Multi-rank handles all-reduce the target sums.       */
+int cpd_sigma2_init(cpd_ctx* h, double* sigma2);
+
+/* Set the state the EM loop starts from: family, RigidCPD(update_scale=...) (cpd.py:136),
+ * the outlier weight w of registration() (cpd.py:106), tf_init_params (cpd.py:149-152:
+ * lin = rot or b, t, scale) and sigma2 / q of _initialize (cpd.py:145-153).             */
+int cpd_set_state(cpd_ctx* h, int tf_kind, int update_scale, double w, const cpd_params* init);
+
+/* One EM iteration == the loop body cpd.py:111-113: transform(source) -> expectation_step
+ * -> maximization_step, entirely on the device; `out` receives the new MstepResult.
+ * out may be NULL (no host sync).                                                       */
+int cpd_em_step(cpd_ctx* h, cpd_params* out);
+
+/* CoherentPointDrift.registration (cpd.py:106-120) without callbacks: at most maxiter
+ * iterations, stopping after the first one with |q - q_prev| < tol.  trace (may be NULL)
+ * receives 2 doubles (sigma2, q) per iteration run.                                     */
+int cpd_em_run(cpd_ctx* h, int maxiter, double tol, cpd_params* out, int* iters_run, double* trace);
+
+/* CoherentPointDrift.expectation_step(t_source, target, sigma2, w) (cpd.py:71-88) against the
+ * handle's target shard.  t_source is m x D (m as given to cpd_set_source).  Any of
+ * pt1 (n_local), p1 (m), px (m x D) may be NULL.  In a multi-rank handle p1/px/n_p are
+ * all-reduced so every rank receives the global sums; pt1 stays per-shard.              */
+int cpd_estep(cpd_ctx* h, const double* t_source, double sigma2, double w,
+              double* pt1, double* p1, double* px, double* n_p);
+
+/* RigidCPD._maximization_step (cpd.py:160-192) / AffineCPD._maximization_step (:219-244)
+ * from a caller-supplied EstepResult (host arrays as returned by cpd_estep) against the
+ * handle's source and target.                                                           */
+int cpd_mstep(cpd_ctx* h, int tf_kind, int update_scale, const double* pt1, const double* p1,
+              const double* px, double n_p, cpd_params* out);
+
+/* Copies of the last E-step's reductions (device -> host), valid after cpd_em_step/run. */
+int cpd_last_estep(cpd_ctx* h, double* pt1, double* p1, double* px, double* n_p);
+
+/* _math.rbf_kernel (cc/math_utils_py.cc:15 -> cc/math_utils.cc:17-19):
+ * out[i*ny + j] = exp(-|x_i - y_j|^2 / (2*beta)) as float32, x: nx x D, y: ny x D.       */
+int cpd_rbf_kernel(int device, const double* x, int64_t nx, const double* y, int64_t ny, int dim,
+                   double beta, float* out);
+
+/* math_utils.squared_kernel_sum on two host clouds without a handle.                    */
+int cpd_squared_kernel_sum(int device, const double* x, int64_t nx, const double* y, int64_t ny,
+                           int dim, double* out);
+
+/* -- multi-GPU: one process (or handle) per GPU, targets sharded, sources replicated ----
+ * cpd_comm_unique_id fills 128 bytes (an ncclUniqueId) on one rank; after it has been
+ * distributed, every rank calls cpd_comm_init.  From then on cpd_em_step/cpd_estep/
+ * cpd_sigma2_init issue ONE ncclAllReduce(sum, double) on the handle's stream.          */
+int cpd_comm_unique_id(char id[128]);
+int cpd_comm_init(cpd_ctx* h, int world_size, int rank, const char id[128]);
+
+/* -- measurement helpers (bench.py): CUDA events on the handle's stream ---------------- */
+int cpd_timer_start(cpd_ctx* h);
+int cpd_timer_stop(cpd_ctx* h, float* ms);           /* synchronises */
+int cpd_sync(cpd_ctx* h);
+/* a pool of CUDA events on the handle's stream: record slot `idx` (0 <= idx < 8192) now; elapsed
+ * ms between two recorded slots (the caller synchronises first, e.g. cpd_sync).             */
+int cpd_event_record(cpd_ctx* h, int idx);
+int cpd_event_elapsed(cpd_ctx* h, int idx_start, int idx_stop, float* ms);
+/* duration of the last run of each kernel stage, ms (events recorded when profiling is on):
+ * [0] pack [1] pass1 [2] finalize1 [3] pass2 [4] finalize2 [5] moments+mstep (+allreduce)  */
+int cpd_set_profiling(cpd_ctx* h, int on);
+int cpd_stage_times(cpd_ctx* h, float ms[6]);
+/* launches issued by this handle since creation (kernels only).                         */
+int64_t cpd_launch_count(cpd_ctx* h);
+/* overwrite `bytes` of scratch to evict L2 (bench hygiene); 0 => default 256 MiB.        */
+int cpd_flush_l2(cpd_ctx* h, int64_t bytes);
+/* FP32 FMA / MUFU.EX2 issue-rate micro-benchmark: out[0] = FFMA TFLOP/s, out[1] = MUFU.EX2
+ * Gop/s, out[2] = SM clock MHz seen by the probe, out[3] = SM count.                      */
+int cpd_microbench(int device, double out[4]);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CPD_B200_H */

@@ -1,0 +1,250 @@
+"""ctypes binding of libcpd_b200.so (include/cpd_b200.h).  No torch, no cupy, no CPU fallback:
+if the shared library is missing or no CUDA device is visible, using the package raises."""
+import ctypes
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libcpd_b200.so")
+
+TF_RIGID, TF_AFFINE, TF_NONRIGID = 0, 1, 2
+
+
+class CpdParams(ctypes.Structure):
+    _fields_ = [("lin", ctypes.c_double * 9), ("t", ctypes.c_double * 3), ("scale", ctypes.c_double),
+                ("sigma2", ctypes.c_double), ("q", ctypes.c_double), ("n_p", ctypes.c_double)]
+
+
+class CpdError(RuntimeError):
+    pass
+
+
+_c_dp = ctypes.POINTER(ctypes.c_double)
+_c_fp = ctypes.POINTER(ctypes.c_float)
+_PROTOS = {
+    "cpd_last_error": (ctypes.c_char_p, []),
+    "cpd_version": (ctypes.c_int, []),
+    "cpd_device_count": (ctypes.c_int, []),
+    "cpd_create": (ctypes.c_int, [ctypes.POINTER(ctypes.c_void_p), ctypes.c_int, ctypes.c_int, ctypes.c_void_p]),
+    "cpd_destroy": (None, [ctypes.c_void_p]),
+    "cpd_set_source": (ctypes.c_int, [ctypes.c_void_p, _c_dp, ctypes.c_int64]),
+    "cpd_set_target": (ctypes.c_int, [ctypes.c_void_p, _c_dp, ctypes.c_int64, ctypes.c_int64, _c_dp]),
+    "cpd_sigma2_init": (ctypes.c_int, [ctypes.c_void_p, _c_dp]),
+    "cpd_set_state": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_double, ctypes.POINTER(CpdParams)]),
+    "cpd_em_step": (ctypes.c_int, [ctypes.c_void_p, ctypes.POINTER(CpdParams)]),
+    "cpd_em_run": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_double, ctypes.POINTER(CpdParams),
+                                  ctypes.POINTER(ctypes.c_int), _c_dp]),
+    "cpd_estep": (ctypes.c_int, [ctypes.c_void_p, _c_dp, ctypes.c_double, ctypes.c_double, _c_dp, _c_dp, _c_dp, _c_dp]),
+    "cpd_mstep": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, _c_dp, _c_dp, _c_dp, ctypes.c_double,
+                                 ctypes.POINTER(CpdParams)]),
+    "cpd_last_estep": (ctypes.c_int, [ctypes.c_void_p, _c_dp, _c_dp, _c_dp, _c_dp]),
+    "cpd_rbf_kernel": (ctypes.c_int, [ctypes.c_int, _c_dp, ctypes.c_int64, _c_dp, ctypes.c_int64, ctypes.c_int,
+                                      ctypes.c_double, _c_fp]),
+    "cpd_squared_kernel_sum": (ctypes.c_int, [ctypes.c_int, _c_dp, ctypes.c_int64, _c_dp, ctypes.c_int64, ctypes.c_int, _c_dp]),
+    "cpd_comm_unique_id": (ctypes.c_int, [ctypes.c_char_p]),
+    "cpd_comm_init": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_char_p]),
+    "cpd_timer_start": (ctypes.c_int, [ctypes.c_void_p]),
+    "cpd_timer_stop": (ctypes.c_int, [ctypes.c_void_p, _c_fp]),
+    "cpd_sync": (ctypes.c_int, [ctypes.c_void_p]),
+    "cpd_event_record": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int]),
+    "cpd_event_elapsed": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, _c_fp]),
+    "cpd_set_profiling": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int]),
+    "cpd_stage_times": (ctypes.c_int, [ctypes.c_void_p, _c_fp]),
+    "cpd_launch_count": (ctypes.c_int64, [ctypes.c_void_p]),
+    "cpd_flush_l2": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int64]),
+    "cpd_microbench": (ctypes.c_int, [ctypes.c_int, _c_dp]),
+}
+EXPORTED = tuple(_PROTOS)
+_lib = None
+
+
+def lib():
+    """The loaded shared library (raises if it has not been built)."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise CpdError("%s not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                           "(or `make -C probreg_b200/csrc`); probreg_b200 has no CPU path" % LIB_PATH)
+        handle = ctypes.CDLL(LIB_PATH)
+        for name, (res, args) in _PROTOS.items():
+            fn = getattr(handle, name)
+            fn.restype = res
+            fn.argtypes = args
+        _lib = handle
+    return _lib
+
+
+def check(code):
+    if code != 0:
+        raise CpdError("libcpd_b200: %s (code %d)" % (lib().cpd_last_error().decode(), code))
+
+
+def as_cloud(a, dim=None):
+    """C-order float64 (count x D) view/copy of `a` (what cv() at probreg/cpd.py:444 hands on)."""
+    arr = np.ascontiguousarray(np.asarray(a, dtype=np.float64))
+    assert arr.ndim == 2, "source and target must have 2 dimensions."
+    if dim is not None and arr.shape[1] != dim:
+        raise ValueError("expected %d-D points, got %d-D" % (dim, arr.shape[1]))
+    return arr
+
+
+def dptr(a):
+    return a.ctypes.data_as(_c_dp) if a is not None else None
+
+
+class Handle(object):
+    """RAII wrapper of cpd_ctx*: one GPU, one stream."""
+
+    def __init__(self, dim, device=0, stream=None):
+        if dim not in (2, 3):
+            raise ValueError("probreg_b200 supports 2-D and 3-D points, got %d-D" % dim)
+        self._h = ctypes.c_void_p()
+        self.dim = dim
+        self.device = device
+        check(lib().cpd_create(ctypes.byref(self._h), device, dim, ctypes.c_void_p(stream) if stream else None))
+        self.m = 0
+        self.n = 0
+
+    def close(self):
+        if getattr(self, "_h", None) is not None and self._h.value:
+            lib().cpd_destroy(self._h)
+            self._h = ctypes.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # -- data
+    def set_source(self, source):
+        src = as_cloud(source, self.dim)
+        check(lib().cpd_set_source(self._h, dptr(src), src.shape[0]))
+        self.m = src.shape[0]
+
+    def set_target(self, target, n_global=None, frame_origin=None):
+        tgt = as_cloud(target, self.dim)
+        n_global = tgt.shape[0] if n_global is None else int(n_global)
+        org = None if frame_origin is None else np.ascontiguousarray(frame_origin, dtype=np.float64)
+        check(lib().cpd_set_target(self._h, dptr(tgt), tgt.shape[0], n_global, dptr(org)))
+        self.n = tgt.shape[0]
+
+    def sigma2_init(self):
+        out = ctypes.c_double()
+        check(lib().cpd_sigma2_init(self._h, ctypes.byref(out)))
+        return out.value
+
+    # -- EM
+    def set_state(self, tf_kind, update_scale, w, lin, t, scale, sigma2, q):
+        p = CpdParams()
+        d = self.dim
+        lin = np.asarray(lin, dtype=np.float64).reshape(d, d)
+        for i in range(d):
+            for j in range(d):
+                p.lin[i * d + j] = lin[i, j]
+        tt = np.asarray(t, dtype=np.float64).reshape(d)
+        for i in range(d):
+            p.t[i] = tt[i]
+        p.scale, p.sigma2, p.q = float(scale), float(sigma2), float(q)
+        check(lib().cpd_set_state(self._h, tf_kind, int(bool(update_scale)), float(w), ctypes.byref(p)))
+
+    def _unpack(self, p):
+        d = self.dim
+        lin = np.array(p.lin[: d * d], dtype=np.float64).reshape(d, d)
+        t = np.array(p.t[:d], dtype=np.float64)
+        return lin, t, p.scale, p.sigma2, p.q, p.n_p
+
+    def em_step(self, read=True):
+        if not read:
+            check(lib().cpd_em_step(self._h, None))
+            return None
+        p = CpdParams()
+        check(lib().cpd_em_step(self._h, ctypes.byref(p)))
+        return self._unpack(p)
+
+    def em_run(self, maxiter, tol, trace=False):
+        p = CpdParams()
+        it = ctypes.c_int()
+        tr = np.zeros((max(maxiter, 1), 2)) if trace else None
+        check(lib().cpd_em_run(self._h, int(maxiter), float(tol), ctypes.byref(p), ctypes.byref(it), dptr(tr)))
+        out = self._unpack(p) + (it.value,)
+        return out + (tr[: it.value],) if trace else out
+
+    def estep(self, t_source, sigma2, w, want_pt1=True, want_p1=True, want_px=True):
+        ts = as_cloud(t_source, self.dim)
+        if ts.shape[0] != self.m:
+            raise ValueError("t_source has %d rows, the handle's source has %d" % (ts.shape[0], self.m))
+        pt1 = np.empty(self.n) if want_pt1 else None
+        p1 = np.empty(self.m) if want_p1 else None
+        px = np.empty((self.m, self.dim)) if want_px else None
+        n_p = ctypes.c_double()
+        check(lib().cpd_estep(self._h, dptr(ts), float(sigma2), float(w), dptr(pt1), dptr(p1), dptr(px), ctypes.byref(n_p)))
+        return pt1, p1, px, n_p.value
+
+    def last_estep(self):
+        pt1, p1, px = np.empty(self.n), np.empty(self.m), np.empty((self.m, self.dim))
+        n_p = ctypes.c_double()
+        check(lib().cpd_last_estep(self._h, dptr(pt1), dptr(p1), dptr(px), ctypes.byref(n_p)))
+        return pt1, p1, px, n_p.value
+
+    def mstep(self, tf_kind, update_scale, pt1, p1, px, n_p):
+        pt1 = np.ascontiguousarray(pt1, dtype=np.float64)
+        p1 = np.ascontiguousarray(p1, dtype=np.float64)
+        px = as_cloud(px, self.dim)
+        if pt1.shape[0] != self.n or p1.shape[0] != self.m or px.shape[0] != self.m:
+            raise ValueError("EstepResult shapes do not match the handle's source/target")
+        p = CpdParams()
+        check(lib().cpd_mstep(self._h, tf_kind, int(bool(update_scale)), dptr(pt1), dptr(p1), dptr(px), float(n_p),
+                              ctypes.byref(p)))
+        return self._unpack(p)
+
+    # -- multi-GPU
+    def comm_init(self, world_size, rank, uid):
+        check(lib().cpd_comm_init(self._h, world_size, rank, uid))
+
+    # -- measurement
+    def timer_start(self):
+        check(lib().cpd_timer_start(self._h))
+
+    def timer_stop(self):
+        ms = ctypes.c_float()
+        check(lib().cpd_timer_stop(self._h, ctypes.byref(ms)))
+        return ms.value
+
+    def sync(self):
+        check(lib().cpd_sync(self._h))
+
+    def event_record(self, idx):
+        check(lib().cpd_event_record(self._h, idx))
+
+    def event_elapsed(self, a, b):
+        ms = ctypes.c_float()
+        check(lib().cpd_event_elapsed(self._h, a, b, ctypes.byref(ms)))
+        return ms.value
+
+    def set_profiling(self, on):
+        check(lib().cpd_set_profiling(self._h, int(on)))
+
+    def stage_times(self):
+        ms = (ctypes.c_float * 6)()
+        check(lib().cpd_stage_times(self._h, ms))
+        return list(ms)
+
+    def launch_count(self):
+        return int(lib().cpd_launch_count(self._h))
+
+    def flush_l2(self, nbytes=0):
+        check(lib().cpd_flush_l2(self._h, nbytes))
+
+
+def unique_id():
+    buf = ctypes.create_string_buffer(128)
+    check(lib().cpd_comm_unique_id(buf))
+    return buf.raw
+
+
+def microbench(device=0):
+    out = (ctypes.c_double * 4)()
+    check(lib().cpd_microbench(device, out))
+    return {"ffma_tflops": out[0], "mufu_ex2_gops": out[1], "sm_mhz": out[2], "sm_count": int(out[3])}

@@ -1,0 +1,365 @@
+"""Coherent Point Drift on one or more B200s -- the API surface of ``probreg.cpd``.
+
+Drop-in for probreg/cpd.py: ``registration_cpd``, ``RigidCPD``, ``AffineCPD``, ``NonRigidCPD``,
+``EstepResult``, ``MstepResult`` keep their names, arguments, return types and error behaviour.
+What differs is where the work happens: every E-step / M-step runs in hand-written sm_100a
+kernels behind the C ABI of ``libcpd_b200.so`` (include/cpd_b200.h).  There is no numpy path
+and no CPU fallback; ``use_cuda`` is accepted for signature compatibility and ignored (the
+reference's False default would select its numpy path, which does not exist here).
+
+Extensions over the reference signature (all optional, keyword-only in spirit):
+``device`` (CUDA ordinal) and ``comm`` (a ``probreg_b200.dist.Communicator``: the target is
+sharded over the ranks, one NCCL all-reduce per EM iteration).
+"""
+import abc
+import logging
+from collections import namedtuple
+
+import numpy as np
+
+from . import _cabi
+from . import transformation as tf
+from .log import log
+
+EstepResult = namedtuple("EstepResult", ["pt1", "p1", "px", "n_p"])
+MstepResult = namedtuple("MstepResult", ["transformation", "sigma2", "q"])
+MstepResult.__doc__ = """Result of Maximization step.
+
+    Attributes:
+        transformation (tf.Transformation): Transformation from source to target.
+        sigma2 (float): Variance of Gaussian distribution.
+        q (float): Result of likelihood.
+"""
+
+try:  # optional: accept open3d point clouds like probreg/cpd.py:444 does
+    import open3d as _o3
+
+    _PointCloud = _o3.geometry.PointCloud
+except Exception:  # pragma: no cover
+    class _PointCloud(object):
+        pass
+
+
+def _points(x):
+    return np.asarray(x.points if isinstance(x, _PointCloud) else x)
+
+
+class CoherentPointDrift(abc.ABC):
+    """EM driver (probreg/cpd.py:28-120).  The E-step is implemented here, the M-step in the
+    subclasses -- both as calls into the CUDA library.
+
+    Args:
+        source (numpy.ndarray, optional): Source point cloud data.
+        use_cuda (bool, optional): ignored; the sm_100a kernels are the only implementation.
+        device (int, optional): CUDA device ordinal (default: the communicator's, else 0).
+        comm (probreg_b200.dist.Communicator, optional): multi-GPU target sharding.
+    """
+
+    def __init__(self, source=None, use_cuda=False, device=None, comm=None):
+        self._source = None if source is None else _points(source)
+        self._tf_type = None
+        self._callbacks = []
+        self.xp = np
+        self._comm = comm
+        self._device = (comm.device if comm is not None else 0) if device is None else device
+        self._em = None          # handle used by registration()/maximization_step (source = self._source)
+        self._es = None          # handle used by stand-alone expectation_step (source = t_source)
+        self._squared_kernel_sum = self._sigma2_from_handle
+
+    # -- reference API ------------------------------------------------------------------------
+    def set_source(self, source):
+        self._source = _points(source)
+
+    def set_callbacks(self, callbacks):
+        self._callbacks.extend(callbacks)
+
+    @abc.abstractmethod
+    def _initialize(self, target):
+        return MstepResult(None, None, None)
+
+    def expectation_step(self, t_source, target, sigma2, w=0.0):
+        """Expectation step for CPD (probreg/cpd.py:71-88) on the device.
+
+        Host arrays in, host arrays out; P is never materialised.  With a communicator,
+        ``target`` is the full cloud, each rank evaluates its shard and ``pt1`` is returned for
+        the local shard only while ``p1``/``px``/``n_p`` are the all-reduced global sums.
+        """
+        t_source, target = np.asarray(t_source), np.asarray(target)
+        assert t_source.ndim == 2 and target.ndim == 2, "source and target must have 2 dimensions."
+        dim = t_source.shape[1]
+        if self._es is None or self._es.dim != dim:
+            self._es = self._new_handle(dim)
+        self._es.set_source(t_source)
+        self._set_target(self._es, target)
+        pt1, p1, px, n_p = self._es.estep(t_source, sigma2, w)
+        return EstepResult(pt1, p1, px, n_p)
+
+    def maximization_step(self, target, estep_res, sigma2_p=None):
+        return self._maximization_step(self._source, target, estep_res, sigma2_p, xp=self.xp)
+
+    @staticmethod
+    @abc.abstractmethod
+    def _maximization_step(source, target, estep_res, sigma2_p=None, xp=np):
+        return None
+
+    def registration(self, target, w=0.0, maxiter=50, tol=0.001):
+        """The EM loop of probreg/cpd.py:106-120, resident on the GPU.
+
+        Source and target are uploaded once; each iteration is a fixed sequence of kernel
+        launches (transform+pack, E-step pass 1/2, moments, M-step) and the only per-iteration
+        host traffic is the 16-double MstepResult needed for callbacks / the ``tol`` test.
+        """
+        assert not self._tf_type is None, "transformation type is None."
+        target = _points(target)
+        res = self._initialize(target)      # uploads source/target, sigma2_0 from the device
+        h = self._em
+        self._push_state(h, res, w)
+        q = res.q
+        per_iter = bool(self._callbacks) or log.isEnabledFor(logging.DEBUG)
+        if not per_iter:
+            out = h.em_run(maxiter, tol)
+            return self._result_from(out[:6]) if out[6] > 0 else res
+        for i in range(maxiter):
+            res = self._result_from(h.em_step())
+            for c in self._callbacks:
+                c(res.transformation)
+            log.debug("Iteration: {}, Criteria: {}".format(i, res.q))
+            if abs(res.q - q) < tol:
+                break
+            q = res.q
+        return res
+
+    # -- plumbing -----------------------------------------------------------------------------
+    def _new_handle(self, dim):
+        h = _cabi.Handle(dim, device=self._device)
+        if self._comm is not None and self._comm.world_size > 1:
+            h.comm_init(self._comm.world_size, self._comm.rank, self._comm.unique_id())
+        return h
+
+    def _set_target(self, h, target):
+        if self._comm is not None and self._comm.world_size > 1:
+            lo, hi = self._comm.shard_bounds(target.shape[0])
+            h.set_target(target[lo:hi], n_global=target.shape[0], frame_origin=self._comm.frame_origin(target))
+        else:
+            h.set_target(target)
+
+    def _em_handle(self, target):
+        assert self._source is not None, "source is None."
+        dim = self._source.shape[1]
+        if self._em is None or self._em.dim != dim:
+            self._em = self._new_handle(dim)
+        self._em.set_source(self._source)      # always re-uploaded: the caller may have edited it in place
+        self._set_target(self._em, target)
+        return self._em
+
+    def _sigma2_from_handle(self, source, target):
+        # math_utils.squared_kernel_sum (math_utils.py:28-29) on the handle's resident clouds
+        return self._em_handle(_points(target)).sigma2_init()
+
+    @abc.abstractmethod
+    def _push_state(self, h, res, w):
+        pass
+
+    @abc.abstractmethod
+    def _result_from(self, out):
+        pass
+
+
+class RigidCPD(CoherentPointDrift):
+    """Coherent Point Drift for rigid transformation (probreg/cpd.py:123-192).
+
+    Args:
+        source (numpy.ndarray, optional): Source point cloud data.
+        update_scale (bool, optional): If this flag is True, compute the scale parameter.
+        tf_init_params (dict, optional): Parameters to initialize transformation.
+        use_cuda (bool, optional): ignored (see module docstring).
+    """
+
+    def __init__(self, source=None, update_scale=True, tf_init_params=None, use_cuda=False, device=None, comm=None):
+        super(RigidCPD, self).__init__(source, use_cuda, device, comm)
+        self._tf_type = tf.RigidTransformation
+        self._update_scale = update_scale
+        self._tf_init_params = dict(tf_init_params) if tf_init_params else {}
+
+    def _initialize(self, target):
+        dim = self._source.shape[1]
+        sigma2 = self._squared_kernel_sum(self._source, target)
+        q = 1.0 + target.shape[0] * dim * 0.5 * np.log(sigma2)
+        params = dict(self._tf_init_params)
+        if len(params) == 0:
+            params = {"rot": np.identity(dim), "t": np.zeros(dim)}
+        params.setdefault("xp", np)
+        return MstepResult(self._tf_type(**params), sigma2, q)
+
+    def _push_state(self, h, res, w):
+        t = res.transformation
+        h.set_state(_cabi.TF_RIGID, self._update_scale, w, t.rot, t.t, t.scale, res.sigma2, res.q)
+
+    def _result_from(self, out):
+        rot, t, scale, sigma2, q, _ = out
+        return MstepResult(tf.RigidTransformation(rot, t, scale, xp=np), sigma2, q)
+
+    def maximization_step(self, target, estep_res, sigma2_p=None):
+        h = self._em_handle(_points(target))
+        pt1, p1, px, n_p = estep_res
+        return self._result_from(h.mstep(_cabi.TF_RIGID, self._update_scale, pt1, p1, px, n_p))
+
+    @staticmethod
+    def _maximization_step(source, target, estep_res, sigma2_p=None, update_scale=True, xp=np):
+        """Static form of probreg/cpd.py:160-192 (weighted Procrustes from an EstepResult)."""
+        obj = RigidCPD(source, update_scale=update_scale)
+        return obj.maximization_step(target, estep_res, sigma2_p)
+
+
+class AffineCPD(CoherentPointDrift):
+    """Coherent Point Drift for affine transformation (probreg/cpd.py:195-244).
+
+    Args:
+        source (numpy.ndarray, optional): Source point cloud data.
+        tf_init_params (dict, optional): Parameters to initialize transformation.
+        use_cuda (bool, optional): ignored (see module docstring).
+    """
+
+    def __init__(self, source=None, tf_init_params=None, use_cuda=False, device=None, comm=None):
+        super(AffineCPD, self).__init__(source, use_cuda, device, comm)
+        self._tf_type = tf.AffineTransformation
+        self._tf_init_params = dict(tf_init_params) if tf_init_params else {}
+
+    def _initialize(self, target):
+        dim = self._source.shape[1]
+        sigma2 = self._squared_kernel_sum(self._source, target)
+        q = 1.0 + target.shape[0] * dim * 0.5 * np.log(sigma2)
+        params = dict(self._tf_init_params)
+        if len(params) == 0:
+            params = {"b": np.identity(dim), "t": np.zeros(dim)}
+        params.setdefault("xp", np)
+        return MstepResult(self._tf_type(**params), sigma2, q)
+
+    def _push_state(self, h, res, w):
+        t = res.transformation
+        h.set_state(_cabi.TF_AFFINE, True, w, t.b, t.t, 1.0, res.sigma2, res.q)
+
+    def _result_from(self, out):
+        b, t, _, sigma2, q, _ = out
+        return MstepResult(tf.AffineTransformation(b, t), sigma2, q)
+
+    def maximization_step(self, target, estep_res, sigma2_p=None):
+        h = self._em_handle(_points(target))
+        pt1, p1, px, n_p = estep_res
+        return self._result_from(h.mstep(_cabi.TF_AFFINE, True, pt1, p1, px, n_p))
+
+    @staticmethod
+    def _maximization_step(source, target, estep_res, sigma2_p=None, xp=np):
+        """Static form of probreg/cpd.py:219-244."""
+        return AffineCPD(source).maximization_step(target, estep_res, sigma2_p)
+
+
+class NonRigidCPD(CoherentPointDrift):
+    """Coherent Point Drift for nonrigid transformation (probreg/cpd.py:247-303).
+
+    SURVEY section 8(f) row, not yet fused: G comes from the CUDA RBF kernel and every E-step
+    runs on the device, but the M x M solve of cpd.py:296 is still numpy on the host (as
+    ``np.linalg.svd`` is in the reference even on its cupy path) -- dense, so M <~ 10k.
+
+    Args:
+        source (numpy.ndarray, optional): Source point cloud data.
+        beta (float, optional): Parameter of RBF kernel.
+        lmd (float, optional): Parameter for regularization term.
+        use_cuda (bool, optional): ignored (see module docstring).
+    """
+
+    def __init__(self, source=None, beta=2.0, lmd=2.0, use_cuda=False, device=None, comm=None):
+        super(NonRigidCPD, self).__init__(source, use_cuda, device, comm)
+        self._tf_type = tf.NonRigidTransformation
+        self._beta = beta
+        self._lmd = lmd
+        self._tf_obj = None
+        if not self._source is None:
+            self._tf_obj = self._tf_type(None, self._source, self._beta, self.xp)
+
+    def set_source(self, source):
+        super(NonRigidCPD, self).set_source(source)
+        self._tf_obj = self._tf_type(None, self._source, self._beta)
+
+    def maximization_step(self, target, estep_res, sigma2_p=None):
+        return self._maximization_step(self._source, target, estep_res, sigma2_p, self._tf_obj, self._lmd, self.xp)
+
+    def _initialize(self, target):
+        dim = self._source.shape[1]
+        sigma2 = self._squared_kernel_sum(self._source, target)
+        q = 1.0 + target.shape[0] * dim * 0.5 * np.log(sigma2)
+        self._tf_obj.w = np.zeros_like(self._source, dtype=np.float64)
+        return MstepResult(self._tf_obj, sigma2, q)
+
+    @staticmethod
+    def _maximization_step(source, target, estep_res, sigma2_p, tf_obj, lmd, xp=np):
+        pt1, p1, px, n_p = estep_res
+        dim = source.shape[1]
+        lhs = (p1 * tf_obj.g).T + lmd * sigma2_p * np.identity(source.shape[0])
+        w = np.linalg.solve(lhs, px - (source.T * p1).T)
+        t = source + np.dot(tf_obj.g, w)
+        tr_xp1x = np.trace(np.dot(target.T * pt1, target))
+        tr_pxt = np.trace(np.dot(px.T, t))
+        tr_tpt = np.trace(np.dot(t.T * p1, t))
+        sigma2 = (tr_xp1x - 2.0 * tr_pxt + tr_tpt) / (n_p * dim)
+        tf_obj.w = w
+        return MstepResult(tf_obj, sigma2, sigma2)
+
+    def registration(self, target, w=0.0, maxiter=50, tol=0.001):
+        assert not self._tf_type is None, "transformation type is None."
+        target = _points(target)
+        res = self._initialize(target)
+        q = res.q
+        for i in range(maxiter):
+            t_source = res.transformation.transform(self._source)
+            estep_res = self.expectation_step(t_source, target, res.sigma2, w)
+            res = self.maximization_step(target, estep_res, res.sigma2)
+            for c in self._callbacks:
+                c(res.transformation)
+            log.debug("Iteration: {}, Criteria: {}".format(i, res.q))
+            if abs(res.q - q) < tol:
+                break
+            q = res.q
+        return res
+
+    def _push_state(self, h, res, w):  # unused: the non-rigid loop is driven from Python
+        raise NotImplementedError
+
+    def _result_from(self, out):
+        raise NotImplementedError
+
+
+def registration_cpd(source, target, tf_type_name="rigid", w=0.0, maxiter=50, tol=0.001, callbacks=(),
+                     use_cuda=False, **kwargs):
+    """CPD Registraion (probreg/cpd.py:407-456).
+
+    Args:
+        source (numpy.ndarray): Source point cloud data.
+        target (numpy.ndarray): Target point cloud data.
+        tf_type_name (str, optional): Transformation type('rigid', 'affine', 'nonrigid')
+        w (float, optional): Weight of the uniform distribution, 0 < `w` < 1.
+        maxitr (int, optional): Maximum number of iterations to EM algorithm.
+        tol (float, optional): Tolerance for termination.
+        callback (:obj:`list` of :obj:`function`, optional): Called after each iteration.
+            `callback(probreg.Transformation)`
+        use_cuda (bool, optional): ignored -- the B200 kernels are the only implementation.
+
+    Keyword Args:
+        update_scale (bool, optional): If this flag is true and tf_type is rigid transformation,
+            then the scale is treated. The default is true.
+        tf_init_params (dict, optional): Parameters to initialize transformation (for rigid or affine).
+        device (int, optional), comm (probreg_b200.dist.Communicator, optional): see the classes.
+
+    Returns:
+        MstepResult: Result of the registration (transformation, sigma2, q)
+    """
+    if tf_type_name == "rigid":
+        cpd = RigidCPD(_points(source), use_cuda=use_cuda, **kwargs)
+    elif tf_type_name == "affine":
+        cpd = AffineCPD(_points(source), use_cuda=use_cuda, **kwargs)
+    elif tf_type_name == "nonrigid":
+        cpd = NonRigidCPD(_points(source), use_cuda=use_cuda, **kwargs)
+    else:
+        raise ValueError("Unknown transformation type %s" % tf_type_name)
+    cpd.set_callbacks(list(callbacks))
+    return cpd.registration(_points(target), w, maxiter, tol)

@@ -1,0 +1,682 @@
+// cpd_b200.cu -- host side of libcpd_b200.so: the C ABI declared in include/cpd_b200.h.
+// One handle = one device + one stream; every EM iteration is a fixed sequence of launches on
+// that stream (pack, pass 1, finalize 1, pass 2, finalize 2, moments [+ all-reduce] + M-step).
+#include "cpd_b200.h"
+#include "kernels.cuh"
+
+#include <dlfcn.h>
+#include <math.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <algorithm>
+#include <vector>
+
+using namespace cpd;
+
+// ---------------------------------------------------------------------------------------------
+// errors
+// ---------------------------------------------------------------------------------------------
+static thread_local char g_err[512] = "";
+static int fail(int code, const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return code;
+}
+#define CU(call)                                                                                   \
+    do {                                                                                           \
+        cudaError_t e_ = (call);                                                                   \
+        if (e_ != cudaSuccess)                                                                     \
+            return fail(CPD_ERR_CUDA, "%s failed at %s:%d: %s", #call, __FILE__, __LINE__, cudaGetErrorString(e_)); \
+    } while (0)
+#define KCHECK() CU(cudaGetLastError())
+
+extern "C" const char* cpd_last_error(void) { return g_err; }
+extern "C" int cpd_version(void) { return 100; }
+extern "C" int cpd_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+
+// ---------------------------------------------------------------------------------------------
+// NCCL, bound at run time (libnccl.so.2 -- torch's bundled copy if it is already loaded)
+// ---------------------------------------------------------------------------------------------
+namespace {
+typedef struct { char internal[128]; } nccl_uid;
+typedef void* nccl_comm;
+struct NcclApi {
+    void* lib = nullptr;
+    int (*GetUniqueId)(nccl_uid*) = nullptr;
+    int (*CommInitRank)(nccl_comm*, int, nccl_uid, int) = nullptr;
+    int (*AllReduce)(const void*, void*, size_t, int, int, nccl_comm, cudaStream_t) = nullptr;
+    int (*CommDestroy)(nccl_comm) = nullptr;
+    const char* (*GetErrorString)(int) = nullptr;
+};
+NcclApi g_nccl;
+int load_nccl() {
+    if (g_nccl.lib) return CPD_OK;
+    const char* names[] = {"libnccl.so.2", "libnccl.so"};
+    void* lib = nullptr;
+    for (const char* nm : names) { lib = dlopen(nm, RTLD_NOW | RTLD_GLOBAL); if (lib) break; }
+    if (!lib) return fail(CPD_ERR_NCCL, "cannot dlopen libnccl.so.2: %s", dlerror());
+    g_nccl.GetUniqueId = (int (*)(nccl_uid*))dlsym(lib, "ncclGetUniqueId");
+    g_nccl.CommInitRank = (int (*)(nccl_comm*, int, nccl_uid, int))dlsym(lib, "ncclCommInitRank");
+    g_nccl.AllReduce = (int (*)(const void*, void*, size_t, int, int, nccl_comm, cudaStream_t))dlsym(lib, "ncclAllReduce");
+    g_nccl.CommDestroy = (int (*)(nccl_comm))dlsym(lib, "ncclCommDestroy");
+    g_nccl.GetErrorString = (const char* (*)(int))dlsym(lib, "ncclGetErrorString");
+    if (!g_nccl.GetUniqueId || !g_nccl.CommInitRank || !g_nccl.AllReduce || !g_nccl.CommDestroy)
+        return fail(CPD_ERR_NCCL, "libnccl lacks an expected symbol");
+    g_nccl.lib = lib;
+    return CPD_OK;
+}
+constexpr int NCCL_DOUBLE = 8, NCCL_SUM = 0;
+}  // namespace
+#define NC(call)                                                                                                   \
+    do {                                                                                                           \
+        int r_ = (call);                                                                                           \
+        if (r_ != 0)                                                                                               \
+            return fail(CPD_ERR_NCCL, "%s failed: %s", #call, g_nccl.GetErrorString ? g_nccl.GetErrorString(r_) : "?"); \
+    } while (0)
+
+// ---------------------------------------------------------------------------------------------
+// handle
+// ---------------------------------------------------------------------------------------------
+struct cpd_ctx {
+    int device = 0, dim = 3, sm_count = 148, slots = 296;
+    cudaStream_t stream = nullptr;
+    bool own_stream = false;
+    long long m = 0, mpad = 0, n = 0, npad = 0, n_global = 0;
+    double *d_yc = nullptr, *d_ts = nullptr, *d_xc = nullptr, *d_raw = nullptr;
+    size_t raw_cap = 0;
+    float4 *d_srcP = nullptr, *d_tgtP = nullptr, *d_tgtQ = nullptr;
+    float2* d_part1 = nullptr;
+    double* d_part2 = nullptr;
+    size_t part1_cap = 0, part2_cap = 0;
+    double *d_pt1 = nullptr, *d_p1 = nullptr, *d_pxc = nullptr, *d_px = nullptr;
+    double *d_mom_src = nullptr, *d_mom_tgt = nullptr, *d_mom = nullptr, *d_sums = nullptr;
+    size_t mom_src_cap = 0, mom_tgt_cap = 0, sums_cap = 0;
+    DevState* d_state = nullptr;
+    DevState h_state;
+    double* h_pin = nullptr;   // 64 pinned doubles for small D2H reads
+    int it1 = 0, it2 = 0, j1 = 1, j2 = 1;
+    bool have_source = false, have_target = false, have_state = false, prepared = false;
+    nccl_comm comm = nullptr;
+    int world = 1, rank = 0;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr, sev[7] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    bool profiling = false;
+    int64_t launches = 0;
+    void* d_flush = nullptr;
+    size_t flush_cap = 0;
+    std::vector<cudaEvent_t> pool;
+};
+
+namespace {
+template <typename T>
+int dev_alloc(T** p, size_t count) {
+    if (*p) { cudaFree(*p); *p = nullptr; }
+    cudaError_t e = cudaMalloc((void**)p, std::max<size_t>(count, 1) * sizeof(T));
+    if (e != cudaSuccess) return fail(CPD_ERR_CUDA, "cudaMalloc(%zu bytes) failed: %s", count * sizeof(T), cudaGetErrorString(e));
+    return CPD_OK;
+}
+#define TRY(x) do { int r__ = (x); if (r__ != CPD_OK) return r__; } while (0)
+
+inline unsigned blocks_for(long long n) { return (unsigned)((n + THREADS - 1) / THREADS); }
+
+// number of j-splits: fill `slots` resident CTAs as evenly as possible, keep >= 2 stages per split
+int choose_split(int itiles, int nstages, int slots) {
+    int best = 1;
+    double best_eff = -1.0;
+    const int jmax = std::max(1, std::min(nstages / 2, 4 * slots));
+    for (int j = 1; j <= jmax; ++j) {
+        const double waves = (double)itiles * j / slots;
+        const double eff = waves / ceil(waves);      // fraction of the resident-CTA slots doing work
+        if (eff > best_eff + 0.02) { best_eff = eff; best = j; }
+        if (eff > 0.97) break;
+    }
+    return best;
+}
+
+int upload_state(cpd_ctx* h) {
+    CU(cudaMemcpyAsync(h->d_state, &h->h_state, sizeof(DevState), cudaMemcpyHostToDevice, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    return CPD_OK;
+}
+
+// copy a host cloud (count x dim doubles) into a device count x 3 array
+int upload_cloud(cpd_ctx* h, const double* src, long long count, double* dst3) {
+    if (h->dim == 3) {
+        CU(cudaMemcpyAsync(dst3, src, (size_t)count * 3 * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    } else {
+        CU(cudaMemsetAsync(dst3, 0, (size_t)count * 3 * sizeof(double), h->stream));
+        CU(cudaMemcpy2DAsync(dst3, 3 * sizeof(double), src, 2 * sizeof(double), 2 * sizeof(double), (size_t)count,
+                             cudaMemcpyHostToDevice, h->stream));
+    }
+    return CPD_OK;
+}
+int download_cloud(cpd_ctx* h, const double* src3, long long count, double* dst) {
+    if (h->dim == 3) {
+        CU(cudaMemcpyAsync(dst, src3, (size_t)count * 3 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    } else {
+        CU(cudaMemcpy2DAsync(dst, 2 * sizeof(double), src3, 3 * sizeof(double), 2 * sizeof(double), (size_t)count,
+                             cudaMemcpyDeviceToHost, h->stream));
+    }
+    return CPD_OK;
+}
+
+// sums[0] = sum |p|^2, sums[1..3] = sum p   over a device count x 3 cloud (result on host)
+int cloud_sums(cpd_ctx* h, const double* d_pts, long long count, double out[4]) {
+    const unsigned nb = blocks_for(count);
+    if (h->sums_cap < (size_t)nb * 4 + 4) {
+        TRY(dev_alloc(&h->d_sums, (size_t)nb * 4 + 4));
+        h->sums_cap = (size_t)nb * 4 + 4;
+    }
+    cloud_sums_kernel<<<nb, THREADS, 0, h->stream>>>(d_pts, count, h->d_sums + 4);
+    reduce_cols_kernel<<<1, 32, 0, h->stream>>>(h->d_sums + 4, (int)nb, 4, h->d_sums);
+    KCHECK();
+    h->launches += 2;
+    CU(cudaMemcpyAsync(h->h_pin, h->d_sums, 4 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    for (int k = 0; k < 4; ++k) out[k] = h->h_pin[k];
+    return CPD_OK;
+}
+
+int prepare(cpd_ctx* h) {
+    if (h->prepared) return CPD_OK;
+    if (!h->have_source || !h->have_target) return fail(CPD_ERR_STATE, "source and target must both be set");
+    h->it1 = (int)((h->n + ITILE - 1) / ITILE);
+    h->it2 = (int)((h->m + ITILE - 1) / ITILE);
+    h->j1 = choose_split(h->it1, (int)(h->mpad / P1_STAGE), h->slots);
+    h->j2 = choose_split(h->it2, (int)(h->npad / P2_STAGE), h->slots);
+    const size_t need1 = (size_t)h->j1 * h->n, need2 = (size_t)h->j2 * h->m * 4;
+    if (need1 > h->part1_cap) { TRY(dev_alloc(&h->d_part1, need1)); h->part1_cap = need1; }
+    if (need2 > h->part2_cap) { TRY(dev_alloc(&h->d_part2, need2)); h->part2_cap = need2; }
+    const size_t ms = (size_t)blocks_for(h->m) * MOM_SRC, mt = (size_t)blocks_for(h->npad) * MOM_TGT;
+    if (ms > h->mom_src_cap) { TRY(dev_alloc(&h->d_mom_src, ms)); h->mom_src_cap = ms; }
+    if (mt > h->mom_tgt_cap) { TRY(dev_alloc(&h->d_mom_tgt, mt)); h->mom_tgt_cap = mt; }
+    h->prepared = true;
+    return CPD_OK;
+}
+
+int allreduce(cpd_ctx* h, double* buf, size_t count) {
+    if (!h->comm) return CPD_OK;
+    NC(g_nccl.AllReduce(buf, buf, count, NCCL_DOUBLE, NCCL_SUM, h->comm, h->stream));
+    return CPD_OK;
+}
+
+inline void mark(cpd_ctx* h, int k) {
+    if (h->profiling) cudaEventRecord(h->sev[k], h->stream);
+}
+
+// pack + pass 1 + finalize 1 + pass 2 + finalize 2; sigma2/w read from the given device scalars
+int launch_estep(cpd_ctx* h, const double* d_sigma2, const double* d_w, const double* d_ts) {
+    TRY(prepare(h));
+    const long long cover = std::max(h->mpad, h->n);
+    mark(h, 0);
+    pack_kernel<<<blocks_for(cover), THREADS, 0, h->stream>>>(h->d_state, d_sigma2, h->d_yc, d_ts, h->d_xc, h->m, h->mpad,
+                                                              h->n, h->d_srcP, h->d_tgtP);
+    mark(h, 1);
+    pass1_kernel<<<h->it1 * h->j1, THREADS, PASS_SMEM, h->stream>>>(h->d_tgtP, (int)h->n, h->d_srcP, (int)(h->mpad / P1_STAGE),
+                                                                    h->j1, h->d_part1);
+    mark(h, 2);
+    finalize1_kernel<<<blocks_for(h->npad), THREADS, 0, h->stream>>>(h->d_state, d_sigma2, d_w, h->d_part1, h->j1, (int)h->n,
+                                                                     h->d_tgtP, h->d_xc, h->d_tgtQ, h->npad, h->d_pt1,
+                                                                     h->d_mom_tgt);
+    mark(h, 3);
+    pass2_kernel<<<h->it2 * h->j2, THREADS, PASS_SMEM, h->stream>>>(h->d_srcP, (int)h->m, h->d_tgtQ, (int)(h->npad / P2_STAGE),
+                                                                    h->j2, h->d_part2);
+    mark(h, 4);
+    finalize2_kernel<true><<<blocks_for(h->m), THREADS, 0, h->stream>>>(d_sigma2, h->d_part2, h->j2, (int)h->m, h->d_yc, h->d_p1,
+                                                                        h->d_pxc, h->d_mom_src);
+    mark(h, 5);
+    KCHECK();
+    h->launches += 5;
+    return CPD_OK;
+}
+
+int read_params(cpd_ctx* h, cpd_params* out) {
+    CU(cudaMemcpyAsync(h->h_pin, h->d_state, 16 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    const int d = h->dim;
+    for (int i = 0; i < 9; ++i) out->lin[i] = 0.0;
+    for (int i = 0; i < d; ++i)
+        for (int j = 0; j < d; ++j) out->lin[i * d + j] = h->h_pin[3 * i + j];
+    for (int i = 0; i < 3; ++i) out->t[i] = (i < d) ? h->h_pin[9 + i] : 0.0;
+    out->scale = h->h_pin[12];
+    out->sigma2 = h->h_pin[13];
+    out->q = h->h_pin[14];
+    out->n_p = h->h_pin[15];
+    return CPD_OK;
+}
+}  // namespace
+
+extern "C" int cpd_create(cpd_ctx** out, int device, int dim, void* stream) {
+    if (!out) return fail(CPD_ERR_ARG, "out is NULL");
+    if (dim != 2 && dim != 3) return fail(CPD_ERR_ARG, "dim must be 2 or 3, got %d", dim);
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+        cudaGetLastError();
+        return fail(CPD_ERR_CUDA, "no CUDA device: this library has no CPU path");
+    }
+    if (device < 0 || device >= ndev) return fail(CPD_ERR_ARG, "device %d out of range (%d visible)", device, ndev);
+    CU(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    CU(cudaGetDeviceProperties(&prop, device));
+    if (prop.major < 10) return fail(CPD_ERR_CUDA, "device %d is sm_%d%d; this library is built for sm_100a only", device, prop.major, prop.minor);
+    cpd_ctx* h = new cpd_ctx();
+    h->device = device;
+    h->dim = dim;
+    h->sm_count = prop.multiProcessorCount;
+    if (stream) { h->stream = (cudaStream_t)stream; h->own_stream = false; }
+    else { CU(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking)); h->own_stream = true; }
+    CU(cudaFuncSetAttribute(pass1_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, PASS_SMEM));
+    CU(cudaFuncSetAttribute(pass2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, PASS_SMEM));
+    int occ1 = 0, occ2 = 0;
+    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ1, pass1_kernel, THREADS, PASS_SMEM));
+    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ2, pass2_kernel, THREADS, PASS_SMEM));
+    h->slots = h->sm_count * std::max(1, std::min(occ1, occ2));
+    TRY(dev_alloc(&h->d_state, 1));
+    TRY(dev_alloc(&h->d_mom, (size_t)MOM_PAD));
+    CU(cudaMallocHost((void**)&h->h_pin, 64 * sizeof(double)));
+    CU(cudaEventCreate(&h->ev0));
+    CU(cudaEventCreate(&h->ev1));
+    for (int k = 0; k < 7; ++k) CU(cudaEventCreate(&h->sev[k]));
+    memset(&h->h_state, 0, sizeof(DevState));
+    h->h_state.dim = dim;
+    h->h_state.scale = 1.0;
+    h->h_state.lin[0] = h->h_state.lin[4] = h->h_state.lin[8] = 1.0;
+    h->h_state.update_scale = 1;
+    *out = h;
+    return CPD_OK;
+}
+
+extern "C" void cpd_destroy(cpd_ctx* h) {
+    if (!h) return;
+    cudaSetDevice(h->device);
+    cudaStreamSynchronize(h->stream);
+    if (h->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(h->comm);
+    void* ptrs[] = {h->d_yc, h->d_ts, h->d_xc, h->d_raw, h->d_srcP, h->d_tgtP, h->d_tgtQ, h->d_part1, h->d_part2, h->d_pt1, h->d_p1,
+                    h->d_pxc, h->d_px, h->d_mom_src, h->d_mom_tgt, h->d_mom, h->d_sums, h->d_state, h->d_flush};
+    for (void* p : ptrs) if (p) cudaFree(p);
+    if (h->h_pin) cudaFreeHost(h->h_pin);
+    if (h->ev0) cudaEventDestroy(h->ev0);
+    if (h->ev1) cudaEventDestroy(h->ev1);
+    for (int k = 0; k < 7; ++k) if (h->sev[k]) cudaEventDestroy(h->sev[k]);
+    for (cudaEvent_t e : h->pool) if (e) cudaEventDestroy(e);
+    if (h->own_stream) cudaStreamDestroy(h->stream);
+    delete h;
+}
+
+extern "C" int cpd_set_source(cpd_ctx* h, const double* source, int64_t m) {
+    if (!h || !source) return fail(CPD_ERR_ARG, "null argument");
+    if (m < 1 || m > 0x7fffffffLL - ITILE) return fail(CPD_ERR_ARG, "source count %lld out of range", (long long)m);
+    CU(cudaSetDevice(h->device));
+    if (m != h->m || !h->d_yc) {
+        h->m = m;
+        h->mpad = (m + P1_STAGE - 1) / P1_STAGE * P1_STAGE;
+        TRY(dev_alloc(&h->d_yc, (size_t)m * 3));
+        TRY(dev_alloc(&h->d_ts, (size_t)m * 3));
+        TRY(dev_alloc(&h->d_srcP, (size_t)h->mpad));
+        TRY(dev_alloc(&h->d_p1, (size_t)m));
+        TRY(dev_alloc(&h->d_pxc, (size_t)m * 3));
+        TRY(dev_alloc(&h->d_px, (size_t)m * 3));
+        h->prepared = false;
+    }
+    if (h->raw_cap < (size_t)m * 3) { TRY(dev_alloc(&h->d_raw, (size_t)m * 3)); h->raw_cap = (size_t)m * 3; }
+    TRY(upload_cloud(h, source, m, h->d_raw));
+    double s[4];
+    TRY(cloud_sums(h, h->d_raw, m, s));
+    for (int a = 0; a < 3; ++a) h->h_state.cy[a] = s[1 + a] / (double)m;
+    centre_kernel<<<blocks_for(m), THREADS, 0, h->stream>>>(h->d_raw, m, h->h_state.cy[0], h->h_state.cy[1], h->h_state.cy[2], h->d_yc);
+    KCHECK();
+    h->launches += 1;
+    h->h_state.m = m;
+    h->have_source = true;
+    return upload_state(h);
+}
+
+extern "C" int cpd_set_target(cpd_ctx* h, const double* target, int64_t n_local, int64_t n_global, const double* frame_origin) {
+    if (!h || !target) return fail(CPD_ERR_ARG, "null argument");
+    if (n_local < 1 || n_local > 0x7fffffffLL - ITILE) return fail(CPD_ERR_ARG, "target count %lld out of range", (long long)n_local);
+    if (n_global < n_local) return fail(CPD_ERR_ARG, "n_global (%lld) < n_local (%lld)", (long long)n_global, (long long)n_local);
+    if (!frame_origin && n_global != n_local) return fail(CPD_ERR_ARG, "a sharded target needs an explicit frame_origin");
+    CU(cudaSetDevice(h->device));
+    if (n_local != h->n || !h->d_xc) {
+        h->n = n_local;
+        h->npad = (n_local + P2_STAGE - 1) / P2_STAGE * P2_STAGE;
+        TRY(dev_alloc(&h->d_xc, (size_t)n_local * 3));
+        TRY(dev_alloc(&h->d_tgtP, (size_t)n_local));
+        TRY(dev_alloc(&h->d_tgtQ, (size_t)h->npad * 2));
+        TRY(dev_alloc(&h->d_pt1, (size_t)n_local));
+        h->prepared = false;
+    }
+    h->n_global = n_global;
+    if (h->raw_cap < (size_t)n_local * 3) { TRY(dev_alloc(&h->d_raw, (size_t)n_local * 3)); h->raw_cap = (size_t)n_local * 3; }
+    TRY(upload_cloud(h, target, n_local, h->d_raw));
+    if (frame_origin) {
+        for (int a = 0; a < 3; ++a) h->h_state.cx[a] = (a < h->dim) ? frame_origin[a] : 0.0;
+    } else {
+        double s[4];
+        TRY(cloud_sums(h, h->d_raw, n_local, s));
+        for (int a = 0; a < 3; ++a) h->h_state.cx[a] = s[1 + a] / (double)n_local;
+    }
+    centre_kernel<<<blocks_for(n_local), THREADS, 0, h->stream>>>(h->d_raw, n_local, h->h_state.cx[0], h->h_state.cx[1], h->h_state.cx[2], h->d_xc);
+    KCHECK();
+    h->launches += 1;
+    h->h_state.n_global = n_global;
+    h->have_target = true;
+    return upload_state(h);
+}
+
+extern "C" int cpd_sigma2_init(cpd_ctx* h, double* sigma2) {
+    if (!h || !sigma2) return fail(CPD_ERR_ARG, "null argument");
+    if (!h->have_source || !h->have_target) return fail(CPD_ERR_STATE, "source and target must both be set");
+    CU(cudaSetDevice(h->device));
+    double sx[4], sy[4];
+    TRY(cloud_sums(h, h->d_xc, h->n, sx));
+    if (h->comm) {   // sum the target-side sums over ranks
+        CU(cudaMemcpyAsync(h->d_mom, sx, 4 * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+        TRY(allreduce(h, h->d_mom, 4));
+        CU(cudaMemcpyAsync(h->h_pin, h->d_mom, 4 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+        CU(cudaStreamSynchronize(h->stream));
+        for (int k = 0; k < 4; ++k) sx[k] = h->h_pin[k];
+    }
+    TRY(cloud_sums(h, h->d_yc, h->m, sy));
+    // move the source sums into the targets' frame: y' = y~ + (cy - cx)
+    double dlt[3], d2 = 0.0, dsy = 0.0;
+    for (int a = 0; a < 3; ++a) { dlt[a] = h->h_state.cy[a] - h->h_state.cx[a]; d2 += dlt[a] * dlt[a]; dsy += dlt[a] * sy[1 + a]; }
+    const double M = (double)h->m, N = (double)h->n_global;
+    const double syy = sy[0] + 2.0 * dsy + M * d2;
+    double cross = 0.0;
+    for (int a = 0; a < 3; ++a) cross += sx[1 + a] * (sy[1 + a] + M * dlt[a]);
+    *sigma2 = (M * sx[0] + N * syy - 2.0 * cross) / (M * N * h->dim);
+    return CPD_OK;
+}
+
+extern "C" int cpd_set_state(cpd_ctx* h, int tf_kind, int update_scale, double w, const cpd_params* init) {
+    if (!h || !init) return fail(CPD_ERR_ARG, "null argument");
+    if (tf_kind != CPD_TF_RIGID && tf_kind != CPD_TF_AFFINE) return fail(CPD_ERR_ARG, "tf_kind %d not supported by the fused EM loop", tf_kind);
+    if (!(w >= 0.0 && w < 1.0)) return fail(CPD_ERR_ARG, "w must be in [0, 1), got %g", w);
+    if (!(init->sigma2 > 0.0)) return fail(CPD_ERR_ARG, "sigma2 must be positive, got %g", init->sigma2);
+    CU(cudaSetDevice(h->device));
+    DevState& s = h->h_state;
+    const int d = h->dim;
+    for (int i = 0; i < 3; ++i)
+        for (int j = 0; j < 3; ++j) s.lin[3 * i + j] = (i < d && j < d) ? init->lin[i * d + j] : (i == j ? 1.0 : 0.0);
+    for (int i = 0; i < 3; ++i) s.t[i] = (i < d) ? init->t[i] : 0.0;
+    s.scale = (tf_kind == CPD_TF_RIGID) ? init->scale : 1.0;
+    s.sigma2 = init->sigma2;
+    s.q = init->q;
+    s.n_p = 0.0;
+    s.w = w;
+    s.tf_kind = tf_kind;
+    s.update_scale = update_scale ? 1 : 0;
+    s.dim = d;
+    h->have_state = true;
+    return upload_state(h);
+}
+
+extern "C" int cpd_em_step(cpd_ctx* h, cpd_params* out) {
+    if (!h) return fail(CPD_ERR_ARG, "null handle");
+    if (!h->have_state) return fail(CPD_ERR_STATE, "cpd_set_state has not been called");
+    CU(cudaSetDevice(h->device));
+    TRY(launch_estep(h, &h->d_state->sigma2, &h->d_state->w, nullptr));
+    const int nbs = (int)blocks_for(h->m), nbt = (int)blocks_for(h->npad);
+    if (h->comm) {
+        moments_kernel<false><<<1, 32, 0, h->stream>>>(h->d_state, h->d_mom_src, nbs, h->d_mom_tgt, nbt, h->d_mom);
+        TRY(allreduce(h, h->d_mom, MOM_PAD));
+        mstep_kernel<<<1, 32, 0, h->stream>>>(h->d_state, h->d_mom);
+        h->launches += 2;
+    } else {
+        moments_kernel<true><<<1, 32, 0, h->stream>>>(h->d_state, h->d_mom_src, nbs, h->d_mom_tgt, nbt, h->d_mom);
+        h->launches += 1;
+    }
+    mark(h, 6);
+    KCHECK();
+    if (out) return read_params(h, out);
+    return CPD_OK;
+}
+
+extern "C" int cpd_em_run(cpd_ctx* h, int maxiter, double tol, cpd_params* out, int* iters_run, double* trace) {
+    if (!h || !out) return fail(CPD_ERR_ARG, "null argument");
+    if (!h->have_state) return fail(CPD_ERR_STATE, "cpd_set_state has not been called");
+    double q = h->h_state.q;
+    int it = 0;
+    cpd_params cur;
+    memset(&cur, 0, sizeof(cur));
+    for (it = 0; it < maxiter; ++it) {
+        TRY(cpd_em_step(h, &cur));
+        if (trace) { trace[2 * it] = cur.sigma2; trace[2 * it + 1] = cur.q; }
+        if (fabs(cur.q - q) < tol) { ++it; break; }          // cpd.py:117
+        q = cur.q;
+    }
+    if (maxiter <= 0) TRY(read_params(h, &cur));
+    *out = cur;
+    if (iters_run) *iters_run = it;
+    return CPD_OK;
+}
+
+extern "C" int cpd_estep(cpd_ctx* h, const double* t_source, double sigma2, double w, double* pt1, double* p1, double* px, double* n_p) {
+    if (!h || !t_source) return fail(CPD_ERR_ARG, "null argument");
+    if (!(sigma2 > 0.0)) return fail(CPD_ERR_ARG, "sigma2 must be positive, got %g", sigma2);
+    if (!(w >= 0.0 && w < 1.0)) return fail(CPD_ERR_ARG, "w must be in [0, 1), got %g", w);
+    if (!h->have_source || !h->have_target) return fail(CPD_ERR_STATE, "source and target must both be set");
+    CU(cudaSetDevice(h->device));
+    TRY(upload_cloud(h, t_source, h->m, h->d_ts));
+    h->h_pin[32] = sigma2;
+    h->h_pin[33] = w;
+    CU(cudaMemcpyAsync(&h->d_state->es_sigma2, h->h_pin + 32, 2 * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    TRY(launch_estep(h, &h->d_state->es_sigma2, &h->d_state->es_w, h->d_ts));
+    if (h->comm) {
+        TRY(allreduce(h, h->d_p1, (size_t)h->m));
+        TRY(allreduce(h, h->d_pxc, (size_t)h->m * 3));
+    }
+    return cpd_last_estep(h, pt1, p1, px, n_p);
+}
+
+extern "C" int cpd_last_estep(cpd_ctx* h, double* pt1, double* p1, double* px, double* n_p) {
+    if (!h) return fail(CPD_ERR_ARG, "null handle");
+    if (!h->prepared) return fail(CPD_ERR_STATE, "no E-step has run on this handle");
+    CU(cudaSetDevice(h->device));
+    if (pt1) CU(cudaMemcpyAsync(pt1, h->d_pt1, (size_t)h->n * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    if (p1) CU(cudaMemcpyAsync(p1, h->d_p1, (size_t)h->m * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    if (px) {
+        uncentre_px_kernel<<<blocks_for(h->m), THREADS, 0, h->stream>>>(h->d_state, h->d_p1, h->d_pxc, (int)h->m, h->d_px);
+        KCHECK();
+        h->launches += 1;
+        TRY(download_cloud(h, h->d_px, h->m, px));
+    }
+    if (n_p) {
+        // n_p = sum(p1) (cpd.py:88): block partials of the (possibly all-reduced) p1
+        const unsigned nb = blocks_for(h->m);
+        if (h->sums_cap < (size_t)nb * 4 + 4) { TRY(dev_alloc(&h->d_sums, (size_t)nb * 4 + 4)); h->sums_cap = (size_t)nb * 4 + 4; }
+        finalize2_kernel<false><<<nb, THREADS, 0, h->stream>>>(nullptr, nullptr, 0, (int)h->m, h->d_yc, h->d_p1, h->d_pxc, h->d_mom_src);
+        reduce_cols_kernel<<<1, 32, 0, h->stream>>>(h->d_mom_src, (int)nb, MOM_SRC, h->d_mom);
+        KCHECK();
+        h->launches += 2;
+        CU(cudaMemcpyAsync(h->h_pin + 40, h->d_mom, sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    }
+    CU(cudaStreamSynchronize(h->stream));
+    if (n_p) *n_p = h->h_pin[40];
+    return CPD_OK;
+}
+
+extern "C" int cpd_mstep(cpd_ctx* h, int tf_kind, int update_scale, const double* pt1, const double* p1, const double* px, double n_p,
+                         cpd_params* out) {
+    (void)n_p;   // recomputed as sum(p1), which is what the reference passes (cpd.py:88)
+    if (!h || !pt1 || !p1 || !px || !out) return fail(CPD_ERR_ARG, "null argument");
+    if (tf_kind != CPD_TF_RIGID && tf_kind != CPD_TF_AFFINE) return fail(CPD_ERR_ARG, "tf_kind %d not supported", tf_kind);
+    if (!h->have_source || !h->have_target) return fail(CPD_ERR_STATE, "source and target must both be set");
+    CU(cudaSetDevice(h->device));
+    TRY(prepare(h));
+    h->h_state.tf_kind = tf_kind;
+    h->h_state.update_scale = update_scale ? 1 : 0;
+    // only the two selectors: the rest of the device state may be ahead of the host mirror
+    CU(cudaMemcpyAsync(&h->d_state->tf_kind, &h->h_state.tf_kind, 2 * sizeof(int), cudaMemcpyHostToDevice, h->stream));
+    CU(cudaMemcpyAsync(h->d_pt1, pt1, (size_t)h->n * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    CU(cudaMemcpyAsync(h->d_p1, p1, (size_t)h->m * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    TRY(upload_cloud(h, px, h->m, h->d_px));
+    const int nbs = (int)blocks_for(h->m), nbt = (int)blocks_for(h->n);
+    centre_px_kernel<<<nbs, THREADS, 0, h->stream>>>(h->d_state, h->d_p1, h->d_px, (int)h->m, h->d_pxc);
+    finalize2_kernel<false><<<nbs, THREADS, 0, h->stream>>>(nullptr, nullptr, 0, (int)h->m, h->d_yc, h->d_p1, h->d_pxc, h->d_mom_src);
+    tgt_moments_kernel<<<nbt, THREADS, 0, h->stream>>>(h->d_pt1, h->d_xc, (int)h->n, h->d_mom_tgt);
+    moments_kernel<false><<<1, 32, 0, h->stream>>>(h->d_state, h->d_mom_src, nbs, h->d_mom_tgt, nbt, h->d_mom);
+    KCHECK();
+    if (h->comm) TRY(allreduce(h, h->d_mom + MOM_SRC, MOM_TGT));   // p1/px are already global; pt1 is per shard
+    mstep_kernel<<<1, 32, 0, h->stream>>>(h->d_state, h->d_mom);
+    KCHECK();
+    h->launches += 5;
+    return read_params(h, out);
+}
+
+extern "C" int cpd_rbf_kernel(int device, const double* x, int64_t nx, const double* y, int64_t ny, int dim, double beta, float* out) {
+    if (!x || !y || !out || nx < 1 || ny < 1 || dim < 1 || dim > 16) return fail(CPD_ERR_ARG, "bad argument");
+    if (cpd_device_count() == 0) return fail(CPD_ERR_CUDA, "no CUDA device: this library has no CPU path");
+    CU(cudaSetDevice(device));
+    std::vector<float> xf((size_t)nx * dim), yf((size_t)ny * dim);   // the pybind11/Eigen cast to float32 (cc/types.h:19)
+    for (size_t i = 0; i < xf.size(); ++i) xf[i] = (float)x[i];
+    for (size_t i = 0; i < yf.size(); ++i) yf[i] = (float)y[i];
+    float *dx = nullptr, *dy = nullptr, *dout = nullptr;
+    TRY(dev_alloc(&dx, xf.size()));
+    TRY(dev_alloc(&dy, yf.size()));
+    TRY(dev_alloc(&dout, (size_t)nx * ny));
+    CU(cudaMemcpy(dx, xf.data(), xf.size() * sizeof(float), cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(dy, yf.data(), yf.size() * sizeof(float), cudaMemcpyHostToDevice));
+    dim3 grid(blocks_for(ny), (unsigned)nx);
+    rbf_kernel_kernel<<<grid, THREADS>>>(dx, nx, dy, ny, dim, (float)(1.0 / (2.0 * beta)), dout);
+    KCHECK();
+    CU(cudaMemcpy(out, dout, (size_t)nx * ny * sizeof(float), cudaMemcpyDeviceToHost));
+    cudaFree(dx); cudaFree(dy); cudaFree(dout);
+    return CPD_OK;
+}
+
+extern "C" int cpd_squared_kernel_sum(int device, const double* x, int64_t nx, const double* y, int64_t ny, int dim, double* out) {
+    if (!x || !y || !out) return fail(CPD_ERR_ARG, "null argument");
+    cpd_ctx* h = nullptr;
+    TRY(cpd_create(&h, device, dim, nullptr));
+    int r = cpd_set_source(h, x, nx);
+    if (r == CPD_OK) r = cpd_set_target(h, y, ny, ny, nullptr);
+    if (r == CPD_OK) r = cpd_sigma2_init(h, out);
+    cpd_destroy(h);
+    return r;
+}
+
+extern "C" int cpd_comm_unique_id(char id[128]) {
+    TRY(load_nccl());
+    nccl_uid u;
+    NC(g_nccl.GetUniqueId(&u));
+    memcpy(id, u.internal, 128);
+    return CPD_OK;
+}
+
+extern "C" int cpd_comm_init(cpd_ctx* h, int world_size, int rank, const char id[128]) {
+    if (!h || !id) return fail(CPD_ERR_ARG, "null argument");
+    if (world_size < 1 || rank < 0 || rank >= world_size) return fail(CPD_ERR_ARG, "bad world_size/rank %d/%d", world_size, rank);
+    TRY(load_nccl());
+    CU(cudaSetDevice(h->device));
+    nccl_uid u;
+    memcpy(u.internal, id, 128);
+    NC(g_nccl.CommInitRank(&h->comm, world_size, u, rank));
+    h->world = world_size;
+    h->rank = rank;
+    return CPD_OK;
+}
+
+extern "C" int cpd_timer_start(cpd_ctx* h) {
+    if (!h) return fail(CPD_ERR_ARG, "null handle");
+    CU(cudaEventRecord(h->ev0, h->stream));
+    return CPD_OK;
+}
+extern "C" int cpd_timer_stop(cpd_ctx* h, float* ms) {
+    if (!h || !ms) return fail(CPD_ERR_ARG, "null argument");
+    CU(cudaEventRecord(h->ev1, h->stream));
+    CU(cudaEventSynchronize(h->ev1));
+    CU(cudaEventElapsedTime(ms, h->ev0, h->ev1));
+    return CPD_OK;
+}
+extern "C" int cpd_sync(cpd_ctx* h) {
+    if (!h) return fail(CPD_ERR_ARG, "null handle");
+    CU(cudaStreamSynchronize(h->stream));
+    return CPD_OK;
+}
+extern "C" int cpd_event_record(cpd_ctx* h, int idx) {
+    if (!h || idx < 0 || idx >= 8192) return fail(CPD_ERR_ARG, "bad event slot %d", idx);
+    if ((int)h->pool.size() <= idx) h->pool.resize((size_t)idx + 1, nullptr);
+    if (!h->pool[idx]) CU(cudaEventCreate(&h->pool[idx]));
+    CU(cudaEventRecord(h->pool[idx], h->stream));
+    return CPD_OK;
+}
+extern "C" int cpd_event_elapsed(cpd_ctx* h, int a, int b, float* ms) {
+    if (!h || !ms || a < 0 || b < 0 || a >= (int)h->pool.size() || b >= (int)h->pool.size() || !h->pool[a] || !h->pool[b])
+        return fail(CPD_ERR_ARG, "event slot not recorded");
+    CU(cudaEventSynchronize(h->pool[b]));
+    CU(cudaEventElapsedTime(ms, h->pool[a], h->pool[b]));
+    return CPD_OK;
+}
+extern "C" int cpd_set_profiling(cpd_ctx* h, int on) {
+    if (!h) return fail(CPD_ERR_ARG, "null handle");
+    h->profiling = on != 0;
+    return CPD_OK;
+}
+extern "C" int cpd_stage_times(cpd_ctx* h, float ms[6]) {
+    if (!h || !ms) return fail(CPD_ERR_ARG, "null argument");
+    CU(cudaEventSynchronize(h->sev[6]));
+    for (int k = 0; k < 6; ++k) CU(cudaEventElapsedTime(&ms[k], h->sev[k], h->sev[k + 1]));
+    return CPD_OK;
+}
+extern "C" int64_t cpd_launch_count(cpd_ctx* h) { return h ? h->launches : 0; }
+
+extern "C" int cpd_flush_l2(cpd_ctx* h, int64_t bytes) {
+    if (!h) return fail(CPD_ERR_ARG, "null handle");
+    const size_t want = bytes > 0 ? (size_t)bytes : ((size_t)256 << 20);
+    if (h->flush_cap < want) {
+        if (h->d_flush) cudaFree(h->d_flush);
+        h->d_flush = nullptr;
+        CU(cudaMalloc(&h->d_flush, want));
+        h->flush_cap = want;
+    }
+    CU(cudaMemsetAsync(h->d_flush, 0x5a, want, h->stream));
+    return CPD_OK;
+}
+
+extern "C" int cpd_microbench(int device, double out[4]) {
+    if (!out) return fail(CPD_ERR_ARG, "null argument");
+    if (cpd_device_count() == 0) return fail(CPD_ERR_CUDA, "no CUDA device");
+    CU(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    CU(cudaGetDeviceProperties(&prop, device));
+    float* d = nullptr;
+    long long* dc = nullptr;
+    TRY(dev_alloc(&d, 16));
+    TRY(dev_alloc(&dc, 2));
+    cudaEvent_t e0, e1;
+    CU(cudaEventCreate(&e0));
+    CU(cudaEventCreate(&e1));
+    const int blocks = prop.multiProcessorCount * 8, iters = 200000;
+    float ms = 0.f;
+    probe_ffma_kernel<<<blocks, 256>>>(d, 1000, 1.0f);
+    CU(cudaEventRecord(e0));
+    probe_ffma_kernel<<<blocks, 256>>>(d, iters, 1.0f);
+    CU(cudaEventRecord(e1));
+    CU(cudaEventSynchronize(e1));
+    CU(cudaEventElapsedTime(&ms, e0, e1));
+    out[0] = (double)blocks * 256.0 * iters * 16.0 * 2.0 / (ms * 1e-3) / 1e12;
+    probe_mufu_kernel<<<blocks, 256>>>(d, 1000, 1.0f);
+    CU(cudaEventRecord(e0));
+    probe_mufu_kernel<<<blocks, 256>>>(d, iters / 4, 1.0f);
+    CU(cudaEventRecord(e1));
+    CU(cudaEventSynchronize(e1));
+    CU(cudaEventElapsedTime(&ms, e0, e1));
+    out[1] = (double)blocks * 256.0 * (iters / 4) * 8.0 / (ms * 1e-3) / 1e9;
+    probe_clock_kernel<<<1, 1>>>(dc);
+    long long hc[2];
+    CU(cudaMemcpy(hc, dc, sizeof(hc), cudaMemcpyDeviceToHost));
+    out[2] = (double)hc[0] / ((double)hc[1] * 1e-9) / 1e6;
+    out[3] = prop.multiProcessorCount;
+    cudaFree(d); cudaFree(dc);
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    return CPD_OK;
+}

@@ -1,0 +1,66 @@
+"""Multi-GPU plumbing: one process per GPU, targets sharded, sources replicated.
+
+The reference has no distributed path at all; this is the B200-side design of SURVEY section
+8(e).  ``den_n`` is a sum over sources for a fixed target, so with the sources replicated the
+first E-step pass needs no communication; the second pass yields per-rank partial sums of the
+M-step moments, which are combined by ONE ``ncclAllReduce(sum, float64)`` of 32 doubles per EM
+iteration, issued by libcpd_b200.so on its own stream (cpd_comm_init / cpd_em_step).
+
+``torch.distributed`` is used only as the rendezvous: to hand the 128-byte NCCL unique id from
+rank 0 to the other ranks.  Any backend works for that (``gloo`` in the CPU tests).
+"""
+import os
+
+import numpy as np
+
+
+def shard_bounds(n, rank, world_size):
+    """Contiguous, balanced split of n target rows: rank r owns [lo, hi)."""
+    return (n * rank) // world_size, (n * (rank + 1)) // world_size
+
+
+class Communicator(object):
+    def __init__(self, rank=0, world_size=1, device=0, exchange=None):
+        """exchange(obj_or_None) -> obj : broadcast of a small picklable object from rank 0."""
+        self.rank = int(rank)
+        self.world_size = int(world_size)
+        self.device = int(device)
+        self._exchange = exchange
+
+    @classmethod
+    def from_torch(cls, device=None):
+        """Build from an initialised ``torch.distributed`` process group (torchrun env)."""
+        import torch.distributed as dist
+
+        if not dist.is_initialized():
+            raise RuntimeError("torch.distributed is not initialised")
+        rank, world = dist.get_rank(), dist.get_world_size()
+        if device is None:
+            device = int(os.environ.get("LOCAL_RANK", rank))
+
+        def exchange(obj):
+            box = [obj]
+            dist.broadcast_object_list(box, src=0)
+            return box[0]
+
+        return cls(rank, world, device, exchange)
+
+    def shard_bounds(self, n):
+        return shard_bounds(n, self.rank, self.world_size)
+
+    def frame_origin(self, target):
+        """Common origin every rank centres on.  Each rank holds the full host array in this API,
+        so the mean of the full cloud is computed locally and is bit-identical everywhere."""
+        return np.asarray(target, dtype=np.float64).mean(axis=0)
+
+    def unique_id(self):
+        """A fresh ncclUniqueId, created on rank 0 and broadcast.  Collective: every rank must
+        call it the same number of times, in the same order."""
+        from . import _cabi
+
+        uid = _cabi.unique_id() if self.rank == 0 else None
+        if self.world_size > 1:
+            if self._exchange is None:
+                raise RuntimeError("Communicator needs an exchange function when world_size > 1")
+            uid = self._exchange(uid)
+        return uid

@@ -116,3 +116,27 @@ def test_appendix_c_values(bunny):
     assert float(bunny["rigid_default_sigma2"]) == pytest.approx(1.1920928955078125e-07)
     assert float(bunny["rigid10_sigma2"]) == pytest.approx(3.9235098811641994e-05, rel=1e-9)
     assert float(bunny["rigid10_scale"]) == pytest.approx(0.9571492390382025, rel=1e-10)
+
+
+def test_c_oracle_matches_numpy_oracle(syn1500):
+    from oracle import c_oracle
+    ts, tgt = syn1500["es_tsource"], syn1500["target_outl"]
+    for s2, w in [(1e-4, 0.0), (1e-4, 0.1), (3e-3, 0.0), (0.2, 0.3)]:
+        a = orc.expectation_step(ts, tgt, s2, w)
+        b = c_oracle.expectation_step(ts, tgt, s2, w)
+        np.testing.assert_allclose(b.pt1, a.pt1, rtol=1e-11, atol=0)   # libm exp vs numpy SIMD exp
+        np.testing.assert_allclose(b.p1, a.p1, rtol=1e-11, atol=1e-300)
+        np.testing.assert_allclose(b.px, a.px, rtol=1e-11, atol=1e-300)
+        assert b.n_p == pytest.approx(a.n_p, rel=1e-13)
+    fs = np.random.default_rng(0).random((50, 2))
+    a = orc.expectation_step(fs, fs[::-1] + 0.01, 0.02, 0.1)
+    b = c_oracle.expectation_step(fs, fs[::-1] + 0.01, 0.02, 0.1)
+    np.testing.assert_allclose(b.p1, a.p1, rtol=1e-12)
+
+
+def test_bench_workload_is_the_oracles():
+    from probreg_b200 import synthetic
+    for kind in ("rigid", "affine"):
+        a = orc.synthetic_pair(777, kind)
+        b = synthetic.synthetic_pair(777, kind)
+        assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1])
