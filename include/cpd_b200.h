@@ -130,9 +130,11 @@ int cpd_stage_times(cpd_ctx* h, float ms[6]);
 int64_t cpd_launch_count(cpd_ctx* h);
 /* overwrite `bytes` of scratch to evict L2 (bench hygiene); 0 => default 256 MiB.        */
 int cpd_flush_l2(cpd_ctx* h, int64_t bytes);
-/* FP32 FMA / MUFU.EX2 issue-rate micro-benchmark: out[0] = FFMA TFLOP/s, out[1] = MUFU.EX2
- * Gop/s, out[2] = SM clock MHz seen by the probe, out[3] = SM count.                      */
-int cpd_microbench(int device, double out[4]);
+/* Issue-rate micro-benchmarks for the roofline denominators: out[0] = FFMA TFLOP/s, out[1] =
+ * MUFU.EX2 Gop/s, out[2] = SM clock MHz seen by the probe, out[3] = SM count, out[4] = packed
+ * FFMA2 TFLOP/s, out[5..7] = Gpairs/s of synthetic (11 FP32 + 1 MUFU), packed (6 FFMA2-class + 2
+ * MUFU per 2 pairs) and (7 FP32 + 1 MUFU) instruction mixes.                               */
+int cpd_microbench(int device, double out[8]);
 
 #ifdef __cplusplus
 }

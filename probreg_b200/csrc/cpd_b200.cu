@@ -93,7 +93,7 @@ struct cpd_ctx {
     double *d_yc = nullptr, *d_ts = nullptr, *d_xc = nullptr, *d_raw = nullptr;
     size_t raw_cap = 0;
     float4 *d_srcP = nullptr, *d_tgtP = nullptr, *d_tgtQ = nullptr;
-    float2* d_part1 = nullptr;
+    P1Part* d_part1 = nullptr;
     double* d_part2 = nullptr;
     size_t part1_cap = 0, part2_cap = 0;
     double *d_pt1 = nullptr, *d_p1 = nullptr, *d_pxc = nullptr, *d_px = nullptr;
@@ -194,7 +194,7 @@ int prepare(cpd_ctx* h) {
     const size_t need1 = (size_t)h->j1 * h->n, need2 = (size_t)h->j2 * h->m * 4;
     if (need1 > h->part1_cap) { TRY(dev_alloc(&h->d_part1, need1)); h->part1_cap = need1; }
     if (need2 > h->part2_cap) { TRY(dev_alloc(&h->d_part2, need2)); h->part2_cap = need2; }
-    const size_t ms = (size_t)blocks_for(h->m) * MOM_SRC, mt = (size_t)blocks_for(h->npad) * MOM_TGT;
+    const size_t ms = (size_t)blocks_for(h->m) * MOM_SRC, mt = (size_t)blocks_for(h->npad) * MOM_TGT;   // MOM_* >= RM_*
     if (ms > h->mom_src_cap) { TRY(dev_alloc(&h->d_mom_src, ms)); h->mom_src_cap = ms; }
     if (mt > h->mom_tgt_cap) { TRY(dev_alloc(&h->d_mom_tgt, mt)); h->mom_tgt_cap = mt; }
     h->prepared = true;
@@ -223,14 +223,13 @@ int launch_estep(cpd_ctx* h, const double* d_sigma2, const double* d_w, const do
                                                                     h->j1, h->d_part1);
     mark(h, 2);
     finalize1_kernel<<<blocks_for(h->npad), THREADS, 0, h->stream>>>(h->d_state, d_sigma2, d_w, h->d_part1, h->j1, (int)h->n,
-                                                                     h->d_tgtP, h->d_xc, h->d_tgtQ, h->npad, h->d_pt1,
-                                                                     h->d_mom_tgt);
+                                                                     h->d_tgtP, h->d_tgtQ, h->npad, h->d_pt1, h->d_mom_tgt);
     mark(h, 3);
     pass2_kernel<<<h->it2 * h->j2, THREADS, PASS_SMEM, h->stream>>>(h->d_srcP, (int)h->m, h->d_tgtQ, (int)(h->npad / P2_STAGE),
                                                                     h->j2, h->d_part2);
     mark(h, 4);
-    finalize2_kernel<true><<<blocks_for(h->m), THREADS, 0, h->stream>>>(d_sigma2, h->d_part2, h->j2, (int)h->m, h->d_yc, h->d_p1,
-                                                                        h->d_pxc, h->d_mom_src);
+    finalize2_kernel<<<blocks_for(h->m), THREADS, 0, h->stream>>>(h->d_state, d_sigma2, h->d_part2, h->j2, (int)h->m, h->d_yc,
+                                                                  d_ts, h->d_p1, h->d_pxc, h->d_mom_src);
     mark(h, 5);
     KCHECK();
     h->launches += 5;
@@ -426,12 +425,12 @@ extern "C" int cpd_em_step(cpd_ctx* h, cpd_params* out) {
     TRY(launch_estep(h, &h->d_state->sigma2, &h->d_state->w, nullptr));
     const int nbs = (int)blocks_for(h->m), nbt = (int)blocks_for(h->npad);
     if (h->comm) {
-        moments_kernel<false><<<1, 32, 0, h->stream>>>(h->d_state, h->d_mom_src, nbs, h->d_mom_tgt, nbt, h->d_mom);
+        moments_kernel<0><<<1, 32, 0, h->stream>>>(h->d_state, h->d_mom_src, nbs, RM_SRC, h->d_mom_tgt, nbt, RM_TGT, h->d_mom);
         TRY(allreduce(h, h->d_mom, MOM_PAD));
-        mstep_kernel<<<1, 32, 0, h->stream>>>(h->d_state, h->d_mom);
+        mstep_residual_kernel<<<1, 32, 0, h->stream>>>(h->d_state, h->d_mom);
         h->launches += 2;
     } else {
-        moments_kernel<true><<<1, 32, 0, h->stream>>>(h->d_state, h->d_mom_src, nbs, h->d_mom_tgt, nbt, h->d_mom);
+        moments_kernel<1><<<1, 32, 0, h->stream>>>(h->d_state, h->d_mom_src, nbs, RM_SRC, h->d_mom_tgt, nbt, RM_TGT, h->d_mom);
         h->launches += 1;
     }
     mark(h, 6);
@@ -493,7 +492,7 @@ extern "C" int cpd_last_estep(cpd_ctx* h, double* pt1, double* p1, double* px, d
         // n_p = sum(p1) (cpd.py:88): block partials of the (possibly all-reduced) p1
         const unsigned nb = blocks_for(h->m);
         if (h->sums_cap < (size_t)nb * 4 + 4) { TRY(dev_alloc(&h->d_sums, (size_t)nb * 4 + 4)); h->sums_cap = (size_t)nb * 4 + 4; }
-        finalize2_kernel<false><<<nb, THREADS, 0, h->stream>>>(nullptr, nullptr, 0, (int)h->m, h->d_yc, h->d_p1, h->d_pxc, h->d_mom_src);
+        src_moments_api_kernel<<<nb, THREADS, 0, h->stream>>>((int)h->m, h->d_yc, h->d_p1, h->d_pxc, h->d_mom_src);
         reduce_cols_kernel<<<1, 32, 0, h->stream>>>(h->d_mom_src, (int)nb, MOM_SRC, h->d_mom);
         KCHECK();
         h->launches += 2;
@@ -521,12 +520,12 @@ extern "C" int cpd_mstep(cpd_ctx* h, int tf_kind, int update_scale, const double
     TRY(upload_cloud(h, px, h->m, h->d_px));
     const int nbs = (int)blocks_for(h->m), nbt = (int)blocks_for(h->n);
     centre_px_kernel<<<nbs, THREADS, 0, h->stream>>>(h->d_state, h->d_p1, h->d_px, (int)h->m, h->d_pxc);
-    finalize2_kernel<false><<<nbs, THREADS, 0, h->stream>>>(nullptr, nullptr, 0, (int)h->m, h->d_yc, h->d_p1, h->d_pxc, h->d_mom_src);
-    tgt_moments_kernel<<<nbt, THREADS, 0, h->stream>>>(h->d_pt1, h->d_xc, (int)h->n, h->d_mom_tgt);
-    moments_kernel<false><<<1, 32, 0, h->stream>>>(h->d_state, h->d_mom_src, nbs, h->d_mom_tgt, nbt, h->d_mom);
+    src_moments_api_kernel<<<nbs, THREADS, 0, h->stream>>>((int)h->m, h->d_yc, h->d_p1, h->d_pxc, h->d_mom_src);
+    tgt_moments_api_kernel<<<nbt, THREADS, 0, h->stream>>>(h->d_pt1, h->d_xc, (int)h->n, h->d_mom_tgt);
+    moments_kernel<0><<<1, 32, 0, h->stream>>>(h->d_state, h->d_mom_src, nbs, MOM_SRC, h->d_mom_tgt, nbt, MOM_TGT, h->d_mom);
     KCHECK();
     if (h->comm) TRY(allreduce(h, h->d_mom + MOM_SRC, MOM_TGT));   // p1/px are already global; pt1 is per shard
-    mstep_kernel<<<1, 32, 0, h->stream>>>(h->d_state, h->d_mom);
+    mstep_api_kernel<<<1, 32, 0, h->stream>>>(h->d_state, h->d_mom);
     KCHECK();
     h->launches += 5;
     return read_params(h, out);
@@ -642,7 +641,7 @@ extern "C" int cpd_flush_l2(cpd_ctx* h, int64_t bytes) {
     return CPD_OK;
 }
 
-extern "C" int cpd_microbench(int device, double out[4]) {
+extern "C" int cpd_microbench(int device, double out[8]) {
     if (!out) return fail(CPD_ERR_ARG, "null argument");
     if (cpd_device_count() == 0) return fail(CPD_ERR_CUDA, "no CUDA device");
     CU(cudaSetDevice(device));
@@ -655,22 +654,30 @@ extern "C" int cpd_microbench(int device, double out[4]) {
     cudaEvent_t e0, e1;
     CU(cudaEventCreate(&e0));
     CU(cudaEventCreate(&e1));
-    const int blocks = prop.multiProcessorCount * 8, iters = 200000;
+    const int blocks = prop.multiProcessorCount * 8, iters = 100000;
     float ms = 0.f;
-    probe_ffma_kernel<<<blocks, 256>>>(d, 1000, 1.0f);
-    CU(cudaEventRecord(e0));
-    probe_ffma_kernel<<<blocks, 256>>>(d, iters, 1.0f);
-    CU(cudaEventRecord(e1));
-    CU(cudaEventSynchronize(e1));
+#define TIME_PROBE(KERNEL, IT)                       \
+    KERNEL<<<blocks, 256>>>(d, 500, 1.0f);           \
+    CU(cudaEventRecord(e0));                         \
+    KERNEL<<<blocks, 256>>>(d, (IT), 1.0f);          \
+    CU(cudaEventRecord(e1));                         \
+    CU(cudaEventSynchronize(e1));                    \
     CU(cudaEventElapsedTime(&ms, e0, e1));
-    out[0] = (double)blocks * 256.0 * iters * 16.0 * 2.0 / (ms * 1e-3) / 1e12;
-    probe_mufu_kernel<<<blocks, 256>>>(d, 1000, 1.0f);
-    CU(cudaEventRecord(e0));
-    probe_mufu_kernel<<<blocks, 256>>>(d, iters / 4, 1.0f);
-    CU(cudaEventRecord(e1));
-    CU(cudaEventSynchronize(e1));
-    CU(cudaEventElapsedTime(&ms, e0, e1));
-    out[1] = (double)blocks * 256.0 * (iters / 4) * 8.0 / (ms * 1e-3) / 1e9;
+    const double threads = (double)blocks * 256.0;
+    TIME_PROBE(probe_ffma_kernel, iters);
+    out[0] = threads * iters * 16.0 * 2.0 / (ms * 1e-3) / 1e12;              // FFMA TFLOP/s
+    TIME_PROBE(probe_mufu_kernel, iters / 4);
+    out[1] = threads * (iters / 4) * 8.0 / (ms * 1e-3) / 1e9;                // MUFU.EX2 Gop/s
+    TIME_PROBE(probe_ffma2_kernel, iters);
+    out[4] = threads * iters * 8.0 * 4.0 / (ms * 1e-3) / 1e12;               // FFMA2 TFLOP/s
+    // pairs/s of an (11 FP32 + 1 MUFU) mix, scalar and packed (6 FFMA2 ~ 12 FP32 per 2 pairs), and (7 + 1)
+    TIME_PROBE((probe_mix_kernel<11, false>), iters / 8);
+    out[5] = threads * (iters / 8) * 8.0 / (ms * 1e-3) / 1e9;                // Gpairs/s, scalar 11+1
+    TIME_PROBE((probe_mix_kernel<5, true>), iters / 8);
+    out[6] = threads * (iters / 8) * 8.0 / (ms * 1e-3) / 1e9;                // Gpairs/s, packed (5 FFMA2 + FMUL) + 1 MUFU
+    TIME_PROBE((probe_mix_kernel<7, false>), iters / 8);
+    out[7] = threads * (iters / 8) * 8.0 / (ms * 1e-3) / 1e9;                // Gpairs/s, scalar 7+1
+#undef TIME_PROBE
     probe_clock_kernel<<<1, 1>>>(dc);
     long long hc[2];
     CU(cudaMemcpy(hc, dc, sizeof(hc), cudaMemcpyDeviceToHost));

@@ -5,15 +5,25 @@
 //   P = K / den,  pt1_n = sum_m P_mn,  p1_m = sum_n P_mn,  px_m = sum_n P_mn x_n.
 // How: two tiled passes over the M x N pair space that never store P.
 //   pass 1  (i = targets in registers, j = sources streamed through shared memory by TMA bulk
-//            copies): per-target log2 of the column sum, kept as (integer offset o, FP32 sum S)
-//            with  sum_m 2^(-u_mn) = S * 2^(-o)   -- a lazily rebased log-sum-exp.
-//   pass 2  (i = sources in registers, j = targets streamed): p = 2^(-u - L_n) recomputed,
-//            p1/px accumulated in FP32 per 64-target sub-chunk and flushed into FP64.
+//            copies): per target an integer offset o and FP64 sums S, SU with
+//              sum_m 2^(-u_mn) = S 2^(-o),   sum_m 2^(-u_mn) u_mn = SU 2^(-o)
+//            -- a lazily rebased log-sum-exp that also yields the weighted squared residual.
+//   pass 2  (i = sources in registers, j = targets streamed): K = 2^(o_n - u) recomputed with the
+//            SAME integer offset (so MUFU.EX2 sees the same fractional argument as in pass 1 and
+//            its approximation error cancels in K / sum K), P = K * rn_n, and per source
+//            p1_m = sum_n P and the RESIDUAL sum  sd_m = sum_n P (a_m - b_n)  -- not sum_n P b_n.
 // u_mn = |a_m - b_n|^2 where a, b are the two clouds centred on a common origin and scaled by
 // sqrt(log2(e) / (2 sigma^2)), so that exp(-d^2/2sigma^2) == 2^(-u): one MUFU.EX2 per pair and
 // no multiply by 1/(2 sigma^2).  Pair arithmetic is FP32 on direct differences (never the
 // |a|^2+|b|^2-2ab expansion, which cancels catastrophically once sigma << extent); every
-// accumulation that crosses a sub-chunk is FP64.
+// accumulation that crosses a 64-point sub-chunk is FP64.
+//
+// Why residual sums: the reference's M-step forms sigma2 = (tr_xp1x - s tr_atr)/(Np D), a
+// difference of two sums that agree to extent^2/(3 sigma^2) -- 40x on the bunny after ten
+// iterations, >1e4x near convergence.  FP64 P (the reference) survives that; FP32-accurate P does
+// not (measured: 5e-6 relative on sigma2).  Accumulating P*(a-b) and P*u instead gives the same
+// M-step as an UPDATE of the previous transform (mstep_solve_residual) in which every large term
+// is formed in FP64 from p1 alone and the FP32-accurate sums only enter through small quantities.
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -32,17 +42,30 @@ constexpr int PASS_SMEM = NSTAGE * STAGE_BYTES + 64;
 
 constexpr float O_INIT = 1048576.0f;   // 2^20: "no source seen yet" offset; u above it is dead anyway
 constexpr float TWO100 = 1.2676506002282294e30f;
-constexpr float TWO64 = 18446744073709551616.0f;
-constexpr float TWOM64 = 5.421010862427522e-20f;
 constexpr float FAR_COORD = 1.0e18f;   // padding sources: u = 3e36, 2^(o-u) == 0
 
 constexpr double LOG2E = 1.4426950408889634074;
 constexpr double DEAD_LOG2 = -1075.0;  // float64 exp(x) == 0  <=>  x*log2(e) < -1075 (half the least denormal)
 constexpr double EPS32 = 1.1920928955078125e-07;
 
-// moments layout (extended with the pt1-side sums the reference uses)
+// Moments of the fused EM loop (residual form, all-reduced across ranks):
+//   source side, per block of finalize2:  Np, Sy = sum p1 y~, C = sum p1 y~ y~^T (6), V1 = sum v, VY = sum v y~^T (9)
+//   target side, per block of finalize1:  Srr = sum_n sum_m P_mn u_mn (scaled units), Npt = sum pt1
+// with v_m = sum_n P_mn (x_n - T(y_m)) the weighted residual of source m and y~ = y - cy.
+enum { RM_NP = 0, RM_SY = 1, RM_C = 4, RM_V1 = 10, RM_VY = 13, RM_SRC = 22, RM_SRR = 22, RM_NPT = 23, RM_TGT = 2,
+       RM_COUNT = 24, MOM_PAD = 32 };
+// Moments of the API-faithful M-step (cpd_mstep: a caller-supplied EstepResult; SURVEY appendix A.3
+// extended with the pt1-side sums the reference uses)
 enum { MOM_NP = 0, MOM_SX = 1, MOM_SY = 4, MOM_B = 7, MOM_C = 16, MOM_NPT = 22, MOM_SXT = 23, MOM_TXX = 26,
-       MOM_COUNT = 27, MOM_PAD = 32, MOM_SRC = 22, MOM_TGT = 5 };
+       MOM_COUNT = 27, MOM_SRC = 22, MOM_TGT = 5 };
+
+// per-split, per-target result of pass 1
+struct P1Part {
+    double S;    // sum_m 2^(o - u)
+    double SU;   // sum_m 2^(o - u) u
+    float o;     // integer-valued offset
+    float pad;
+};
 
 // Device-resident EM state.  The first 16 doubles mirror cpd_params.
 struct DevState {
@@ -124,9 +147,6 @@ __device__ __forceinline__ void block_reduce_store(double (&v)[K], double* out) 
         out[threadIdx.x] = s;
     }
 }
-__device__ __forceinline__ float pow2i(float k) {   // 2^k for integer-valued k <= 0, exact
-    return (k < -126.0f) ? 0.0f : __int_as_float((__float2int_rn(k) + 127) << 23);
-}
 
 // ---------------------------------------------------------------------------------------------
 // pack: transform + centre + scale both clouds into the FP32 working frame
@@ -176,21 +196,24 @@ pack_kernel(const DevState* __restrict__ st, const double* __restrict__ sigma2_p
 }
 
 // ---------------------------------------------------------------------------------------------
-// pass 1: per target n, (o_n, S_n) with  sum_{m in split} 2^(-u_mn) = S_n * 2^(-o_n)
-// grid = itiles * nsplit CTAs; CTA (itile, split) owns 1024 targets and stages [st0, st1) of
-// the padded source array.  7 FP32-pipe + 1 MUFU instruction per pair in the common path.
+// pass 1: per target n and split:  (o, S, SU) with  sum_m 2^(-u) = S 2^(-o),  sum_m 2^(-u) u = SU 2^(-o)
+// grid = itiles * nsplit CTAs; CTA (itile, split) owns 1024 targets and stages [st0, st1) of the
+// padded source array.  8 FP32-pipe + 1 MUFU instruction per pair in the common path.
 //
-// Lazy offset: o is integer-valued and only ever lowered.  A sub-chunk of 64 sources is summed
-// with the current o; if any lane's partial sum exceeds 2^100 (a source much nearer than any
-// seen before, i.e. 2^(o-u) overflowed or nearly did) the warp re-does that sub-chunk: one
-// sweep for the sub-chunk minimum of u, o := min(o, floor(umin)), S rescaled by the exact power
-// of two, sub-chunk summed again.  Otherwise S += partial and, when S > 2^64, (S, o) are
-// rebased by exactly 2^-64.  Hence 2^-20 <= largest term <= 2^100 at all times: no overflow,
-// and every term that matters stays a normal FP32 number.
+// Lazy log-sum-exp: each target carries an integer-valued offset o (only ever lowered).  A
+// sub-chunk of 64 sources is summed in FP32 from zero with the current o -- Sc = sum e,
+// Uc = sum e*t with t = o - u, e = 2^t -- and folded into the FP64 running sums
+// (S += Sc, SU += o*Sc - Uc).  FP32 running sums over thousands of terms systematically drop
+// the small ones (absorption); 64 from zero, FP64 beyond, keeps that below 1e-8.  If any lane's
+// sub-chunk sum reaches 2^100 (a source much nearer than any seen before: 2^(o-u) overflowed or
+// nearly did) the warp re-does that sub-chunk: one sweep for the sub-chunk minimum of u,
+// o := min(o, floor(umin)), S and SU rescaled by the exact power of two, sub-chunk summed again.
+// The largest term of a target is >= 2^-1 right after its offset was set and <= 2^100 always, so
+// every term that matters stays a normal FP32 number.
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(THREADS, 2)
 pass1_kernel(const float4* __restrict__ ipts, int ni, const float4* __restrict__ jpts, int nstages, int nsplit,
-             float2* __restrict__ part) {
+             P1Part* __restrict__ part) {
     extern __shared__ __align__(128) unsigned char smraw[];
     float4* sm = reinterpret_cast<float4*>(smraw);
     uint64_t* full = reinterpret_cast<uint64_t*>(smraw + NSTAGE * STAGE_BYTES);
@@ -210,14 +233,15 @@ pass1_kernel(const float4* __restrict__ ipts, int ni, const float4* __restrict__
             tma_load_1d(sm + s * P1_STAGE, jpts + (size_t)(st0 + s) * P1_STAGE, STAGE_BYTES, &full[s]);
         }
     }
-    float ax[RI], ay[RI], az[RI], o[RI], S[RI];
+    float ax[RI], ay[RI], az[RI], o[RI];
+    double S[RI], SU[RI];
 #pragma unroll
     for (int r = 0; r < RI; ++r) {
         int n = itile * ITILE + r * THREADS + tid;
         n = n < ni ? n : ni - 1;
         const float4 p = ipts[n];
         ax[r] = p.x; ay[r] = p.y; az[r] = p.z;
-        o[r] = O_INIT; S[r] = 0.0f;
+        o[r] = O_INIT; S[r] = 0.0; SU[r] = 0.0;
     }
     for (int it = 0; it < nst; ++it) {
         const int s = it % NSTAGE;
@@ -226,9 +250,9 @@ pass1_kernel(const float4* __restrict__ ipts, int ni, const float4* __restrict__
 #pragma unroll 1
         for (int sc = 0; sc < P1_STAGE / SUB; ++sc) {
             const float4* q = sp + sc * SUB;
-            float Sc[RI];
+            float Sc[RI], Uc[RI];
 #pragma unroll
-            for (int r = 0; r < RI; ++r) Sc[r] = 0.0f;
+            for (int r = 0; r < RI; ++r) { Sc[r] = 0.0f; Uc[r] = 0.0f; }
 #pragma unroll 8
             for (int jj = 0; jj < SUB; ++jj) {
                 const float4 b = q[jj];
@@ -238,7 +262,9 @@ pass1_kernel(const float4* __restrict__ ipts, int ni, const float4* __restrict__
                     float t = fmaf(-dx, dx, o[r]);
                     t = fmaf(-dy, dy, t);
                     t = fmaf(-dz, dz, t);
-                    Sc[r] += ex2(t);
+                    const float e = ex2(t);
+                    Sc[r] += e;
+                    Uc[r] = fmaf(e, t, Uc[r]);
                 }
             }
             bool bad = false;
@@ -260,9 +286,11 @@ pass1_kernel(const float4* __restrict__ ipts, int ni, const float4* __restrict__
 #pragma unroll
                 for (int r = 0; r < RI; ++r) {
                     const float on = fminf(o[r], floorf(cm[r]));
-                    S[r] *= pow2i(on - o[r]);
+                    const int sh = (int)fmaxf(on - o[r], -4000.0f);
+                    S[r] = ldexp(S[r], sh);
+                    SU[r] = ldexp(SU[r], sh);
                     o[r] = on;
-                    Sc[r] = 0.0f;
+                    Sc[r] = 0.0f; Uc[r] = 0.0f;
                 }
 #pragma unroll 8
                 for (int jj = 0; jj < SUB; ++jj) {
@@ -273,16 +301,17 @@ pass1_kernel(const float4* __restrict__ ipts, int ni, const float4* __restrict__
                         float t = fmaf(-dx, dx, o[r]);
                         t = fmaf(-dy, dy, t);
                         t = fmaf(-dz, dz, t);
-                        Sc[r] += ex2(t);
+                        const float e = ex2(t);
+                        Sc[r] += e;
+                        Uc[r] = fmaf(e, t, Uc[r]);
                     }
                 }
             }
 #pragma unroll
             for (int r = 0; r < RI; ++r) {
-                float s2 = S[r] + Sc[r];
-                const bool big = s2 > TWO64;
-                S[r] = big ? s2 * TWOM64 : s2;
-                o[r] = big ? o[r] - 64.0f : o[r];
+                const double sc64 = (double)Sc[r];
+                S[r] += sc64;
+                SU[r] += (double)o[r] * sc64 - (double)Uc[r];     // sum e*u = o*sum e - sum e*(o-u)
             }
         }
         __syncthreads();
@@ -294,64 +323,69 @@ pass1_kernel(const float4* __restrict__ ipts, int ni, const float4* __restrict__
 #pragma unroll
     for (int r = 0; r < RI; ++r) {
         const int n = itile * ITILE + r * THREADS + tid;
-        if (n < ni) part[(size_t)split * ni + n] = make_float2(o[r], S[r]);
+        if (n < ni) {
+            P1Part out;
+            out.S = S[r]; out.SU = SU[r]; out.o = o[r]; out.pad = 0.0f;
+            part[(size_t)split * ni + n] = out;
+        }
     }
 }
 
 // ---------------------------------------------------------------------------------------------
-// finalize 1: merge the per-split (o, S), apply the reference's column semantics, emit pt1 and
-// the pass-2 target records.
-//   log2S  = log2 sum_m K_mn                          (FP64)
+// finalize 1: merge the per-split sums, apply the reference's column semantics, emit pt1 and the
+// pass-2 target records.
+//   omin   = smallest offset of any split that saw something; S, SU rebased to it (exact)
+//   log2S  = log2 sum_m K_mn = log2(S) - omin                                  (FP64)
 //   dead   = log2S < -1075  -> the float64 column sum of the reference is exactly 0 (cpd.py:81:
 //            den = eps32 + c, every K_mn == 0, so P == 0 and pt1 == 0)
-//   L      = log2(den) = log2(2^log2S + c)            c = (2 pi s2)^(D/2) w/(1-w) M/N (cpd.py:78-79)
-//   pt1    = 2^(log2S - L)                            (cpd.py:85; == 1 when w == 0)
-//   record = {b, -Lhi}, {g, g*b}   with L = Lhi + Llo, Lhi a multiple of 2^-10 (exact in FP32),
-//            g = 2^-Llo in [1 - 3.4e-4, 1 + 3.4e-4]: the low part of L rides on the accumulation
-//            FMAs of pass 2 for free instead of costing precision or an extra multiply.
-// Also the pt1-side moments of the M-step: sum pt1, sum pt1*x~, sum pt1*|x~|^2 per block.
+//   L      = log2(den) = log2(2^log2S + c)          c = (2 pi s2)^(D/2) w/(1-w) M/N  (cpd.py:78-79)
+//   pt1    = 2^(log2S - L)                          (cpd.py:85; == 1 when w == 0)
+//   rn     = 2^(-omin) / den = 2^-(L + omin)        P_mn = 2^(omin - u_mn) * rn in pass 2
+//   record = {b, omin}, {rn, -, -, -}               dead: {b, -inf}, {0}
+// and the target-side moments: Srr = sum_n SU_n rn_n (= sum_mn P_mn u_mn), Npt = sum pt1.
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(THREADS)
 finalize1_kernel(const DevState* __restrict__ st, const double* __restrict__ sigma2_ptr, const double* __restrict__ w_ptr,
-                 const float2* __restrict__ part, int nsplit, int n, const float4* __restrict__ tgtP,
-                 const double* __restrict__ xc, float4* __restrict__ tgtQ, long long npad, double* __restrict__ pt1,
-                 double* __restrict__ mom_part) {
+                 const P1Part* __restrict__ part, int nsplit, int n, const float4* __restrict__ tgtP,
+                 float4* __restrict__ tgtQ, long long npad, double* __restrict__ pt1, double* __restrict__ mom_part) {
     const int i = blockIdx.x * THREADS + threadIdx.x;
-    double v[MOM_TGT] = {0.0, 0.0, 0.0, 0.0, 0.0};
+    double v[RM_TGT] = {0.0, 0.0};
     if (i < n) {
         float omin = 3.0e38f;
         for (int s = 0; s < nsplit; ++s) {
-            const float2 p = part[(size_t)s * n + i];
-            if (p.y > 0.0f) omin = fminf(omin, p.x);
+            const P1Part p = part[(size_t)s * n + i];
+            if (p.S > 0.0) omin = fminf(omin, p.o);
         }
-        double log2S = -INFINITY;
+        double log2S = -INFINITY, SU = 0.0;
         if (omin < 3.0e38f) {
-            double acc = 0.0;
+            double S = 0.0;
             for (int s = 0; s < nsplit; ++s) {
-                const float2 p = part[(size_t)s * n + i];
-                const float e = omin - p.x;            // integer-valued, <= 0
-                if (p.y > 0.0f && e > -1100.0f) acc += ldexp((double)p.y, (int)e);
+                const P1Part p = part[(size_t)s * n + i];
+                if (p.S > 0.0) {
+                    const int sh = (int)fmaxf(omin - p.o, -4000.0f);       // integer-valued, <= 0
+                    S += ldexp(p.S, sh);
+                    SU += ldexp(p.SU, sh);
+                }
             }
-            log2S = log2(acc) - (double)omin;
+            log2S = log2(S) - (double)omin;
         }
         const double sigma2 = *sigma2_ptr, w = *w_ptr;
-        const int dim = st->dim;
         double c = 0.0;
         if (w > 0.0) {
             const double tps = 2.0 * 3.14159265358979323846 * sigma2;
-            c = (dim == 3 ? tps * sqrt(tps) : tps) * (w / (1.0 - w) * (double)st->m / (double)st->n_global);
+            c = (st->dim == 3 ? tps * sqrt(tps) : tps) * (w / (1.0 - w) * (double)st->m / (double)st->n_global);
         }
         const bool dead = !(log2S >= DEAD_LOG2);
-        double L, p1n;
-        if (dead) {
-            L = INFINITY; p1n = 0.0;
-        } else if (c > 0.0) {
-            const double lc = log2(c);
-            const double hi = fmax(log2S, lc), lo = fmin(log2S, lc);
-            L = hi + log2(1.0 + exp2(lo - hi));
-            p1n = exp2(log2S - L);
-        } else {
-            L = log2S; p1n = 1.0;
+        double L = 0.0, p1n = 0.0;
+        if (!dead) {
+            if (c > 0.0) {
+                const double lc = log2(c);
+                const double hi = fmax(log2S, lc), lo = fmin(log2S, lc);
+                L = hi + log2(1.0 + exp2(lo - hi));
+                p1n = exp2(log2S - L);
+            } else {
+                L = log2S; p1n = 1.0;
+            }
         }
         pt1[i] = p1n;
         const float4 b = tgtP[i];
@@ -360,25 +394,24 @@ finalize1_kernel(const DevState* __restrict__ st, const double* __restrict__ sig
             q0 = make_float4(b.x, b.y, b.z, -INFINITY);
             q1 = make_float4(0.f, 0.f, 0.f, 0.f);
         } else {
-            const double Lhi = rint(L * 1024.0) * (1.0 / 1024.0);
-            const double g = exp2(Lhi - L);
-            q0 = make_float4(b.x, b.y, b.z, (float)(-Lhi));
-            q1 = make_float4((float)g, (float)(g * (double)b.x), (float)(g * (double)b.y), (float)(g * (double)b.z));
+            const double rn = exp2(-(L + (double)omin));
+            q0 = make_float4(b.x, b.y, b.z, omin);
+            q1 = make_float4((float)rn, 0.f, 0.f, 0.f);
+            v[0] = SU * rn;
         }
+        v[1] = p1n;
         tgtQ[2 * (size_t)i] = q0;
         tgtQ[2 * (size_t)i + 1] = q1;
-        const double x0 = xc[3 * (size_t)i], x1 = xc[3 * (size_t)i + 1], x2 = xc[3 * (size_t)i + 2];
-        v[0] = p1n; v[1] = p1n * x0; v[2] = p1n * x1; v[3] = p1n * x2; v[4] = p1n * (x0 * x0 + x1 * x1 + x2 * x2);
     } else if (i < npad) {
         tgtQ[2 * (size_t)i] = make_float4(0.f, 0.f, 0.f, -INFINITY);
         tgtQ[2 * (size_t)i + 1] = make_float4(0.f, 0.f, 0.f, 0.f);
     }
-    block_reduce_store<MOM_TGT>(v, mom_part + (size_t)blockIdx.x * MOM_TGT);
+    block_reduce_store<RM_TGT>(v, mom_part + (size_t)blockIdx.x * RM_TGT);
 }
 
 // ---------------------------------------------------------------------------------------------
-// pass 2: per source m, partial p1_m and px_m (in scaled centred coordinates) over one split of
-// the targets.  10 FP32-pipe + 1 MUFU instruction per pair.
+// pass 2: per source m and split of the targets:  p1_m = sum_n P_mn,  sd_m = sum_n P_mn (a_m - b_n)
+// with P_mn = 2^(o_n - u_mn) * rn_n.  11 FP32-pipe + 1 MUFU instruction per pair.
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(THREADS, 2)
 pass2_kernel(const float4* __restrict__ ipts, int ni, const float4* __restrict__ jrec, int nstages, int nsplit,
@@ -426,18 +459,18 @@ pass2_kernel(const float4* __restrict__ ipts, int ni, const float4* __restrict__
 #pragma unroll 4
             for (int jj = 0; jj < SUB; ++jj) {
                 const float4 b = q[2 * jj];
-                const float4 g = q[2 * jj + 1];
+                const float rn = q[2 * jj + 1].x;
 #pragma unroll
                 for (int r = 0; r < RI; ++r) {
                     const float dx = ax[r] - b.x, dy = ay[r] - b.y, dz = az[r] - b.z;
                     float t = fmaf(-dx, dx, b.w);
                     t = fmaf(-dy, dy, t);
                     t = fmaf(-dz, dz, t);
-                    const float p = ex2(t);
-                    s1[r] = fmaf(p, g.x, s1[r]);
-                    sx[r] = fmaf(p, g.y, sx[r]);
-                    sy[r] = fmaf(p, g.z, sy[r]);
-                    sz[r] = fmaf(p, g.w, sz[r]);
+                    const float p = ex2(t) * rn;
+                    s1[r] += p;
+                    sx[r] = fmaf(p, dx, sx[r]);
+                    sy[r] = fmaf(p, dy, sy[r]);
+                    sz[r] = fmaf(p, dz, sz[r]);
                 }
             }
 #pragma unroll
@@ -463,36 +496,72 @@ pass2_kernel(const float4* __restrict__ ipts, int ni, const float4* __restrict__
 }
 
 // ---------------------------------------------------------------------------------------------
-// finalize 2: p1_m, px~_m (centred, unscaled) from the pass-2 partials -- or, for cpd_mstep, from
-// caller-supplied arrays -- and the source-side moments of the M-step per block:
-//   Np, Sx = sum px~, Sy = sum p1 y~, B = sum px~ y~^T, C = sum p1 y~ y~^T     (y~ = y - cy)
+// finalize 2: per source m  p1_m,  v_m = sum_n P_mn (x_n - z_m) = -sd_m / sk,  px~_m = p1_m z~_m + v_m
+// (z~ = transformed source in the targets' frame, recomputed in FP64) and the source-side moments
+//   Np, Sy = sum p1 y~, C = sum p1 y~ y~^T, V1 = sum v, VY = sum v y~^T          (y~ = y - cy)
 // ---------------------------------------------------------------------------------------------
-template <bool FROM_PART>
 __global__ void __launch_bounds__(THREADS)
-finalize2_kernel(const double* __restrict__ sigma2_ptr, const double* __restrict__ part, int nsplit, int m,
-                 const double* __restrict__ yc, double* __restrict__ p1, double* __restrict__ pxc,
-                 double* __restrict__ mom_part) {
+finalize2_kernel(const DevState* __restrict__ st, const double* __restrict__ sigma2_ptr, const double* __restrict__ part,
+                 int nsplit, int m, const double* __restrict__ yc, const double* __restrict__ ts, double* __restrict__ p1,
+                 double* __restrict__ pxc, double* __restrict__ mom_part) {
+    const int i = blockIdx.x * THREADS + threadIdx.x;
+    double v[RM_SRC];
+#pragma unroll
+    for (int k = 0; k < RM_SRC; ++k) v[k] = 0.0;
+    if (i < m) {
+        double a1 = 0.0, a[3] = {0.0, 0.0, 0.0};
+        for (int s = 0; s < nsplit; ++s) {
+            const double2* src = reinterpret_cast<const double2*>(part + ((size_t)s * m + i) * 4);
+            const double2 u0 = src[0], u1 = src[1];
+            a1 += u0.x; a[0] += u0.y; a[1] += u1.x; a[2] += u1.y;
+        }
+        const double inv_sk = 1.0 / sqrt(LOG2E / (2.0 * *sigma2_ptr));
+        const double vv[3] = {-a[0] * inv_sk, -a[1] * inv_sk, -a[2] * inv_sk};
+        const double y[3] = {yc[3 * (size_t)i], yc[3 * (size_t)i + 1], yc[3 * (size_t)i + 2]};
+        double z[3];
+        if (ts != nullptr) {
+#pragma unroll
+            for (int d = 0; d < 3; ++d) z[d] = ts[3 * (size_t)i + d] - st->cx[d];
+        } else {
+            const double sc = (st->tf_kind == 0) ? st->scale : 1.0;
+#pragma unroll
+            for (int d = 0; d < 3; ++d) {
+                const double l0 = sc * st->lin[3 * d], l1 = sc * st->lin[3 * d + 1], l2 = sc * st->lin[3 * d + 2];
+                const double tp = l0 * st->cy[0] + l1 * st->cy[1] + l2 * st->cy[2] + st->t[d] - st->cx[d];
+                z[d] = l0 * y[0] + l1 * y[1] + l2 * y[2] + tp;
+            }
+        }
+        p1[i] = a1;
+#pragma unroll
+        for (int d = 0; d < 3; ++d) pxc[3 * (size_t)i + d] = a1 * z[d] + vv[d];
+        v[RM_NP] = a1;
+#pragma unroll
+        for (int d = 0; d < 3; ++d) {
+            v[RM_SY + d] = a1 * y[d];
+            v[RM_V1 + d] = vv[d];
+#pragma unroll
+            for (int e = 0; e < 3; ++e) v[RM_VY + 3 * d + e] = vv[d] * y[e];
+        }
+        v[RM_C + 0] = a1 * y[0] * y[0]; v[RM_C + 1] = a1 * y[0] * y[1]; v[RM_C + 2] = a1 * y[0] * y[2];
+        v[RM_C + 3] = a1 * y[1] * y[1]; v[RM_C + 4] = a1 * y[1] * y[2]; v[RM_C + 5] = a1 * y[2] * y[2];
+    }
+    block_reduce_store<RM_SRC>(v, mom_part + (size_t)blockIdx.x * RM_SRC);
+}
+
+// ---------------------------------------------------------------------------------------------
+// API-faithful M-step inputs (cpd_mstep: an EstepResult supplied by the caller, FP64-accurate):
+// the reference's own moment form.  Source side from p1 / px~ arrays, target side from pt1.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(THREADS)
+src_moments_api_kernel(int m, const double* __restrict__ yc, const double* __restrict__ p1, const double* __restrict__ pxc,
+                       double* __restrict__ mom_part) {
     const int i = blockIdx.x * THREADS + threadIdx.x;
     double v[MOM_SRC];
 #pragma unroll
     for (int k = 0; k < MOM_SRC; ++k) v[k] = 0.0;
     if (i < m) {
-        double a1, a[3];
-        if (FROM_PART) {
-            a1 = 0.0; a[0] = 0.0; a[1] = 0.0; a[2] = 0.0;
-            for (int s = 0; s < nsplit; ++s) {
-                const double2* src = reinterpret_cast<const double2*>(part + ((size_t)s * m + i) * 4);
-                const double2 u0 = src[0], u1 = src[1];
-                a1 += u0.x; a[0] += u0.y; a[1] += u1.x; a[2] += u1.y;
-            }
-            const double inv_sk = 1.0 / sqrt(LOG2E / (2.0 * *sigma2_ptr));
-            a[0] *= inv_sk; a[1] *= inv_sk; a[2] *= inv_sk;
-            p1[i] = a1;
-            pxc[3 * (size_t)i] = a[0]; pxc[3 * (size_t)i + 1] = a[1]; pxc[3 * (size_t)i + 2] = a[2];
-        } else {
-            a1 = p1[i];
-            a[0] = pxc[3 * (size_t)i]; a[1] = pxc[3 * (size_t)i + 1]; a[2] = pxc[3 * (size_t)i + 2];
-        }
+        const double a1 = p1[i];
+        const double a[3] = {pxc[3 * (size_t)i], pxc[3 * (size_t)i + 1], pxc[3 * (size_t)i + 2]};
         const double y[3] = {yc[3 * (size_t)i], yc[3 * (size_t)i + 1], yc[3 * (size_t)i + 2]};
         v[MOM_NP] = a1;
 #pragma unroll
@@ -508,9 +577,8 @@ finalize2_kernel(const double* __restrict__ sigma2_ptr, const double* __restrict
     block_reduce_store<MOM_SRC>(v, mom_part + (size_t)blockIdx.x * MOM_SRC);
 }
 
-// pt1-side moments from a caller-supplied pt1 (cpd_mstep only)
 __global__ void __launch_bounds__(THREADS)
-tgt_moments_kernel(const double* __restrict__ pt1, const double* __restrict__ xc, int n, double* __restrict__ mom_part) {
+tgt_moments_api_kernel(const double* __restrict__ pt1, const double* __restrict__ xc, int n, double* __restrict__ mom_part) {
     const int i = blockIdx.x * THREADS + threadIdx.x;
     double v[MOM_TGT] = {0.0, 0.0, 0.0, 0.0, 0.0};
     if (i < n) {
@@ -521,8 +589,9 @@ tgt_moments_kernel(const double* __restrict__ pt1, const double* __restrict__ xc
 }
 
 // ---------------------------------------------------------------------------------------------
-// M-step solve in FP64 from the 27 moments (one thread).
-// Rigid:  probreg/cpd.py:169-192.   Affine: probreg/cpd.py:227-244.
+// M-step solves in FP64 (one thread).  Rigid: probreg/cpd.py:169-192.  Affine: probreg/cpd.py:227-244.
+// mstep_solve_api     : the reference's moment form, from a caller-supplied EstepResult (27 moments)
+// mstep_solve_residual: the same optimum written as an update of the previous transform (24 moments)
 // ---------------------------------------------------------------------------------------------
 // One-sided Jacobi SVD of the leading n x n block (n = 2 or 3): a = U diag(s) V^T, s descending.
 __device__ inline void jacobi_svd(int n, const double a[3][3], double U[3][3], double s[3], double V[3][3]) {
@@ -610,7 +679,7 @@ __device__ inline void solve_affine(int n, const double Y[3][3], const double A[
     for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) B[i][j] = (i < n && j < n) ? Z[j][i] : (i == j ? 1.0 : 0.0);
 }
 
-__device__ inline void mstep_solve(DevState* st, const double* __restrict__ mom) {
+__device__ inline void mstep_solve_api(DevState* st, const double* __restrict__ mom) {
     const int n = st->dim;
     const double Np = mom[MOM_NP];
     double mux[3], muy[3], A[3][3], Y[3][3];
@@ -664,31 +733,118 @@ __device__ inline void mstep_solve(DevState* st, const double* __restrict__ mom)
     st->scale = scale; st->sigma2 = sigma2; st->q = q; st->n_p = Np;
 }
 
-// Fixed-order reduction of the per-block moment partials into mom[0..27); with SOLVE the same
-// (single) block then runs the M-step.  In multi-rank runs the all-reduce sits between the two.
-template <bool SOLVE>
-__global__ void __launch_bounds__(32)
-moments_kernel(DevState* st, const double* __restrict__ part_src, int nb_src, const double* __restrict__ part_tgt, int nb_tgt,
-               double* __restrict__ mom) {
-    const int k = threadIdx.x;
-    if (k < MOM_SRC) {
-        double s = 0.0;
-        for (int b = 0; b < nb_src; ++b) s += part_src[(size_t)b * MOM_SRC + k];
-        mom[k] = s;
-    } else if (k < MOM_COUNT) {
-        double s = 0.0;
-        for (int b = 0; b < nb_tgt; ++b) s += part_tgt[(size_t)b * MOM_TGT + (k - MOM_SRC)];
-        mom[k] = s;
-    } else {
-        mom[k] = 0.0;
+// ---------------------------------------------------------------------------------------------
+// Residual-form M-step.  With A = previous linear part (s R or B), z~ = A y~ + t' the previous
+// transformed source, v_m = sum_n P_mn (x_n - z_m):
+//   Ycov = C - Sy Sy^T / Np,  Vcov = VY - V1 Sy^T / Np
+//   A_mat = sum_mn P x^ y^T (cpd.py:175 / :233) = A Ycov + Vcov           -- FP64, no FP32 sum enters a large term
+//   rigid : R' from the SVD of A_mat, s' = tr(A_mat^T R') / tr(Ycov)        (cpd.py:176-182)
+//   affine: B' = A_mat Ycov^-1                                               (cpd.py:234-235)
+//   Q = sum_mn P |x_n - T'(y_m)|^2 = Srr + 2 <dA, Vcov> - |V1|^2 / Np + tr(dA Ycov dA^T),  dA = A - A'
+//   sigma2' = Q / (Np D)           [== (tr_xp1x - s tr_atr)/(Np D) at the optimal s, cpd.py:186 / :239]
+//           = (Q + tr_atr)/(Np D)  when update_scale is False (the reference's formula, cpd.py:188)
+//   q = Q / (2 sigma2') + D Np / 2 log sigma2'                                (cpd.py:190-191 / :242-243)
+//   t' = mu_x - A' mu_y,  mu_x = cx + A mu~_y + t'_old + V1/Np,  mu_y = cy + Sy/Np
+// ---------------------------------------------------------------------------------------------
+__device__ inline void mstep_solve_residual(DevState* st, const double* __restrict__ mom) {
+    const int n = st->dim;
+    const double Np = mom[RM_NP];
+    const double sk2 = LOG2E / (2.0 * st->sigma2);
+    const double Srr = mom[RM_SRR] / sk2;
+    double muy[3], V1[3], Aold[3][3], Y[3][3], Vc[3][3], Am[3][3], told[3];
+    const double sc = (st->tf_kind == 0) ? st->scale : 1.0;
+    for (int a = 0; a < 3; ++a) {
+        muy[a] = mom[RM_SY + a] / Np;
+        V1[a] = mom[RM_V1 + a];
+        for (int b = 0; b < 3; ++b) Aold[a][b] = sc * st->lin[3 * a + b];
     }
+    for (int a = 0; a < 3; ++a)
+        told[a] = Aold[a][0] * st->cy[0] + Aold[a][1] * st->cy[1] + Aold[a][2] * st->cy[2] + st->t[a] - st->cx[a];
+    const double Cs[3][3] = {{mom[RM_C + 0], mom[RM_C + 1], mom[RM_C + 2]},
+                             {mom[RM_C + 1], mom[RM_C + 3], mom[RM_C + 4]},
+                             {mom[RM_C + 2], mom[RM_C + 4], mom[RM_C + 5]}};
+    for (int a = 0; a < 3; ++a)
+        for (int b = 0; b < 3; ++b) {
+            Y[a][b] = Cs[a][b] - mom[RM_SY + a] * mom[RM_SY + b] / Np;
+            Vc[a][b] = mom[RM_VY + 3 * a + b] - V1[a] * mom[RM_SY + b] / Np;
+        }
+    for (int a = 0; a < 3; ++a)
+        for (int b = 0; b < 3; ++b) {
+            double t = Vc[a][b];
+            for (int k = 0; k < 3; ++k) t += Aold[a][k] * Y[k][b];
+            Am[a][b] = (a < n && b < n) ? t : 0.0;
+        }
+    double tr_yp1y = 0.0;
+    for (int a = 0; a < n; ++a) tr_yp1y += Y[a][a];
+    double lin[3][3], Anew[3][3], scale = 1.0, tr_atr = 0.0;
+    if (st->tf_kind == 0) {
+        double U[3][3], s[3], V[3][3], UVt[3][3];
+        jacobi_svd(n, Am, U, s, V);
+        for (int i = 0; i < 3; ++i)
+            for (int j = 0; j < 3; ++j) { double t = 0; for (int k = 0; k < n; ++k) t += U[i][k] * V[j][k]; UVt[i][j] = t; }
+        const double dt = det_n(n, UVt);
+        for (int i = 0; i < 3; ++i)
+            for (int j = 0; j < 3; ++j) {
+                double t = 0;
+                for (int k = 0; k < n; ++k) t += U[i][k] * (k == n - 1 ? dt : 1.0) * V[j][k];
+                lin[i][j] = (i < n && j < n) ? t : (i == j ? 1.0 : 0.0);
+            }
+        for (int i = 0; i < n; ++i) for (int j = 0; j < n; ++j) tr_atr += Am[i][j] * lin[i][j];
+        scale = st->update_scale ? tr_atr / tr_yp1y : 1.0;
+    } else {
+        solve_affine(n, Y, Am, lin);
+    }
+    for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) Anew[i][j] = scale * lin[i][j];
+    // Q = Srr + 2 <dA, Vcov> - |V1|^2/Np + tr(dA Ycov dA^T)
+    double Q = Srr - (V1[0] * V1[0] + V1[1] * V1[1] + V1[2] * V1[2]) / Np;
+    for (int a = 0; a < n; ++a)
+        for (int b = 0; b < n; ++b) {
+            const double dab = Aold[a][b] - Anew[a][b];
+            Q += 2.0 * dab * Vc[a][b];
+            double t = 0.0;
+            for (int k = 0; k < n; ++k) t += (Aold[a][k] - Anew[a][k]) * Y[k][b];
+            Q += t * dab;
+        }
+    double sigma2;
+    if (st->tf_kind == 0 && !st->update_scale) sigma2 = (Q + tr_atr) / (Np * n);      // cpd.py:188
+    else sigma2 = Q / (Np * n);                                                        // cpd.py:186 / :239
+    sigma2 = fmax(sigma2, EPS32);                                                      // cpd.py:189 / :241
+    const double q = Q / (2.0 * sigma2) + n * Np * 0.5 * log(sigma2);
+    // t' = mu_x - A' mu_y
+    for (int a = 0; a < 3; ++a) {
+        double mux = st->cx[a] + told[a] + V1[a] / Np, r = 0.0;
+        for (int b = 0; b < 3; ++b) { mux += Aold[a][b] * muy[b]; r += Anew[a][b] * (st->cy[b] + muy[b]); }
+        st->t[a] = (a < n) ? mux - r : 0.0;
+    }
+    for (int a = 0; a < 3; ++a) for (int b = 0; b < 3; ++b) st->lin[3 * a + b] = lin[a][b];
+    st->scale = scale; st->sigma2 = sigma2; st->q = q; st->n_p = Np;
+}
+
+// Fixed-order reduction of per-block moment partials: column k < ka of part_a, then kb columns of
+// part_b, into mom[0 .. ka+kb); the rest of mom[0..32) is zeroed.  SOLVE = 1: the same (single)
+// block then runs the residual-form M-step.  In multi-rank runs the all-reduce sits in between.
+template <int SOLVE>
+__global__ void __launch_bounds__(32)
+moments_kernel(DevState* st, const double* __restrict__ part_a, int nb_a, int ka, const double* __restrict__ part_b, int nb_b,
+               int kb, double* __restrict__ mom) {
+    const int k = threadIdx.x;
+    double s = 0.0;
+    if (k < ka) {
+        for (int b = 0; b < nb_a; ++b) s += part_a[(size_t)b * ka + k];
+    } else if (k < ka + kb) {
+        for (int b = 0; b < nb_b; ++b) s += part_b[(size_t)b * kb + (k - ka)];
+    }
+    mom[k] = s;
     if (SOLVE) {
         __syncwarp();
-        if (k == 0) mstep_solve(st, mom);
+        if (k == 0) mstep_solve_residual(st, mom);
     }
 }
-__global__ void mstep_kernel(DevState* st, const double* __restrict__ mom) {
-    if (threadIdx.x == 0) mstep_solve(st, mom);
+__global__ void mstep_residual_kernel(DevState* st, const double* __restrict__ mom) {
+    if (threadIdx.x == 0) mstep_solve_residual(st, mom);
+}
+__global__ void mstep_api_kernel(DevState* st, const double* __restrict__ mom) {
+    if (threadIdx.x == 0) mstep_solve_api(st, mom);
 }
 
 // sums for sigma^2 initialisation: out[block][0..4) = sum |p|^2, sum p (3)
@@ -778,6 +934,76 @@ probe_mufu_kernel(float* out, int iters, float seed) {
     float s = 0.f;
 #pragma unroll
     for (int k = 0; k < 8; ++k) s += a[k];
+    if (s == 123.456f) out[0] = s;
+}
+// packed FP32 (FFMA2): 2 FMAs per lane per instruction -- does it raise the FLOP rate or only save issue slots?
+__device__ __forceinline__ unsigned long long ffma2(unsigned long long a, unsigned long long b, unsigned long long c) {
+    unsigned long long d;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+    return d;
+}
+__device__ __forceinline__ unsigned long long pack2(float lo, float hi) {
+    unsigned long long r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ float2 unpack2(unsigned long long v) {
+    float2 r;
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(r.x), "=f"(r.y) : "l"(v));
+    return r;
+}
+__global__ void __launch_bounds__(256)
+probe_ffma2_kernel(float* out, int iters, float seed) {
+    unsigned long long a[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) a[k] = pack2(seed + k, seed - k);
+    const unsigned long long m = pack2(0.9999f + seed * 1e-9f, 0.9998f), c = pack2(1e-7f, 2e-7f);
+    for (int i = 0; i < iters; ++i) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) a[k] = ffma2(a[k], m, c);
+    }
+    float s = 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) { const float2 v = unpack2(a[k]); s += v.x + v.y; }
+    if (s == 123.456f) out[0] = s;
+}
+// instruction mix of the E-step inner loop: NF FP32-pipe instructions + 1 MUFU.EX2 per "pair", 8 chains
+template <int NF, bool PACKED>
+__global__ void __launch_bounds__(256)
+probe_mix_kernel(float* out, int iters, float seed) {
+    float x[8], acc[8];
+    unsigned long long pa[4];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) { x[k] = seed * 0.01f - 0.1f * k; acc[k] = 0.f; }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) pa[k] = pack2(seed, seed + k);
+    const float m = 0.999f + seed * 1e-9f;
+    const unsigned long long pm = pack2(m, m);
+    for (int i = 0; i < iters; ++i) {
+        if (PACKED) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+#pragma unroll
+                for (int f = 0; f < NF; ++f) pa[k] = ffma2(pa[k], pm, pm);
+                const float2 v = unpack2(pa[k]);
+                pa[k] = pack2(ex2(-v.x * v.x), ex2(-v.y * v.y));     // 2 MUFU (+2 FMUL) per 2 pairs
+            }
+        } else {
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                float t = x[k];
+#pragma unroll
+                for (int f = 0; f < NF - 1; ++f) t = fmaf(t, m, acc[k]);
+                const float e = ex2(-t * t);                          // NF-th FP32 instruction + MUFU
+                acc[k] = e;
+            }
+        }
+    }
+    float s = 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) s += acc[k];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) { const float2 v = unpack2(pa[k]); s += v.x + v.y; }
     if (s == 123.456f) out[0] = s;
 }
 __global__ void probe_clock_kernel(long long* out) {
