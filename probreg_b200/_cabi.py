@@ -6,7 +6,8 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libcpd_b200.so")
+# CPD_B200_LIB: load another build of the same library (tools/tune.sh variants); never a different implementation
+LIB_PATH = os.environ.get("CPD_B200_LIB") or os.path.join(_HERE, "libcpd_b200.so")
 
 TF_RIGID, TF_AFFINE, TF_NONRIGID = 0, 1, 2
 

@@ -86,13 +86,13 @@ constexpr int NCCL_DOUBLE = 8, NCCL_SUM = 0;
 // handle
 // ---------------------------------------------------------------------------------------------
 struct cpd_ctx {
-    int device = 0, dim = 3, sm_count = 148, slots = 296;
+    int device = 0, dim = 3, sm_count = 148, slots1 = 296, slots2 = 296;
     cudaStream_t stream = nullptr;
     bool own_stream = false;
     long long m = 0, mpad = 0, n = 0, npad = 0, n_global = 0;
     double *d_yc = nullptr, *d_ts = nullptr, *d_xc = nullptr, *d_raw = nullptr;
     size_t raw_cap = 0;
-    float4 *d_srcP = nullptr, *d_tgtP = nullptr, *d_tgtQ = nullptr;
+    float4 *d_srcP = nullptr, *d_srcJ = nullptr, *d_tgtP = nullptr, *d_tgtQ = nullptr;
     P1Part* d_part1 = nullptr;
     double* d_part2 = nullptr;
     size_t part1_cap = 0, part2_cap = 0;
@@ -187,10 +187,10 @@ int cloud_sums(cpd_ctx* h, const double* d_pts, long long count, double out[4]) 
 int prepare(cpd_ctx* h) {
     if (h->prepared) return CPD_OK;
     if (!h->have_source || !h->have_target) return fail(CPD_ERR_STATE, "source and target must both be set");
-    h->it1 = (int)((h->n + ITILE - 1) / ITILE);
-    h->it2 = (int)((h->m + ITILE - 1) / ITILE);
-    h->j1 = choose_split(h->it1, (int)(h->mpad / P1_STAGE), h->slots);
-    h->j2 = choose_split(h->it2, (int)(h->npad / P2_STAGE), h->slots);
+    h->it1 = (int)((h->n + ITILE1 - 1) / ITILE1);
+    h->it2 = (int)((h->m + ITILE2 - 1) / ITILE2);
+    h->j1 = choose_split(h->it1, (int)(h->mpad / P1_STAGE), h->slots1);
+    h->j2 = choose_split(h->it2, (int)(h->npad / P2_STAGE), h->slots2);
     const size_t need1 = (size_t)h->j1 * h->n, need2 = (size_t)h->j2 * h->m * 4;
     if (need1 > h->part1_cap) { TRY(dev_alloc(&h->d_part1, need1)); h->part1_cap = need1; }
     if (need2 > h->part2_cap) { TRY(dev_alloc(&h->d_part2, need2)); h->part2_cap = need2; }
@@ -217,16 +217,16 @@ int launch_estep(cpd_ctx* h, const double* d_sigma2, const double* d_w, const do
     const long long cover = std::max(h->mpad, h->n);
     mark(h, 0);
     pack_kernel<<<blocks_for(cover), THREADS, 0, h->stream>>>(h->d_state, d_sigma2, h->d_yc, d_ts, h->d_xc, h->m, h->mpad,
-                                                              h->n, h->d_srcP, h->d_tgtP);
+                                                              h->n, h->d_srcP, h->d_srcJ, h->d_tgtP);
     mark(h, 1);
-    pass1_kernel<<<h->it1 * h->j1, THREADS, PASS_SMEM, h->stream>>>(h->d_tgtP, (int)h->n, h->d_srcP, (int)(h->mpad / P1_STAGE),
-                                                                    h->j1, h->d_part1);
+    pass1_kernel<<<h->it1 * h->j1, THREADS, PASS1_SMEM, h->stream>>>(h->d_tgtP, (int)h->n, h->d_srcJ, (int)(h->mpad / P1_STAGE),
+                                                                     h->j1, h->d_part1);
     mark(h, 2);
     finalize1_kernel<<<blocks_for(h->npad), THREADS, 0, h->stream>>>(h->d_state, d_sigma2, d_w, h->d_part1, h->j1, (int)h->n,
                                                                      h->d_tgtP, h->d_tgtQ, h->npad, h->d_pt1, h->d_mom_tgt);
     mark(h, 3);
-    pass2_kernel<<<h->it2 * h->j2, THREADS, PASS_SMEM, h->stream>>>(h->d_srcP, (int)h->m, h->d_tgtQ, (int)(h->npad / P2_STAGE),
-                                                                    h->j2, h->d_part2);
+    pass2_kernel<<<h->it2 * h->j2, THREADS, PASS2_SMEM, h->stream>>>(h->d_srcP, (int)h->m, h->d_tgtQ, (int)(h->npad / P2_STAGE),
+                                                                     h->j2, h->d_part2);
     mark(h, 4);
     finalize2_kernel<<<blocks_for(h->m), THREADS, 0, h->stream>>>(h->d_state, d_sigma2, h->d_part2, h->j2, (int)h->m, h->d_yc,
                                                                   d_ts, h->d_p1, h->d_pxc, h->d_mom_src);
@@ -271,12 +271,13 @@ extern "C" int cpd_create(cpd_ctx** out, int device, int dim, void* stream) {
     h->sm_count = prop.multiProcessorCount;
     if (stream) { h->stream = (cudaStream_t)stream; h->own_stream = false; }
     else { CU(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking)); h->own_stream = true; }
-    CU(cudaFuncSetAttribute(pass1_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, PASS_SMEM));
-    CU(cudaFuncSetAttribute(pass2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, PASS_SMEM));
+    CU(cudaFuncSetAttribute(pass1_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, PASS1_SMEM));
+    CU(cudaFuncSetAttribute(pass2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, PASS2_SMEM));
     int occ1 = 0, occ2 = 0;
-    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ1, pass1_kernel, THREADS, PASS_SMEM));
-    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ2, pass2_kernel, THREADS, PASS_SMEM));
-    h->slots = h->sm_count * std::max(1, std::min(occ1, occ2));
+    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ1, pass1_kernel, THREADS, PASS1_SMEM));
+    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ2, pass2_kernel, THREADS, PASS2_SMEM));
+    h->slots1 = h->sm_count * std::max(1, occ1);
+    h->slots2 = h->sm_count * std::max(1, occ2);
     TRY(dev_alloc(&h->d_state, 1));
     TRY(dev_alloc(&h->d_mom, (size_t)MOM_PAD));
     CU(cudaMallocHost((void**)&h->h_pin, 64 * sizeof(double)));
@@ -297,7 +298,7 @@ extern "C" void cpd_destroy(cpd_ctx* h) {
     cudaSetDevice(h->device);
     cudaStreamSynchronize(h->stream);
     if (h->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(h->comm);
-    void* ptrs[] = {h->d_yc, h->d_ts, h->d_xc, h->d_raw, h->d_srcP, h->d_tgtP, h->d_tgtQ, h->d_part1, h->d_part2, h->d_pt1, h->d_p1,
+    void* ptrs[] = {h->d_yc, h->d_ts, h->d_xc, h->d_raw, h->d_srcP, h->d_srcJ, h->d_tgtP, h->d_tgtQ, h->d_part1, h->d_part2, h->d_pt1, h->d_p1,
                     h->d_pxc, h->d_px, h->d_mom_src, h->d_mom_tgt, h->d_mom, h->d_sums, h->d_state, h->d_flush};
     for (void* p : ptrs) if (p) cudaFree(p);
     if (h->h_pin) cudaFreeHost(h->h_pin);
@@ -311,7 +312,7 @@ extern "C" void cpd_destroy(cpd_ctx* h) {
 
 extern "C" int cpd_set_source(cpd_ctx* h, const double* source, int64_t m) {
     if (!h || !source) return fail(CPD_ERR_ARG, "null argument");
-    if (m < 1 || m > 0x7fffffffLL - ITILE) return fail(CPD_ERR_ARG, "source count %lld out of range", (long long)m);
+    if (m < 1 || m > 0x7fffffffLL - 65536) return fail(CPD_ERR_ARG, "source count %lld out of range", (long long)m);
     CU(cudaSetDevice(h->device));
     if (m != h->m || !h->d_yc) {
         h->m = m;
@@ -319,6 +320,7 @@ extern "C" int cpd_set_source(cpd_ctx* h, const double* source, int64_t m) {
         TRY(dev_alloc(&h->d_yc, (size_t)m * 3));
         TRY(dev_alloc(&h->d_ts, (size_t)m * 3));
         TRY(dev_alloc(&h->d_srcP, (size_t)h->mpad));
+        TRY(dev_alloc(&h->d_srcJ, (size_t)h->mpad * 2));
         TRY(dev_alloc(&h->d_p1, (size_t)m));
         TRY(dev_alloc(&h->d_pxc, (size_t)m * 3));
         TRY(dev_alloc(&h->d_px, (size_t)m * 3));
@@ -339,7 +341,7 @@ extern "C" int cpd_set_source(cpd_ctx* h, const double* source, int64_t m) {
 
 extern "C" int cpd_set_target(cpd_ctx* h, const double* target, int64_t n_local, int64_t n_global, const double* frame_origin) {
     if (!h || !target) return fail(CPD_ERR_ARG, "null argument");
-    if (n_local < 1 || n_local > 0x7fffffffLL - ITILE) return fail(CPD_ERR_ARG, "target count %lld out of range", (long long)n_local);
+    if (n_local < 1 || n_local > 0x7fffffffLL - 65536) return fail(CPD_ERR_ARG, "target count %lld out of range", (long long)n_local);
     if (n_global < n_local) return fail(CPD_ERR_ARG, "n_global (%lld) < n_local (%lld)", (long long)n_global, (long long)n_local);
     if (!frame_origin && n_global != n_local) return fail(CPD_ERR_ARG, "a sharded target needs an explicit frame_origin");
     CU(cudaSetDevice(h->device));
@@ -348,7 +350,7 @@ extern "C" int cpd_set_target(cpd_ctx* h, const double* target, int64_t n_local,
         h->npad = (n_local + P2_STAGE - 1) / P2_STAGE * P2_STAGE;
         TRY(dev_alloc(&h->d_xc, (size_t)n_local * 3));
         TRY(dev_alloc(&h->d_tgtP, (size_t)n_local));
-        TRY(dev_alloc(&h->d_tgtQ, (size_t)h->npad * 2));
+        TRY(dev_alloc(&h->d_tgtQ, (size_t)h->npad * 3));
         TRY(dev_alloc(&h->d_pt1, (size_t)n_local));
         h->prepared = false;
     }

@@ -30,15 +30,40 @@
 
 namespace cpd {
 
+// tunables (tools/tune.sh builds variants with -D...; the defaults are the measured best)
+#ifndef CPD_RI1
+#define CPD_RI1 4
+#endif
+#ifndef CPD_RI2
+#define CPD_RI2 4
+#endif
+#ifndef CPD_MINB1
+#define CPD_MINB1 2
+#endif
+#ifndef CPD_MINB2
+#define CPD_MINB2 2
+#endif
+#ifndef CPD_UNROLL1
+#define CPD_UNROLL1 4
+#endif
+#ifndef CPD_UNROLL2
+#define CPD_UNROLL2 4
+#endif
+#ifndef CPD_SUB
+#define CPD_SUB 64
+#endif
+constexpr int UNROLL1 = CPD_UNROLL1, UNROLL2 = CPD_UNROLL2;
 constexpr int THREADS = 256;           // threads per CTA in both passes
-constexpr int RI = 4;                  // i-points held in registers per thread
-constexpr int ITILE = THREADS * RI;    // i-points per CTA
-constexpr int P1_STAGE = 1024;         // sources per TMA stage in pass 1 (16 B each -> 16 KB)
-constexpr int P2_STAGE = 512;          // targets per TMA stage in pass 2 (32 B each -> 16 KB)
+constexpr int RI1 = CPD_RI1, RI2 = CPD_RI2;            // i-points held in registers per thread (pass 1 / pass 2)
+constexpr int ITILE1 = THREADS * RI1, ITILE2 = THREADS * RI2;   // i-points per CTA
+constexpr int NPAIR1 = RI1 / 2, NPAIR2 = RI2 / 2;      // i-points are processed as packed f32x2 pairs (FADD2 / FFMA2)
+constexpr int P1_STAGE = 512;          // sources per TMA stage in pass 1 (32 B records -> 16 KB)
+constexpr int P2_STAGE = 512;          // targets per TMA stage in pass 2 (48 B records -> 24 KB)
+constexpr int P1_REC = 32, P2_REC = 48;    // bytes per streamed j-record (coordinates duplicated for f32x2)
 constexpr int NSTAGE = 3;              // TMA pipeline depth
-constexpr int STAGE_BYTES = 16384;
-constexpr int SUB = 64;                // j-points between offset checks / FP64 flushes
-constexpr int PASS_SMEM = NSTAGE * STAGE_BYTES + 64;
+constexpr int P1_STAGE_BYTES = P1_STAGE * P1_REC, P2_STAGE_BYTES = P2_STAGE * P2_REC;
+constexpr int SUB = CPD_SUB;           // j-points between offset checks / FP64 flushes
+constexpr int PASS1_SMEM = NSTAGE * P1_STAGE_BYTES + 64, PASS2_SMEM = NSTAGE * P2_STAGE_BYTES + 64;
 
 constexpr float O_INIT = 1048576.0f;   // 2^20: "no source seen yet" offset; u above it is dead anyway
 constexpr float TWO100 = 1.2676506002282294e30f;
@@ -96,6 +121,16 @@ __device__ __forceinline__ float ex2(float x) {
     asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
     return y;
 }
+// packed FP32 pairs (sm_100 FADD2 / FMUL2 / FFMA2): one issue slot for two lanes' worth of FP32 work.
+// The E-step is issue-bound in scalar form (19 FP32-pipe + 2 MUFU slots per pair and iteration);
+// packed, the same work takes 10.5 slots and the MUFU / FMA pipes become the limit (profiles/).
+typedef unsigned long long u64;
+__device__ __forceinline__ u64 fsub2(u64 a, u64 b) { u64 d; asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
+__device__ __forceinline__ u64 fadd2(u64 a, u64 b) { u64 d; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
+__device__ __forceinline__ u64 fmul2(u64 a, u64 b) { u64 d; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
+__device__ __forceinline__ u64 ffma2(u64 a, u64 b, u64 c) { u64 d; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c)); return d; }
+__device__ __forceinline__ u64 pack2(float lo, float hi) { u64 r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi)); return r; }
+__device__ __forceinline__ float2 unpack2(u64 v) { float2 r; asm("mov.b64 {%0, %1}, %2;" : "=f"(r.x), "=f"(r.y) : "l"(v)); return r; }
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
@@ -160,7 +195,8 @@ __global__ void __launch_bounds__(THREADS)
 pack_kernel(const DevState* __restrict__ st, const double* __restrict__ sigma2_ptr,
             const double* __restrict__ yc /* m x 3 centred sources */, const double* __restrict__ ts /* explicit transformed sources or null */,
             const double* __restrict__ xc /* n x 3 centred targets */, long long m, long long mpad, long long n,
-            float4* __restrict__ srcP, float4* __restrict__ tgtP) {
+            float4* __restrict__ srcP /* i-points of pass 2 */, float4* __restrict__ srcJ /* j-records of pass 1: {x,x,y,y},{z,z,0,0} */,
+            float4* __restrict__ tgtP /* i-points of pass 1 */) {
     const long long i = (long long)blockIdx.x * THREADS + threadIdx.x;
     const double sk = sqrt(LOG2E / (2.0 * *sigma2_ptr));
     if (i < mpad) {
@@ -189,6 +225,8 @@ pack_kernel(const DevState* __restrict__ st, const double* __restrict__ sigma2_p
             o = make_float4(FAR_COORD, FAR_COORD, FAR_COORD, 0.0f);
         }
         srcP[i] = o;
+        srcJ[2 * i] = make_float4(o.x, o.x, o.y, o.y);
+        srcJ[2 * i + 1] = make_float4(o.z, o.z, 0.0f, 0.0f);
     }
     if (i < n) {
         tgtP[i] = make_float4((float)(sk * xc[3 * i]), (float)(sk * xc[3 * i + 1]), (float)(sk * xc[3 * i + 2]), 0.0f);
@@ -198,7 +236,7 @@ pack_kernel(const DevState* __restrict__ st, const double* __restrict__ sigma2_p
 // ---------------------------------------------------------------------------------------------
 // pass 1: per target n and split:  (o, S, SU) with  sum_m 2^(-u) = S 2^(-o),  sum_m 2^(-u) u = SU 2^(-o)
 // grid = itiles * nsplit CTAs; CTA (itile, split) owns 1024 targets and stages [st0, st1) of the
-// padded source array.  8 FP32-pipe + 1 MUFU instruction per pair in the common path.
+// padded source array.  Per two pairs: 8 packed FP32 instructions + 2 MUFU in the common path.
 //
 // Lazy log-sum-exp: each target carries an integer-valued offset o (only ever lowered).  A
 // sub-chunk of 64 sources is summed in FP32 from zero with the current o -- Sc = sum e,
@@ -211,17 +249,17 @@ pack_kernel(const DevState* __restrict__ st, const double* __restrict__ sigma2_p
 // The largest term of a target is >= 2^-1 right after its offset was set and <= 2^100 always, so
 // every term that matters stays a normal FP32 number.
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(THREADS, 2)
-pass1_kernel(const float4* __restrict__ ipts, int ni, const float4* __restrict__ jpts, int nstages, int nsplit,
+__global__ void __launch_bounds__(THREADS, CPD_MINB1)
+pass1_kernel(const float4* __restrict__ ipts, int ni, const float4* __restrict__ jrec, int nstages, int nsplit,
              P1Part* __restrict__ part) {
     extern __shared__ __align__(128) unsigned char smraw[];
-    float4* sm = reinterpret_cast<float4*>(smraw);
-    uint64_t* full = reinterpret_cast<uint64_t*>(smraw + NSTAGE * STAGE_BYTES);
+    uint64_t* full = reinterpret_cast<uint64_t*>(smraw + NSTAGE * P1_STAGE_BYTES);
     const int tid = threadIdx.x;
     const int split = blockIdx.x % nsplit, itile = blockIdx.x / nsplit;
     const int st0 = (int)((long long)nstages * split / nsplit);
     const int st1 = (int)((long long)nstages * (split + 1) / nsplit);
     const int nst = st1 - st0;
+    const unsigned char* jbytes = reinterpret_cast<const unsigned char*>(jrec);
     if (tid == 0) {
         for (int s = 0; s < NSTAGE; ++s) mbar_init(&full[s], 1);
         mbar_fence_init();
@@ -229,104 +267,126 @@ pass1_kernel(const float4* __restrict__ ipts, int ni, const float4* __restrict__
     __syncthreads();
     if (tid == 0) {
         for (int s = 0; s < NSTAGE && s < nst; ++s) {
-            mbar_expect_tx(&full[s], STAGE_BYTES);
-            tma_load_1d(sm + s * P1_STAGE, jpts + (size_t)(st0 + s) * P1_STAGE, STAGE_BYTES, &full[s]);
+            mbar_expect_tx(&full[s], P1_STAGE_BYTES);
+            tma_load_1d(smraw + s * P1_STAGE_BYTES, jbytes + (size_t)(st0 + s) * P1_STAGE_BYTES, P1_STAGE_BYTES, &full[s]);
         }
     }
-    float ax[RI], ay[RI], az[RI], o[RI];
-    double S[RI], SU[RI];
+    // two packed pairs of targets per thread: pair p = targets (2p, 2p+1) of this thread
+    u64 ax[NPAIR1], ay[NPAIR1], az[NPAIR1], no[NPAIR1];    // no = (-o, -o'): negated integer offsets
+    double S[RI1], SU[RI1];
 #pragma unroll
-    for (int r = 0; r < RI; ++r) {
-        int n = itile * ITILE + r * THREADS + tid;
-        n = n < ni ? n : ni - 1;
-        const float4 p = ipts[n];
-        ax[r] = p.x; ay[r] = p.y; az[r] = p.z;
-        o[r] = O_INIT; S[r] = 0.0; SU[r] = 0.0;
+    for (int p = 0; p < NPAIR1; ++p) {
+        int n0 = itile * ITILE1 + (2 * p) * THREADS + tid, n1 = n0 + THREADS;
+        n0 = n0 < ni ? n0 : ni - 1;
+        n1 = n1 < ni ? n1 : ni - 1;
+        const float4 p0 = ipts[n0], p1 = ipts[n1];
+        ax[p] = pack2(p0.x, p1.x); ay[p] = pack2(p0.y, p1.y); az[p] = pack2(p0.z, p1.z);
+        no[p] = pack2(-O_INIT, -O_INIT);
     }
+#pragma unroll
+    for (int r = 0; r < RI1; ++r) { S[r] = 0.0; SU[r] = 0.0; }
     for (int it = 0; it < nst; ++it) {
         const int s = it % NSTAGE;
         mbar_wait(&full[s], (uint32_t)((it / NSTAGE) & 1));
-        const float4* sp = sm + s * P1_STAGE;
+        const ulonglong2* sp = reinterpret_cast<const ulonglong2*>(smraw + s * P1_STAGE_BYTES);
 #pragma unroll 1
         for (int sc = 0; sc < P1_STAGE / SUB; ++sc) {
-            const float4* q = sp + sc * SUB;
-            float Sc[RI], Uc[RI];
+            const ulonglong2* q = sp + sc * (2 * SUB);
+            u64 Sc[NPAIR1], Uc[NPAIR1];          // Sc = sum e,  Uc = sum e * t'  with t' = u - o, e = 2^-t'
 #pragma unroll
-            for (int r = 0; r < RI; ++r) { Sc[r] = 0.0f; Uc[r] = 0.0f; }
-#pragma unroll 8
+            for (int p = 0; p < NPAIR1; ++p) { Sc[p] = 0ull; Uc[p] = 0ull; }
+#pragma unroll UNROLL1
             for (int jj = 0; jj < SUB; ++jj) {
-                const float4 b = q[jj];
+                const ulonglong2 bxy = q[2 * jj];
+                const u64 bz = q[2 * jj + 1].x;
 #pragma unroll
-                for (int r = 0; r < RI; ++r) {
-                    const float dx = ax[r] - b.x, dy = ay[r] - b.y, dz = az[r] - b.z;
-                    float t = fmaf(-dx, dx, o[r]);
-                    t = fmaf(-dy, dy, t);
-                    t = fmaf(-dz, dz, t);
-                    const float e = ex2(t);
-                    Sc[r] += e;
-                    Uc[r] = fmaf(e, t, Uc[r]);
+                for (int p = 0; p < NPAIR1; ++p) {
+                    const u64 dx = fsub2(ax[p], bxy.x), dy = fsub2(ay[p], bxy.y), dz = fsub2(az[p], bz);
+                    u64 t = ffma2(dx, dx, no[p]);
+                    t = ffma2(dy, dy, t);
+                    t = ffma2(dz, dz, t);
+                    const float2 tt = unpack2(t);
+                    const u64 e = pack2(ex2(-tt.x), ex2(-tt.y));
+                    Sc[p] = fadd2(Sc[p], e);
+                    Uc[p] = ffma2(e, t, Uc[p]);
                 }
             }
             bool bad = false;
 #pragma unroll
-            for (int r = 0; r < RI; ++r) bad |= !(Sc[r] < TWO100);
+            for (int p = 0; p < NPAIR1; ++p) {
+                const float2 v = unpack2(Sc[p]);
+                bad |= !(v.x < TWO100) | !(v.y < TWO100);
+            }
             if (__any_sync(0xffffffffu, bad)) {
-                float cm[RI];
+                float cm[RI1];
 #pragma unroll
-                for (int r = 0; r < RI; ++r) cm[r] = 3.0e38f;
-#pragma unroll 8
+                for (int r = 0; r < RI1; ++r) cm[r] = 3.0e38f;
+#pragma unroll UNROLL1
                 for (int jj = 0; jj < SUB; ++jj) {
-                    const float4 b = q[jj];
+                    const ulonglong2 bxy = q[2 * jj];
+                    const u64 bz = q[2 * jj + 1].x;
 #pragma unroll
-                    for (int r = 0; r < RI; ++r) {
-                        const float dx = ax[r] - b.x, dy = ay[r] - b.y, dz = az[r] - b.z;
-                        cm[r] = fminf(cm[r], fmaf(dz, dz, fmaf(dy, dy, dx * dx)));
+                    for (int p = 0; p < NPAIR1; ++p) {
+                        const u64 dx = fsub2(ax[p], bxy.x), dy = fsub2(ay[p], bxy.y), dz = fsub2(az[p], bz);
+                        const float2 u = unpack2(ffma2(dz, dz, ffma2(dy, dy, fmul2(dx, dx))));
+                        cm[2 * p] = fminf(cm[2 * p], u.x);
+                        cm[2 * p + 1] = fminf(cm[2 * p + 1], u.y);
                     }
                 }
 #pragma unroll
-                for (int r = 0; r < RI; ++r) {
-                    const float on = fminf(o[r], floorf(cm[r]));
-                    const int sh = (int)fmaxf(on - o[r], -4000.0f);
-                    S[r] = ldexp(S[r], sh);
-                    SU[r] = ldexp(SU[r], sh);
-                    o[r] = on;
-                    Sc[r] = 0.0f; Uc[r] = 0.0f;
+                for (int p = 0; p < NPAIR1; ++p) {
+                    const float2 nv = unpack2(no[p]);
+                    const float o0 = -nv.x, o1 = -nv.y;
+                    const float on0 = fminf(o0, floorf(cm[2 * p])), on1 = fminf(o1, floorf(cm[2 * p + 1]));
+                    const int sh0 = (int)fmaxf(on0 - o0, -4000.0f), sh1 = (int)fmaxf(on1 - o1, -4000.0f);
+                    S[2 * p] = ldexp(S[2 * p], sh0); SU[2 * p] = ldexp(SU[2 * p], sh0);
+                    S[2 * p + 1] = ldexp(S[2 * p + 1], sh1); SU[2 * p + 1] = ldexp(SU[2 * p + 1], sh1);
+                    no[p] = pack2(-on0, -on1);
+                    Sc[p] = 0ull; Uc[p] = 0ull;
                 }
-#pragma unroll 8
+#pragma unroll UNROLL1
                 for (int jj = 0; jj < SUB; ++jj) {
-                    const float4 b = q[jj];
+                    const ulonglong2 bxy = q[2 * jj];
+                    const u64 bz = q[2 * jj + 1].x;
 #pragma unroll
-                    for (int r = 0; r < RI; ++r) {
-                        const float dx = ax[r] - b.x, dy = ay[r] - b.y, dz = az[r] - b.z;
-                        float t = fmaf(-dx, dx, o[r]);
-                        t = fmaf(-dy, dy, t);
-                        t = fmaf(-dz, dz, t);
-                        const float e = ex2(t);
-                        Sc[r] += e;
-                        Uc[r] = fmaf(e, t, Uc[r]);
+                    for (int p = 0; p < NPAIR1; ++p) {
+                        const u64 dx = fsub2(ax[p], bxy.x), dy = fsub2(ay[p], bxy.y), dz = fsub2(az[p], bz);
+                        u64 t = ffma2(dx, dx, no[p]);
+                        t = ffma2(dy, dy, t);
+                        t = ffma2(dz, dz, t);
+                        const float2 tt = unpack2(t);
+                        const u64 e = pack2(ex2(-tt.x), ex2(-tt.y));
+                        Sc[p] = fadd2(Sc[p], e);
+                        Uc[p] = ffma2(e, t, Uc[p]);
                     }
                 }
             }
 #pragma unroll
-            for (int r = 0; r < RI; ++r) {
-                const double sc64 = (double)Sc[r];
-                S[r] += sc64;
-                SU[r] += (double)o[r] * sc64 - (double)Uc[r];     // sum e*u = o*sum e - sum e*(o-u)
+            for (int p = 0; p < NPAIR1; ++p) {
+                const float2 sv = unpack2(Sc[p]), uv = unpack2(Uc[p]), nv = unpack2(no[p]);
+                S[2 * p] += (double)sv.x;
+                S[2 * p + 1] += (double)sv.y;
+                SU[2 * p] += (double)uv.x - (double)nv.x * (double)sv.x;         // sum e*u = sum e*t' + o * sum e
+                SU[2 * p + 1] += (double)uv.y - (double)nv.y * (double)sv.y;
             }
         }
         __syncthreads();
         if (tid == 0 && it + NSTAGE < nst) {
-            mbar_expect_tx(&full[s], STAGE_BYTES);
-            tma_load_1d(sm + s * P1_STAGE, jpts + (size_t)(st0 + it + NSTAGE) * P1_STAGE, STAGE_BYTES, &full[s]);
+            mbar_expect_tx(&full[s], P1_STAGE_BYTES);
+            tma_load_1d(smraw + s * P1_STAGE_BYTES, jbytes + (size_t)(st0 + it + NSTAGE) * P1_STAGE_BYTES, P1_STAGE_BYTES, &full[s]);
         }
     }
 #pragma unroll
-    for (int r = 0; r < RI; ++r) {
-        const int n = itile * ITILE + r * THREADS + tid;
-        if (n < ni) {
-            P1Part out;
-            out.S = S[r]; out.SU = SU[r]; out.o = o[r]; out.pad = 0.0f;
-            part[(size_t)split * ni + n] = out;
+    for (int p = 0; p < NPAIR1; ++p) {
+        const float2 nv = unpack2(no[p]);
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const int n = itile * ITILE1 + (2 * p + h) * THREADS + tid;
+            if (n < ni) {
+                P1Part out;
+                out.S = S[2 * p + h]; out.SU = SU[2 * p + h]; out.o = h ? -nv.y : -nv.x; out.pad = 0.0f;
+                part[(size_t)split * ni + n] = out;
+            }
         }
     }
 }
@@ -341,7 +401,8 @@ pass1_kernel(const float4* __restrict__ ipts, int ni, const float4* __restrict__
 //   L      = log2(den) = log2(2^log2S + c)          c = (2 pi s2)^(D/2) w/(1-w) M/N  (cpd.py:78-79)
 //   pt1    = 2^(log2S - L)                          (cpd.py:85; == 1 when w == 0)
 //   rn     = 2^(-omin) / den = 2^-(L + omin)        P_mn = 2^(omin - u_mn) * rn in pass 2
-//   record = {b, omin}, {rn, -, -, -}               dead: {b, -inf}, {0}
+//   record = {bx,bx,by,by},{bz,bz,-omin,-omin},{rn,rn,0,0}   (48 B, duplicated for the f32x2 inner loop)
+//            dead / padding: -omin = +inf (so 2^-(u - omin) == 0), rn = 0
 // and the target-side moments: Srr = sum_n SU_n rn_n (= sum_mn P_mn u_mn), Npt = sum pt1.
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(THREADS)
@@ -389,42 +450,40 @@ finalize1_kernel(const DevState* __restrict__ st, const double* __restrict__ sig
         }
         pt1[i] = p1n;
         const float4 b = tgtP[i];
-        float4 q0, q1;
-        if (dead) {
-            q0 = make_float4(b.x, b.y, b.z, -INFINITY);
-            q1 = make_float4(0.f, 0.f, 0.f, 0.f);
-        } else {
+        float no = INFINITY, rnf = 0.0f;
+        if (!dead) {
             const double rn = exp2(-(L + (double)omin));
-            q0 = make_float4(b.x, b.y, b.z, omin);
-            q1 = make_float4((float)rn, 0.f, 0.f, 0.f);
+            no = -omin;
+            rnf = (float)rn;
             v[0] = SU * rn;
         }
         v[1] = p1n;
-        tgtQ[2 * (size_t)i] = q0;
-        tgtQ[2 * (size_t)i + 1] = q1;
+        tgtQ[3 * (size_t)i] = make_float4(b.x, b.x, b.y, b.y);
+        tgtQ[3 * (size_t)i + 1] = make_float4(b.z, b.z, no, no);
+        tgtQ[3 * (size_t)i + 2] = make_float4(rnf, rnf, 0.f, 0.f);
     } else if (i < npad) {
-        tgtQ[2 * (size_t)i] = make_float4(0.f, 0.f, 0.f, -INFINITY);
-        tgtQ[2 * (size_t)i + 1] = make_float4(0.f, 0.f, 0.f, 0.f);
+        tgtQ[3 * (size_t)i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        tgtQ[3 * (size_t)i + 1] = make_float4(0.f, 0.f, INFINITY, INFINITY);
+        tgtQ[3 * (size_t)i + 2] = make_float4(0.f, 0.f, 0.f, 0.f);
     }
     block_reduce_store<RM_TGT>(v, mom_part + (size_t)blockIdx.x * RM_TGT);
 }
 
 // ---------------------------------------------------------------------------------------------
 // pass 2: per source m and split of the targets:  p1_m = sum_n P_mn,  sd_m = sum_n P_mn (a_m - b_n)
-// with P_mn = 2^(o_n - u_mn) * rn_n.  11 FP32-pipe + 1 MUFU instruction per pair.
+// with P_mn = 2^(o_n - u_mn) * rn_n.  Per two pairs: 11 packed FP32 instructions + 2 MUFU.
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(THREADS, 2)
+__global__ void __launch_bounds__(THREADS, CPD_MINB2)
 pass2_kernel(const float4* __restrict__ ipts, int ni, const float4* __restrict__ jrec, int nstages, int nsplit,
              double* __restrict__ part /* [nsplit][ni][4] */) {
     extern __shared__ __align__(128) unsigned char smraw[];
-    float4* sm = reinterpret_cast<float4*>(smraw);
-    uint64_t* full = reinterpret_cast<uint64_t*>(smraw + NSTAGE * STAGE_BYTES);
+    uint64_t* full = reinterpret_cast<uint64_t*>(smraw + NSTAGE * P2_STAGE_BYTES);
     const int tid = threadIdx.x;
     const int split = blockIdx.x % nsplit, itile = blockIdx.x / nsplit;
     const int st0 = (int)((long long)nstages * split / nsplit);
     const int st1 = (int)((long long)nstages * (split + 1) / nsplit);
     const int nst = st1 - st0;
-    constexpr int STAGE_F4 = 2 * P2_STAGE;
+    const unsigned char* jbytes = reinterpret_cast<const unsigned char*>(jrec);
     if (tid == 0) {
         for (int s = 0; s < NSTAGE; ++s) mbar_init(&full[s], 1);
         mbar_fence_init();
@@ -432,61 +491,67 @@ pass2_kernel(const float4* __restrict__ ipts, int ni, const float4* __restrict__
     __syncthreads();
     if (tid == 0) {
         for (int s = 0; s < NSTAGE && s < nst; ++s) {
-            mbar_expect_tx(&full[s], STAGE_BYTES);
-            tma_load_1d(sm + s * STAGE_F4, jrec + (size_t)(st0 + s) * STAGE_F4, STAGE_BYTES, &full[s]);
+            mbar_expect_tx(&full[s], P2_STAGE_BYTES);
+            tma_load_1d(smraw + s * P2_STAGE_BYTES, jbytes + (size_t)(st0 + s) * P2_STAGE_BYTES, P2_STAGE_BYTES, &full[s]);
         }
     }
-    float ax[RI], ay[RI], az[RI];
-    double A1[RI], AX[RI], AY[RI], AZ[RI];
+    u64 ax[NPAIR2], ay[NPAIR2], az[NPAIR2];
+    double A1[RI2], AX[RI2], AY[RI2], AZ[RI2];
 #pragma unroll
-    for (int r = 0; r < RI; ++r) {
-        int m = itile * ITILE + r * THREADS + tid;
-        m = m < ni ? m : ni - 1;
-        const float4 p = ipts[m];
-        ax[r] = p.x; ay[r] = p.y; az[r] = p.z;
-        A1[r] = 0.0; AX[r] = 0.0; AY[r] = 0.0; AZ[r] = 0.0;
+    for (int p = 0; p < NPAIR2; ++p) {
+        int m0 = itile * ITILE2 + (2 * p) * THREADS + tid, m1 = m0 + THREADS;
+        m0 = m0 < ni ? m0 : ni - 1;
+        m1 = m1 < ni ? m1 : ni - 1;
+        const float4 p0 = ipts[m0], p1 = ipts[m1];
+        ax[p] = pack2(p0.x, p1.x); ay[p] = pack2(p0.y, p1.y); az[p] = pack2(p0.z, p1.z);
     }
+#pragma unroll
+    for (int r = 0; r < RI2; ++r) { A1[r] = 0.0; AX[r] = 0.0; AY[r] = 0.0; AZ[r] = 0.0; }
     for (int it = 0; it < nst; ++it) {
         const int s = it % NSTAGE;
         mbar_wait(&full[s], (uint32_t)((it / NSTAGE) & 1));
-        const float4* sp = sm + s * STAGE_F4;
+        const ulonglong2* sp = reinterpret_cast<const ulonglong2*>(smraw + s * P2_STAGE_BYTES);
 #pragma unroll 1
         for (int sc = 0; sc < P2_STAGE / SUB; ++sc) {
-            const float4* q = sp + sc * (2 * SUB);
-            float s1[RI], sx[RI], sy[RI], sz[RI];
+            const ulonglong2* q = sp + sc * (3 * SUB);
+            u64 s1[NPAIR2], sx[NPAIR2], sy[NPAIR2], sz[NPAIR2];
 #pragma unroll
-            for (int r = 0; r < RI; ++r) { s1[r] = 0.f; sx[r] = 0.f; sy[r] = 0.f; sz[r] = 0.f; }
-#pragma unroll 4
+            for (int p = 0; p < NPAIR2; ++p) { s1[p] = 0ull; sx[p] = 0ull; sy[p] = 0ull; sz[p] = 0ull; }
+#pragma unroll UNROLL2
             for (int jj = 0; jj < SUB; ++jj) {
-                const float4 b = q[2 * jj];
-                const float rn = q[2 * jj + 1].x;
+                const ulonglong2 bxy = q[3 * jj];
+                const ulonglong2 bzo = q[3 * jj + 1];
+                const u64 rn = q[3 * jj + 2].x;
 #pragma unroll
-                for (int r = 0; r < RI; ++r) {
-                    const float dx = ax[r] - b.x, dy = ay[r] - b.y, dz = az[r] - b.z;
-                    float t = fmaf(-dx, dx, b.w);
-                    t = fmaf(-dy, dy, t);
-                    t = fmaf(-dz, dz, t);
-                    const float p = ex2(t) * rn;
-                    s1[r] += p;
-                    sx[r] = fmaf(p, dx, sx[r]);
-                    sy[r] = fmaf(p, dy, sy[r]);
-                    sz[r] = fmaf(p, dz, sz[r]);
+                for (int p = 0; p < NPAIR2; ++p) {
+                    const u64 dx = fsub2(ax[p], bxy.x), dy = fsub2(ay[p], bxy.y), dz = fsub2(az[p], bzo.x);
+                    u64 t = ffma2(dx, dx, bzo.y);         // t' = u - o_n: the same FMA chain and offset as pass 1
+                    t = ffma2(dy, dy, t);
+                    t = ffma2(dz, dz, t);
+                    const float2 tt = unpack2(t);
+                    const u64 pr = fmul2(pack2(ex2(-tt.x), ex2(-tt.y)), rn);
+                    s1[p] = fadd2(s1[p], pr);
+                    sx[p] = ffma2(pr, dx, sx[p]);
+                    sy[p] = ffma2(pr, dy, sy[p]);
+                    sz[p] = ffma2(pr, dz, sz[p]);
                 }
             }
 #pragma unroll
-            for (int r = 0; r < RI; ++r) {
-                A1[r] += (double)s1[r]; AX[r] += (double)sx[r]; AY[r] += (double)sy[r]; AZ[r] += (double)sz[r];
+            for (int p = 0; p < NPAIR2; ++p) {
+                const float2 v1 = unpack2(s1[p]), vx = unpack2(sx[p]), vy = unpack2(sy[p]), vz = unpack2(sz[p]);
+                A1[2 * p] += (double)v1.x; AX[2 * p] += (double)vx.x; AY[2 * p] += (double)vy.x; AZ[2 * p] += (double)vz.x;
+                A1[2 * p + 1] += (double)v1.y; AX[2 * p + 1] += (double)vx.y; AY[2 * p + 1] += (double)vy.y; AZ[2 * p + 1] += (double)vz.y;
             }
         }
         __syncthreads();
         if (tid == 0 && it + NSTAGE < nst) {
-            mbar_expect_tx(&full[s], STAGE_BYTES);
-            tma_load_1d(sm + s * STAGE_F4, jrec + (size_t)(st0 + it + NSTAGE) * STAGE_F4, STAGE_BYTES, &full[s]);
+            mbar_expect_tx(&full[s], P2_STAGE_BYTES);
+            tma_load_1d(smraw + s * P2_STAGE_BYTES, jbytes + (size_t)(st0 + it + NSTAGE) * P2_STAGE_BYTES, P2_STAGE_BYTES, &full[s]);
         }
     }
 #pragma unroll
-    for (int r = 0; r < RI; ++r) {
-        const int m = itile * ITILE + r * THREADS + tid;
+    for (int r = 0; r < RI2; ++r) {
+        const int m = itile * ITILE2 + r * THREADS + tid;
         if (m < ni) {
             double2* dst = reinterpret_cast<double2*>(part + ((size_t)split * ni + m) * 4);
             dst[0] = make_double2(A1[r], AX[r]);
@@ -937,27 +1002,12 @@ probe_mufu_kernel(float* out, int iters, float seed) {
     if (s == 123.456f) out[0] = s;
 }
 // packed FP32 (FFMA2): 2 FMAs per lane per instruction -- does it raise the FLOP rate or only save issue slots?
-__device__ __forceinline__ unsigned long long ffma2(unsigned long long a, unsigned long long b, unsigned long long c) {
-    unsigned long long d;
-    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
-    return d;
-}
-__device__ __forceinline__ unsigned long long pack2(float lo, float hi) {
-    unsigned long long r;
-    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
-    return r;
-}
-__device__ __forceinline__ float2 unpack2(unsigned long long v) {
-    float2 r;
-    asm("mov.b64 {%0, %1}, %2;" : "=f"(r.x), "=f"(r.y) : "l"(v));
-    return r;
-}
 __global__ void __launch_bounds__(256)
 probe_ffma2_kernel(float* out, int iters, float seed) {
-    unsigned long long a[8];
+    u64 a[8];
 #pragma unroll
     for (int k = 0; k < 8; ++k) a[k] = pack2(seed + k, seed - k);
-    const unsigned long long m = pack2(0.9999f + seed * 1e-9f, 0.9998f), c = pack2(1e-7f, 2e-7f);
+    const u64 m = pack2(0.9999f + seed * 1e-9f, 0.9998f), c = pack2(1e-7f, 2e-7f);
     for (int i = 0; i < iters; ++i) {
 #pragma unroll
         for (int k = 0; k < 8; ++k) a[k] = ffma2(a[k], m, c);
