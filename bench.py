@@ -197,7 +197,7 @@ def run_ours(args):
     # ---- device-resident arm -------------------------------------------------------------------
     h = _cabi.Handle(3, device=local_rank)
     if comm is not None:
-        h.comm_init(world, rank, comm.unique_id())
+        h.attach_comm(comm.nccl_comm(), world, rank)
     h.set_source(src)
     h.set_target(tgt[lo:hi], n_global=n, frame_origin=origin)
     s2 = h.sigma2_init()

@@ -107,12 +107,16 @@ int cpd_rbf_kernel(int device, const double* x, int64_t nx, const double* y, int
 int cpd_squared_kernel_sum(int device, const double* x, int64_t nx, const double* y, int64_t ny,
                            int dim, double* out);
 
-/* -- multi-GPU: one process (or handle) per GPU, targets sharded, sources replicated ----
+/* -- multi-GPU: one process per GPU, targets sharded, sources replicated -------------------
  * cpd_comm_unique_id fills 128 bytes (an ncclUniqueId) on one rank; after it has been
- * distributed, every rank calls cpd_comm_init.  From then on cpd_em_step/cpd_estep/
- * cpd_sigma2_init issue ONE ncclAllReduce(sum, double) on the handle's stream.          */
+ * distributed (any side channel), every rank calls cpd_comm_create ONCE -- a collective -- and
+ * attaches the communicator to as many handles as it likes.  From then on cpd_em_step /
+ * cpd_estep / cpd_sigma2_init issue one ncclAllReduce(sum, double) on the handle's stream.
+ * The communicator outlives the handles; destroy it explicitly (or let the process exit).   */
 int cpd_comm_unique_id(char id[128]);
-int cpd_comm_init(cpd_ctx* h, int world_size, int rank, const char id[128]);
+int cpd_comm_create(void** comm, int device, int world_size, int rank, const char id[128]);
+int cpd_comm_destroy(void* comm);
+int cpd_comm_attach(cpd_ctx* h, void* comm, int world_size, int rank);
 
 /* -- measurement helpers (bench.py): CUDA events on the handle's stream ---------------- */
 int cpd_timer_start(cpd_ctx* h);

@@ -44,7 +44,9 @@ _PROTOS = {
                                       ctypes.c_double, _c_fp]),
     "cpd_squared_kernel_sum": (ctypes.c_int, [ctypes.c_int, _c_dp, ctypes.c_int64, _c_dp, ctypes.c_int64, ctypes.c_int, _c_dp]),
     "cpd_comm_unique_id": (ctypes.c_int, [ctypes.c_char_p]),
-    "cpd_comm_init": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_char_p]),
+    "cpd_comm_create": (ctypes.c_int, [ctypes.POINTER(ctypes.c_void_p), ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_char_p]),
+    "cpd_comm_destroy": (ctypes.c_int, [ctypes.c_void_p]),
+    "cpd_comm_attach": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_int]),
     "cpd_timer_start": (ctypes.c_int, [ctypes.c_void_p]),
     "cpd_timer_stop": (ctypes.c_int, [ctypes.c_void_p, _c_fp]),
     "cpd_sync": (ctypes.c_int, [ctypes.c_void_p]),
@@ -201,8 +203,9 @@ class Handle(object):
         return self._unpack(p)
 
     # -- multi-GPU
-    def comm_init(self, world_size, rank, uid):
-        check(lib().cpd_comm_init(self._h, world_size, rank, uid))
+    def attach_comm(self, nccl_comm, world_size, rank):
+        """nccl_comm: the value returned by comm_create (borrowed; it must outlive the handle)."""
+        check(lib().cpd_comm_attach(self._h, nccl_comm, world_size, rank))
 
     # -- measurement
     def timer_start(self):
@@ -243,6 +246,17 @@ def unique_id():
     buf = ctypes.create_string_buffer(128)
     check(lib().cpd_comm_unique_id(buf))
     return buf.raw
+
+
+def comm_create(device, world_size, rank, uid):
+    """Collective: every rank calls it once with the same unique id.  Returns an opaque pointer."""
+    c = ctypes.c_void_p()
+    check(lib().cpd_comm_create(ctypes.byref(c), device, world_size, rank, uid))
+    return c
+
+
+def comm_destroy(c):
+    check(lib().cpd_comm_destroy(c))
 
 
 def microbench(device=0):

@@ -64,7 +64,6 @@ class CoherentPointDrift(abc.ABC):
         self._device = (comm.device if comm is not None else 0) if device is None else device
         self._em = None          # handle used by registration()/maximization_step (source = self._source)
         self._es = None          # handle used by stand-alone expectation_step (source = t_source)
-        self._squared_kernel_sum = self._sigma2_from_handle
 
     # -- reference API ------------------------------------------------------------------------
     def set_source(self, source):
@@ -133,7 +132,7 @@ class CoherentPointDrift(abc.ABC):
     def _new_handle(self, dim):
         h = _cabi.Handle(dim, device=self._device)
         if self._comm is not None and self._comm.world_size > 1:
-            h.comm_init(self._comm.world_size, self._comm.rank, self._comm.unique_id())
+            h.attach_comm(self._comm.nccl_comm(), self._comm.world_size, self._comm.rank)
         return h
 
     def _set_target(self, h, target):
@@ -152,7 +151,7 @@ class CoherentPointDrift(abc.ABC):
         self._set_target(self._em, target)
         return self._em
 
-    def _sigma2_from_handle(self, source, target):
+    def _squared_kernel_sum(self, source, target):
         # math_utils.squared_kernel_sum (math_utils.py:28-29) on the handle's resident clouds
         return self._em_handle(_points(target)).sigma2_init()
 

@@ -297,7 +297,6 @@ extern "C" void cpd_destroy(cpd_ctx* h) {
     if (!h) return;
     cudaSetDevice(h->device);
     cudaStreamSynchronize(h->stream);
-    if (h->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(h->comm);
     void* ptrs[] = {h->d_yc, h->d_ts, h->d_xc, h->d_raw, h->d_srcP, h->d_srcJ, h->d_tgtP, h->d_tgtQ, h->d_part1, h->d_part2, h->d_pt1, h->d_p1,
                     h->d_pxc, h->d_px, h->d_mom_src, h->d_mom_tgt, h->d_mom, h->d_sums, h->d_state, h->d_flush};
     for (void* p : ptrs) if (p) cudaFree(p);
@@ -573,16 +572,32 @@ extern "C" int cpd_comm_unique_id(char id[128]) {
     return CPD_OK;
 }
 
-extern "C" int cpd_comm_init(cpd_ctx* h, int world_size, int rank, const char id[128]) {
-    if (!h || !id) return fail(CPD_ERR_ARG, "null argument");
+extern "C" int cpd_comm_create(void** comm, int device, int world_size, int rank, const char id[128]) {
+    if (!comm || !id) return fail(CPD_ERR_ARG, "null argument");
     if (world_size < 1 || rank < 0 || rank >= world_size) return fail(CPD_ERR_ARG, "bad world_size/rank %d/%d", world_size, rank);
     TRY(load_nccl());
-    CU(cudaSetDevice(h->device));
+    CU(cudaSetDevice(device));
     nccl_uid u;
     memcpy(u.internal, id, 128);
-    NC(g_nccl.CommInitRank(&h->comm, world_size, u, rank));
-    h->world = world_size;
-    h->rank = rank;
+    nccl_comm c = nullptr;
+    NC(g_nccl.CommInitRank(&c, world_size, u, rank));
+    *comm = c;
+    return CPD_OK;
+}
+
+extern "C" int cpd_comm_destroy(void* comm) {
+    if (!comm) return CPD_OK;
+    TRY(load_nccl());
+    NC(g_nccl.CommDestroy((nccl_comm)comm));
+    return CPD_OK;
+}
+
+extern "C" int cpd_comm_attach(cpd_ctx* h, void* comm, int world_size, int rank) {
+    if (!h) return fail(CPD_ERR_ARG, "null handle");
+    if (comm && (world_size < 1 || rank < 0 || rank >= world_size)) return fail(CPD_ERR_ARG, "bad world_size/rank %d/%d", world_size, rank);
+    h->comm = (nccl_comm)comm;
+    h->world = comm ? world_size : 1;
+    h->rank = comm ? rank : 0;
     return CPD_OK;
 }
 

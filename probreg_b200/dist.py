@@ -26,6 +26,7 @@ class Communicator(object):
         self.world_size = int(world_size)
         self.device = int(device)
         self._exchange = exchange
+        self._nccl = None
 
     @classmethod
     def from_torch(cls, device=None):
@@ -52,6 +53,25 @@ class Communicator(object):
         """Common origin every rank centres on.  Each rank holds the full host array in this API,
         so the mean of the full cloud is computed locally and is bit-identical everywhere."""
         return np.asarray(target, dtype=np.float64).mean(axis=0)
+
+    def nccl_comm(self):
+        """The process's NCCL communicator inside libcpd_b200.so, created on first use (a collective:
+        every rank must reach its first use together) and shared by all handles of this process.
+        It is deliberately never tied to the lifetime of a Python object: NCCL teardown has
+        collective semantics and garbage collection is not synchronised across ranks."""
+        if self._nccl is None and self.world_size > 1:
+            from . import _cabi
+
+            self._nccl = _cabi.comm_create(self.device, self.world_size, self.rank, self.unique_id())
+        return self._nccl
+
+    def close(self):
+        """Collective, optional: destroy the NCCL communicator (all handles must be gone)."""
+        if self._nccl is not None:
+            from . import _cabi
+
+            _cabi.comm_destroy(self._nccl)
+            self._nccl = None
 
     def unique_id(self):
         """A fresh ncclUniqueId, created on rank 0 and broadcast.  Collective: every rank must
