@@ -195,15 +195,28 @@ def mstep_affine(source, target, es):
     return Mstep((b, t), float(sigma2), float(q))
 
 
-def mstep_nonrigid(source, target, es, sigma2_p, g, lmd):
-    """probreg/cpd.py:284-303.  ``g`` is the (float32) RBF Gram matrix of the source.
+def constraint_terms(m, target, idx_source, idx_target):
+    """probreg/cpd.py:370-374: the dense M x N indicator matrix of known correspondences,
+    reduced the way the reference reduces it (row sums, product with the target)."""
+    p_tilde = np.zeros((m, target.shape[0]))
+    if idx_source is not None and idx_target is not None:
+        p_tilde[idx_source, idx_target] = 1
+    return p_tilde.sum(axis=1), p_tilde.dot(target)
 
-    Returns Mstep((w,), sigma2, q) with q == sigma2 as in the reference (cpd.py:303).
+
+def mstep_nonrigid(source, target, es, sigma2_p, g, lmd, alpha=None, p1_tilde=None, px_tilde=None):
+    """probreg/cpd.py:284-303; with alpha / p1_tilde / px_tilde the constrained variant cpd.py:376-404.
+    ``g`` is the (float32) RBF Gram matrix of the source.
+
+    Returns Mstep((w,), sigma2, q) with q == sigma2 as in the reference (cpd.py:303 / :404).
     """
     pt1, p1, px, n_p = es
     m, dim = source.shape
     lhs = (p1 * g).T + lmd * sigma2_p * np.identity(m)   # cpd.py:296
     rhs = px - (source.T * p1).T
+    if alpha is not None:
+        lhs = lhs + sigma2_p / alpha * (p1_tilde * g).T  # cpd.py:392-394
+        rhs = rhs + sigma2_p / alpha * (px_tilde - (source.T * p1_tilde).T)   # cpd.py:395
     wmat = np.linalg.solve(lhs, rhs)
     t = source + g.dot(wmat)                             # cpd.py:297
     tr_xp1x = np.trace((target.T * pt1).dot(target))
@@ -233,7 +246,7 @@ def apply_nonrigid(points, g, wmat):
 # ---------------------------------------------------------------------------
 def registration(source, target, tf_type="rigid", w=0.0, maxiter=50, tol=1e-3,
                  update_scale=True, beta=2.0, lmd=2.0, sigma2_0=None, init=None,
-                 block=None, trace=None):
+                 block=None, trace=None, alpha=None, idx_source=None, idx_target=None):
     """Runs the reference's loop.  Returns (Mstep, iterations_run).
 
     ``sigma2_0`` overrides the float32-emulated initial variance; ``init`` overrides
@@ -251,9 +264,13 @@ def registration(source, target, tf_type="rigid", w=0.0, maxiter=50, tol=1e-3,
         params = (np.identity(dim), np.zeros(dim), 1.0) if init is None else init
     elif tf_type == "affine":
         params = (np.identity(dim), np.zeros(dim)) if init is None else init
-    elif tf_type == "nonrigid":
+    elif tf_type in ("nonrigid", "nonrigid_constrained"):
         g = rbf_kernel_f32(source, source, beta)          # transformation.py:91-99
         params = (np.zeros_like(source),)                 # cpd.py:281
+        prior = {}
+        if tf_type == "nonrigid_constrained":
+            p1t, pxt = constraint_terms(m, target, idx_source, idx_target)
+            prior = {"alpha": 1e-8 if alpha is None else alpha, "p1_tilde": p1t, "px_tilde": pxt}
     else:
         raise ValueError("Unknown transformation type %s" % tf_type)
     res = Mstep(params, sigma2, q)
@@ -271,7 +288,7 @@ def registration(source, target, tf_type="rigid", w=0.0, maxiter=50, tol=1e-3,
         elif tf_type == "affine":
             res = mstep_affine(source, target, es)
         else:
-            res = mstep_nonrigid(source, target, es, res.sigma2, g, lmd)
+            res = mstep_nonrigid(source, target, es, res.sigma2, g, lmd, **prior)
         if trace is not None:
             trace.append((res.sigma2, res.q))
         if abs(res.q - q) < tol:                          # cpd.py:117

@@ -1,6 +1,6 @@
 """Coherent Point Drift on one or more B200s -- the API surface of ``probreg.cpd``.
 
-Drop-in for probreg/cpd.py: ``registration_cpd``, ``RigidCPD``, ``AffineCPD``, ``NonRigidCPD``,
+Drop-in for probreg/cpd.py: ``registration_cpd``, ``RigidCPD``, ``AffineCPD``, ``NonRigidCPD``, ``ConstrainedNonRigidCPD``,
 ``EstepResult``, ``MstepResult`` keep their names, arguments, return types and error behaviour.
 What differs is where the work happens: every E-step / M-step runs in hand-written sm_100a
 kernels behind the C ABI of ``libcpd_b200.so`` (include/cpd_b200.h).  There is no numpy path
@@ -292,17 +292,7 @@ class NonRigidCPD(CoherentPointDrift):
 
     @staticmethod
     def _maximization_step(source, target, estep_res, sigma2_p, tf_obj, lmd, xp=np):
-        pt1, p1, px, n_p = estep_res
-        dim = source.shape[1]
-        lhs = (p1 * tf_obj.g).T + lmd * sigma2_p * np.identity(source.shape[0])
-        w = np.linalg.solve(lhs, px - (source.T * p1).T)
-        t = source + np.dot(tf_obj.g, w)
-        tr_xp1x = np.trace(np.dot(target.T * pt1, target))
-        tr_pxt = np.trace(np.dot(px.T, t))
-        tr_tpt = np.trace(np.dot(t.T * p1, t))
-        sigma2 = (tr_xp1x - 2.0 * tr_pxt + tr_tpt) / (n_p * dim)
-        tf_obj.w = w
-        return MstepResult(tf_obj, sigma2, sigma2)
+        return _nonrigid_mstep(source, target, estep_res, sigma2_p, tf_obj, lmd)
 
     def registration(self, target, w=0.0, maxiter=50, tol=0.001):
         assert not self._tf_type is None, "transformation type is None."
@@ -328,6 +318,72 @@ class NonRigidCPD(CoherentPointDrift):
         raise NotImplementedError
 
 
+def _nonrigid_mstep(source, target, estep_res, sigma2_p, tf_obj, lmd, prior=None):
+    """Non-rigid M-step (probreg/cpd.py:284-303; with ``prior`` the constrained one, cpd.py:376-404).
+
+    Solves (diag(p1 + k p1~) G + lmd sigma2 I) W = px + k px~ - diag(p1 + k p1~) Y with k = sigma2/alpha
+    (k = 0 without priors), then T = Y + G W and sigma2 from the three traces.  Host numpy for now
+    (the dense M x M solve is the next row to move onto the device).
+    """
+    pt1, p1, px, n_p = estep_res
+    m, dim = source.shape
+    wgt, rhs = p1, px
+    if prior is not None:
+        k = sigma2_p / prior[0]
+        wgt = p1 + k * prior[1]
+        rhs = px + k * prior[2]
+    lhs = tf_obj.g * wgt[:, None]
+    lhs[np.diag_indices(m)] += lmd * sigma2_p
+    w = np.linalg.solve(lhs, rhs - source * wgt[:, None])
+    moved = source + np.dot(tf_obj.g, w)
+    tr_xp1x = float(np.dot(pt1, np.einsum("ij,ij->i", target, target)))
+    tr_pxt = float(np.einsum("ij,ij->", px, moved))
+    tr_tpt = float(np.dot(p1, np.einsum("ij,ij->i", moved, moved)))
+    sigma2 = (tr_xp1x - 2.0 * tr_pxt + tr_tpt) / (n_p * dim)
+    tf_obj.w = w
+    return MstepResult(tf_obj, sigma2, sigma2)
+
+
+class ConstrainedNonRigidCPD(NonRigidCPD):
+    """Extended CPD with point-correspondence priors (probreg/cpd.py:306-404,
+    https://people.mpi-inf.mpg.de/~golyanik/04_DRAFTS/ECPD2016.pdf).
+
+    Args:
+        source (numpy.ndarray, optional): Source point cloud data.
+        beta (float, optional): Parameter of RBF kernel.
+        lmd (float, optional): Parameter for regularization term.
+        alpha (float): Degree of reliability of priors (1e-8 highly reliable ... 1 highly unreliable).
+        use_cuda (bool, optional): ignored (see module docstring).
+        idx_source / idx_target (numpy.ndarray of ints, optional): known correspondences.
+
+    The reference materialises a dense M x N indicator matrix for the priors (cpd.py:370-374); its row
+    sums and its product with the target are a sparse gather, which is what is computed here.
+    """
+
+    def __init__(self, source=None, beta=2.0, lmd=2.0, alpha=1e-8, use_cuda=False, idx_source=None, idx_target=None,
+                 device=None, comm=None):
+        super(ConstrainedNonRigidCPD, self).__init__(source, beta, lmd, use_cuda, device, comm)
+        self.alpha = alpha
+        self.idx_source, self.idx_target = idx_source, idx_target
+        self.p1_tilde = None
+        self.px_tilde = None
+
+    def _initialize(self, target):
+        res = super(ConstrainedNonRigidCPD, self)._initialize(target)
+        m, dim = self._source.shape
+        self.p1_tilde = np.zeros(m)
+        self.px_tilde = np.zeros((m, dim))
+        if self.idx_source is not None and self.idx_target is not None:
+            pairs = np.unique(np.c_[np.asarray(self.idx_source).ravel(), np.asarray(self.idx_target).ravel()], axis=0)
+            np.add.at(self.p1_tilde, pairs[:, 0], 1.0)
+            np.add.at(self.px_tilde, pairs[:, 0], np.asarray(target, dtype=np.float64)[pairs[:, 1]])
+        return res
+
+    def maximization_step(self, target, estep_res, sigma2_p=None):
+        return _nonrigid_mstep(self._source, target, estep_res, sigma2_p, self._tf_obj, self._lmd,
+                               prior=(self.alpha, self.p1_tilde, self.px_tilde))
+
+
 def registration_cpd(source, target, tf_type_name="rigid", w=0.0, maxiter=50, tol=0.001, callbacks=(),
                      use_cuda=False, **kwargs):
     """CPD Registraion (probreg/cpd.py:407-456).
@@ -335,7 +391,7 @@ def registration_cpd(source, target, tf_type_name="rigid", w=0.0, maxiter=50, to
     Args:
         source (numpy.ndarray): Source point cloud data.
         target (numpy.ndarray): Target point cloud data.
-        tf_type_name (str, optional): Transformation type('rigid', 'affine', 'nonrigid')
+        tf_type_name (str, optional): Transformation type('rigid', 'affine', 'nonrigid', 'nonrigid_constrained')
         w (float, optional): Weight of the uniform distribution, 0 < `w` < 1.
         maxitr (int, optional): Maximum number of iterations to EM algorithm.
         tol (float, optional): Tolerance for termination.
@@ -358,6 +414,8 @@ def registration_cpd(source, target, tf_type_name="rigid", w=0.0, maxiter=50, to
         cpd = AffineCPD(_points(source), use_cuda=use_cuda, **kwargs)
     elif tf_type_name == "nonrigid":
         cpd = NonRigidCPD(_points(source), use_cuda=use_cuda, **kwargs)
+    elif tf_type_name == "nonrigid_constrained":
+        cpd = ConstrainedNonRigidCPD(_points(source), use_cuda=use_cuda, **kwargs)
     else:
         raise ValueError("Unknown transformation type %s" % tf_type_name)
     cpd.set_callbacks(list(callbacks))

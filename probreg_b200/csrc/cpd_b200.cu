@@ -426,12 +426,12 @@ extern "C" int cpd_em_step(cpd_ctx* h, cpd_params* out) {
     TRY(launch_estep(h, &h->d_state->sigma2, &h->d_state->w, nullptr));
     const int nbs = (int)blocks_for(h->m), nbt = (int)blocks_for(h->npad);
     if (h->comm) {
-        moments_kernel<0><<<1, 32, 0, h->stream>>>(h->d_state, h->d_mom_src, nbs, RM_SRC, h->d_mom_tgt, nbt, RM_TGT, h->d_mom);
+        moments_kernel<0><<<1, 256, 0, h->stream>>>(h->d_state, h->d_mom_src, nbs, RM_SRC, h->d_mom_tgt, nbt, RM_TGT, h->d_mom);
         TRY(allreduce(h, h->d_mom, MOM_PAD));
         mstep_residual_kernel<<<1, 32, 0, h->stream>>>(h->d_state, h->d_mom);
         h->launches += 2;
     } else {
-        moments_kernel<1><<<1, 32, 0, h->stream>>>(h->d_state, h->d_mom_src, nbs, RM_SRC, h->d_mom_tgt, nbt, RM_TGT, h->d_mom);
+        moments_kernel<1><<<1, 256, 0, h->stream>>>(h->d_state, h->d_mom_src, nbs, RM_SRC, h->d_mom_tgt, nbt, RM_TGT, h->d_mom);
         h->launches += 1;
     }
     mark(h, 6);
@@ -523,7 +523,7 @@ extern "C" int cpd_mstep(cpd_ctx* h, int tf_kind, int update_scale, const double
     centre_px_kernel<<<nbs, THREADS, 0, h->stream>>>(h->d_state, h->d_p1, h->d_px, (int)h->m, h->d_pxc);
     src_moments_api_kernel<<<nbs, THREADS, 0, h->stream>>>((int)h->m, h->d_yc, h->d_p1, h->d_pxc, h->d_mom_src);
     tgt_moments_api_kernel<<<nbt, THREADS, 0, h->stream>>>(h->d_pt1, h->d_xc, (int)h->n, h->d_mom_tgt);
-    moments_kernel<0><<<1, 32, 0, h->stream>>>(h->d_state, h->d_mom_src, nbs, MOM_SRC, h->d_mom_tgt, nbt, MOM_TGT, h->d_mom);
+    moments_kernel<0><<<1, 256, 0, h->stream>>>(h->d_state, h->d_mom_src, nbs, MOM_SRC, h->d_mom_tgt, nbt, MOM_TGT, h->d_mom);
     KCHECK();
     if (h->comm) TRY(allreduce(h, h->d_mom + MOM_SRC, MOM_TGT));   // p1/px are already global; pt1 is per shard
     mstep_api_kernel<<<1, 32, 0, h->stream>>>(h->d_state, h->d_mom);

@@ -889,20 +889,30 @@ __device__ inline void mstep_solve_residual(DevState* st, const double* __restri
 // part_b, into mom[0 .. ka+kb); the rest of mom[0..32) is zeroed.  SOLVE = 1: the same (single)
 // block then runs the residual-form M-step.  In multi-rank runs the all-reduce sits in between.
 template <int SOLVE>
-__global__ void __launch_bounds__(32)
+__global__ void __launch_bounds__(256)
 moments_kernel(DevState* st, const double* __restrict__ part_a, int nb_a, int ka, const double* __restrict__ part_b, int nb_b,
                int kb, double* __restrict__ mom) {
-    const int k = threadIdx.x;
+    // 32 columns x 8 lanes of blocks; lane w takes blocks w, w+8, ... (fixed order), then the 8 lane sums are
+    // combined in a fixed order: bit-reproducible, and 8x shorter dependent chains than one thread per column.
+    __shared__ double sh[8][32];
+    const int k = threadIdx.x & 31, w = threadIdx.x >> 5;
     double s = 0.0;
     if (k < ka) {
-        for (int b = 0; b < nb_a; ++b) s += part_a[(size_t)b * ka + k];
+        for (int b = w; b < nb_a; b += 8) s += part_a[(size_t)b * ka + k];
     } else if (k < ka + kb) {
-        for (int b = 0; b < nb_b; ++b) s += part_b[(size_t)b * kb + (k - ka)];
+        for (int b = w; b < nb_b; b += 8) s += part_b[(size_t)b * kb + (k - ka)];
     }
-    mom[k] = s;
-    if (SOLVE) {
-        __syncwarp();
-        if (k == 0) mstep_solve_residual(st, mom);
+    sh[w][k] = s;
+    __syncthreads();
+    if (w == 0) {
+        double t = 0.0;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) t += sh[i][k];
+        mom[k] = t;
+        if (SOLVE) {
+            __syncwarp();
+            if (k == 0) mstep_solve_residual(st, mom);
+        }
     }
 }
 __global__ void mstep_residual_kernel(DevState* st, const double* __restrict__ mom) {

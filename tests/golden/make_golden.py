@@ -178,6 +178,15 @@ def main():
     res = run_fixed(cpd, cpd.NonRigidCPD, s3, t3, 12, beta=0.5, lmd=1.0)
     for k, v in pack_tf(res).items():
         n["nr12_%s" % k] = v
+    # constrained non-rigid (cpd.py:306-404): 25 known correspondences, one of them listed twice
+    idx = np.random.default_rng(5).choice(400, 25, replace=False)
+    idx_s = np.r_[idx, idx[:1]]
+    idx_t = np.r_[idx, idx[:1]]
+    n["nrc_idx_source"], n["nrc_idx_target"] = idx_s, idx_t
+    res = cpd.ConstrainedNonRigidCPD(s3, beta=0.5, lmd=1.0, alpha=1e-2, idx_source=idx_s, idx_target=idx_t).registration(
+        t3, maxiter=8, tol=-1.0)
+    for k, v in pack_tf(res).items():
+        n["nrc8_%s" % k] = v
     np.savez_compressed(os.path.join(out_dir, "nonrigid.npz"), **n)
 
     # ---- 4. reference's own known-answer test (tests/test_math_utils.py:6-16)

@@ -79,12 +79,16 @@ CASES = [
     ("nonrigid.npz", "fishaffine15", "affine", 15, 0.0, {}, "fish_source", "fish_target"),
     ("nonrigid.npz", "fishrigid15", "rigid", 15, 0.0, {}, "fish_source", "fish_target"),
     ("nonrigid.npz", "nr12", "nonrigid", 12, 0.0, {"beta": 0.5, "lmd": 1.0}, "nr_source", "nr_target"),
+    ("nonrigid.npz", "nrc8", "nonrigid_constrained", 8, 0.0, {"beta": 0.5, "lmd": 1.0, "alpha": 1e-2}, "nr_source", "nr_target"),
 ]
 
 
 @pytest.mark.parametrize("fname,tag,tf_type,iters,w,kw,sk,tk", CASES)
 def test_fixed_iteration_registration(fname, tag, tf_type, iters, w, kw, sk, tk):
     g = load_golden(fname)
+    kw = dict(kw)
+    if tf_type == "nonrigid_constrained":
+        kw["idx_source"], kw["idx_target"] = g["nrc_idx_source"], g["nrc_idx_target"]
     res, it = orc.registration(g[sk], g[tk], tf_type, w=w, maxiter=iters, tol=-1.0, **kw)
     assert it == iters
     assert res.sigma2 == pytest.approx(float(g[tag + "_sigma2"]), rel=1e-9)
