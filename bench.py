@@ -197,7 +197,7 @@ def run_ours(args):
     # ---- device-resident arm -------------------------------------------------------------------
     h = _cabi.Handle(3, device=local_rank)
     if comm is not None:
-        h.attach_comm(comm.nccl_comm(), world, rank)
+        comm.attach(h)
     h.set_source(src)
     h.set_target(tgt[lo:hi], n_global=n, frame_origin=origin)
     s2 = h.sigma2_init()
@@ -315,7 +315,9 @@ def run_ours(args):
         "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
         "dtype": "f32 pair math, f64 accumulation and M-step", "data": "synthetic",
         "config": {"workload": "rigid CPD, synthetic 3-D N=M=%d, sigma2 auto, w=0, update_scale" % n,
-                   "parallelism": "target-sharded x%d, sources replicated, 1 NCCL all-reduce(32 f64)/iteration" % world,
+                   "parallelism": "target-sharded x%d, sources replicated, one 32-double all-reduce per iteration (%s)"
+                                  % (world, "fused into the M-step kernel over NVLink peer memory" if (comm is not None and comm.use_p2p)
+                                     else ("ncclAllReduce" if world > 1 else "none needed")),
                    "l2": "flushed (256 MiB memset) between timed iterations, outside the event pairs",
                    "timing": "CUDA event pair per iteration on the library stream, summed, max over ranks"},
         "wall_ms_per_step_incl_flush": t_wall * 1e3 / args.steps,

@@ -117,6 +117,13 @@ int cpd_comm_unique_id(char id[128]);
 int cpd_comm_create(void** comm, int device, int world_size, int rank, const char id[128]);
 int cpd_comm_destroy(void* comm);
 int cpd_comm_attach(cpd_ctx* h, void* comm, int world_size, int rank);
+/* Fused exchange for the EM loop (single node): each rank exports a 64-byte cudaIpcMemHandle of its
+ * mailbox (cpd_p2p_local_handle), the handles of all ranks are concatenated in rank order and given to
+ * cpd_p2p_attach.  cpd_em_step then reduces the moments, exchanges them through NVLink peer memory and runs
+ * the M-step in ONE kernel; the NCCL communicator is still used for the M-sized sums of cpd_estep and for
+ * cpd_sigma2_init.  Every rank must have attached before any rank calls cpd_em_step.              */
+int cpd_p2p_local_handle(cpd_ctx* h, char out[64]);
+int cpd_p2p_attach(cpd_ctx* h, const char* handles, int world_size, int rank);
 
 /* -- measurement helpers (bench.py): CUDA events on the handle's stream ---------------- */
 int cpd_timer_start(cpd_ctx* h);

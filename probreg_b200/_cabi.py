@@ -47,6 +47,8 @@ _PROTOS = {
     "cpd_comm_create": (ctypes.c_int, [ctypes.POINTER(ctypes.c_void_p), ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_char_p]),
     "cpd_comm_destroy": (ctypes.c_int, [ctypes.c_void_p]),
     "cpd_comm_attach": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_int]),
+    "cpd_p2p_local_handle": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_char_p]),
+    "cpd_p2p_attach": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_char_p, ctypes.c_int, ctypes.c_int]),
     "cpd_timer_start": (ctypes.c_int, [ctypes.c_void_p]),
     "cpd_timer_stop": (ctypes.c_int, [ctypes.c_void_p, _c_fp]),
     "cpd_sync": (ctypes.c_int, [ctypes.c_void_p]),
@@ -206,6 +208,16 @@ class Handle(object):
     def attach_comm(self, nccl_comm, world_size, rank):
         """nccl_comm: the value returned by comm_create (borrowed; it must outlive the handle)."""
         check(lib().cpd_comm_attach(self._h, nccl_comm, world_size, rank))
+
+    def p2p_local_handle(self):
+        buf = ctypes.create_string_buffer(64)
+        check(lib().cpd_p2p_local_handle(self._h, buf))
+        return buf.raw
+
+    def p2p_attach(self, handles, world_size, rank):
+        blob = b"".join(handles)
+        assert len(blob) == 64 * world_size
+        check(lib().cpd_p2p_attach(self._h, blob, world_size, rank))
 
     # -- measurement
     def timer_start(self):

@@ -131,8 +131,8 @@ class CoherentPointDrift(abc.ABC):
     # -- plumbing -----------------------------------------------------------------------------
     def _new_handle(self, dim):
         h = _cabi.Handle(dim, device=self._device)
-        if self._comm is not None and self._comm.world_size > 1:
-            h.attach_comm(self._comm.nccl_comm(), self._comm.world_size, self._comm.rank)
+        if self._comm is not None:
+            self._comm.attach(h)
         return h
 
     def _set_target(self, h, target):

@@ -106,6 +106,9 @@ struct cpd_ctx {
     bool have_source = false, have_target = false, have_state = false, prepared = false;
     nccl_comm comm = nullptr;
     int world = 1, rank = 0;
+    P2PMailbox* d_box = nullptr;          // this rank's mailbox (peers write into it)
+    P2PInfo* d_p2p = nullptr;             // device copy of the peer table; non-null => fused P2P exchange
+    void* peer_ptr[P2P_MAX] = {nullptr};  // mappings opened with cudaIpcOpenMemHandle
     cudaEvent_t ev0 = nullptr, ev1 = nullptr, sev[7] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     bool profiling = false;
     int64_t launches = 0;
@@ -237,8 +240,11 @@ int launch_estep(cpd_ctx* h, const double* d_sigma2, const double* d_w, const do
 }
 
 int read_params(cpd_ctx* h, cpd_params* out) {
-    CU(cudaMemcpyAsync(h->h_pin, h->d_state, 16 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    static_assert(sizeof(DevState) <= 48 * sizeof(double), "DevState outgrew the pinned staging buffer");
+    CU(cudaMemcpyAsync(h->h_pin, h->d_state, sizeof(DevState), cudaMemcpyDeviceToHost, h->stream));
     CU(cudaStreamSynchronize(h->stream));
+    if (reinterpret_cast<const DevState*>(h->h_pin)->err)
+        return fail(CPD_ERR_STATE, "a peer rank did not deliver its moments within the P2P exchange timeout");
     const int d = h->dim;
     for (int i = 0; i < 9; ++i) out->lin[i] = 0.0;
     for (int i = 0; i < d; ++i)
@@ -297,6 +303,9 @@ extern "C" void cpd_destroy(cpd_ctx* h) {
     if (!h) return;
     cudaSetDevice(h->device);
     cudaStreamSynchronize(h->stream);
+    for (int r = 0; r < P2P_MAX; ++r) if (h->peer_ptr[r]) cudaIpcCloseMemHandle(h->peer_ptr[r]);
+    if (h->d_box) cudaFree(h->d_box);
+    if (h->d_p2p) cudaFree(h->d_p2p);
     void* ptrs[] = {h->d_yc, h->d_ts, h->d_xc, h->d_raw, h->d_srcP, h->d_srcJ, h->d_tgtP, h->d_tgtQ, h->d_part1, h->d_part2, h->d_pt1, h->d_p1,
                     h->d_pxc, h->d_px, h->d_mom_src, h->d_mom_tgt, h->d_mom, h->d_sums, h->d_state, h->d_flush};
     for (void* p : ptrs) if (p) cudaFree(p);
@@ -425,7 +434,11 @@ extern "C" int cpd_em_step(cpd_ctx* h, cpd_params* out) {
     CU(cudaSetDevice(h->device));
     TRY(launch_estep(h, &h->d_state->sigma2, &h->d_state->w, nullptr));
     const int nbs = (int)blocks_for(h->m), nbt = (int)blocks_for(h->npad);
-    if (h->comm) {
+    if (h->d_p2p) {
+        moments_p2p_kernel<<<1, 256, 0, h->stream>>>(h->d_state, h->d_mom_src, nbs, RM_SRC, h->d_mom_tgt, nbt, RM_TGT, h->d_mom,
+                                                     h->d_p2p);
+        h->launches += 1;
+    } else if (h->comm) {
         moments_kernel<0><<<1, 256, 0, h->stream>>>(h->d_state, h->d_mom_src, nbs, RM_SRC, h->d_mom_tgt, nbt, RM_TGT, h->d_mom);
         TRY(allreduce(h, h->d_mom, MOM_PAD));
         mstep_residual_kernel<<<1, 32, 0, h->stream>>>(h->d_state, h->d_mom);
@@ -598,6 +611,46 @@ extern "C" int cpd_comm_attach(cpd_ctx* h, void* comm, int world_size, int rank)
     h->comm = (nccl_comm)comm;
     h->world = comm ? world_size : 1;
     h->rank = comm ? rank : 0;
+    return CPD_OK;
+}
+
+extern "C" int cpd_p2p_local_handle(cpd_ctx* h, char out[64]) {
+    if (!h || !out) return fail(CPD_ERR_ARG, "null argument");
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t is expected to be 64 bytes");
+    CU(cudaSetDevice(h->device));
+    if (!h->d_box) {
+        TRY(dev_alloc(&h->d_box, 1));
+        CU(cudaMemset(h->d_box, 0, sizeof(P2PMailbox)));
+        CU(cudaDeviceSynchronize());
+    }
+    cudaIpcMemHandle_t mh;
+    CU(cudaIpcGetMemHandle(&mh, h->d_box));
+    memcpy(out, &mh, 64);
+    return CPD_OK;
+}
+
+extern "C" int cpd_p2p_attach(cpd_ctx* h, const char* handles, int world_size, int rank) {
+    if (!h || !handles) return fail(CPD_ERR_ARG, "null argument");
+    if (world_size < 2 || world_size > P2P_MAX || rank < 0 || rank >= world_size)
+        return fail(CPD_ERR_ARG, "bad world_size/rank %d/%d (2..%d ranks)", world_size, rank, P2P_MAX);
+    if (!h->d_box) return fail(CPD_ERR_STATE, "cpd_p2p_local_handle must be called first");
+    if (h->d_p2p) return fail(CPD_ERR_STATE, "P2P exchange already attached to this handle");
+    CU(cudaSetDevice(h->device));
+    P2PInfo info;
+    memset(&info, 0, sizeof(info));
+    info.world = world_size;
+    info.rank = rank;
+    for (int r = 0; r < world_size; ++r) {
+        if (r == rank) { info.box[r] = h->d_box; continue; }
+        cudaIpcMemHandle_t mh;
+        memcpy(&mh, handles + (size_t)r * 64, 64);
+        CU(cudaIpcOpenMemHandle(&h->peer_ptr[r], mh, cudaIpcMemLazyEnablePeerAccess));
+        info.box[r] = (P2PMailbox*)h->peer_ptr[r];
+    }
+    TRY(dev_alloc(&h->d_p2p, 1));
+    CU(cudaMemcpy(h->d_p2p, &info, sizeof(info), cudaMemcpyHostToDevice));
+    h->world = world_size;
+    h->rank = rank;
     return CPD_OK;
 }
 

@@ -110,7 +110,21 @@ struct DevState {
     int tf_kind;
     int update_scale;
     int dim;
-    int pad;
+    int err;             // set by a kernel that gave up waiting for a peer (P2P exchange); checked by the host
+};
+
+// One-shot all-reduce of the 32 moment doubles over NVLink peer memory: every rank owns
+// a mailbox that its peers write into; slots are double-buffered by exchange parity, flags carry the
+// exchange sequence number (monotonic, never reset), sums are formed in rank order => bit-identical on all ranks.
+constexpr int P2P_MAX = 16;
+struct P2PMailbox {
+    double slots[2][P2P_MAX][MOM_PAD];
+    unsigned long long flags[2][P2P_MAX];
+};
+struct P2PInfo {
+    P2PMailbox* box[P2P_MAX];     // box[r]: rank r's mailbox mapped into this process (box[rank] is local memory)
+    int world, rank;
+    unsigned long long seq;       // exchanges completed
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -920,6 +934,81 @@ __global__ void mstep_residual_kernel(DevState* st, const double* __restrict__ m
 }
 __global__ void mstep_api_kernel(DevState* st, const double* __restrict__ mom) {
     if (threadIdx.x == 0) mstep_solve_api(st, mom);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Fused "reduce moments -> all-reduce over NVLink -> M-step" for multi-GPU runs: ONE launch instead of
+// (reduce kernel, ncclAllReduce, M-step kernel).  The collective is 32 doubles, i.e. pure latency, so it is
+// done as a one-shot exchange through peer-mapped memory inside the kernel that needs the result:
+//   1. fixed-order reduction of this rank's block partials (as moments_kernel)
+//   2. store the 32 sums into slot [parity][my rank] of EVERY rank's mailbox (st.global over NVLink / local)
+//   3. __threadfence_system, then a release store of the sequence number into every mailbox's flag
+//   4. acquire-spin on my own mailbox's flags until every rank's sequence number has arrived (bounded)
+//   5. sum the slots in rank order (identical arithmetic on every rank), run the FP64 M-step
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned long long v) {
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long* p) {
+    unsigned long long v;
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ double ld_relaxed_sys(const double* p) {
+    double v;
+    asm volatile("ld.relaxed.sys.global.f64 %0, [%1];" : "=d"(v) : "l"(p) : "memory");
+    return v;
+}
+__global__ void __launch_bounds__(256)
+moments_p2p_kernel(DevState* st, const double* __restrict__ part_a, int nb_a, int ka, const double* __restrict__ part_b,
+                   int nb_b, int kb, double* __restrict__ mom, P2PInfo* info) {
+    __shared__ double sh[8][32];
+    __shared__ double loc[32];
+    __shared__ int timeout;
+    const int k = threadIdx.x & 31, w = threadIdx.x >> 5;
+    double s = 0.0;
+    if (k < ka) {
+        for (int b = w; b < nb_a; b += 8) s += part_a[(size_t)b * ka + k];
+    } else if (k < ka + kb) {
+        for (int b = w; b < nb_b; b += 8) s += part_b[(size_t)b * kb + (k - ka)];
+    }
+    sh[w][k] = s;
+    if (threadIdx.x == 0) timeout = 0;
+    __syncthreads();
+    if (w == 0) {
+        double t = 0.0;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) t += sh[i][k];
+        loc[k] = t;
+    }
+    __syncthreads();
+    const int world = info->world, rank = info->rank;
+    const unsigned long long seq = info->seq + 1;
+    const int par = (int)(seq & 1ull);
+    for (int r = w; r < world; r += 8) info->box[r]->slots[par][rank][k] = loc[k];
+    __threadfence_system();
+    __syncthreads();
+    if ((int)threadIdx.x < world) {
+        st_release_sys(&info->box[threadIdx.x]->flags[par][rank], seq);
+        const unsigned long long* f = &info->box[rank]->flags[par][threadIdx.x];
+        long long spins = 0;
+        while (ld_acquire_sys(f) < seq) {
+            __nanosleep(64);
+            if (++spins > 4000000ll) { timeout = 1; break; }        // seconds: a peer is gone; fail instead of hanging the GPU
+        }
+    }
+    __syncthreads();
+    if (w == 0) {
+        double t = 0.0;
+        for (int r = 0; r < world; ++r) t += ld_relaxed_sys(&info->box[rank]->slots[par][r][k]);
+        mom[k] = t;
+        __syncwarp();
+        if (k == 0) {
+            info->seq = seq;
+            if (timeout) st->err = 1;
+            mstep_solve_residual(st, mom);
+        }
+    }
 }
 
 // sums for sigma^2 initialisation: out[block][0..4) = sum |p|^2, sum p (3)

@@ -20,13 +20,17 @@ def shard_bounds(n, rank, world_size):
 
 
 class Communicator(object):
-    def __init__(self, rank=0, world_size=1, device=0, exchange=None):
-        """exchange(obj_or_None) -> obj : broadcast of a small picklable object from rank 0."""
+    def __init__(self, rank=0, world_size=1, device=0, exchange=None, gather=None, use_p2p=None):
+        """exchange(obj_or_None) -> obj : broadcast of a small picklable object from rank 0.
+        gather(obj) -> [obj of rank 0, ..., obj of rank W-1] on every rank (all-gather; also a barrier)."""
         self.rank = int(rank)
         self.world_size = int(world_size)
         self.device = int(device)
         self._exchange = exchange
+        self._gather = gather
         self._nccl = None
+        # fused NVLink peer-memory exchange of the moments inside the M-step kernel (default) vs ncclAllReduce
+        self.use_p2p = (os.environ.get("CPD_B200_NO_P2P", "0") != "1") if use_p2p is None else bool(use_p2p)
 
     @classmethod
     def from_torch(cls, device=None):
@@ -44,7 +48,12 @@ class Communicator(object):
             dist.broadcast_object_list(box, src=0)
             return box[0]
 
-        return cls(rank, world, device, exchange)
+        def gather(obj):
+            box = [None] * world
+            dist.all_gather_object(box, obj)
+            return box
+
+        return cls(rank, world, device, exchange, gather)
 
     def shard_bounds(self, n):
         return shard_bounds(n, self.rank, self.world_size)
@@ -64,6 +73,18 @@ class Communicator(object):
 
             self._nccl = _cabi.comm_create(self.device, self.world_size, self.rank, self.unique_id())
         return self._nccl
+
+    def attach(self, handle):
+        """Wire a _cabi.Handle for multi-rank use (collective: every rank, same order)."""
+        if self.world_size <= 1:
+            return
+        handle.attach_comm(self.nccl_comm(), self.world_size, self.rank)
+        if self.use_p2p:
+            if self._gather is None:
+                raise RuntimeError("Communicator needs a gather function for the P2P exchange")
+            handles = self._gather(handle.p2p_local_handle())
+            handle.p2p_attach(handles, self.world_size, self.rank)
+            self._gather(b"attached")          # barrier: nobody steps before everybody has mapped everybody
 
     def close(self):
         """Collective, optional: destroy the NCCL communicator (all handles must be gone)."""
