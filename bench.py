@@ -162,7 +162,7 @@ def run_reference(args):
            "cpu_baseline": last,
            "e2e": {"value": 1.0 / t, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
            "gpu_launches": 0}
-    print(json.dumps(out))
+    emit(out)
 
 
 # ---------------------------------------------------------------------------------------------
@@ -334,9 +334,19 @@ def run_ours(args):
         "probe": probe,
         "result_check": {"sigma2_after_run": final[3], "scale": final[2]},
     }
-    print(json.dumps(out))
+    emit(out)
     if world > 1:
         tdist.destroy_process_group()
+
+
+def emit(obj):
+    """The ONE JSON line goes to the real stdout; everything else this process (or NCCL, which
+    prints its version banner to fd 1) writes during the run has been diverted to stderr."""
+    os.write(_REAL_STDOUT, (json.dumps(obj) + "\n").encode())
+
+
+_REAL_STDOUT = os.dup(1)
+os.dup2(2, 1)
 
 
 def main():
