@@ -47,22 +47,23 @@ def hbm_bytes_per_iter(n_local, m):
 
 
 class ClockSampler(object):
-    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    """nvidia-smi clocks / throttle reasons (B200_PROFILING.md recipe).  ONE poller (rank 0) for all the
+    job's GPUs, started before the warm-up so that NVML start-up (slow with 8 GPUs, and it takes driver
+    locks) does not land inside the timed region; samples taken while the GPUs are busy are kept."""
 
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,utilization.gpu,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
 
-    def __init__(self, gpu_index):
-        self.idx = gpu_index
+    def __init__(self, n_gpus):
+        self.n_gpus = n_gpus
         self.rows = []
         self.proc = None
 
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
-                                          "-i", str(self.idx), "-lms", "100"], stdout=subprocess.PIPE,
-                                         stderr=subprocess.DEVNULL, text=True)
+                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
         except Exception:
@@ -70,32 +71,40 @@ class ClockSampler(object):
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append(line.strip())
+            self.rows.append((time.perf_counter(), line.strip()))
 
-    def stop(self):
+    def count(self):
+        return len(self.rows)
+
+    def stop(self, t0=None, t1=None):
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
         self.proc.terminate()
         try:
             self.proc.wait(timeout=2)
         except Exception:
             self.proc.kill()
-        sm, smax, reasons, power = [], [], set(), []
+        sm, smax, reasons, power, timed = [], [], set(), [], 0
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
+        for ts, r in self.rows:
             f = [x.strip() for x in r.split(",")]
-            if len(f) < 8:
+            if len(f) < 9:
                 continue
             try:
+                idx, util = int(f[0]), float(f[4])
+                if idx >= self.n_gpus or util < 50.0:      # keep samples taken under load on this job's GPUs
+                    continue
                 sm.append(float(f[1])); smax.append(float(f[2])); power.append(float(f[3]))
             except ValueError:
                 continue
-            for nm, v in zip(names, f[4:8]):
+            if t0 is not None and t0 <= ts <= t1 + 0.11:
+                timed += 1
+            for nm, v in zip(names, f[5:9]):
                 if v.lower().startswith("active"):
                     reasons.add(nm)
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(smax) if smax else None,
-                "power_w_max": max(power) if power else None, "samples": len(sm), "reasons": sorted(reasons)}
+                "power_w_max": max(power) if power else None, "samples_under_load": len(sm),
+                "samples_in_timed_region": timed, "reasons": sorted(reasons)}
 
 
 def workload(points):
@@ -207,12 +216,30 @@ def run_ours(args):
         h.set_state(_cabi.TF_RIGID, True, 0.0, np.identity(3), np.zeros(3), 1.0, s2, q0)
 
     reset()
+    sampler = ClockSampler(world) if rank == 0 else None
+    if sampler:
+        sampler.start()
     for _ in range(max(args.warmup, 3)):
         h.em_step(read=False)
     h.sync()
-    sampler = ClockSampler(local_rank)
+    # keep the GPUs under the same load until the poller is up (its start-up must not fall into the timed
+    # region); then rewind the EM state so that the timed iterations are the first ones of a registration
+    t_up = time.perf_counter()
+    ready = torch.zeros(1, device="cuda")
+    while True:
+        for _ in range(10):
+            h.em_step(read=False)
+        h.sync()
+        ready[0] = 1.0 if (sampler is None or sampler.count() >= 2 * world or time.perf_counter() - t_up > 3.0) else 0.0
+        if world > 1:
+            tdist.broadcast(ready, src=0)
+        if ready.item() > 0:
+            break
+    reset()
+    for _ in range(3):
+        h.em_step(read=False)
+    h.sync()
     barrier()
-    sampler.start()
     launches0 = h.launch_count()
     t_wall0 = time.perf_counter()
     for i in range(args.steps):
@@ -222,9 +249,10 @@ def run_ours(args):
         h.event_record(2 * i + 1)
     h.sync()
     barrier()
-    t_wall = time.perf_counter() - t_wall0
+    t_wall1 = time.perf_counter()
+    t_wall = t_wall1 - t_wall0
     launches = h.launch_count() - launches0
-    clocks = sampler.stop()
+    clocks = sampler.stop(t_wall0, t_wall1) if sampler else None
     per_step = np.array([h.event_elapsed(2 * i, 2 * i + 1) for i in range(args.steps)])
     total_ms = float(per_step.sum())
     if world > 1:

@@ -98,6 +98,15 @@ int cpd_mstep(cpd_ctx* h, int tf_kind, int update_scale, const double* pt1, cons
 /* Copies of the last E-step's reductions (device -> host), valid after cpd_em_step/run. */
 int cpd_last_estep(cpd_ctx* h, double* pt1, double* p1, double* px, double* n_p);
 
+/* NonRigidCPD with a dense G (cpd.py:247-303, transformation.py:81-102), resident on the device.
+ * cpd_nonrigid_begin: after cpd_set_source/target; builds G (float32, like _math.rbf_kernel), W = 0
+ * (cpd.py:281) and starts from sigma2 (cpd.py:279).  cpd_nonrigid_step: one loop body of cpd.py:111-113 --
+ * T = Y + G W, E-step, the M x M solve of cpd.py:296 (cuSOLVER LU), sigma2 of cpd.py:298-301; returns the
+ * new sigma2 (== q, cpd.py:303).  cpd_nonrigid_get: W (m x D) and/or the moved source Y + G W.      */
+int cpd_nonrigid_begin(cpd_ctx* h, double beta, double lmd, double sigma2, double w);
+int cpd_nonrigid_step(cpd_ctx* h, double* sigma2_out);
+int cpd_nonrigid_get(cpd_ctx* h, double* w_out, double* moved_out);
+
 /* _math.rbf_kernel (cc/math_utils_py.cc:15 -> cc/math_utils.cc:17-19):
  * out[i*ny + j] = exp(-|x_i - y_j|^2 / (2*beta)) as float32, x: nx x D, y: ny x D.       */
 int cpd_rbf_kernel(int device, const double* x, int64_t nx, const double* y, int64_t ny, int dim,

@@ -40,6 +40,9 @@ _PROTOS = {
     "cpd_mstep": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, _c_dp, _c_dp, _c_dp, ctypes.c_double,
                                  ctypes.POINTER(CpdParams)]),
     "cpd_last_estep": (ctypes.c_int, [ctypes.c_void_p, _c_dp, _c_dp, _c_dp, _c_dp]),
+    "cpd_nonrigid_begin": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_double, ctypes.c_double, ctypes.c_double, ctypes.c_double]),
+    "cpd_nonrigid_step": (ctypes.c_int, [ctypes.c_void_p, _c_dp]),
+    "cpd_nonrigid_get": (ctypes.c_int, [ctypes.c_void_p, _c_dp, _c_dp]),
     "cpd_rbf_kernel": (ctypes.c_int, [ctypes.c_int, _c_dp, ctypes.c_int64, _c_dp, ctypes.c_int64, ctypes.c_int,
                                       ctypes.c_double, _c_fp]),
     "cpd_squared_kernel_sum": (ctypes.c_int, [ctypes.c_int, _c_dp, ctypes.c_int64, _c_dp, ctypes.c_int64, ctypes.c_int, _c_dp]),
@@ -203,6 +206,20 @@ class Handle(object):
         check(lib().cpd_mstep(self._h, tf_kind, int(bool(update_scale)), dptr(pt1), dptr(p1), dptr(px), float(n_p),
                               ctypes.byref(p)))
         return self._unpack(p)
+
+    # -- non-rigid (dense G on the device)
+    def nonrigid_begin(self, beta, lmd, sigma2, w):
+        check(lib().cpd_nonrigid_begin(self._h, float(beta), float(lmd), float(sigma2), float(w)))
+
+    def nonrigid_step(self):
+        out = ctypes.c_double()
+        check(lib().cpd_nonrigid_step(self._h, ctypes.byref(out)))
+        return out.value
+
+    def nonrigid_w(self):
+        w = np.empty((self.m, self.dim))
+        check(lib().cpd_nonrigid_get(self._h, dptr(w), None))
+        return w
 
     # -- multi-GPU
     def attach_comm(self, nccl_comm, world_size, rank):

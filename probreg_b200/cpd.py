@@ -256,9 +256,10 @@ class AffineCPD(CoherentPointDrift):
 class NonRigidCPD(CoherentPointDrift):
     """Coherent Point Drift for nonrigid transformation (probreg/cpd.py:247-303).
 
-    SURVEY section 8(f) row, not yet fused: G comes from the CUDA RBF kernel and every E-step
-    runs on the device, but the M x M solve of cpd.py:296 is still numpy on the host (as
-    ``np.linalg.svd`` is in the reference even on its cupy path) -- dense, so M <~ 10k.
+    SURVEY section 8(f) row 1: ``registration`` keeps G (float32, like ``_math.rbf_kernel``), W and the
+    M x M system on the device -- E-step by the CPD kernels, the dense solve of cpd.py:296 by cuSOLVER's LU,
+    sigma2 in residual form.  ``maximization_step`` on a caller-supplied EstepResult stays a host numpy
+    solve (the reference's own arithmetic on host arrays).
 
     Args:
         source (numpy.ndarray, optional): Source point cloud data.
@@ -295,9 +296,33 @@ class NonRigidCPD(CoherentPointDrift):
         return _nonrigid_mstep(source, target, estep_res, sigma2_p, tf_obj, lmd)
 
     def registration(self, target, w=0.0, maxiter=50, tol=0.001):
+        """The loop of probreg/cpd.py:106-120 with G, W, the M x M system and its LU resident on the GPU
+        (cpd_nonrigid_begin / cpd_nonrigid_step); per iteration only sigma2 (== q, cpd.py:303) comes back,
+        plus W when a callback wants the transformation."""
         assert not self._tf_type is None, "transformation type is None."
         target = _points(target)
         res = self._initialize(target)
+        if type(self).maximization_step is not NonRigidCPD.maximization_step:
+            return self._host_loop(target, res, w, maxiter, tol)       # subclasses with their own M-step
+        h = self._em
+        h.nonrigid_begin(self._beta, self._lmd, res.sigma2, w)
+        q = res.q
+        want_tf = bool(self._callbacks)
+        for i in range(maxiter):
+            sigma2 = h.nonrigid_step()
+            if want_tf:
+                self._tf_obj.w = h.nonrigid_w()
+            res = MstepResult(self._tf_obj, sigma2, sigma2)
+            for c in self._callbacks:
+                c(res.transformation)
+            log.debug("Iteration: {}, Criteria: {}".format(i, res.q))
+            if abs(res.q - q) < tol:
+                break
+            q = res.q
+        self._tf_obj.w = h.nonrigid_w()
+        return res
+
+    def _host_loop(self, target, res, w, maxiter, tol):
         q = res.q
         for i in range(maxiter):
             t_source = res.transformation.transform(self._source)

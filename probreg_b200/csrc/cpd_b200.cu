@@ -4,6 +4,8 @@
 #include "cpd_b200.h"
 #include "kernels.cuh"
 
+#include <cub/device/device_radix_sort.cuh>
+
 #include <dlfcn.h>
 #include <math.h>
 #include <stdarg.h>
@@ -74,7 +76,48 @@ int load_nccl() {
     return CPD_OK;
 }
 constexpr int NCCL_DOUBLE = 8, NCCL_SUM = 0;
+
+// cuSOLVER (dense LU of the non-rigid M-step only), bound at run time like NCCL
+struct SolverApi {
+    void* lib = nullptr;
+    int (*Create)(void**) = nullptr;
+    int (*Destroy)(void*) = nullptr;
+    int (*SetStream)(void*, cudaStream_t) = nullptr;
+    int (*CreateParams)(void**) = nullptr;
+    int (*DestroyParams)(void*) = nullptr;
+    int (*XgetrfBuf)(void*, void*, int64_t, int64_t, int, const void*, int64_t, int, size_t*, size_t*) = nullptr;
+    int (*Xgetrf)(void*, void*, int64_t, int64_t, int, void*, int64_t, int64_t*, int, void*, size_t, void*, size_t, int*) = nullptr;
+    int (*Xgetrs)(void*, void*, int, int64_t, int64_t, int, const void*, int64_t, const int64_t*, int, void*, int64_t, int*) = nullptr;
+};
+SolverApi g_sol;
+int load_cusolver() {
+    if (g_sol.lib) return CPD_OK;
+    const char* names[] = {"libcusolver.so.11", "/usr/local/cuda/lib64/libcusolver.so.11", "libcusolver.so"};
+    void* lib = nullptr;
+    for (const char* nm : names) { lib = dlopen(nm, RTLD_NOW | RTLD_GLOBAL); if (lib) break; }
+    if (!lib) return fail(CPD_ERR_CUDA, "cannot dlopen libcusolver.so.11: %s", dlerror());
+#define SOLSYM(field, name) g_sol.field = (decltype(g_sol.field))dlsym(lib, name)
+    SOLSYM(Create, "cusolverDnCreate");
+    SOLSYM(Destroy, "cusolverDnDestroy");
+    SOLSYM(SetStream, "cusolverDnSetStream");
+    SOLSYM(CreateParams, "cusolverDnCreateParams");
+    SOLSYM(DestroyParams, "cusolverDnDestroyParams");
+    SOLSYM(XgetrfBuf, "cusolverDnXgetrf_bufferSize");
+    SOLSYM(Xgetrf, "cusolverDnXgetrf");
+    SOLSYM(Xgetrs, "cusolverDnXgetrs");
+#undef SOLSYM
+    if (!g_sol.Create || !g_sol.SetStream || !g_sol.CreateParams || !g_sol.XgetrfBuf || !g_sol.Xgetrf || !g_sol.Xgetrs)
+        return fail(CPD_ERR_CUDA, "libcusolver lacks an expected symbol");
+    g_sol.lib = lib;
+    return CPD_OK;
+}
+constexpr int CUDA_R_64F_ = 1, CUBLAS_OP_T_ = 1;
 }  // namespace
+#define SOLV(call)                                                                          \
+    do {                                                                                    \
+        int r_ = (call);                                                                    \
+        if (r_ != 0) return fail(CPD_ERR_CUDA, "%s failed with cusolverStatus %d", #call, r_); \
+    } while (0)
 #define NC(call)                                                                                                   \
     do {                                                                                                           \
         int r_ = (call);                                                                                           \
@@ -106,6 +149,22 @@ struct cpd_ctx {
     bool have_source = false, have_target = false, have_state = false, prepared = false;
     nccl_comm comm = nullptr;
     int world = 1, rank = 0;
+    // Morton ordering (internal permutation; results leave in the caller's order)
+    int *d_perm_src = nullptr, *d_perm_tgt = nullptr, *d_idx_tmp = nullptr;
+    unsigned *d_codes = nullptr, *d_codes_out = nullptr;
+    size_t sort_cap = 0, sort_tmp_cap = 0;
+    void* d_sort_tmp = nullptr;
+    double *d_outN = nullptr, *d_outM = nullptr;      // staging for un-permuted outputs / permuted inputs
+    // non-rigid CPD (dense G)
+    float* d_G = nullptr;
+    double *d_W = nullptr, *d_A = nullptr, *d_B = nullptr, *d_ts2 = nullptr, *d_nrpart = nullptr;
+    int64_t* d_ipiv = nullptr;
+    int* d_info = nullptr;
+    void *d_work = nullptr, *h_work = nullptr, *sol = nullptr, *sol_params = nullptr;
+    size_t work_dev = 0, work_host = 0;
+    long long nr_m = 0;
+    double nr_lmd = 0.0;
+    bool nr_ready = false;
     P2PMailbox* d_box = nullptr;          // this rank's mailbox (peers write into it)
     P2PInfo* d_p2p = nullptr;             // device copy of the peer table; non-null => fused P2P exchange
     void* peer_ptr[P2P_MAX] = {nullptr};  // mappings opened with cudaIpcOpenMemHandle
@@ -184,6 +243,51 @@ int cloud_sums(cpd_ctx* h, const double* d_pts, long long count, double out[4]) 
     CU(cudaMemcpyAsync(h->h_pin, h->d_sums, 4 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
     CU(cudaStreamSynchronize(h->stream));
     for (int k = 0; k < 4; ++k) out[k] = h->h_pin[k];
+    return CPD_OK;
+}
+
+// Morton-sort a raw device cloud (count x 3): perm[k] = index (in the caller's order) of the k-th point in Z-order,
+// out[k] = raw[perm[k]] - origin.  Host-side statistics (bounding box) come from the caller's array.
+struct HostStats { double mean[3], lo[3], hi[3]; };
+void host_stats(const double* p, long long n, int dim, HostStats& st) {
+    for (int a = 0; a < 3; ++a) { st.mean[a] = 0.0; st.lo[a] = 0.0; st.hi[a] = 0.0; }
+    for (int a = 0; a < dim; ++a) { st.lo[a] = p[a]; st.hi[a] = p[a]; }
+    double acc[3] = {0.0, 0.0, 0.0};
+    for (long long i = 0; i < n; ++i)
+        for (int a = 0; a < dim; ++a) {
+            const double v = p[i * dim + a];
+            acc[a] += v;
+            st.lo[a] = v < st.lo[a] ? v : st.lo[a];
+            st.hi[a] = v > st.hi[a] ? v : st.hi[a];
+        }
+    for (int a = 0; a < dim; ++a) st.mean[a] = acc[a] / (double)n;
+}
+int sort_cloud(cpd_ctx* h, const double* d_rawpts, long long count, const HostStats& st, const double origin[3], int* d_perm,
+               double* d_out) {
+    if (h->sort_cap < (size_t)count) {
+        TRY(dev_alloc(&h->d_codes, (size_t)count));
+        TRY(dev_alloc(&h->d_codes_out, (size_t)count));
+        TRY(dev_alloc(&h->d_idx_tmp, (size_t)count));
+        h->sort_cap = (size_t)count;
+    }
+    double range = 0.0;
+    for (int a = 0; a < 3; ++a) range = std::max(range, st.hi[a] - st.lo[a]);
+    const double inv = range > 0.0 ? 1.0 / range : 0.0;
+    morton_kernel<<<blocks_for(count), THREADS, 0, h->stream>>>(d_rawpts, count, st.lo[0], st.lo[1], st.lo[2], inv, h->d_codes,
+                                                                h->d_idx_tmp);
+    size_t need = 0;
+    CU(cub::DeviceRadixSort::SortPairs(nullptr, need, h->d_codes, h->d_codes_out, h->d_idx_tmp, d_perm, (int)count, 0, 30, h->stream));
+    if (need > h->sort_tmp_cap) {
+        if (h->d_sort_tmp) cudaFree(h->d_sort_tmp);
+        h->d_sort_tmp = nullptr;
+        CU(cudaMalloc(&h->d_sort_tmp, need));
+        h->sort_tmp_cap = need;
+    }
+    CU(cub::DeviceRadixSort::SortPairs(h->d_sort_tmp, need, h->d_codes, h->d_codes_out, h->d_idx_tmp, d_perm, (int)count, 0, 30,
+                                       h->stream));
+    gather3_kernel<<<blocks_for(count), THREADS, 0, h->stream>>>(d_rawpts, d_perm, count, origin[0], origin[1], origin[2], d_out);
+    KCHECK();
+    h->launches += 3;
     return CPD_OK;
 }
 
@@ -303,6 +407,13 @@ extern "C" void cpd_destroy(cpd_ctx* h) {
     if (!h) return;
     cudaSetDevice(h->device);
     cudaStreamSynchronize(h->stream);
+    void* srt[] = {h->d_perm_src, h->d_perm_tgt, h->d_idx_tmp, h->d_codes, h->d_codes_out, h->d_sort_tmp, h->d_outN, h->d_outM};
+    for (void* p : srt) if (p) cudaFree(p);
+    void* nrp[] = {h->d_G, h->d_W, h->d_A, h->d_B, h->d_ts2, h->d_nrpart, h->d_ipiv, h->d_info, h->d_work};
+    for (void* p : nrp) if (p) cudaFree(p);
+    if (h->h_work) free(h->h_work);
+    if (h->sol_params && g_sol.DestroyParams) g_sol.DestroyParams(h->sol_params);
+    if (h->sol && g_sol.Destroy) g_sol.Destroy(h->sol);
     for (int r = 0; r < P2P_MAX; ++r) if (h->peer_ptr[r]) cudaIpcCloseMemHandle(h->peer_ptr[r]);
     if (h->d_box) cudaFree(h->d_box);
     if (h->d_p2p) cudaFree(h->d_p2p);
@@ -332,16 +443,17 @@ extern "C" int cpd_set_source(cpd_ctx* h, const double* source, int64_t m) {
         TRY(dev_alloc(&h->d_p1, (size_t)m));
         TRY(dev_alloc(&h->d_pxc, (size_t)m * 3));
         TRY(dev_alloc(&h->d_px, (size_t)m * 3));
+        TRY(dev_alloc(&h->d_perm_src, (size_t)m));
+        TRY(dev_alloc(&h->d_outM, (size_t)m * 3));
         h->prepared = false;
+        h->nr_ready = false;
     }
     if (h->raw_cap < (size_t)m * 3) { TRY(dev_alloc(&h->d_raw, (size_t)m * 3)); h->raw_cap = (size_t)m * 3; }
     TRY(upload_cloud(h, source, m, h->d_raw));
-    double s[4];
-    TRY(cloud_sums(h, h->d_raw, m, s));
-    for (int a = 0; a < 3; ++a) h->h_state.cy[a] = s[1 + a] / (double)m;
-    centre_kernel<<<blocks_for(m), THREADS, 0, h->stream>>>(h->d_raw, m, h->h_state.cy[0], h->h_state.cy[1], h->h_state.cy[2], h->d_yc);
-    KCHECK();
-    h->launches += 1;
+    HostStats st;
+    host_stats(source, m, h->dim, st);
+    for (int a = 0; a < 3; ++a) h->h_state.cy[a] = st.mean[a];
+    TRY(sort_cloud(h, h->d_raw, m, st, h->h_state.cy, h->d_perm_src, h->d_yc));
     h->h_state.m = m;
     h->have_source = true;
     return upload_state(h);
@@ -360,21 +472,17 @@ extern "C" int cpd_set_target(cpd_ctx* h, const double* target, int64_t n_local,
         TRY(dev_alloc(&h->d_tgtP, (size_t)n_local));
         TRY(dev_alloc(&h->d_tgtQ, (size_t)h->npad * 3));
         TRY(dev_alloc(&h->d_pt1, (size_t)n_local));
+        TRY(dev_alloc(&h->d_perm_tgt, (size_t)n_local));
+        TRY(dev_alloc(&h->d_outN, (size_t)n_local));
         h->prepared = false;
     }
     h->n_global = n_global;
     if (h->raw_cap < (size_t)n_local * 3) { TRY(dev_alloc(&h->d_raw, (size_t)n_local * 3)); h->raw_cap = (size_t)n_local * 3; }
     TRY(upload_cloud(h, target, n_local, h->d_raw));
-    if (frame_origin) {
-        for (int a = 0; a < 3; ++a) h->h_state.cx[a] = (a < h->dim) ? frame_origin[a] : 0.0;
-    } else {
-        double s[4];
-        TRY(cloud_sums(h, h->d_raw, n_local, s));
-        for (int a = 0; a < 3; ++a) h->h_state.cx[a] = s[1 + a] / (double)n_local;
-    }
-    centre_kernel<<<blocks_for(n_local), THREADS, 0, h->stream>>>(h->d_raw, n_local, h->h_state.cx[0], h->h_state.cx[1], h->h_state.cx[2], h->d_xc);
-    KCHECK();
-    h->launches += 1;
+    HostStats st;
+    host_stats(target, n_local, h->dim, st);
+    for (int a = 0; a < 3; ++a) h->h_state.cx[a] = frame_origin ? ((a < h->dim) ? frame_origin[a] : 0.0) : st.mean[a];
+    TRY(sort_cloud(h, h->d_raw, n_local, st, h->h_state.cx, h->d_perm_tgt, h->d_xc));
     h->h_state.n_global = n_global;
     h->have_target = true;
     return upload_state(h);
@@ -478,7 +586,10 @@ extern "C" int cpd_estep(cpd_ctx* h, const double* t_source, double sigma2, doub
     if (!(w >= 0.0 && w < 1.0)) return fail(CPD_ERR_ARG, "w must be in [0, 1), got %g", w);
     if (!h->have_source || !h->have_target) return fail(CPD_ERR_STATE, "source and target must both be set");
     CU(cudaSetDevice(h->device));
-    TRY(upload_cloud(h, t_source, h->m, h->d_ts));
+    if (h->raw_cap < (size_t)h->m * 3) { TRY(dev_alloc(&h->d_raw, (size_t)h->m * 3)); h->raw_cap = (size_t)h->m * 3; }
+    TRY(upload_cloud(h, t_source, h->m, h->d_raw));
+    gather3_kernel<<<blocks_for(h->m), THREADS, 0, h->stream>>>(h->d_raw, h->d_perm_src, h->m, 0.0, 0.0, 0.0, h->d_ts);
+    h->launches += 1;
     h->h_pin[32] = sigma2;
     h->h_pin[33] = w;
     CU(cudaMemcpyAsync(&h->d_state->es_sigma2, h->h_pin + 32, 2 * sizeof(double), cudaMemcpyHostToDevice, h->stream));
@@ -494,13 +605,23 @@ extern "C" int cpd_last_estep(cpd_ctx* h, double* pt1, double* p1, double* px, d
     if (!h) return fail(CPD_ERR_ARG, "null handle");
     if (!h->prepared) return fail(CPD_ERR_STATE, "no E-step has run on this handle");
     CU(cudaSetDevice(h->device));
-    if (pt1) CU(cudaMemcpyAsync(pt1, h->d_pt1, (size_t)h->n * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
-    if (p1) CU(cudaMemcpyAsync(p1, h->d_p1, (size_t)h->m * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    if (pt1) {
+        scatter_kernel<<<blocks_for(h->n), THREADS, 0, h->stream>>>(h->d_pt1, h->d_perm_tgt, h->n, 1, h->d_outN);
+        CU(cudaMemcpyAsync(pt1, h->d_outN, (size_t)h->n * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+        h->launches += 1;
+    }
+    if (p1) {
+        scatter_kernel<<<blocks_for(h->m), THREADS, 0, h->stream>>>(h->d_p1, h->d_perm_src, h->m, 1, h->d_outM);
+        CU(cudaMemcpyAsync(p1, h->d_outM, (size_t)h->m * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+        CU(cudaStreamSynchronize(h->stream));      // d_outM is reused for px below
+        h->launches += 1;
+    }
     if (px) {
         uncentre_px_kernel<<<blocks_for(h->m), THREADS, 0, h->stream>>>(h->d_state, h->d_p1, h->d_pxc, (int)h->m, h->d_px);
+        scatter_kernel<<<blocks_for(h->m), THREADS, 0, h->stream>>>(h->d_px, h->d_perm_src, h->m, 3, h->d_outM);
         KCHECK();
-        h->launches += 1;
-        TRY(download_cloud(h, h->d_px, h->m, px));
+        h->launches += 2;
+        TRY(download_cloud(h, h->d_outM, h->m, px));
     }
     if (n_p) {
         // n_p = sum(p1) (cpd.py:88): block partials of the (possibly all-reduced) p1
@@ -529,9 +650,15 @@ extern "C" int cpd_mstep(cpd_ctx* h, int tf_kind, int update_scale, const double
     h->h_state.update_scale = update_scale ? 1 : 0;
     // only the two selectors: the rest of the device state may be ahead of the host mirror
     CU(cudaMemcpyAsync(&h->d_state->tf_kind, &h->h_state.tf_kind, 2 * sizeof(int), cudaMemcpyHostToDevice, h->stream));
-    CU(cudaMemcpyAsync(h->d_pt1, pt1, (size_t)h->n * sizeof(double), cudaMemcpyHostToDevice, h->stream));
-    CU(cudaMemcpyAsync(h->d_p1, p1, (size_t)h->m * sizeof(double), cudaMemcpyHostToDevice, h->stream));
-    TRY(upload_cloud(h, px, h->m, h->d_px));
+    // caller's order -> internal (Morton) order
+    CU(cudaMemcpyAsync(h->d_outN, pt1, (size_t)h->n * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    gather1_kernel<<<blocks_for(h->n), THREADS, 0, h->stream>>>(h->d_outN, h->d_perm_tgt, h->n, h->d_pt1);
+    CU(cudaMemcpyAsync(h->d_outM, p1, (size_t)h->m * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    gather1_kernel<<<blocks_for(h->m), THREADS, 0, h->stream>>>(h->d_outM, h->d_perm_src, h->m, h->d_p1);
+    if (h->raw_cap < (size_t)h->m * 3) { TRY(dev_alloc(&h->d_raw, (size_t)h->m * 3)); h->raw_cap = (size_t)h->m * 3; }
+    TRY(upload_cloud(h, px, h->m, h->d_raw));
+    gather3_kernel<<<blocks_for(h->m), THREADS, 0, h->stream>>>(h->d_raw, h->d_perm_src, h->m, 0.0, 0.0, 0.0, h->d_px);
+    h->launches += 3;
     const int nbs = (int)blocks_for(h->m), nbt = (int)blocks_for(h->n);
     centre_px_kernel<<<nbs, THREADS, 0, h->stream>>>(h->d_state, h->d_p1, h->d_px, (int)h->m, h->d_pxc);
     src_moments_api_kernel<<<nbs, THREADS, 0, h->stream>>>((int)h->m, h->d_yc, h->d_p1, h->d_pxc, h->d_mom_src);
@@ -543,6 +670,126 @@ extern "C" int cpd_mstep(cpd_ctx* h, int tf_kind, int update_scale, const double
     KCHECK();
     h->launches += 5;
     return read_params(h, out);
+}
+
+// ---------------------------------------------------------------------------------------------
+// non-rigid CPD with a dense G, resident on the device
+// ---------------------------------------------------------------------------------------------
+extern "C" int cpd_nonrigid_begin(cpd_ctx* h, double beta, double lmd, double sigma2, double w) {
+    if (!h) return fail(CPD_ERR_ARG, "null handle");
+    if (!h->have_source || !h->have_target) return fail(CPD_ERR_STATE, "source and target must both be set");
+    if (!(beta > 0.0) || !(sigma2 > 0.0) || !(w >= 0.0 && w < 1.0)) return fail(CPD_ERR_ARG, "bad beta/sigma2/w");
+    CU(cudaSetDevice(h->device));
+    TRY(load_cusolver());
+    const long long m = h->m;
+    if (h->nr_m != m) {
+        TRY(dev_alloc(&h->d_G, (size_t)m * m));
+        TRY(dev_alloc(&h->d_A, (size_t)m * m));
+        TRY(dev_alloc(&h->d_W, (size_t)m * 3));
+        TRY(dev_alloc(&h->d_B, (size_t)m * 3));
+        TRY(dev_alloc(&h->d_ts2, (size_t)m * 3));
+        TRY(dev_alloc(&h->d_nrpart, (size_t)blocks_for(m) * 2));
+        TRY(dev_alloc(&h->d_ipiv, (size_t)m));
+        TRY(dev_alloc(&h->d_info, 1));
+        h->nr_m = m;
+        h->work_dev = 0;
+    }
+    if (!h->sol) {
+        SOLV(g_sol.Create(&h->sol));
+        SOLV(g_sol.SetStream(h->sol, h->stream));
+        SOLV(g_sol.CreateParams(&h->sol_params));
+    }
+    size_t wd = 0, wh = 0;
+    SOLV(g_sol.XgetrfBuf(h->sol, h->sol_params, m, m, CUDA_R_64F_, h->d_A, m, CUDA_R_64F_, &wd, &wh));
+    if (wd > h->work_dev) {
+        if (h->d_work) cudaFree(h->d_work);
+        h->d_work = nullptr;
+        CU(cudaMalloc(&h->d_work, std::max<size_t>(wd, 16)));
+        h->work_dev = wd;
+    }
+    if (wh > h->work_host) {
+        free(h->h_work);
+        h->h_work = malloc(std::max<size_t>(wh, 16));
+        h->work_host = wh;
+    }
+    const DevState& hs = h->h_state;
+    dim3 grid(blocks_for(m), (unsigned)m);
+    nr_gram_kernel<<<grid, THREADS, 0, h->stream>>>(h->d_yc, hs.cy[0], hs.cy[1], hs.cy[2], m, h->dim, (float)(1.0 / (2.0 * beta)),
+                                                  h->d_G);
+    CU(cudaMemsetAsync(h->d_W, 0, (size_t)m * 3 * sizeof(double), h->stream));                       // cpd.py:281
+    nr_apply_kernel<<<(unsigned)((m + 7) / 8), THREADS, 0, h->stream>>>(h->d_G, h->d_W, h->d_yc, hs.cy[0], hs.cy[1], hs.cy[2], m,
+                                                                        h->d_ts);
+    KCHECK();
+    h->launches += 2;
+    h->nr_lmd = lmd;
+    h->h_state.sigma2 = sigma2;
+    h->h_state.q = 0.0;
+    h->h_state.w = w;
+    h->h_state.tf_kind = CPD_TF_NONRIGID;
+    h->h_state.err = 0;
+    TRY(upload_state(h));
+    h->nr_ready = true;
+    return CPD_OK;
+}
+
+// one EM iteration of probreg/cpd.py:111-113 for NonRigidCPD: E-step on T = Y + G W, solve cpd.py:296, sigma2 cpd.py:298-301
+extern "C" int cpd_nonrigid_step(cpd_ctx* h, double* sigma2_out) {
+    if (!h) return fail(CPD_ERR_ARG, "null handle");
+    if (!h->nr_ready) return fail(CPD_ERR_STATE, "cpd_nonrigid_begin has not been called");
+    CU(cudaSetDevice(h->device));
+    const long long m = h->m;
+    const DevState& hs = h->h_state;
+    TRY(launch_estep(h, &h->d_state->sigma2, &h->d_state->w, h->d_ts));
+    const int nbs = (int)blocks_for(m), nbt = (int)blocks_for(h->npad);
+    moments_kernel<0><<<1, 256, 0, h->stream>>>(h->d_state, h->d_mom_src, nbs, RM_SRC, h->d_mom_tgt, nbt, RM_TGT, h->d_mom);
+    if (h->comm) {   // every rank solves the same (global) system
+        TRY(allreduce(h, h->d_p1, (size_t)m));
+        TRY(allreduce(h, h->d_pxc, (size_t)m * 3));
+        TRY(allreduce(h, h->d_mom, MOM_PAD));
+    }
+    dim3 grid(blocks_for(m), (unsigned)m);
+    nr_system_kernel<<<grid, THREADS, 0, h->stream>>>(h->d_G, h->d_p1, &h->d_state->sigma2, h->nr_lmd, m, h->d_A);
+    nr_rhs_kernel<<<nbs, THREADS, 0, h->stream>>>(h->d_state, h->d_p1, h->d_pxc, h->d_yc, m, h->d_B);
+    KCHECK();
+    SOLV(g_sol.Xgetrf(h->sol, h->sol_params, m, m, CUDA_R_64F_, h->d_A, m, h->d_ipiv, CUDA_R_64F_, h->d_work, h->work_dev, h->h_work,
+                      h->work_host, h->d_info));
+    SOLV(g_sol.Xgetrs(h->sol, h->sol_params, CUBLAS_OP_T_, m, 3, CUDA_R_64F_, h->d_A, m, h->d_ipiv, CUDA_R_64F_, h->d_B, m, h->d_info));
+    nr_unpack_kernel<<<nbs, THREADS, 0, h->stream>>>(h->d_B, m, h->d_W);
+    nr_apply_kernel<<<(unsigned)((m + 7) / 8), THREADS, 0, h->stream>>>(h->d_G, h->d_W, h->d_yc, hs.cy[0], hs.cy[1], hs.cy[2], m,
+                                                                        h->d_ts2);
+    nr_resid_kernel<<<nbs, THREADS, 0, h->stream>>>(h->d_state, h->d_p1, h->d_pxc, h->d_ts, h->d_ts2, m, h->d_nrpart);
+    nr_sigma_kernel<<<1, 32, 0, h->stream>>>(h->d_state, h->d_nrpart, nbs, h->d_mom);
+    KCHECK();
+    h->launches += 7;
+    std::swap(h->d_ts, h->d_ts2);
+    if (sigma2_out) {
+        int info = 0;
+        CU(cudaMemcpyAsync(&info, h->d_info, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+        cpd_params p;
+        TRY(read_params(h, &p));
+        if (info != 0) return fail(CPD_ERR_STATE, "LU factorisation of the non-rigid system failed (info = %d)", info);
+        *sigma2_out = p.sigma2;
+    }
+    return CPD_OK;
+}
+
+// W (m x D) of the current NonRigidTransformation, and optionally the moved source T = Y + G W (m x D)
+extern "C" int cpd_nonrigid_get(cpd_ctx* h, double* w_out, double* moved_out) {
+    if (!h) return fail(CPD_ERR_ARG, "null handle");
+    if (!h->nr_ready) return fail(CPD_ERR_STATE, "cpd_nonrigid_begin has not been called");
+    CU(cudaSetDevice(h->device));
+    if (w_out) {
+        scatter_kernel<<<blocks_for(h->m), THREADS, 0, h->stream>>>(h->d_W, h->d_perm_src, h->m, 3, h->d_outM);
+        TRY(download_cloud(h, h->d_outM, h->m, w_out));
+        CU(cudaStreamSynchronize(h->stream));
+    }
+    if (moved_out) {
+        scatter_kernel<<<blocks_for(h->m), THREADS, 0, h->stream>>>(h->d_ts, h->d_perm_src, h->m, 3, h->d_outM);
+        TRY(download_cloud(h, h->d_outM, h->m, moved_out));
+        CU(cudaStreamSynchronize(h->stream));
+    }
+    KCHECK();
+    return CPD_OK;
 }
 
 extern "C" int cpd_rbf_kernel(int device, const double* x, int64_t nx, const double* y, int64_t ny, int dim, double beta, float* out) {

@@ -52,6 +52,9 @@ namespace cpd {
 #ifndef CPD_SUB
 #define CPD_SUB 64
 #endif
+#ifndef CPD_GRP
+#define CPD_GRP 8
+#endif
 constexpr int UNROLL1 = CPD_UNROLL1, UNROLL2 = CPD_UNROLL2;
 constexpr int THREADS = 256;           // threads per CTA in both passes
 constexpr int RI1 = CPD_RI1, RI2 = CPD_RI2;            // i-points held in registers per thread (pass 1 / pass 2)
@@ -63,6 +66,7 @@ constexpr int P1_REC = 32, P2_REC = 48;    // bytes per streamed j-record (coord
 constexpr int NSTAGE = 3;              // TMA pipeline depth
 constexpr int P1_STAGE_BYTES = P1_STAGE * P1_REC, P2_STAGE_BYTES = P2_STAGE * P2_REC;
 constexpr int SUB = CPD_SUB;           // j-points between offset checks / FP64 flushes
+constexpr int GRP = CPD_GRP;           // j-points summed from zero before joining the sub-chunk sum (0: off)
 constexpr int PASS1_SMEM = NSTAGE * P1_STAGE_BYTES + 64, PASS2_SMEM = NSTAGE * P2_STAGE_BYTES + 64;
 
 constexpr float O_INIT = 1048576.0f;   // 2^20: "no source seen yet" offset; u above it is dead anyway
@@ -263,6 +267,56 @@ pack_kernel(const DevState* __restrict__ st, const double* __restrict__ sigma2_p
 // The largest term of a target is >= 2^-1 right after its offset was set and <= 2^100 always, so
 // every term that matters stays a normal FP32 number.
 // ---------------------------------------------------------------------------------------------
+// Sum one sub-chunk of pass 1 into Sc (sum e) and Uc (sum e*t'), both starting from zero.  With GRP > 0 the
+// terms are first summed in groups of GRP from zero and the group sums joined: a two-level FP32 summation.
+// Why: adding thousands of tiny terms one by one to a partial sum that already holds a dominant term drops
+// them (absorption), a SYSTEMATIC loss that does not average out -- measured -1.2e-6 on sigma2 with a flat
+// 64-term sum, -2e-6 with 128 (profiles/r1_precision_subchunk.txt).
+__device__ __forceinline__ void pass1_sum(const ulonglong2* __restrict__ q, const u64 (&ax)[NPAIR1], const u64 (&ay)[NPAIR1],
+                                          const u64 (&az)[NPAIR1], const u64 (&no)[NPAIR1], u64 (&Sc)[NPAIR1], u64 (&Uc)[NPAIR1]) {
+    if (GRP > 0) {
+#pragma unroll 1
+        for (int g0 = 0; g0 < SUB; g0 += (GRP > 0 ? GRP : SUB)) {
+            u64 gs[NPAIR1], gu[NPAIR1];
+#pragma unroll
+            for (int jj = 0; jj < (GRP > 0 ? GRP : 1); ++jj) {
+                const ulonglong2 bxy = q[2 * (g0 + jj)];
+                const u64 bz = q[2 * (g0 + jj) + 1].x;
+#pragma unroll
+                for (int p = 0; p < NPAIR1; ++p) {
+                    const u64 dx = fsub2(ax[p], bxy.x), dy = fsub2(ay[p], bxy.y), dz = fsub2(az[p], bz);
+                    u64 t = ffma2(dx, dx, no[p]);
+                    t = ffma2(dy, dy, t);
+                    t = ffma2(dz, dz, t);
+                    const float2 tt = unpack2(t);
+                    const u64 e = pack2(ex2(-tt.x), ex2(-tt.y));
+                    gs[p] = jj == 0 ? e : fadd2(gs[p], e);
+                    gu[p] = jj == 0 ? fmul2(e, t) : ffma2(e, t, gu[p]);
+                }
+            }
+#pragma unroll
+            for (int p = 0; p < NPAIR1; ++p) { Sc[p] = fadd2(Sc[p], gs[p]); Uc[p] = fadd2(Uc[p], gu[p]); }
+        }
+    } else {
+#pragma unroll UNROLL1
+        for (int jj = 0; jj < SUB; ++jj) {
+            const ulonglong2 bxy = q[2 * jj];
+            const u64 bz = q[2 * jj + 1].x;
+#pragma unroll
+            for (int p = 0; p < NPAIR1; ++p) {
+                const u64 dx = fsub2(ax[p], bxy.x), dy = fsub2(ay[p], bxy.y), dz = fsub2(az[p], bz);
+                u64 t = ffma2(dx, dx, no[p]);
+                t = ffma2(dy, dy, t);
+                t = ffma2(dz, dz, t);
+                const float2 tt = unpack2(t);
+                const u64 e = pack2(ex2(-tt.x), ex2(-tt.y));
+                Sc[p] = fadd2(Sc[p], e);
+                Uc[p] = ffma2(e, t, Uc[p]);
+            }
+        }
+    }
+}
+
 __global__ void __launch_bounds__(THREADS, CPD_MINB1)
 pass1_kernel(const float4* __restrict__ ipts, int ni, const float4* __restrict__ jrec, int nstages, int nsplit,
              P1Part* __restrict__ part) {
@@ -303,28 +357,36 @@ pass1_kernel(const float4* __restrict__ ipts, int ni, const float4* __restrict__
         const int s = it % NSTAGE;
         mbar_wait(&full[s], (uint32_t)((it / NSTAGE) & 1));
         const ulonglong2* sp = reinterpret_cast<const ulonglong2*>(smraw + s * P1_STAGE_BYTES);
+        if (it == 0) {
+            // seed the offsets from the first 8 sources of the split (a 16x cheaper sweep than letting the
+            // first 64-source sub-chunk overflow into the slow path, which matters when a CTA only sees a
+            // few thousand sources, i.e. in multi-GPU runs)
+            float cm[RI1];
+#pragma unroll
+            for (int r = 0; r < RI1; ++r) cm[r] = 3.0e38f;
+#pragma unroll
+            for (int jj = 0; jj < 8; ++jj) {
+                const ulonglong2 bxy = sp[2 * jj];
+                const u64 bz = sp[2 * jj + 1].x;
+#pragma unroll
+                for (int p = 0; p < NPAIR1; ++p) {
+                    const u64 dx = fsub2(ax[p], bxy.x), dy = fsub2(ay[p], bxy.y), dz = fsub2(az[p], bz);
+                    const float2 u = unpack2(ffma2(dz, dz, ffma2(dy, dy, fmul2(dx, dx))));
+                    cm[2 * p] = fminf(cm[2 * p], u.x);
+                    cm[2 * p + 1] = fminf(cm[2 * p + 1], u.y);
+                }
+            }
+#pragma unroll
+            for (int p = 0; p < NPAIR1; ++p)
+                no[p] = pack2(-fminf(O_INIT, floorf(cm[2 * p])), -fminf(O_INIT, floorf(cm[2 * p + 1])));
+        }
 #pragma unroll 1
         for (int sc = 0; sc < P1_STAGE / SUB; ++sc) {
             const ulonglong2* q = sp + sc * (2 * SUB);
             u64 Sc[NPAIR1], Uc[NPAIR1];          // Sc = sum e,  Uc = sum e * t'  with t' = u - o, e = 2^-t'
 #pragma unroll
             for (int p = 0; p < NPAIR1; ++p) { Sc[p] = 0ull; Uc[p] = 0ull; }
-#pragma unroll UNROLL1
-            for (int jj = 0; jj < SUB; ++jj) {
-                const ulonglong2 bxy = q[2 * jj];
-                const u64 bz = q[2 * jj + 1].x;
-#pragma unroll
-                for (int p = 0; p < NPAIR1; ++p) {
-                    const u64 dx = fsub2(ax[p], bxy.x), dy = fsub2(ay[p], bxy.y), dz = fsub2(az[p], bz);
-                    u64 t = ffma2(dx, dx, no[p]);
-                    t = ffma2(dy, dy, t);
-                    t = ffma2(dz, dz, t);
-                    const float2 tt = unpack2(t);
-                    const u64 e = pack2(ex2(-tt.x), ex2(-tt.y));
-                    Sc[p] = fadd2(Sc[p], e);
-                    Uc[p] = ffma2(e, t, Uc[p]);
-                }
-            }
+            pass1_sum(q, ax, ay, az, no, Sc, Uc);
             bool bad = false;
 #pragma unroll
             for (int p = 0; p < NPAIR1; ++p) {
@@ -358,22 +420,7 @@ pass1_kernel(const float4* __restrict__ ipts, int ni, const float4* __restrict__
                     no[p] = pack2(-on0, -on1);
                     Sc[p] = 0ull; Uc[p] = 0ull;
                 }
-#pragma unroll UNROLL1
-                for (int jj = 0; jj < SUB; ++jj) {
-                    const ulonglong2 bxy = q[2 * jj];
-                    const u64 bz = q[2 * jj + 1].x;
-#pragma unroll
-                    for (int p = 0; p < NPAIR1; ++p) {
-                        const u64 dx = fsub2(ax[p], bxy.x), dy = fsub2(ay[p], bxy.y), dz = fsub2(az[p], bz);
-                        u64 t = ffma2(dx, dx, no[p]);
-                        t = ffma2(dy, dy, t);
-                        t = ffma2(dz, dz, t);
-                        const float2 tt = unpack2(t);
-                        const u64 e = pack2(ex2(-tt.x), ex2(-tt.y));
-                        Sc[p] = fadd2(Sc[p], e);
-                        Uc[p] = ffma2(e, t, Uc[p]);
-                    }
-                }
+                pass1_sum(q, ax, ay, az, no, Sc, Uc);
             }
 #pragma unroll
             for (int p = 0; p < NPAIR1; ++p) {
@@ -469,7 +516,7 @@ finalize1_kernel(const DevState* __restrict__ st, const double* __restrict__ sig
             const double rn = exp2(-(L + (double)omin));
             no = -omin;
             rnf = (float)rn;
-            v[0] = SU * rn;
+            v[0] = SU * (double)rnf;       // the same (rounded) rn that pass 2 multiplies by
         }
         v[1] = p1n;
         tgtQ[3 * (size_t)i] = make_float4(b.x, b.x, b.y, b.y);
@@ -531,23 +578,54 @@ pass2_kernel(const float4* __restrict__ ipts, int ni, const float4* __restrict__
             u64 s1[NPAIR2], sx[NPAIR2], sy[NPAIR2], sz[NPAIR2];
 #pragma unroll
             for (int p = 0; p < NPAIR2; ++p) { s1[p] = 0ull; sx[p] = 0ull; sy[p] = 0ull; sz[p] = 0ull; }
-#pragma unroll UNROLL2
-            for (int jj = 0; jj < SUB; ++jj) {
-                const ulonglong2 bxy = q[3 * jj];
-                const ulonglong2 bzo = q[3 * jj + 1];
-                const u64 rn = q[3 * jj + 2].x;
+            if (GRP > 0) {
+#pragma unroll 1
+                for (int g0 = 0; g0 < SUB; g0 += (GRP > 0 ? GRP : SUB)) {
+                    u64 g1[NPAIR2], gx[NPAIR2], gy[NPAIR2], gz[NPAIR2];
 #pragma unroll
-                for (int p = 0; p < NPAIR2; ++p) {
-                    const u64 dx = fsub2(ax[p], bxy.x), dy = fsub2(ay[p], bxy.y), dz = fsub2(az[p], bzo.x);
-                    u64 t = ffma2(dx, dx, bzo.y);         // t' = u - o_n: the same FMA chain and offset as pass 1
-                    t = ffma2(dy, dy, t);
-                    t = ffma2(dz, dz, t);
-                    const float2 tt = unpack2(t);
-                    const u64 pr = fmul2(pack2(ex2(-tt.x), ex2(-tt.y)), rn);
-                    s1[p] = fadd2(s1[p], pr);
-                    sx[p] = ffma2(pr, dx, sx[p]);
-                    sy[p] = ffma2(pr, dy, sy[p]);
-                    sz[p] = ffma2(pr, dz, sz[p]);
+                    for (int jj = 0; jj < (GRP > 0 ? GRP : 1); ++jj) {
+                        const ulonglong2 bxy = q[3 * (g0 + jj)];
+                        const ulonglong2 bzo = q[3 * (g0 + jj) + 1];
+                        const u64 rn = q[3 * (g0 + jj) + 2].x;
+#pragma unroll
+                        for (int p = 0; p < NPAIR2; ++p) {
+                            const u64 dx = fsub2(ax[p], bxy.x), dy = fsub2(ay[p], bxy.y), dz = fsub2(az[p], bzo.x);
+                            u64 t = ffma2(dx, dx, bzo.y);         // t' = u - o_n: the same FMA chain and offset as pass 1
+                            t = ffma2(dy, dy, t);
+                            t = ffma2(dz, dz, t);
+                            const float2 tt = unpack2(t);
+                            const u64 pr = fmul2(pack2(ex2(-tt.x), ex2(-tt.y)), rn);
+                            g1[p] = jj == 0 ? pr : fadd2(g1[p], pr);
+                            gx[p] = jj == 0 ? fmul2(pr, dx) : ffma2(pr, dx, gx[p]);
+                            gy[p] = jj == 0 ? fmul2(pr, dy) : ffma2(pr, dy, gy[p]);
+                            gz[p] = jj == 0 ? fmul2(pr, dz) : ffma2(pr, dz, gz[p]);
+                        }
+                    }
+#pragma unroll
+                    for (int p = 0; p < NPAIR2; ++p) {
+                        s1[p] = fadd2(s1[p], g1[p]); sx[p] = fadd2(sx[p], gx[p]);
+                        sy[p] = fadd2(sy[p], gy[p]); sz[p] = fadd2(sz[p], gz[p]);
+                    }
+                }
+            } else {
+#pragma unroll UNROLL2
+                for (int jj = 0; jj < SUB; ++jj) {
+                    const ulonglong2 bxy = q[3 * jj];
+                    const ulonglong2 bzo = q[3 * jj + 1];
+                    const u64 rn = q[3 * jj + 2].x;
+#pragma unroll
+                    for (int p = 0; p < NPAIR2; ++p) {
+                        const u64 dx = fsub2(ax[p], bxy.x), dy = fsub2(ay[p], bxy.y), dz = fsub2(az[p], bzo.x);
+                        u64 t = ffma2(dx, dx, bzo.y);
+                        t = ffma2(dy, dy, t);
+                        t = ffma2(dz, dz, t);
+                        const float2 tt = unpack2(t);
+                        const u64 pr = fmul2(pack2(ex2(-tt.x), ex2(-tt.y)), rn);
+                        s1[p] = fadd2(s1[p], pr);
+                        sx[p] = ffma2(pr, dx, sx[p]);
+                        sy[p] = ffma2(pr, dy, sy[p]);
+                        sz[p] = ffma2(pr, dz, sz[p]);
+                    }
                 }
             }
 #pragma unroll
@@ -1011,6 +1089,60 @@ moments_p2p_kernel(DevState* st, const double* __restrict__ part_a, int nb_a, in
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Spatial (Morton / Z-order) ordering of both clouds inside the library.  Purely an internal permutation:
+// every result leaves the library in the caller's order.  Why it exists: consecutive j-points are then
+// spatial neighbours, so the 8-point groups / 64-point sub-chunks of the FP32 summations hold terms of
+// similar magnitude and the systematic loss of small terms (absorption) vanishes -- on the 1500-point
+// fixture the CPU emulation of the kernel arithmetic (tools/emulate_resid.py) goes from -1.7e-7 to +1.6e-8
+// relative error on sigma2; it also makes a warp's lanes spatially coherent, so the rare offset slow path of
+// pass 1 fires for whole warps at once instead of for one lane at a time.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ unsigned spread3(unsigned v) {       // 10 bits -> every third bit
+    v &= 0x3ffu;
+    v = (v | (v << 16)) & 0x030000ffu;
+    v = (v | (v << 8)) & 0x0300f00fu;
+    v = (v | (v << 4)) & 0x030c30c3u;
+    v = (v | (v << 2)) & 0x09249249u;
+    return v;
+}
+__global__ void __launch_bounds__(THREADS)
+morton_kernel(const double* __restrict__ pts, long long n, double lo0, double lo1, double lo2, double inv_range,
+              unsigned* __restrict__ codes, int* __restrict__ idx) {
+    const long long i = (long long)blockIdx.x * THREADS + threadIdx.x;
+    if (i < n) {
+        const double q0 = (pts[3 * i] - lo0) * inv_range, q1 = (pts[3 * i + 1] - lo1) * inv_range, q2 = (pts[3 * i + 2] - lo2) * inv_range;
+        const unsigned a = (unsigned)fmin(fmax(q0 * 1023.0, 0.0), 1023.0), b = (unsigned)fmin(fmax(q1 * 1023.0, 0.0), 1023.0),
+                       c = (unsigned)fmin(fmax(q2 * 1023.0, 0.0), 1023.0);
+        codes[i] = spread3(a) | (spread3(b) << 1) | (spread3(c) << 2);
+        idx[i] = (int)i;
+    }
+}
+// out[k] = in[perm[k]] - origin   (n x 3)
+__global__ void __launch_bounds__(THREADS)
+gather3_kernel(const double* __restrict__ in, const int* __restrict__ perm, long long n, double o0, double o1, double o2,
+               double* __restrict__ out) {
+    const long long k = (long long)blockIdx.x * THREADS + threadIdx.x;
+    if (k < n) {
+        const long long j = perm[k];
+        out[3 * k] = in[3 * j] - o0; out[3 * k + 1] = in[3 * j + 1] - o1; out[3 * k + 2] = in[3 * j + 2] - o2;
+    }
+}
+__global__ void __launch_bounds__(THREADS)
+gather1_kernel(const double* __restrict__ in, const int* __restrict__ perm, long long n, double* __restrict__ out) {
+    const long long k = (long long)blockIdx.x * THREADS + threadIdx.x;
+    if (k < n) out[k] = in[perm[k]];
+}
+// out[perm[k]] = in[k]   (n x ncomp): back to the caller's order
+__global__ void __launch_bounds__(THREADS)
+scatter_kernel(const double* __restrict__ in, const int* __restrict__ perm, long long n, int ncomp, double* __restrict__ out) {
+    const long long k = (long long)blockIdx.x * THREADS + threadIdx.x;
+    if (k < n) {
+        const long long j = perm[k];
+        for (int c = 0; c < ncomp; ++c) out[ncomp * j + c] = in[ncomp * k + c];
+    }
+}
+
 // sums for sigma^2 initialisation: out[block][0..4) = sum |p|^2, sum p (3)
 __global__ void __launch_bounds__(THREADS)
 cloud_sums_kernel(const double* __restrict__ pts, long long n, double* __restrict__ out) {
@@ -1067,6 +1199,104 @@ rbf_kernel_kernel(const float* __restrict__ x, long long nx, const float* __rest
         float d2 = 0.f;
         for (int a = 0; a < dim; ++a) { const float d = x[i * dim + a] - y[j * dim + a]; d2 += d * d; }
         out[i * ny + j] = expf(-d2 * inv2beta);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Non-rigid CPD, dense G (probreg/cpd.py:247-303, transformation.py:81-102) -- SURVEY section 8(f) row 1.
+// G stays on the device as float32 (the reference's _math.rbf_kernel is float32, cc/types.h:19); the
+// M x M system of cpd.py:296 is assembled in FP64 and handed to cuSOLVER's LU (a plain library solve).
+// ---------------------------------------------------------------------------------------------
+// G[i][j] = exp(-|y_i - y_j|^2 / (2 beta)) from the float32 casts of the ORIGINAL coordinates (cc/math_utils.cc:17-19)
+__global__ void __launch_bounds__(THREADS)
+nr_gram_kernel(const double* __restrict__ yc, double c0, double c1, double c2, long long m, int dim, float inv2beta,
+               float* __restrict__ G) {
+    const long long j = (long long)blockIdx.x * THREADS + threadIdx.x;
+    const long long i = blockIdx.y;
+    if (j < m) {
+        const double cc[3] = {c0, c1, c2};
+        float d2 = 0.f;
+        for (int a = 0; a < dim; ++a) {
+            const float d = (float)(yc[3 * i + a] + cc[a]) - (float)(yc[3 * j + a] + cc[a]);
+            d2 += d * d;
+        }
+        G[i * m + j] = expf(-d2 * inv2beta);
+    }
+}
+// ts_i = y_i + sum_j G_ij W_j   (transformation.py:101-102), one warp per row, FP64 accumulation
+__global__ void __launch_bounds__(THREADS)
+nr_apply_kernel(const float* __restrict__ G, const double* __restrict__ W, const double* __restrict__ yc, double c0, double c1,
+                double c2, long long m, double* __restrict__ ts) {
+    const long long i = (long long)blockIdx.x * (THREADS / 32) + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (i >= m) return;
+    const float* row = G + i * m;
+    double a0 = 0.0, a1 = 0.0, a2 = 0.0;
+    for (long long j = lane; j < m; j += 32) {
+        const double g = (double)row[j];
+        a0 += g * W[3 * j]; a1 += g * W[3 * j + 1]; a2 += g * W[3 * j + 2];
+    }
+    a0 = warp_sum(a0); a1 = warp_sum(a1); a2 = warp_sum(a2);
+    if (lane == 0) {
+        ts[3 * i] = yc[3 * i] + c0 + a0;
+        ts[3 * i + 1] = yc[3 * i + 1] + c1 + a1;
+        ts[3 * i + 2] = yc[3 * i + 2] + c2 + a2;
+    }
+}
+// A = diag(p1) G + lmd sigma2 I, stored row-major (== column-major A^T for the LU; solved with op(T))   cpd.py:296
+__global__ void __launch_bounds__(THREADS)
+nr_system_kernel(const float* __restrict__ G, const double* __restrict__ p1, const double* __restrict__ sigma2_ptr, double lmd,
+                 long long m, double* __restrict__ A) {
+    const long long j = (long long)blockIdx.x * THREADS + threadIdx.x;
+    const long long i = blockIdx.y;
+    if (j < m) A[i * m + j] = p1[i] * (double)G[i * m + j] + (i == j ? lmd * *sigma2_ptr : 0.0);
+}
+// B[c*m + i] = px_ic - p1_i y_ic   (right-hand side of cpd.py:296; px = px~ + cx p1, y = y~ + cy)
+__global__ void __launch_bounds__(THREADS)
+nr_rhs_kernel(const DevState* __restrict__ st, const double* __restrict__ p1, const double* __restrict__ pxc,
+              const double* __restrict__ yc, long long m, double* __restrict__ B) {
+    const long long i = (long long)blockIdx.x * THREADS + threadIdx.x;
+    if (i < m) {
+#pragma unroll
+        for (int c = 0; c < 3; ++c) B[c * m + i] = pxc[3 * i + c] + p1[i] * (st->cx[c] - yc[3 * i + c] - st->cy[c]);
+    }
+}
+__global__ void __launch_bounds__(THREADS)
+nr_unpack_kernel(const double* __restrict__ B, long long m, double* __restrict__ W) {
+    const long long i = (long long)blockIdx.x * THREADS + threadIdx.x;
+    if (i < m) { W[3 * i] = B[i]; W[3 * i + 1] = B[m + i]; W[3 * i + 2] = B[2 * m + i]; }
+}
+// residual-form sigma2 (== tr_xp1x - 2 tr_pxt + tr_tpt of cpd.py:298-301, without its cancellation):
+//   Q = Srr + sum_m ( 2 e_m . v_m + p1_m |e_m|^2 ),  e = T_old - T_new,  v = px~ - p1 (T_old - cx)
+// per-block partials {sum 2 e.v + p1 |e|^2, sum p1}
+__global__ void __launch_bounds__(THREADS)
+nr_resid_kernel(const DevState* __restrict__ st, const double* __restrict__ p1, const double* __restrict__ pxc,
+                const double* __restrict__ ts_old, const double* __restrict__ ts_new, long long m, double* __restrict__ part) {
+    const long long i = (long long)blockIdx.x * THREADS + threadIdx.x;
+    double v[2] = {0.0, 0.0};
+    if (i < m) {
+        double acc = 0.0;
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            const double e = ts_old[3 * i + c] - ts_new[3 * i + c];
+            const double vv = pxc[3 * i + c] - p1[i] * (ts_old[3 * i + c] - st->cx[c]);
+            acc += 2.0 * e * vv + p1[i] * e * e;
+        }
+        v[0] = acc; v[1] = p1[i];
+    }
+    block_reduce_store<2>(v, part + (size_t)blockIdx.x * 2);
+}
+// sigma2 = (Srr / sk^2 + sum part[.][0]) / (Np D);  q := sigma2 (cpd.py:303).  mom[RM_SRR] holds the (all-reduced) Srr.
+__global__ void __launch_bounds__(32)
+nr_sigma_kernel(DevState* st, const double* __restrict__ part, int nb, const double* __restrict__ mom) {
+    if (threadIdx.x == 0) {
+        double a = 0.0, np_ = 0.0;
+        for (int b = 0; b < nb; ++b) { a += part[2 * (size_t)b]; np_ += part[2 * (size_t)b + 1]; }
+        const double sk2 = LOG2E / (2.0 * st->sigma2);
+        const double q = mom[RM_SRR] / sk2 + a;
+        st->sigma2 = q / (np_ * st->dim);
+        st->q = st->sigma2;
+        st->n_p = np_;
     }
 }
 
