@@ -247,20 +247,22 @@ int cloud_sums(cpd_ctx* h, const double* d_pts, long long count, double out[4]) 
 }
 
 // Morton-sort a raw device cloud (count x 3): perm[k] = index (in the caller's order) of the k-th point in Z-order,
-// out[k] = raw[perm[k]] - origin.  Host-side statistics (bounding box) come from the caller's array.
+// out[k] = raw[perm[k]] - origin.
 struct HostStats { double mean[3], lo[3], hi[3]; };
-void host_stats(const double* p, long long n, int dim, HostStats& st) {
-    for (int a = 0; a < 3; ++a) { st.mean[a] = 0.0; st.lo[a] = 0.0; st.hi[a] = 0.0; }
-    for (int a = 0; a < dim; ++a) { st.lo[a] = p[a]; st.hi[a] = p[a]; }
-    double acc[3] = {0.0, 0.0, 0.0};
-    for (long long i = 0; i < n; ++i)
-        for (int a = 0; a < dim; ++a) {
-            const double v = p[i * dim + a];
-            acc[a] += v;
-            st.lo[a] = v < st.lo[a] ? v : st.lo[a];
-            st.hi[a] = v > st.hi[a] ? v : st.hi[a];
-        }
-    for (int a = 0; a < dim; ++a) st.mean[a] = acc[a] / (double)n;
+int device_stats(cpd_ctx* h, const double* d_pts, long long n, HostStats& st) {
+    const unsigned nb = blocks_for(n);
+    if (h->sums_cap < (size_t)nb * 9 + 16) {
+        TRY(dev_alloc(&h->d_sums, (size_t)nb * 9 + 16));
+        h->sums_cap = (size_t)nb * 9 + 16;
+    }
+    stats_kernel<<<nb, THREADS, 0, h->stream>>>(d_pts, n, h->d_sums + 16);
+    stats_fold_kernel<<<1, 32, 0, h->stream>>>(h->d_sums + 16, (int)nb, h->d_sums);
+    KCHECK();
+    h->launches += 2;
+    CU(cudaMemcpyAsync(h->h_pin + 48, h->d_sums, 9 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    for (int a = 0; a < 3; ++a) { st.mean[a] = h->h_pin[48 + a] / (double)n; st.lo[a] = h->h_pin[51 + a]; st.hi[a] = h->h_pin[54 + a]; }
+    return CPD_OK;
 }
 int sort_cloud(cpd_ctx* h, const double* d_rawpts, long long count, const HostStats& st, const double origin[3], int* d_perm,
                double* d_out) {
@@ -451,7 +453,7 @@ extern "C" int cpd_set_source(cpd_ctx* h, const double* source, int64_t m) {
     if (h->raw_cap < (size_t)m * 3) { TRY(dev_alloc(&h->d_raw, (size_t)m * 3)); h->raw_cap = (size_t)m * 3; }
     TRY(upload_cloud(h, source, m, h->d_raw));
     HostStats st;
-    host_stats(source, m, h->dim, st);
+    TRY(device_stats(h, h->d_raw, m, st));
     for (int a = 0; a < 3; ++a) h->h_state.cy[a] = st.mean[a];
     TRY(sort_cloud(h, h->d_raw, m, st, h->h_state.cy, h->d_perm_src, h->d_yc));
     h->h_state.m = m;
@@ -480,7 +482,7 @@ extern "C" int cpd_set_target(cpd_ctx* h, const double* target, int64_t n_local,
     if (h->raw_cap < (size_t)n_local * 3) { TRY(dev_alloc(&h->d_raw, (size_t)n_local * 3)); h->raw_cap = (size_t)n_local * 3; }
     TRY(upload_cloud(h, target, n_local, h->d_raw));
     HostStats st;
-    host_stats(target, n_local, h->dim, st);
+    TRY(device_stats(h, h->d_raw, n_local, st));
     for (int a = 0; a < 3; ++a) h->h_state.cx[a] = frame_origin ? ((a < h->dim) ? frame_origin[a] : 0.0) : st.mean[a];
     TRY(sort_cloud(h, h->d_raw, n_local, st, h->h_state.cx, h->d_perm_tgt, h->d_xc));
     h->h_state.n_global = n_global;

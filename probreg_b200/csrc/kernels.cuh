@@ -1143,6 +1143,50 @@ scatter_kernel(const double* __restrict__ in, const int* __restrict__ perm, long
     }
 }
 
+// per-block {sum(3), min(3), max(3)} of a cloud, then a one-block fold: the centroid and bounding box that
+// the Morton ordering needs, without a host pass over the caller's array
+__global__ void __launch_bounds__(THREADS)
+stats_kernel(const double* __restrict__ pts, long long n, double* __restrict__ part) {
+    __shared__ double sh[9][THREADS / 32];
+    const long long i = (long long)blockIdx.x * THREADS + threadIdx.x;
+    double v[9];
+    if (i < n) {
+        for (int a = 0; a < 3; ++a) { v[a] = pts[3 * i + a]; v[3 + a] = v[a]; v[6 + a] = v[a]; }
+    } else {
+        for (int a = 0; a < 3; ++a) { v[a] = 0.0; v[3 + a] = 1.0e300; v[6 + a] = -1.0e300; }
+    }
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+#pragma unroll
+    for (int k = 0; k < 9; ++k) {
+        double x = v[k];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const double y = __shfl_xor_sync(0xffffffffu, x, o);
+            x = k < 3 ? x + y : (k < 6 ? fmin(x, y) : fmax(x, y));
+        }
+        if (lane == 0) sh[k][wid] = x;
+    }
+    __syncthreads();
+    if (threadIdx.x < 9) {
+        const int k = threadIdx.x;
+        double x = sh[k][0];
+        for (int w = 1; w < THREADS / 32; ++w) x = k < 3 ? x + sh[k][w] : (k < 6 ? fmin(x, sh[k][w]) : fmax(x, sh[k][w]));
+        part[(size_t)blockIdx.x * 9 + k] = x;
+    }
+}
+__global__ void __launch_bounds__(32)
+stats_fold_kernel(const double* __restrict__ part, int nb, double* __restrict__ out) {
+    const int k = threadIdx.x;
+    if (k < 9) {
+        double x = part[k];
+        for (int b = 1; b < nb; ++b) {
+            const double y = part[(size_t)b * 9 + k];
+            x = k < 3 ? x + y : (k < 6 ? fmin(x, y) : fmax(x, y));
+        }
+        out[k] = x;
+    }
+}
+
 // sums for sigma^2 initialisation: out[block][0..4) = sum |p|^2, sum p (3)
 __global__ void __launch_bounds__(THREADS)
 cloud_sums_kernel(const double* __restrict__ pts, long long n, double* __restrict__ out) {
