@@ -322,6 +322,14 @@ def run_ours(args):
     ach_tf = flops / (t_estep_ms * 1e-3) / 1e12
     nominal_tf = 2.0 * 128 * probe["sm_count"] * (clocks.get("sm_max_mhz") or 1965.0) * 1e6 / 1e12
     bytes_iter = hbm_bytes_per_iter(n_local, n)
+    traffic, traffic_src = None, None
+    try:   # dram__bytes_read.sum + dram__bytes_write.sum per launch of the two E-step kernels, from the committed ncu capture
+        tj = json.load(open(os.path.join(ROOT, "profiles", "r1_traffic.json")))
+        if world == 1 and n == 100000:
+            traffic = sum(k["dram_read_bytes"] + k["dram_write_bytes"] for k in tj["kernels"].values())
+            traffic_src = tj["source"]
+    except Exception:
+        pass
     roofline = {
         "bound": "fp32",
         "kernel": "pass1_kernel + pass2_kernel (fused E-step, never materialises P)",
@@ -330,7 +338,8 @@ def run_ours(args):
         "flop_per_pair": FLOP_PER_PAIR_ITER, "pairs_per_launch": float(n_local) * float(n),
         "instruction_ceiling_frac": ach_tf / (probe["ffma_tflops"] * (29.0 / (19.0 * 2.0))),
         "mufu_ex2_gops_probe": probe["mufu_ex2_gops"],
-        "traffic": None,
+        "traffic": traffic,
+        "traffic_source": traffic_src,
         "hbm": {"bound": "hbm", "achieved": bytes_iter / (t_estep_ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
                 "frac": bytes_iter / (t_estep_ms * 1e-3) / 1e9 / hbm_peak, "peak_source": hbm_src,
                 "algorithmic_bytes": bytes_iter,

@@ -256,7 +256,7 @@ int device_stats(cpd_ctx* h, const double* d_pts, long long n, HostStats& st) {
         h->sums_cap = (size_t)nb * 9 + 16;
     }
     stats_kernel<<<nb, THREADS, 0, h->stream>>>(d_pts, n, h->d_sums + 16);
-    stats_fold_kernel<<<1, 32, 0, h->stream>>>(h->d_sums + 16, (int)nb, h->d_sums);
+    stats_fold_kernel<<<1, 288, 0, h->stream>>>(h->d_sums + 16, (int)nb, h->d_sums);
     KCHECK();
     h->launches += 2;
     CU(cudaMemcpyAsync(h->h_pin + 48, h->d_sums, 9 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));

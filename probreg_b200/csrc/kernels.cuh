@@ -1174,17 +1174,20 @@ stats_kernel(const double* __restrict__ pts, long long n, double* __restrict__ p
         part[(size_t)blockIdx.x * 9 + k] = x;
     }
 }
-__global__ void __launch_bounds__(32)
+__global__ void __launch_bounds__(288)
 stats_fold_kernel(const double* __restrict__ part, int nb, double* __restrict__ out) {
-    const int k = threadIdx.x;
-    if (k < 9) {
-        double x = part[k];
-        for (int b = 1; b < nb; ++b) {
-            const double y = part[(size_t)b * 9 + k];
-            x = k < 3 ? x + y : (k < 6 ? fmin(x, y) : fmax(x, y));
-        }
-        out[k] = x;
+    const int k = threadIdx.x >> 5, lane = threadIdx.x & 31;       // one warp per statistic
+    double x = k < 3 ? 0.0 : (k < 6 ? 1.0e300 : -1.0e300);
+    for (int b = lane; b < nb; b += 32) {
+        const double y = part[(size_t)b * 9 + k];
+        x = k < 3 ? x + y : (k < 6 ? fmin(x, y) : fmax(x, y));
     }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const double y = __shfl_xor_sync(0xffffffffu, x, o);
+        x = k < 3 ? x + y : (k < 6 ? fmin(x, y) : fmax(x, y));
+    }
+    if (lane == 0) out[k] = x;
 }
 
 // sums for sigma^2 initialisation: out[block][0..4) = sum |p|^2, sum p (3)
