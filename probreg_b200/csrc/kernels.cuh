@@ -253,8 +253,8 @@ pack_kernel(const DevState* __restrict__ st, const double* __restrict__ sigma2_p
 
 // ---------------------------------------------------------------------------------------------
 // pass 1: per target n and split:  (o, S, SU) with  sum_m 2^(-u) = S 2^(-o),  sum_m 2^(-u) u = SU 2^(-o)
-// grid = itiles * nsplit CTAs; CTA (itile, split) owns 1024 targets and stages [st0, st1) of the
-// padded source array.  Per two pairs: 8 packed FP32 instructions + 2 MUFU in the common path.
+// One CTA per work item {target tile, source-stage range, partial slot}; the host chooses the number of stage ranges per
+// tile that minimises the makespan over the resident CTA slots (build_work in cpd_b200.cu).  Per two pairs: 8 packed FP32 instructions + 2 MUFU in the common path.
 //
 // Lazy log-sum-exp: each target carries an integer-valued offset o (only ever lowered).  A
 // sub-chunk of 64 sources is summed in FP32 from zero with the current o -- Sc = sum e,
@@ -318,15 +318,14 @@ __device__ __forceinline__ void pass1_sum(const ulonglong2* __restrict__ q, cons
 }
 
 __global__ void __launch_bounds__(THREADS, CPD_MINB1)
-pass1_kernel(const float4* __restrict__ ipts, int ni, const float4* __restrict__ jrec, int nstages, int nsplit,
+pass1_kernel(const float4* __restrict__ ipts, int ni, const float4* __restrict__ jrec, const int4* __restrict__ work,
              P1Part* __restrict__ part) {
     extern __shared__ __align__(128) unsigned char smraw[];
     uint64_t* full = reinterpret_cast<uint64_t*>(smraw + NSTAGE * P1_STAGE_BYTES);
     const int tid = threadIdx.x;
-    const int split = blockIdx.x % nsplit, itile = blockIdx.x / nsplit;
-    const int st0 = (int)((long long)nstages * split / nsplit);
-    const int st1 = (int)((long long)nstages * (split + 1) / nsplit);
-    const int nst = st1 - st0;
+    const int4 wk = work[blockIdx.x];               // {i-tile, first stage, end stage, partial slot}: see build_work()
+    const int itile = wk.x, st0 = wk.y, split = wk.w;
+    const int nst = wk.z - wk.y;
     const unsigned char* jbytes = reinterpret_cast<const unsigned char*>(jrec);
     if (tid == 0) {
         for (int s = 0; s < NSTAGE; ++s) mbar_init(&full[s], 1);
@@ -468,11 +467,12 @@ pass1_kernel(const float4* __restrict__ ipts, int ni, const float4* __restrict__
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(THREADS)
 finalize1_kernel(const DevState* __restrict__ st, const double* __restrict__ sigma2_ptr, const double* __restrict__ w_ptr,
-                 const P1Part* __restrict__ part, int nsplit, int n, const float4* __restrict__ tgtP,
+                 const P1Part* __restrict__ part, const int* __restrict__ tile_slots, int n, const float4* __restrict__ tgtP,
                  float4* __restrict__ tgtQ, long long npad, double* __restrict__ pt1, double* __restrict__ mom_part) {
     const int i = blockIdx.x * THREADS + threadIdx.x;
     double v[RM_TGT] = {0.0, 0.0};
     if (i < n) {
+        const int nsplit = tile_slots[i / ITILE1];          // how many CTAs contributed a partial for this tile
         float omin = 3.0e38f;
         for (int s = 0; s < nsplit; ++s) {
             const P1Part p = part[(size_t)s * n + i];
@@ -535,15 +535,14 @@ finalize1_kernel(const DevState* __restrict__ st, const double* __restrict__ sig
 // with P_mn = 2^(o_n - u_mn) * rn_n.  Per two pairs: 11 packed FP32 instructions + 2 MUFU.
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(THREADS, CPD_MINB2)
-pass2_kernel(const float4* __restrict__ ipts, int ni, const float4* __restrict__ jrec, int nstages, int nsplit,
-             double* __restrict__ part /* [nsplit][ni][4] */) {
+pass2_kernel(const float4* __restrict__ ipts, int ni, const float4* __restrict__ jrec, const int4* __restrict__ work,
+             double* __restrict__ part /* [slot][ni][4] */) {
     extern __shared__ __align__(128) unsigned char smraw[];
     uint64_t* full = reinterpret_cast<uint64_t*>(smraw + NSTAGE * P2_STAGE_BYTES);
     const int tid = threadIdx.x;
-    const int split = blockIdx.x % nsplit, itile = blockIdx.x / nsplit;
-    const int st0 = (int)((long long)nstages * split / nsplit);
-    const int st1 = (int)((long long)nstages * (split + 1) / nsplit);
-    const int nst = st1 - st0;
+    const int4 wk = work[blockIdx.x];
+    const int itile = wk.x, st0 = wk.y, split = wk.w;
+    const int nst = wk.z - wk.y;
     const unsigned char* jbytes = reinterpret_cast<const unsigned char*>(jrec);
     if (tid == 0) {
         for (int s = 0; s < NSTAGE; ++s) mbar_init(&full[s], 1);
@@ -659,7 +658,7 @@ pass2_kernel(const float4* __restrict__ ipts, int ni, const float4* __restrict__
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(THREADS)
 finalize2_kernel(const DevState* __restrict__ st, const double* __restrict__ sigma2_ptr, const double* __restrict__ part,
-                 int nsplit, int m, const double* __restrict__ yc, const double* __restrict__ ts, double* __restrict__ p1,
+                 const int* __restrict__ tile_slots, int m, const double* __restrict__ yc, const double* __restrict__ ts, double* __restrict__ p1,
                  double* __restrict__ pxc, double* __restrict__ mom_part) {
     const int i = blockIdx.x * THREADS + threadIdx.x;
     double v[RM_SRC];
@@ -667,6 +666,7 @@ finalize2_kernel(const DevState* __restrict__ st, const double* __restrict__ sig
     for (int k = 0; k < RM_SRC; ++k) v[k] = 0.0;
     if (i < m) {
         double a1 = 0.0, a[3] = {0.0, 0.0, 0.0};
+        const int nsplit = tile_slots[i / ITILE2];
         for (int s = 0; s < nsplit; ++s) {
             const double2* src = reinterpret_cast<const double2*>(part + ((size_t)s * m + i) * 4);
             const double2 u0 = src[0], u1 = src[1];
