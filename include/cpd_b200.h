@@ -153,8 +153,9 @@ int cpd_flush_l2(cpd_ctx* h, int64_t bytes);
 /* Issue-rate micro-benchmarks for the roofline denominators: out[0] = FFMA TFLOP/s, out[1] =
  * MUFU.EX2 Gop/s, out[2] = SM clock MHz seen by the probe, out[3] = SM count, out[4] = packed
  * FFMA2 TFLOP/s, out[5..7] = Gpairs/s of synthetic (11 FP32 + 1 MUFU), packed (6 FFMA2-class + 2
- * MUFU per 2 pairs) and (7 FP32 + 1 MUFU) instruction mixes.                               */
-int cpd_microbench(int device, double out[8]);
+ * MUFU per 2 pairs) and (7 FP32 + 1 MUFU) instruction mixes, out[8] = TFLOP/s of FFMA2 and scalar
+ * FFMA interleaved 1:1.                                                                     */
+int cpd_microbench(int device, double out[9]);
 
 #ifdef __cplusplus
 }

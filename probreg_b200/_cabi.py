@@ -289,7 +289,7 @@ def comm_destroy(c):
 
 
 def microbench(device=0):
-    out = (ctypes.c_double * 8)()
+    out = (ctypes.c_double * 9)()
     check(lib().cpd_microbench(device, out))
     return {"ffma_tflops": out[0], "mufu_ex2_gops": out[1], "sm_mhz": out[2], "sm_count": int(out[3]),
-            "ffma2_tflops": out[4], "mix_11p1_gpairs": out[5], "mix_packed_gpairs": out[6], "mix_7p1_gpairs": out[7]}
+            "ffma2_tflops": out[4], "mix_11p1_gpairs": out[5], "mix_packed_gpairs": out[6], "mix_7p1_gpairs": out[7], "ffma2_plus_ffma_tflops": out[8]}

@@ -994,7 +994,7 @@ extern "C" int cpd_flush_l2(cpd_ctx* h, int64_t bytes) {
     return CPD_OK;
 }
 
-extern "C" int cpd_microbench(int device, double out[8]) {
+extern "C" int cpd_microbench(int device, double out[9]) {
     if (!out) return fail(CPD_ERR_ARG, "null argument");
     if (cpd_device_count() == 0) return fail(CPD_ERR_CUDA, "no CUDA device");
     CU(cudaSetDevice(device));
@@ -1030,6 +1030,8 @@ extern "C" int cpd_microbench(int device, double out[8]) {
     out[6] = threads * (iters / 8) * 8.0 / (ms * 1e-3) / 1e9;                // Gpairs/s, packed (5 FFMA2 + FMUL) + 1 MUFU
     TIME_PROBE((probe_mix_kernel<7, false>), iters / 8);
     out[7] = threads * (iters / 8) * 8.0 / (ms * 1e-3) / 1e9;                // Gpairs/s, scalar 7+1
+    TIME_PROBE(probe_ffma_mixed_kernel, iters);
+    out[8] = threads * iters * 6.0 * (4.0 + 2.0) / (ms * 1e-3) / 1e12;       // TFLOP/s of FFMA2 + FFMA interleaved 1:1
 #undef TIME_PROBE
     probe_clock_kernel<<<1, 1>>>(dc);
     long long hc[2];

@@ -1229,13 +1229,6 @@ centre_px_kernel(const DevState* __restrict__ st, const double* __restrict__ p1,
         for (int d = 0; d < 3; ++d) pxc[3 * (size_t)i + d] = px[3 * (size_t)i + d] - st->cx[d] * p1[i];
     }
 }
-// centred copy: out = in - origin (both n x 3, FP64)
-__global__ void __launch_bounds__(THREADS)
-centre_kernel(const double* __restrict__ in, long long n, double o0, double o1, double o2, double* __restrict__ out) {
-    const long long i = (long long)blockIdx.x * THREADS + threadIdx.x;
-    if (i < n) { out[3 * i] = in[3 * i] - o0; out[3 * i + 1] = in[3 * i + 1] - o1; out[3 * i + 2] = in[3 * i + 2] - o2; }
-}
-
 // _math.rbf_kernel (cc/math_utils.cc:17-19): float32 Gram matrix, 2*beta in the denominator
 __global__ void __launch_bounds__(THREADS)
 rbf_kernel_kernel(const float* __restrict__ x, long long nx, const float* __restrict__ y, long long ny, int dim, float inv2beta,
@@ -1391,6 +1384,24 @@ probe_ffma2_kernel(float* out, int iters, float seed) {
     float s = 0.f;
 #pragma unroll
     for (int k = 0; k < 8; ++k) { const float2 v = unpack2(a[k]); s += v.x + v.y; }
+    if (s == 123.456f) out[0] = s;
+}
+// FFMA2 and scalar FFMA interleaved: is there capacity (an idle "lite" FMA pipe) that packed code leaves unused?
+__global__ void __launch_bounds__(256)
+probe_ffma_mixed_kernel(float* out, int iters, float seed) {
+    u64 a[6];
+    float b[6];
+#pragma unroll
+    for (int k = 0; k < 6; ++k) { a[k] = pack2(seed + k, seed - k); b[k] = seed + 0.5f * k; }
+    const u64 m2 = pack2(0.9999f + seed * 1e-9f, 0.9998f), c2 = pack2(1e-7f, 2e-7f);
+    const float m = 0.9999f + seed * 1e-9f, c = 1e-7f;
+    for (int i = 0; i < iters; ++i) {
+#pragma unroll
+        for (int k = 0; k < 6; ++k) { a[k] = ffma2(a[k], m2, c2); b[k] = fmaf(b[k], m, c); }
+    }
+    float s = 0.f;
+#pragma unroll
+    for (int k = 0; k < 6; ++k) { const float2 v = unpack2(a[k]); s += v.x + v.y + b[k]; }
     if (s == 123.456f) out[0] = s;
 }
 // instruction mix of the E-step inner loop: NF FP32-pipe instructions + 1 MUFU.EX2 per "pair", 8 chains

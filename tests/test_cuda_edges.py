@@ -1,0 +1,111 @@
+"""Edge cases of the CUDA path through the public API / C ABI: collisions (duplicate and coincident points),
+degenerate and tiny clouds, extreme sigma2, handle reuse with other sizes, argument errors.  gpu-marked."""
+import numpy as np
+import pytest
+
+from oracle import cpd_oracle as orc
+from probreg_b200 import _cabi, cpd, math_utils
+
+pytestmark = pytest.mark.gpu
+
+
+def _close(es, ref, rtol=2e-5):
+    np.testing.assert_allclose(es.pt1, ref.pt1, rtol=rtol, atol=1e-12)
+    np.testing.assert_allclose(es.p1, ref.p1, rtol=rtol, atol=1e-9)
+    np.testing.assert_allclose(es.px, ref.px, rtol=rtol, atol=rtol * max(1e-12, np.abs(ref.px).max()))
+
+
+def test_duplicate_points_and_exact_coincidence():
+    """Collisions: every source appears three times, targets coincide exactly with sources (u == 0)."""
+    base = np.random.default_rng(0).random((300, 3))
+    src = np.ascontiguousarray(np.repeat(base, 3, axis=0))
+    tgt = np.ascontiguousarray(np.r_[base, base[:50]])
+    for s2, w in [(1e-2, 0.0), (1e-6, 0.1)]:
+        es = cpd.RigidCPD(src).expectation_step(src, tgt, s2, w)
+        _close(es, orc.expectation_step(src, tgt, s2, w))
+    res = cpd.registration_cpd(src, tgt, maxiter=8, tol=-1.0)
+    oref, _ = orc.registration(src, tgt, "rigid", maxiter=8, tol=-1.0)
+    np.testing.assert_allclose(res.transformation.rot, oref.params[0], atol=1e-5)
+    assert res.sigma2 == pytest.approx(oref.sigma2, rel=1e-6)
+
+
+def test_identical_clouds_hit_the_sigma2_floor_like_the_reference():
+    src = np.random.default_rng(1).random((200, 3))
+    res = cpd.registration_cpd(src, src.copy())
+    oref, it = orc.registration(src, src.copy(), "rigid")
+    assert res.sigma2 == pytest.approx(oref.sigma2, rel=1e-6)
+    assert oref.sigma2 == pytest.approx(float(np.finfo(np.float32).eps))         # cpd.py:189
+    np.testing.assert_allclose(res.transformation.rot, np.identity(3), atol=1e-6)
+
+
+def test_all_points_equal_and_collinear_clouds():
+    one = np.tile(np.array([[0.3, -0.2, 0.9]]), (40, 1))
+    tgt = np.random.default_rng(2).random((25, 3))
+    es = cpd.RigidCPD(one).expectation_step(one, tgt, 0.05, 0.1)            # zero-extent cloud: Morton range is 0
+    _close(es, orc.expectation_step(one, tgt, 0.05, 0.1))
+    line = np.c_[np.linspace(0, 1, 64), np.zeros(64), np.zeros(64)]
+    es = cpd.RigidCPD(line).expectation_step(line, line[::-1] + 0.01, 0.01, 0.0)
+    _close(es, orc.expectation_step(line, np.ascontiguousarray(line[::-1] + 0.01), 0.01, 0.0))
+
+
+@pytest.mark.parametrize("s2", [1e3, 1e-9])
+def test_extreme_sigma2(s2):
+    src, tgt = orc.synthetic_pair(700)
+    es = cpd.RigidCPD(src).expectation_step(src, tgt, s2, 0.0)
+    ref = orc.expectation_step(src, tgt, s2, 0.0)
+    # sigma2 = 1e-9: every column underflows in float64 -> the reference returns all zeros (cpd.py:81); so must we
+    assert (ref.pt1 == 0).sum() == (es.pt1 == 0).sum()
+    _close(es, ref, rtol=2e-5)
+
+
+def test_handle_reuse_with_other_sizes_and_families():
+    rng = np.random.default_rng(3)
+    r = cpd.RigidCPD(rng.random((50, 3)))
+    for m, n in [(50, 70), (3000, 10), (10, 3000), (1200, 1300), (2, 2)]:
+        src, tgt = rng.random((m, 3)), rng.random((n, 3))
+        r.set_source(src)
+        es = r.expectation_step(src, tgt, 0.02, 0.05)
+        _close(es, orc.expectation_step(src, tgt, 0.02, 0.05))
+        res = r.registration(tgt, maxiter=2, tol=-1.0)
+        oref, _ = orc.registration(src, tgt, "rigid", maxiter=2, tol=-1.0)
+        assert res.sigma2 == pytest.approx(oref.sigma2, rel=1e-6)
+
+
+def test_inputs_are_not_modified_and_any_layout_is_accepted():
+    src, tgt = orc.synthetic_pair(500)
+    src_f = np.asfortranarray(src)                      # non C-contiguous, float32, lists: coerced like cv() (cpd.py:444)
+    s0, t0 = src.copy(), tgt.copy()
+    a = cpd.registration_cpd(src_f, tgt.astype(np.float32).astype(np.float64).tolist(), maxiter=3, tol=-1.0)
+    b = cpd.registration_cpd(src, tgt.astype(np.float32).astype(np.float64), maxiter=3, tol=-1.0)
+    assert a.sigma2 == b.sigma2
+    assert np.array_equal(src, s0) and np.array_equal(tgt, t0)
+
+
+def test_argument_errors():
+    with pytest.raises(ValueError):
+        _cabi.Handle(4)
+    h = _cabi.Handle(3)
+    with pytest.raises(_cabi.CpdError, match="source and target"):
+        h.sigma2_init()
+    h.set_source(np.zeros((5, 3)))
+    h.set_target(np.ones((6, 3)))
+    with pytest.raises(_cabi.CpdError, match="w must be"):
+        h.set_state(_cabi.TF_RIGID, True, 1.0, np.identity(3), np.zeros(3), 1.0, 0.1, 0.0)
+    with pytest.raises(_cabi.CpdError, match="sigma2 must be positive"):
+        h.estep(np.zeros((5, 3)), 0.0, 0.0)
+    with pytest.raises(_cabi.CpdError, match="cpd_set_state"):
+        h.em_step()
+    with pytest.raises(ValueError):
+        h.estep(np.zeros((4, 3)), 0.1, 0.0)             # wrong number of rows
+    with pytest.raises(ValueError):
+        h.set_target(np.zeros((4, 2)))                  # wrong dimension
+    with pytest.raises(ValueError, match="same dimensions"):
+        math_utils.squared_kernel_sum(np.zeros((3, 3)), np.zeros((3, 2)))
+
+
+def test_results_are_deterministic():
+    src, tgt = orc.synthetic_pair(4000)
+    a = cpd.registration_cpd(src, tgt, maxiter=6, tol=-1.0)
+    b = cpd.registration_cpd(src, tgt, maxiter=6, tol=-1.0)
+    assert a.sigma2 == b.sigma2 and a.q == b.q
+    assert np.array_equal(a.transformation.rot, b.transformation.rot)

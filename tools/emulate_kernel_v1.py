@@ -1,5 +1,6 @@
 #!/usr/bin/env python
-"""numpy emulation of the CUDA E-step arithmetic (FP32 pair math, FMA chains, 64-point sub-chunks,
+"""[historical: the FIRST formulation (px sums, real-valued offsets); see emulate_resid.py for the current one]
+numpy emulation of the CUDA E-step arithmetic (FP32 pair math, FMA chains, 64-point sub-chunks,
 lazy offset) for small clouds -- a CPU microscope for precision questions, not product code.
 Switches: acc64 (accumulate sub-chunks in float64), coord64 (no FP32 rounding of coordinates),
 pair64 (pair maths in float64), sub (sub-chunk length)."""
