@@ -91,7 +91,11 @@ class ClockSampler(object):
             if len(f) < 9:
                 continue
             try:
-                idx, util = int(f[0]), float(f[4])
+                idx = int(f[0])
+                try:
+                    util = float(f[4])
+                except ValueError:
+                    util = 100.0                          # utilisation not reported: keep the sample
                 if idx >= self.n_gpus or util < 50.0:      # keep samples taken under load on this job's GPUs
                     continue
                 sm.append(float(f[1])); smax.append(float(f[2])); power.append(float(f[3]))

@@ -112,6 +112,11 @@ int cpd_nonrigid_get(cpd_ctx* h, double* w_out, double* moved_out);
 int cpd_rbf_kernel(int device, const double* x, int64_t nx, const double* y, int64_t ny, int dim,
                    double beta, float* out);
 
+/* gauss_transform._gauss_transform_direct / GaussTransform.compute (gauss_transform.py:10-16, 47-60), evaluated
+ * exactly (no IFGT): out[c*n + i] = sum_j weights[c*m + j] * exp(-|target_i - source_j|^2 / h^2).        */
+int cpd_gauss_transform(int device, const double* source, int64_t m, const double* target, int64_t n, int dim, double h,
+                        const double* weights, int k, double* out);
+
 /* math_utils.squared_kernel_sum on two host clouds without a handle.                    */
 int cpd_squared_kernel_sum(int device, const double* x, int64_t nx, const double* y, int64_t ny,
                            int dim, double* out);

@@ -849,6 +849,49 @@ extern "C" int cpd_rbf_kernel(int device, const double* x, int64_t nx, const dou
     return CPD_OK;
 }
 
+// Direct Gauss transform on host arrays (stateless).  weights: k x m row-major, out: k x n.
+extern "C" int cpd_gauss_transform(int device, const double* source, int64_t m, const double* target, int64_t n, int dim, double h,
+                                   const double* weights, int k, double* out) {
+    if (!source || !target || !weights || !out) return fail(CPD_ERR_ARG, "null argument");
+    if (m < 1 || n < 1 || k < 1 || dim < 1 || dim > 3 || !(h > 0.0)) return fail(CPD_ERR_ARG, "bad m/n/k/dim/h");
+    if (cpd_device_count() == 0) return fail(CPD_ERR_CUDA, "no CUDA device: this library has no CPU path");
+    CU(cudaSetDevice(device));
+    const int64_t mpad = (m + GT_TILE - 1) / GT_TILE * GT_TILE;
+    double c[3] = {0.0, 0.0, 0.0};
+    for (int64_t j = 0; j < m; ++j) for (int a = 0; a < dim; ++a) c[a] += source[j * dim + a];
+    for (int a = 0; a < dim; ++a) c[a] /= (double)m;
+    const double sk = sqrt(LOG2E) / h;                   // exp(-d^2/h^2) = 2^-(sk d)^2
+    std::vector<float4> hs((size_t)mpad), ht((size_t)n);
+    std::vector<float> hw((size_t)k * mpad, 0.0f);
+    for (int64_t j = 0; j < mpad; ++j) {
+        float v[3] = {FAR_COORD, FAR_COORD, FAR_COORD};
+        if (j < m) for (int a = 0; a < 3; ++a) v[a] = a < dim ? (float)(sk * (source[j * dim + a] - c[a])) : 0.0f;
+        hs[(size_t)j] = make_float4(v[0], v[1], v[2], 0.0f);
+    }
+    for (int64_t i = 0; i < n; ++i) {
+        float v[3] = {0.f, 0.f, 0.f};
+        for (int a = 0; a < dim; ++a) v[a] = (float)(sk * (target[i * dim + a] - c[a]));
+        ht[(size_t)i] = make_float4(v[0], v[1], v[2], 0.0f);
+    }
+    for (int cc = 0; cc < k; ++cc) for (int64_t j = 0; j < m; ++j) hw[(size_t)cc * mpad + j] = (float)weights[(size_t)cc * m + j];
+    float4 *ds = nullptr, *dt = nullptr;
+    float* dw = nullptr;
+    double* dout = nullptr;
+    TRY(dev_alloc(&ds, hs.size()));
+    TRY(dev_alloc(&dt, ht.size()));
+    TRY(dev_alloc(&dw, hw.size()));
+    TRY(dev_alloc(&dout, (size_t)k * n));
+    CU(cudaMemcpy(ds, hs.data(), hs.size() * sizeof(float4), cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(dt, ht.data(), ht.size() * sizeof(float4), cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(dw, hw.data(), hw.size() * sizeof(float), cudaMemcpyHostToDevice));
+    for (int k0 = 0; k0 < k; k0 += GT_K)
+        gauss_transform_kernel<<<blocks_for(n), THREADS>>>(dt, (int)n, ds, dw, (int)mpad, k0, std::min(GT_K, k - k0), dout);
+    KCHECK();
+    CU(cudaMemcpy(out, dout, (size_t)k * n * sizeof(double), cudaMemcpyDeviceToHost));
+    cudaFree(ds); cudaFree(dt); cudaFree(dw); cudaFree(dout);
+    return CPD_OK;
+}
+
 extern "C" int cpd_squared_kernel_sum(int device, const double* x, int64_t nx, const double* y, int64_t ny, int dim, double* out) {
     if (!x || !y || !out) return fail(CPD_ERR_ARG, "null argument");
     cpd_ctx* h = nullptr;

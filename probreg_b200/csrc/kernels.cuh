@@ -1340,6 +1340,51 @@ nr_sigma_kernel(DevState* st, const double* __restrict__ part, int nb, const dou
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Direct Gauss transform (probreg/gauss_transform.py:10-16): the same pair kernel as
+// pass 1 without the normalisation:  out[c][i] = sum_j w[c][j] exp(-|t_i - s_j|^2 / h^2),  up to GT_K weight
+// vectors per sweep.  Coordinates arrive centred and scaled by sqrt(log2 e)/h, so the exponential is 2^(-u).
+// FP32 pair maths, 32-term FP32 groups, FP64 beyond.  Exact (the reference's default for h >= 0.01 is the
+// IFGT approximation at eps = 1e-4, gauss_transform.py:42-45).
+// ---------------------------------------------------------------------------------------------
+constexpr int GT_K = 4, GT_TILE = 256;
+__global__ void __launch_bounds__(THREADS)
+gauss_transform_kernel(const float4* __restrict__ tg, int n, const float4* __restrict__ sc, const float* __restrict__ wts, int mpad,
+                       int k0, int kn, double* __restrict__ out) {
+    __shared__ float4 sp[GT_TILE];
+    __shared__ float sw[GT_K][GT_TILE];
+    const int i = blockIdx.x * THREADS + threadIdx.x;
+    const float4 t = tg[i < n ? i : n - 1];
+    double acc[GT_K];
+#pragma unroll
+    for (int c = 0; c < GT_K; ++c) acc[c] = 0.0;
+    for (int j0 = 0; j0 < mpad; j0 += GT_TILE) {
+        __syncthreads();
+        sp[threadIdx.x] = sc[j0 + threadIdx.x];
+#pragma unroll
+        for (int c = 0; c < GT_K; ++c) sw[c][threadIdx.x] = c < kn ? wts[(size_t)(k0 + c) * mpad + j0 + threadIdx.x] : 0.0f;
+        __syncthreads();
+#pragma unroll 1
+        for (int g = 0; g < GT_TILE; g += 32) {
+            float a[GT_K];
+#pragma unroll
+            for (int c = 0; c < GT_K; ++c) a[c] = 0.0f;
+#pragma unroll 8
+            for (int jj = 0; jj < 32; ++jj) {
+                const float4 b = sp[g + jj];
+                const float dx = t.x - b.x, dy = t.y - b.y, dz = t.z - b.z;
+                const float e = ex2(-fmaf(dz, dz, fmaf(dy, dy, dx * dx)));
+#pragma unroll
+                for (int c = 0; c < GT_K; ++c) a[c] = fmaf(e, sw[c][g + jj], a[c]);
+            }
+#pragma unroll
+            for (int c = 0; c < GT_K; ++c) acc[c] += (double)a[c];
+        }
+    }
+    if (i < n)
+        for (int c = 0; c < kn; ++c) out[(size_t)(k0 + c) * n + i] = acc[c];
+}
+
 // issue-rate probes for the roofline denominators
 __global__ void __launch_bounds__(256)
 probe_ffma_kernel(float* out, int iters, float seed) {

@@ -109,3 +109,22 @@ def test_results_are_deterministic():
     b = cpd.registration_cpd(src, tgt, maxiter=6, tol=-1.0)
     assert a.sigma2 == b.sigma2 and a.q == b.q
     assert np.array_equal(a.transformation.rot, b.transformation.rot)
+
+
+def test_gauss_transform_vs_direct():
+    """reference tests/test_gauss_transform.py compares IFGT with the direct sum at 1e-4; this is the direct sum itself."""
+    from probreg_b200 import gauss_transform as gt
+    rng = np.random.default_rng(5)
+    src, tgt = rng.random((777, 3)), rng.random((333, 3))
+    w1 = rng.standard_normal(777)
+    for h in (1.0, 0.5, 0.05):
+        direct = np.array([np.dot(w1, np.exp(-np.sum((t - src) ** 2, axis=1) / h ** 2)) for t in tgt])     # gauss_transform.py:10-16
+        np.testing.assert_allclose(gt.GaussTransform(src, h).compute(tgt, w1), direct, rtol=2e-5, atol=2e-5 * np.abs(direct).max())
+    wk = rng.standard_normal((6, 777))
+    out = gt.GaussTransform(src, 0.3).compute(tgt, wk)
+    ref = np.exp(-((tgt[:, None, :] - src[None, :, :]) ** 2).sum(-1) / 0.09).dot(wk.T).T
+    assert out.shape == (6, 333)
+    np.testing.assert_allclose(out, ref, rtol=2e-5, atol=2e-5 * np.abs(ref).max())
+    s2, t2 = rng.random((50, 2)), rng.random((20, 2))
+    ref2 = np.exp(-((t2[:, None, :] - s2[None, :, :]) ** 2).sum(-1) / 0.25).sum(1)
+    np.testing.assert_allclose(gt.GaussTransform(s2, 0.5).compute(t2), ref2, rtol=2e-5)
