@@ -10,6 +10,7 @@
 #include <math.h>
 #include <stdarg.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -146,6 +147,11 @@ struct cpd_ctx {
     DevState h_state;
     double* h_pin = nullptr;   // 64 pinned doubles for small D2H reads
     int it1 = 0, it2 = 0, j1 = 1, j2 = 1, g1 = 1, g2 = 1;   // i-tiles, max partial slots per tile, work items (= grid)
+    // exact culling of far blocks (late iterations): stage bounding boxes, per-stage max offset
+    float4 *d_sbox = nullptr, *d_tbox = nullptr;
+    float* d_omax = nullptr;
+    bool cull_on = true, cull_active = false;
+    double extent = 0.0;              // largest bounding-box edge of the target shard (caller units)
     int4 *d_work1 = nullptr, *d_work2 = nullptr;
     int *d_slots1 = nullptr, *d_slots2 = nullptr;
     bool have_source = false, have_target = false, have_state = false, prepared = false;
@@ -334,6 +340,9 @@ int prepare(cpd_ctx* h) {
     CU(cudaMemcpy(h->d_work2, w2.items.data(), w2.items.size() * sizeof(int4), cudaMemcpyHostToDevice));
     CU(cudaMemcpy(h->d_slots1, w1.tile_slots.data(), w1.tile_slots.size() * sizeof(int), cudaMemcpyHostToDevice));
     CU(cudaMemcpy(h->d_slots2, w2.tile_slots.data(), w2.tile_slots.size() * sizeof(int), cudaMemcpyHostToDevice));
+    TRY(dev_alloc(&h->d_sbox, (size_t)(h->mpad / P1_STAGE) * 2));
+    TRY(dev_alloc(&h->d_tbox, (size_t)(h->npad / P2_STAGE) * 2));
+    TRY(dev_alloc(&h->d_omax, (size_t)(h->npad / P2_STAGE)));
     const size_t need1 = (size_t)h->j1 * h->n, need2 = (size_t)h->j2 * h->m * 4;
     if (need1 > h->part1_cap) { TRY(dev_alloc(&h->d_part1, need1)); h->part1_cap = need1; }
     if (need2 > h->part2_cap) { TRY(dev_alloc(&h->d_part2, need2)); h->part2_cap = need2; }
@@ -362,12 +371,26 @@ int launch_estep(cpd_ctx* h, const double* d_sigma2, const double* d_w, const do
     pack_kernel<<<blocks_for(cover), THREADS, 0, h->stream>>>(h->d_state, d_sigma2, h->d_yc, d_ts, h->d_xc, h->m, h->mpad,
                                                               h->n, h->d_srcP, h->d_srcJ, h->d_tgtP);
     mark(h, 1);
-    pass1_kernel<<<h->g1, THREADS, PASS1_SMEM, h->stream>>>(h->d_tgtP, (int)h->n, h->d_srcJ, h->d_work1, h->d_part1);
+    const bool cull = h->cull_on && h->cull_active;
+    const int nst1 = (int)(h->mpad / P1_STAGE);
+    stage_bbox_kernel<<<(unsigned)nst1, THREADS, 0, h->stream>>>(h->d_srcP, (int)h->m, P1_STAGE, h->d_sbox);   // offset seeding (always)
+    h->launches += 1;
+    if (cull) {
+        stage_bbox_kernel<<<(unsigned)(h->npad / P2_STAGE), THREADS, 0, h->stream>>>(h->d_tgtP, (int)h->n, P2_STAGE, h->d_tbox);
+        h->launches += 1;
+    }
+    if (cull) pass1_kernel<true><<<h->g1, THREADS, PASS1_SMEM, h->stream>>>(h->d_tgtP, (int)h->n, h->d_srcJ, h->d_work1, h->d_part1, h->d_sbox, nst1);
+    else pass1_kernel<false><<<h->g1, THREADS, PASS1_SMEM, h->stream>>>(h->d_tgtP, (int)h->n, h->d_srcJ, h->d_work1, h->d_part1, h->d_sbox, nst1);
     mark(h, 2);
     finalize1_kernel<<<blocks_for(h->npad), THREADS, 0, h->stream>>>(h->d_state, d_sigma2, d_w, h->d_part1, h->d_slots1, (int)h->n,
                                                                      h->d_tgtP, h->d_tgtQ, h->npad, h->d_pt1, h->d_mom_tgt);
     mark(h, 3);
-    pass2_kernel<<<h->g2, THREADS, PASS2_SMEM, h->stream>>>(h->d_srcP, (int)h->m, h->d_tgtQ, h->d_work2, h->d_part2);
+    if (cull) {
+        stage_omax_kernel<<<(unsigned)(h->npad / P2_STAGE), THREADS, 0, h->stream>>>(h->d_tgtQ, h->d_omax);
+        h->launches += 1;
+    }
+    if (cull) pass2_kernel<true><<<h->g2, THREADS, PASS2_SMEM, h->stream>>>(h->d_srcP, (int)h->m, h->d_tgtQ, h->d_work2, h->d_part2, h->d_tbox, h->d_omax);
+    else pass2_kernel<false><<<h->g2, THREADS, PASS2_SMEM, h->stream>>>(h->d_srcP, (int)h->m, h->d_tgtQ, h->d_work2, h->d_part2, nullptr, nullptr);
     mark(h, 4);
     finalize2_kernel<<<blocks_for(h->m), THREADS, 0, h->stream>>>(h->d_state, d_sigma2, h->d_part2, h->d_slots2, (int)h->m, h->d_yc,
                                                                   d_ts, h->d_p1, h->d_pxc, h->d_mom_src);
@@ -390,6 +413,8 @@ int read_params(cpd_ctx* h, cpd_params* out) {
     for (int i = 0; i < 3; ++i) out->t[i] = (i < d) ? h->h_pin[9 + i] : 0.0;
     out->scale = h->h_pin[12];
     out->sigma2 = h->h_pin[13];
+    // a point reaches ~13.3 sigma (2^-127); culling can only pay once that is well inside the cloud
+    h->cull_active = h->extent > 0.0 && 13.3 * sqrt(out->sigma2) < 0.5 * h->extent;
     out->q = h->h_pin[14];
     out->n_p = h->h_pin[15];
     return CPD_OK;
@@ -415,11 +440,13 @@ extern "C" int cpd_create(cpd_ctx** out, int device, int dim, void* stream) {
     h->sm_count = prop.multiProcessorCount;
     if (stream) { h->stream = (cudaStream_t)stream; h->own_stream = false; }
     else { CU(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking)); h->own_stream = true; }
-    CU(cudaFuncSetAttribute(pass1_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, PASS1_SMEM));
-    CU(cudaFuncSetAttribute(pass2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, PASS2_SMEM));
+    CU(cudaFuncSetAttribute(pass1_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, PASS1_SMEM));
+    CU(cudaFuncSetAttribute(pass2_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, PASS2_SMEM));
+    CU(cudaFuncSetAttribute(pass1_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, PASS1_SMEM));
+    CU(cudaFuncSetAttribute(pass2_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, PASS2_SMEM));
     int occ1 = 0, occ2 = 0;
-    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ1, pass1_kernel, THREADS, PASS1_SMEM));
-    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ2, pass2_kernel, THREADS, PASS2_SMEM));
+    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ1, pass1_kernel<false>, THREADS, PASS1_SMEM));
+    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ2, pass2_kernel<false>, THREADS, PASS2_SMEM));
     h->slots1 = h->sm_count * std::max(1, occ1);
     h->slots2 = h->sm_count * std::max(1, occ2);
     TRY(dev_alloc(&h->d_state, 1));
@@ -428,6 +455,7 @@ extern "C" int cpd_create(cpd_ctx** out, int device, int dim, void* stream) {
     CU(cudaEventCreate(&h->ev0));
     CU(cudaEventCreate(&h->ev1));
     for (int k = 0; k < 7; ++k) CU(cudaEventCreate(&h->sev[k]));
+    { const char* e = getenv("CPD_B200_NO_CULL"); h->cull_on = !(e && e[0] == '1'); }
     memset(&h->h_state, 0, sizeof(DevState));
     h->h_state.dim = dim;
     h->h_state.scale = 1.0;
@@ -441,7 +469,7 @@ extern "C" void cpd_destroy(cpd_ctx* h) {
     if (!h) return;
     cudaSetDevice(h->device);
     cudaStreamSynchronize(h->stream);
-    void* wl[] = {h->d_work1, h->d_work2, h->d_slots1, h->d_slots2};
+    void* wl[] = {h->d_work1, h->d_work2, h->d_slots1, h->d_slots2, h->d_sbox, h->d_tbox, h->d_omax};
     for (void* p : wl) if (p) cudaFree(p);
     void* srt[] = {h->d_perm_src, h->d_perm_tgt, h->d_idx_tmp, h->d_codes, h->d_codes_out, h->d_sort_tmp, h->d_outN, h->d_outM};
     for (void* p : srt) if (p) cudaFree(p);
@@ -518,6 +546,7 @@ extern "C" int cpd_set_target(cpd_ctx* h, const double* target, int64_t n_local,
     HostStats st;
     TRY(device_stats(h, h->d_raw, n_local, st));
     for (int a = 0; a < 3; ++a) h->h_state.cx[a] = frame_origin ? ((a < h->dim) ? frame_origin[a] : 0.0) : st.mean[a];
+    h->extent = std::max(st.hi[0] - st.lo[0], std::max(st.hi[1] - st.lo[1], st.hi[2] - st.lo[2]));
     TRY(sort_cloud(h, h->d_raw, n_local, st, h->h_state.cx, h->d_perm_tgt, h->d_xc));
     h->h_state.n_global = n_global;
     h->have_target = true;
@@ -568,6 +597,7 @@ extern "C" int cpd_set_state(cpd_ctx* h, int tf_kind, int update_scale, double w
     s.tf_kind = tf_kind;
     s.update_scale = update_scale ? 1 : 0;
     s.dim = d;
+    h->cull_active = h->extent > 0.0 && 13.3 * sqrt(init->sigma2) < 0.5 * h->extent;
     h->have_state = true;
     return upload_state(h);
 }
@@ -626,6 +656,7 @@ extern "C" int cpd_estep(cpd_ctx* h, const double* t_source, double sigma2, doub
     TRY(upload_cloud(h, t_source, h->m, h->d_raw));
     gather3_kernel<<<blocks_for(h->m), THREADS, 0, h->stream>>>(h->d_raw, h->d_perm_src, h->m, 0.0, 0.0, 0.0, h->d_ts);
     h->launches += 1;
+    h->cull_active = h->extent > 0.0 && 13.3 * sqrt(sigma2) < 0.5 * h->extent;
     h->h_pin[32] = sigma2;
     h->h_pin[33] = w;
     CU(cudaMemcpyAsync(&h->d_state->es_sigma2, h->h_pin + 32, 2 * sizeof(double), cudaMemcpyHostToDevice, h->stream));

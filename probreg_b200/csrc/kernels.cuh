@@ -267,6 +267,95 @@ pack_kernel(const DevState* __restrict__ st, const double* __restrict__ sigma2_p
 // The largest term of a target is >= 2^-1 right after its offset was set and <= 2^100 always, so
 // every term that matters stays a normal FP32 number.
 // ---------------------------------------------------------------------------------------------
+// ---------------------------------------------------------------------------------------------
+// Exact culling of far (warp, stage) blocks.  ex2.approx.ftz returns exactly 0 below 2^-126, so a block of
+// pairs whose every t' = u - o exceeds ~127 contributes exactly nothing to any sum: skipping it is bit-identical
+// to evaluating it.  With Z-ordered clouds both a warp's i-points and a 512-record j-stage are spatially
+// compact, so  dist^2(bbox_warp, bbox_stage) - max(o)  >= CULL_GAP  proves that cheaply.  It only ever
+// triggers once sigma << extent (late iterations: 13 sigma is the reach of a point), which is when the dense
+// sweep wastes most of its work; the host enables it only then (cpd_em_step).
+// ---------------------------------------------------------------------------------------------
+constexpr float CULL_GAP = 130.0f;
+// per block of `blk` consecutive points: {min xyz, 0}, {max xyz, 0}
+__global__ void __launch_bounds__(THREADS)
+stage_bbox_kernel(const float4* __restrict__ pts, int n, int blk, float4* __restrict__ box) {
+    __shared__ float sh[6][THREADS / 32];
+    const int b = blockIdx.x;
+    float lo[3] = {3.0e38f, 3.0e38f, 3.0e38f}, hi[3] = {-3.0e38f, -3.0e38f, -3.0e38f};
+    for (int i = b * blk + threadIdx.x; i < min(n, (b + 1) * blk); i += THREADS) {
+        const float4 p = pts[i];
+        lo[0] = fminf(lo[0], p.x); lo[1] = fminf(lo[1], p.y); lo[2] = fminf(lo[2], p.z);
+        hi[0] = fmaxf(hi[0], p.x); hi[1] = fmaxf(hi[1], p.y); hi[2] = fmaxf(hi[2], p.z);
+    }
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            lo[a] = fminf(lo[a], __shfl_xor_sync(0xffffffffu, lo[a], o));
+            hi[a] = fmaxf(hi[a], __shfl_xor_sync(0xffffffffu, hi[a], o));
+        }
+        if (lane == 0) { sh[a][wid] = lo[a]; sh[3 + a][wid] = hi[a]; }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float l[3], h[3];
+        for (int a = 0; a < 3; ++a) {
+            l[a] = sh[a][0]; h[a] = sh[3 + a][0];
+            for (int w = 1; w < THREADS / 32; ++w) { l[a] = fminf(l[a], sh[a][w]); h[a] = fmaxf(h[a], sh[3 + a][w]); }
+        }
+        box[2 * b] = make_float4(l[0], l[1], l[2], 0.f);
+        box[2 * b + 1] = make_float4(h[0], h[1], h[2], 0.f);
+    }
+}
+// per pass-2 stage: the largest offset o_n of its live targets (records hold -o; dead / padding hold +inf)
+__global__ void __launch_bounds__(THREADS)
+stage_omax_kernel(const float4* __restrict__ tgtQ, float* __restrict__ omax) {
+    __shared__ float sh[THREADS / 32];
+    const int b = blockIdx.x;
+    float m = 3.0e38f;
+    for (int i = threadIdx.x; i < P2_STAGE; i += THREADS) m = fminf(m, tgtQ[3 * ((size_t)b * P2_STAGE + i) + 1].z);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m = fminf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = m;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int w = 1; w < THREADS / 32; ++w) m = fminf(m, sh[w]);
+        omax[b] = -m;                                   // -inf when the whole stage is dead
+    }
+}
+// bounding box of this warp's packed i-points -> wbox[0..6) (shared, one row per warp)
+template <int NP>
+__device__ __forceinline__ void warp_bbox(const u64 (&ax)[NP], const u64 (&ay)[NP], const u64 (&az)[NP], float* __restrict__ wbox) {
+    float lo[3] = {3.0e38f, 3.0e38f, 3.0e38f}, hi[3] = {-3.0e38f, -3.0e38f, -3.0e38f};
+#pragma unroll
+    for (int p = 0; p < NP; ++p) {
+        const float2 x = unpack2(ax[p]), y = unpack2(ay[p]), z = unpack2(az[p]);
+        lo[0] = fminf(lo[0], fminf(x.x, x.y)); hi[0] = fmaxf(hi[0], fmaxf(x.x, x.y));
+        lo[1] = fminf(lo[1], fminf(y.x, y.y)); hi[1] = fmaxf(hi[1], fmaxf(y.x, y.y));
+        lo[2] = fminf(lo[2], fminf(z.x, z.y)); hi[2] = fmaxf(hi[2], fmaxf(z.x, z.y));
+    }
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            lo[a] = fminf(lo[a], __shfl_xor_sync(0xffffffffu, lo[a], o));
+            hi[a] = fmaxf(hi[a], __shfl_xor_sync(0xffffffffu, hi[a], o));
+        }
+    }
+    if ((threadIdx.x & 31) == 0) {
+#pragma unroll
+        for (int a = 0; a < 3; ++a) { wbox[a] = lo[a]; wbox[3 + a] = hi[a]; }
+    }
+    __syncwarp();
+}
+__device__ __forceinline__ float box_gap2(const float* __restrict__ wbox, const float4 blo, const float4 bhi) {
+    const float gx = fmaxf(0.f, fmaxf(blo.x - wbox[3], wbox[0] - bhi.x));
+    const float gy = fmaxf(0.f, fmaxf(blo.y - wbox[4], wbox[1] - bhi.y));
+    const float gz = fmaxf(0.f, fmaxf(blo.z - wbox[5], wbox[2] - bhi.z));
+    return fmaf(gz, gz, fmaf(gy, gy, gx * gx)) * 0.9999f;      // a whisker below the true lower bound of u
+}
+
 // Sum one sub-chunk of pass 1 into Sc (sum e) and Uc (sum e*t'), both starting from zero.  With GRP > 0 the
 // terms are first summed in groups of GRP from zero and the group sums joined: a two-level FP32 summation.
 // Why: adding thousands of tiny terms one by one to a partial sum that already holds a dominant term drops
@@ -317,9 +406,12 @@ __device__ __forceinline__ void pass1_sum(const ulonglong2* __restrict__ q, cons
     }
 }
 
+template <bool CULL>
 __global__ void __launch_bounds__(THREADS, CPD_MINB1)
 pass1_kernel(const float4* __restrict__ ipts, int ni, const float4* __restrict__ jrec, const int4* __restrict__ work,
-             P1Part* __restrict__ part) {
+             P1Part* __restrict__ part, const float4* __restrict__ sbox /* bounding boxes of the source stages */,
+             int nstages_total) {
+    __shared__ float wbox[THREADS / 32][8];
     extern __shared__ __align__(128) unsigned char smraw[];
     uint64_t* full = reinterpret_cast<uint64_t*>(smraw + NSTAGE * P1_STAGE_BYTES);
     const int tid = threadIdx.x;
@@ -343,12 +435,62 @@ pass1_kernel(const float4* __restrict__ ipts, int ni, const float4* __restrict__
     double S[RI1], SU[RI1];
 #pragma unroll
     for (int p = 0; p < NPAIR1; ++p) {
-        int n0 = itile * ITILE1 + (2 * p) * THREADS + tid, n1 = n0 + THREADS;
+        // a warp owns 32*RI1 CONSECUTIVE (Z-ordered) targets: compact for the culling test, still coalesced per 32
+        int n0 = itile * ITILE1 + (tid >> 5) * (32 * RI1) + (2 * p) * 32 + (tid & 31), n1 = n0 + 32;
         n0 = n0 < ni ? n0 : ni - 1;
         n1 = n1 < ni ? n1 : ni - 1;
         const float4 p0 = ipts[n0], p1 = ipts[n1];
         ax[p] = pack2(p0.x, p1.x); ay[p] = pack2(p0.y, p1.y); az[p] = pack2(p0.z, p1.z);
         no[p] = pack2(-O_INIT, -O_INIT);
+    }
+    // Seed the offsets from the source stage whose bounding box is nearest to this warp's targets (any source
+    // gives a valid upper bound of the final offset; a near one gives a tight bound).  With tight seeds the
+    // offset slow path below becomes rare even when sigma << extent, and the culling test bites from the first
+    // stage on.  Cost: one scan of the stage boxes + one 128-source sweep per warp.
+    float* const mybox = wbox[tid >> 5];
+    warp_bbox<NPAIR1>(ax, ay, az, mybox);
+    {
+        const int lane = tid & 31;
+        float best = 3.0e38f;
+        int bi = 0;
+        for (int sidx = lane; sidx < nstages_total; sidx += 32) {
+            const float g2 = box_gap2(mybox, sbox[2 * sidx], sbox[2 * sidx + 1]);
+            if (g2 < best) { best = g2; bi = sidx; }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const float ob = __shfl_xor_sync(0xffffffffu, best, o);
+            const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+            if (ob < best || (ob == best && oi < bi)) { best = ob; bi = oi; }
+        }
+        const ulonglong2* near = reinterpret_cast<const ulonglong2*>(jbytes + (size_t)bi * P1_STAGE_BYTES);
+        float cm[RI1];
+#pragma unroll
+        for (int r = 0; r < RI1; ++r) cm[r] = 3.0e38f;
+#pragma unroll 4
+        for (int jj = 0; jj < 128; ++jj) {
+            const ulonglong2 bxy = near[2 * jj];
+            const u64 bz = near[2 * jj + 1].x;
+#pragma unroll
+            for (int p = 0; p < NPAIR1; ++p) {
+                const u64 dx = fsub2(ax[p], bxy.x), dy = fsub2(ay[p], bxy.y), dz = fsub2(az[p], bz);
+                const float2 u = unpack2(ffma2(dz, dz, ffma2(dy, dy, fmul2(dx, dx))));
+                cm[2 * p] = fminf(cm[2 * p], u.x);
+                cm[2 * p + 1] = fminf(cm[2 * p + 1], u.y);
+            }
+        }
+#pragma unroll
+        for (int p = 0; p < NPAIR1; ++p)
+            no[p] = pack2(-fminf(O_INIT, floorf(cm[2 * p])), -fminf(O_INIT, floorf(cm[2 * p + 1])));
+    }
+    float omax_w = O_INIT;            // warp-uniform upper bound of this warp's offsets (culling test)
+    if (CULL) {
+        float om = -3.0e38f;
+#pragma unroll
+        for (int p = 0; p < NPAIR1; ++p) { const float2 nv = unpack2(no[p]); om = fmaxf(om, fmaxf(-nv.x, -nv.y)); }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) om = fmaxf(om, __shfl_xor_sync(0xffffffffu, om, o));
+        omax_w = om;
     }
 #pragma unroll
     for (int r = 0; r < RI1; ++r) { S[r] = 0.0; SU[r] = 0.0; }
@@ -356,31 +498,13 @@ pass1_kernel(const float4* __restrict__ ipts, int ni, const float4* __restrict__
         const int s = it % NSTAGE;
         mbar_wait(&full[s], (uint32_t)((it / NSTAGE) & 1));
         const ulonglong2* sp = reinterpret_cast<const ulonglong2*>(smraw + s * P1_STAGE_BYTES);
-        if (it == 0) {
-            // seed the offsets from the first 8 sources of the split (a 16x cheaper sweep than letting the
-            // first 64-source sub-chunk overflow into the slow path, which matters when a CTA only sees a
-            // few thousand sources, i.e. in multi-GPU runs)
-            float cm[RI1];
-#pragma unroll
-            for (int r = 0; r < RI1; ++r) cm[r] = 3.0e38f;
-#pragma unroll
-            for (int jj = 0; jj < 8; ++jj) {
-                const ulonglong2 bxy = sp[2 * jj];
-                const u64 bz = sp[2 * jj + 1].x;
-#pragma unroll
-                for (int p = 0; p < NPAIR1; ++p) {
-                    const u64 dx = fsub2(ax[p], bxy.x), dy = fsub2(ay[p], bxy.y), dz = fsub2(az[p], bz);
-                    const float2 u = unpack2(ffma2(dz, dz, ffma2(dy, dy, fmul2(dx, dx))));
-                    cm[2 * p] = fminf(cm[2 * p], u.x);
-                    cm[2 * p + 1] = fminf(cm[2 * p + 1], u.y);
-                }
-            }
-#pragma unroll
-            for (int p = 0; p < NPAIR1; ++p)
-                no[p] = pack2(-fminf(O_INIT, floorf(cm[2 * p])), -fminf(O_INIT, floorf(cm[2 * p + 1])));
+        bool skip = false;
+        if (CULL) {      // every pair of (this warp, this stage) has t' = u - o >= CULL_GAP: exactly zero terms
+            const float4 blo = sbox[2 * (st0 + it)], bhi = sbox[2 * (st0 + it) + 1];
+            skip = box_gap2(mybox, blo, bhi) - omax_w >= CULL_GAP;
         }
 #pragma unroll 1
-        for (int sc = 0; sc < P1_STAGE / SUB; ++sc) {
+        for (int sc = 0; sc < (skip ? 0 : P1_STAGE / SUB); ++sc) {
             const ulonglong2* q = sp + sc * (2 * SUB);
             u64 Sc[NPAIR1], Uc[NPAIR1];          // Sc = sum e,  Uc = sum e * t'  with t' = u - o, e = 2^-t'
 #pragma unroll
@@ -419,6 +543,14 @@ pass1_kernel(const float4* __restrict__ ipts, int ni, const float4* __restrict__
                     no[p] = pack2(-on0, -on1);
                     Sc[p] = 0ull; Uc[p] = 0ull;
                 }
+                if (CULL) {      // the offsets just dropped: tighten the warp's bound for the culling test
+                    float om = -3.0e38f;
+#pragma unroll
+                    for (int p = 0; p < NPAIR1; ++p) { const float2 nv = unpack2(no[p]); om = fmaxf(om, fmaxf(-nv.x, -nv.y)); }
+#pragma unroll
+                    for (int o = 16; o > 0; o >>= 1) om = fmaxf(om, __shfl_xor_sync(0xffffffffu, om, o));
+                    omax_w = om;
+                }
                 pass1_sum(q, ax, ay, az, no, Sc, Uc);
             }
 #pragma unroll
@@ -441,7 +573,7 @@ pass1_kernel(const float4* __restrict__ ipts, int ni, const float4* __restrict__
         const float2 nv = unpack2(no[p]);
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
-            const int n = itile * ITILE1 + (2 * p + h) * THREADS + tid;
+            const int n = itile * ITILE1 + (tid >> 5) * (32 * RI1) + (2 * p + h) * 32 + (tid & 31);
             if (n < ni) {
                 P1Part out;
                 out.S = S[2 * p + h]; out.SU = SU[2 * p + h]; out.o = h ? -nv.y : -nv.x; out.pad = 0.0f;
@@ -534,9 +666,12 @@ finalize1_kernel(const DevState* __restrict__ st, const double* __restrict__ sig
 // pass 2: per source m and split of the targets:  p1_m = sum_n P_mn,  sd_m = sum_n P_mn (a_m - b_n)
 // with P_mn = 2^(o_n - u_mn) * rn_n.  Per two pairs: 11 packed FP32 instructions + 2 MUFU.
 // ---------------------------------------------------------------------------------------------
+template <bool CULL>
 __global__ void __launch_bounds__(THREADS, CPD_MINB2)
 pass2_kernel(const float4* __restrict__ ipts, int ni, const float4* __restrict__ jrec, const int4* __restrict__ work,
-             double* __restrict__ part /* [slot][ni][4] */) {
+             double* __restrict__ part /* [slot][ni][4] */, const float4* __restrict__ tbox /* per target stage bbox or null */,
+             const float* __restrict__ omax_stage) {
+    __shared__ float wbox[THREADS / 32][8];
     extern __shared__ __align__(128) unsigned char smraw[];
     uint64_t* full = reinterpret_cast<uint64_t*>(smraw + NSTAGE * P2_STAGE_BYTES);
     const int tid = threadIdx.x;
@@ -559,20 +694,27 @@ pass2_kernel(const float4* __restrict__ ipts, int ni, const float4* __restrict__
     double A1[RI2], AX[RI2], AY[RI2], AZ[RI2];
 #pragma unroll
     for (int p = 0; p < NPAIR2; ++p) {
-        int m0 = itile * ITILE2 + (2 * p) * THREADS + tid, m1 = m0 + THREADS;
+        int m0 = itile * ITILE2 + (tid >> 5) * (32 * RI2) + (2 * p) * 32 + (tid & 31), m1 = m0 + 32;
         m0 = m0 < ni ? m0 : ni - 1;
         m1 = m1 < ni ? m1 : ni - 1;
         const float4 p0 = ipts[m0], p1 = ipts[m1];
         ax[p] = pack2(p0.x, p1.x); ay[p] = pack2(p0.y, p1.y); az[p] = pack2(p0.z, p1.z);
     }
+    float* const mybox = wbox[tid >> 5];
+    if (CULL) warp_bbox<NPAIR2>(ax, ay, az, mybox);
 #pragma unroll
     for (int r = 0; r < RI2; ++r) { A1[r] = 0.0; AX[r] = 0.0; AY[r] = 0.0; AZ[r] = 0.0; }
     for (int it = 0; it < nst; ++it) {
         const int s = it % NSTAGE;
         mbar_wait(&full[s], (uint32_t)((it / NSTAGE) & 1));
         const ulonglong2* sp = reinterpret_cast<const ulonglong2*>(smraw + s * P2_STAGE_BYTES);
+        bool skip = false;
+        if (CULL) {
+            const float4 blo = tbox[2 * (st0 + it)], bhi = tbox[2 * (st0 + it) + 1];
+            skip = box_gap2(mybox, blo, bhi) - omax_stage[st0 + it] >= CULL_GAP;
+        }
 #pragma unroll 1
-        for (int sc = 0; sc < P2_STAGE / SUB; ++sc) {
+        for (int sc = 0; sc < (skip ? 0 : P2_STAGE / SUB); ++sc) {
             const ulonglong2* q = sp + sc * (3 * SUB);
             u64 s1[NPAIR2], sx[NPAIR2], sy[NPAIR2], sz[NPAIR2];
 #pragma unroll
@@ -642,7 +784,7 @@ pass2_kernel(const float4* __restrict__ ipts, int ni, const float4* __restrict__
     }
 #pragma unroll
     for (int r = 0; r < RI2; ++r) {
-        const int m = itile * ITILE2 + r * THREADS + tid;
+        const int m = itile * ITILE2 + (tid >> 5) * (32 * RI2) + r * 32 + (tid & 31);
         if (m < ni) {
             double2* dst = reinterpret_cast<double2*>(part + ((size_t)split * ni + m) * 4);
             dst[0] = make_double2(A1[r], AX[r]);
