@@ -253,19 +253,18 @@ pack_kernel(const DevState* __restrict__ st, const double* __restrict__ sigma2_p
 
 // ---------------------------------------------------------------------------------------------
 // pass 1: per target n and split:  (o, S, SU) with  sum_m 2^(-u) = S 2^(-o),  sum_m 2^(-u) u = SU 2^(-o)
-// One CTA per work item {target tile, source-stage range, partial slot}; the host chooses the number of stage ranges per
-// tile that minimises the makespan over the resident CTA slots (build_work in cpd_b200.cu).  Per two pairs: 8 packed FP32 instructions + 2 MUFU in the common path.
+// One CTA per work item {target tile, source-stage range, partial slot}; the host chooses the number of stage
+// ranges per tile that minimises the makespan over the resident CTA slots (build_work in cpd_b200.cu).
+// Per two pairs: 8 packed FP32 instructions + 2 MUFU in the common path.
 //
-// Lazy log-sum-exp: each target carries an integer-valued offset o (only ever lowered).  A
-// sub-chunk of 64 sources is summed in FP32 from zero with the current o -- Sc = sum e,
-// Uc = sum e*t with t = o - u, e = 2^t -- and folded into the FP64 running sums
-// (S += Sc, SU += o*Sc - Uc).  FP32 running sums over thousands of terms systematically drop
-// the small ones (absorption); 64 from zero, FP64 beyond, keeps that below 1e-8.  If any lane's
-// sub-chunk sum reaches 2^100 (a source much nearer than any seen before: 2^(o-u) overflowed or
-// nearly did) the warp re-does that sub-chunk: one sweep for the sub-chunk minimum of u,
-// o := min(o, floor(umin)), S and SU rescaled by the exact power of two, sub-chunk summed again.
-// The largest term of a target is >= 2^-1 right after its offset was set and <= 2^100 always, so
-// every term that matters stays a normal FP32 number.
+// Lazy log-sum-exp: each target carries an integer-valued offset o (only ever lowered), seeded per warp from
+// the nearest source stage.  A sub-chunk of 64 sources is summed in FP32 with the current o -- groups of 8 from
+// zero, the 8 group sums joined (pass1_sum): Sc = sum e, Uc = sum e*t' with t' = u - o, e = 2^-t' -- and folded
+// into the FP64 running sums (S += Sc, SU += Uc + o*Sc).  If any lane's sub-chunk sum reaches 2^100 (a source much
+// nearer than any seen before: 2^(o-u) overflowed or nearly did) the warp re-does that sub-chunk: one sweep for
+// the sub-chunk minimum of u, o := min(o, floor(umin)), S and SU rescaled by the exact power of two, sub-chunk
+// summed again.  The largest term of a target is >= 2^-1 right after its offset was set and <= 2^100 always,
+// so every term that matters stays a normal FP32 number.
 // ---------------------------------------------------------------------------------------------
 // ---------------------------------------------------------------------------------------------
 // Exact culling of far (warp, stage) blocks.  ex2.approx.ftz returns exactly 0 below 2^-126, so a block of
