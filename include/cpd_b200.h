@@ -139,6 +139,10 @@ int cpd_comm_attach(cpd_ctx* h, void* comm, int world_size, int rank);
 int cpd_p2p_local_handle(cpd_ctx* h, char out[64]);
 int cpd_p2p_attach(cpd_ctx* h, const char* handles, int world_size, int rank);
 
+/* Host-only: the work list {tile, first stage, end stage, partial slot} a pass over ntiles i-tiles x nstages j-stages is
+ * launched with on `slots` resident CTAs (csrc/cpd_b200.cu: build_work).  items may be NULL to query the counts.      */
+int cpd_plan_work(int ntiles, int nstages, int slots, int* items, int capacity, int* n_items, int* max_slots);
+
 /* -- measurement helpers (bench.py): CUDA events on the handle's stream ---------------- */
 int cpd_timer_start(cpd_ctx* h);
 int cpd_timer_stop(cpd_ctx* h, float* ms);           /* synchronises */

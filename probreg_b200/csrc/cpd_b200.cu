@@ -421,6 +421,23 @@ int read_params(cpd_ctx* h, cpd_params* out) {
 }
 }  // namespace
 
+// Host-only view of the work list a pass would be launched with (no device needed): lets the CPU tests check that
+// every (tile, stage) is covered exactly once and how well the resident CTA slots are filled.
+extern "C" int cpd_plan_work(int ntiles, int nstages, int slots, int* items /* 4 ints each, may be NULL */, int capacity,
+                             int* n_items, int* max_slots) {
+    if (ntiles < 1 || nstages < 1 || slots < 1 || !n_items || !max_slots) return fail(CPD_ERR_ARG, "bad argument");
+    const WorkList w = build_work(ntiles, nstages, slots);
+    *n_items = (int)w.items.size();
+    *max_slots = w.max_slots;
+    if (items) {
+        if (capacity < (int)w.items.size()) return fail(CPD_ERR_ARG, "capacity %d < %d work items", capacity, (int)w.items.size());
+        for (size_t i = 0; i < w.items.size(); ++i) {
+            items[4 * i] = w.items[i].x; items[4 * i + 1] = w.items[i].y; items[4 * i + 2] = w.items[i].z; items[4 * i + 3] = w.items[i].w;
+        }
+    }
+    return CPD_OK;
+}
+
 extern "C" int cpd_create(cpd_ctx** out, int device, int dim, void* stream) {
     if (!out) return fail(CPD_ERR_ARG, "out is NULL");
     if (dim != 2 && dim != 3) return fail(CPD_ERR_ARG, "dim must be 2 or 3, got %d", dim);
