@@ -354,7 +354,8 @@ def run_ours(args):
     out = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
         "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
-        "dtype": "f32 pair math, f64 accumulation and M-step", "data": "synthetic",
+        "dtype": "f32", "dtype_note": "pair arithmetic f32 (packed f32x2); every sum beyond 64 terms, the moments and the M-step f64",
+        "data": "synthetic",
         "config": {"workload": "rigid CPD, synthetic 3-D N=M=%d, sigma2 auto, w=0, update_scale" % n,
                    "parallelism": "target-sharded x%d, sources replicated, one 32-double all-reduce per iteration (%s)"
                                   % (world, "fused into the M-step kernel over NVLink peer memory" if (comm is not None and comm.use_p2p)

@@ -23,12 +23,11 @@ from .log import log
 
 EstepResult = namedtuple("EstepResult", ["pt1", "p1", "px", "n_p"])
 MstepResult = namedtuple("MstepResult", ["transformation", "sigma2", "q"])
-MstepResult.__doc__ = """Result of Maximization step.
+MstepResult.__doc__ = """Outcome of one M-step (field names as in probreg/cpd.py:18-25).
 
-    Attributes:
-        transformation (tf.Transformation): Transformation from source to target.
-        sigma2 (float): Variance of Gaussian distribution.
-        q (float): Result of likelihood.
+    transformation -- the current source->target Transformation (host-side value object)
+    sigma2         -- isotropic variance of the GMM components
+    q              -- objective value used by the convergence test of ``registration``
 """
 
 try:  # optional: accept open3d point clouds like probreg/cpd.py:444 does
@@ -48,11 +47,9 @@ class CoherentPointDrift(abc.ABC):
     """EM driver (probreg/cpd.py:28-120).  The E-step is implemented here, the M-step in the
     subclasses -- both as calls into the CUDA library.
 
-    Args:
-        source (numpy.ndarray, optional): Source point cloud data.
-        use_cuda (bool, optional): ignored; the sm_100a kernels are the only implementation.
-        device (int, optional): CUDA device ordinal (default: the communicator's, else 0).
-        comm (probreg_b200.dist.Communicator, optional): multi-GPU target sharding.
+    ``source``: (M, D) array or None; ``use_cuda``: ignored, the sm_100a kernels are the only implementation;
+    ``device``: CUDA ordinal (default: the communicator's, else 0); ``comm``: a probreg_b200.dist.Communicator
+    for multi-GPU target sharding.
     """
 
     def __init__(self, source=None, use_cuda=False, device=None, comm=None):
@@ -165,13 +162,11 @@ class CoherentPointDrift(abc.ABC):
 
 
 class RigidCPD(CoherentPointDrift):
-    """Coherent Point Drift for rigid transformation (probreg/cpd.py:123-192).
+    """Rigid (rotation + translation, optionally isotropic scale) CPD -- probreg/cpd.py:123-192.
 
-    Args:
-        source (numpy.ndarray, optional): Source point cloud data.
-        update_scale (bool, optional): If this flag is True, compute the scale parameter.
-        tf_init_params (dict, optional): Parameters to initialize transformation.
-        use_cuda (bool, optional): ignored (see module docstring).
+    ``source``: (M, D) array or None (set later with ``set_source``); ``update_scale``: estimate the scale
+    (True, default) or keep it at 1; ``tf_init_params``: warm start, keys ``rot``/``t``/``scale``;
+    ``use_cuda``: accepted, ignored (module docstring); ``device``/``comm``: see CoherentPointDrift.
     """
 
     def __init__(self, source=None, update_scale=True, tf_init_params=None, use_cuda=False, device=None, comm=None):
@@ -211,12 +206,10 @@ class RigidCPD(CoherentPointDrift):
 
 
 class AffineCPD(CoherentPointDrift):
-    """Coherent Point Drift for affine transformation (probreg/cpd.py:195-244).
+    """Affine CPD (x -> B x + t) -- probreg/cpd.py:195-244.
 
-    Args:
-        source (numpy.ndarray, optional): Source point cloud data.
-        tf_init_params (dict, optional): Parameters to initialize transformation.
-        use_cuda (bool, optional): ignored (see module docstring).
+    ``source``: (M, D) array or None; ``tf_init_params``: warm start, keys ``b``/``t``; ``use_cuda``: accepted,
+    ignored (module docstring); ``device``/``comm``: see CoherentPointDrift.
     """
 
     def __init__(self, source=None, tf_init_params=None, use_cuda=False, device=None, comm=None):
@@ -261,11 +254,8 @@ class NonRigidCPD(CoherentPointDrift):
     sigma2 in residual form.  ``maximization_step`` on a caller-supplied EstepResult stays a host numpy
     solve (the reference's own arithmetic on host arrays).
 
-    Args:
-        source (numpy.ndarray, optional): Source point cloud data.
-        beta (float, optional): Parameter of RBF kernel.
-        lmd (float, optional): Parameter for regularization term.
-        use_cuda (bool, optional): ignored (see module docstring).
+    ``source``: (M, D) array or None; ``beta``: RBF width of G (denominator 2*beta, as in the reference);
+    ``lmd``: weight of the smoothness term; ``use_cuda``: accepted, ignored.
     """
 
     def __init__(self, source=None, beta=2.0, lmd=2.0, use_cuda=False, device=None, comm=None):
@@ -373,13 +363,8 @@ class ConstrainedNonRigidCPD(NonRigidCPD):
     """Extended CPD with point-correspondence priors (probreg/cpd.py:306-404,
     https://people.mpi-inf.mpg.de/~golyanik/04_DRAFTS/ECPD2016.pdf).
 
-    Args:
-        source (numpy.ndarray, optional): Source point cloud data.
-        beta (float, optional): Parameter of RBF kernel.
-        lmd (float, optional): Parameter for regularization term.
-        alpha (float): Degree of reliability of priors (1e-8 highly reliable ... 1 highly unreliable).
-        use_cuda (bool, optional): ignored (see module docstring).
-        idx_source / idx_target (numpy.ndarray of ints, optional): known correspondences.
+    ``alpha``: trust in the priors (1e-8 = near-hard constraints ... 1 = weak); ``idx_source``/``idx_target``:
+    integer arrays of equal length naming the known source/target pairs; the rest as NonRigidCPD.
 
     The reference materialises a dense M x N indicator matrix for the priors (cpd.py:370-374); its row
     sums and its product with the target are a sparse gather, which is what is computed here.
@@ -411,27 +396,17 @@ class ConstrainedNonRigidCPD(NonRigidCPD):
 
 def registration_cpd(source, target, tf_type_name="rigid", w=0.0, maxiter=50, tol=0.001, callbacks=(),
                      use_cuda=False, **kwargs):
-    """CPD Registraion (probreg/cpd.py:407-456).
+    """One-call CPD registration with the signature of probreg/cpd.py:407-456.
 
-    Args:
-        source (numpy.ndarray): Source point cloud data.
-        target (numpy.ndarray): Target point cloud data.
-        tf_type_name (str, optional): Transformation type('rigid', 'affine', 'nonrigid', 'nonrigid_constrained')
-        w (float, optional): Weight of the uniform distribution, 0 < `w` < 1.
-        maxitr (int, optional): Maximum number of iterations to EM algorithm.
-        tol (float, optional): Tolerance for termination.
-        callback (:obj:`list` of :obj:`function`, optional): Called after each iteration.
-            `callback(probreg.Transformation)`
-        use_cuda (bool, optional): ignored -- the B200 kernels are the only implementation.
-
-    Keyword Args:
-        update_scale (bool, optional): If this flag is true and tf_type is rigid transformation,
-            then the scale is treated. The default is true.
-        tf_init_params (dict, optional): Parameters to initialize transformation (for rigid or affine).
-        device (int, optional), comm (probreg_b200.dist.Communicator, optional): see the classes.
-
-    Returns:
-        MstepResult: Result of the registration (transformation, sigma2, q)
+    source, target -- (M, D) / (N, D) arrays (or open3d point clouds), D = 2 or 3
+    tf_type_name   -- 'rigid' | 'affine' | 'nonrigid' | 'nonrigid_constrained' (anything else: ValueError)
+    w              -- weight of the uniform outlier component, 0 <= w < 1
+    maxiter, tol   -- at most maxiter EM iterations; stop once |q - q_prev| < tol
+    callbacks      -- callables invoked as cb(transformation) after every iteration
+    use_cuda       -- accepted for compatibility, ignored: the B200 kernels are the only implementation
+    **kwargs       -- forwarded to the class: update_scale, tf_init_params, beta, lmd, alpha, idx_source,
+                      idx_target, and the extensions device= / comm=
+    Returns MstepResult(transformation, sigma2, q).
     """
     if tf_type_name == "rigid":
         cpd = RigidCPD(_points(source), use_cuda=use_cuda, **kwargs)
