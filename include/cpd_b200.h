@@ -138,6 +138,7 @@ int cpd_comm_attach(cpd_ctx* h, void* comm, int world_size, int rank);
  * cpd_sigma2_init.  Every rank must have attached before any rank calls cpd_em_step.              */
 int cpd_p2p_local_handle(cpd_ctx* h, char out[64]);
 int cpd_p2p_attach(cpd_ctx* h, const char* handles, int world_size, int rank);
+int cpd_p2p_detach(cpd_ctx* h);      /* back to ncclAllReduce for the moments (e.g. when a peer could not map the mailboxes) */
 
 /* Host-only: the work list {tile, first stage, end stage, partial slot} a pass over ntiles i-tiles x nstages j-stages is
  * launched with on `slots` resident CTAs (csrc/cpd_b200.cu: build_work).  items may be NULL to query the counts.      */

@@ -56,6 +56,7 @@ _PROTOS = {
     "cpd_p2p_attach": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_char_p, ctypes.c_int, ctypes.c_int]),
     "cpd_plan_work": (ctypes.c_int, [ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.POINTER(ctypes.c_int), ctypes.c_int,
                                      ctypes.POINTER(ctypes.c_int), ctypes.POINTER(ctypes.c_int)]),
+    "cpd_p2p_detach": (ctypes.c_int, [ctypes.c_void_p]),
     "cpd_timer_start": (ctypes.c_int, [ctypes.c_void_p]),
     "cpd_timer_stop": (ctypes.c_int, [ctypes.c_void_p, _c_fp]),
     "cpd_sync": (ctypes.c_int, [ctypes.c_void_p]),
@@ -239,6 +240,9 @@ class Handle(object):
         blob = b"".join(handles)
         assert len(blob) == 64 * world_size
         check(lib().cpd_p2p_attach(self._h, blob, world_size, rank))
+
+    def p2p_detach(self):
+        check(lib().cpd_p2p_detach(self._h))
 
     # -- measurement
     def timer_start(self):

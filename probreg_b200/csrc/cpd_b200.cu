@@ -1018,13 +1018,30 @@ extern "C" int cpd_p2p_attach(cpd_ctx* h, const char* handles, int world_size, i
         if (r == rank) { info.box[r] = h->d_box; continue; }
         cudaIpcMemHandle_t mh;
         memcpy(&mh, handles + (size_t)r * 64, 64);
-        CU(cudaIpcOpenMemHandle(&h->peer_ptr[r], mh, cudaIpcMemLazyEnablePeerAccess));
+        cudaError_t e = cudaIpcOpenMemHandle(&h->peer_ptr[r], mh, cudaIpcMemLazyEnablePeerAccess);
+        if (e != cudaSuccess) {
+            h->peer_ptr[r] = nullptr;
+            cudaGetLastError();
+            for (int q = 0; q < r; ++q)
+                if (h->peer_ptr[q]) { cudaIpcCloseMemHandle(h->peer_ptr[q]); h->peer_ptr[q] = nullptr; }
+            return fail(CPD_ERR_CUDA, "cudaIpcOpenMemHandle(rank %d) failed: %s", r, cudaGetErrorString(e));
+        }
         info.box[r] = (P2PMailbox*)h->peer_ptr[r];
     }
     TRY(dev_alloc(&h->d_p2p, 1));
     CU(cudaMemcpy(h->d_p2p, &info, sizeof(info), cudaMemcpyHostToDevice));
     h->world = world_size;
     h->rank = rank;
+    return CPD_OK;
+}
+
+extern "C" int cpd_p2p_detach(cpd_ctx* h) {
+    if (!h) return fail(CPD_ERR_ARG, "null handle");
+    CU(cudaSetDevice(h->device));
+    CU(cudaStreamSynchronize(h->stream));
+    for (int r = 0; r < P2P_MAX; ++r)
+        if (h->peer_ptr[r]) { cudaIpcCloseMemHandle(h->peer_ptr[r]); h->peer_ptr[r] = nullptr; }
+    if (h->d_p2p) { cudaFree(h->d_p2p); h->d_p2p = nullptr; }
     return CPD_OK;
 }
 

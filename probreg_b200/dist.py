@@ -82,9 +82,24 @@ class Communicator(object):
         if self.use_p2p:
             if self._gather is None:
                 raise RuntimeError("Communicator needs a gather function for the P2P exchange")
+            from . import _cabi
+
             handles = self._gather(handle.p2p_local_handle())
-            handle.p2p_attach(handles, self.world_size, self.rank)
-            self._gather(b"attached")          # barrier: nobody steps before everybody has mapped everybody
+            try:
+                handle.p2p_attach(handles, self.world_size, self.rank)
+                ok, why = True, ""
+            except _cabi.CpdError as e:      # e.g. ranks isolated by CUDA_VISIBLE_DEVICES cannot map each other's memory
+                ok, why = False, str(e)
+            votes = self._gather((ok, why))   # also the barrier: nobody steps before everybody has mapped everybody
+            if not all(v[0] for v in votes):
+                if ok:
+                    handle.p2p_detach()
+                self.use_p2p = False          # every rank takes the ncclAllReduce path from here on
+                if self.rank == 0:
+                    import warnings
+
+                    warnings.warn("probreg_b200: NVLink peer mapping unavailable (%s); using ncclAllReduce for the moments"
+                                  % next(v[1] for v in votes if not v[0]))
 
     def close(self):
         """Collective, optional: destroy the NCCL communicator (all handles must be gone)."""
