@@ -148,8 +148,8 @@ struct cpd_ctx {
     double* h_pin = nullptr;   // 64 pinned doubles for small D2H reads
     int it1 = 0, it2 = 0, j1 = 1, j2 = 1, g1 = 1, g2 = 1;   // i-tiles, max partial slots per tile, work items (= grid)
     // exact culling of far blocks (late iterations): stage bounding boxes, per-stage max offset
-    float4 *d_sbox = nullptr, *d_tbox = nullptr;
-    float* d_omax = nullptr;
+    float4 *d_sbox = nullptr, *d_tbox = nullptr, *d_ssub = nullptr, *d_tsub = nullptr;
+    float *d_omax = nullptr, *d_omax_sub = nullptr;
     bool cull_on = true, cull_active = false;
     double extent = 0.0;              // largest bounding-box edge of the target shard (caller units)
     int4 *d_work1 = nullptr, *d_work2 = nullptr;
@@ -343,6 +343,9 @@ int prepare(cpd_ctx* h) {
     TRY(dev_alloc(&h->d_sbox, (size_t)(h->mpad / P1_STAGE) * 2));
     TRY(dev_alloc(&h->d_tbox, (size_t)(h->npad / P2_STAGE) * 2));
     TRY(dev_alloc(&h->d_omax, (size_t)(h->npad / P2_STAGE)));
+    TRY(dev_alloc(&h->d_ssub, (size_t)(h->mpad / SUB) * 2));
+    TRY(dev_alloc(&h->d_tsub, (size_t)(h->npad / SUB) * 2));
+    TRY(dev_alloc(&h->d_omax_sub, (size_t)(h->npad / SUB)));
     const size_t need1 = (size_t)h->j1 * h->n, need2 = (size_t)h->j2 * h->m * 4;
     if (need1 > h->part1_cap) { TRY(dev_alloc(&h->d_part1, need1)); h->part1_cap = need1; }
     if (need2 > h->part2_cap) { TRY(dev_alloc(&h->d_part2, need2)); h->part2_cap = need2; }
@@ -375,22 +378,26 @@ int launch_estep(cpd_ctx* h, const double* d_sigma2, const double* d_w, const do
     const int nst1 = (int)(h->mpad / P1_STAGE);
     stage_bbox_kernel<<<(unsigned)nst1, THREADS, 0, h->stream>>>(h->d_srcP, (int)h->m, P1_STAGE, h->d_sbox);   // offset seeding (always)
     h->launches += 1;
+    const int nsub1 = (int)(h->mpad / SUB), nsub2 = (int)(h->npad / SUB);
     if (cull) {
         stage_bbox_kernel<<<(unsigned)(h->npad / P2_STAGE), THREADS, 0, h->stream>>>(h->d_tgtP, (int)h->n, P2_STAGE, h->d_tbox);
-        h->launches += 1;
+        sub_bbox_kernel<<<(unsigned)((nsub1 + 7) / 8), THREADS, 0, h->stream>>>(h->d_srcP, (int)h->m, nsub1, h->d_ssub);
+        sub_bbox_kernel<<<(unsigned)((nsub2 + 7) / 8), THREADS, 0, h->stream>>>(h->d_tgtP, (int)h->n, nsub2, h->d_tsub);
+        h->launches += 3;
     }
-    if (cull) pass1_kernel<true><<<h->g1, THREADS, PASS1_SMEM, h->stream>>>(h->d_tgtP, (int)h->n, h->d_srcJ, h->d_work1, h->d_part1, h->d_sbox, nst1);
-    else pass1_kernel<false><<<h->g1, THREADS, PASS1_SMEM, h->stream>>>(h->d_tgtP, (int)h->n, h->d_srcJ, h->d_work1, h->d_part1, h->d_sbox, nst1);
+    if (cull) pass1_kernel<true><<<h->g1, THREADS, PASS1_SMEM, h->stream>>>(h->d_tgtP, (int)h->n, h->d_srcJ, h->d_work1, h->d_part1, h->d_sbox, nst1, h->d_ssub);
+    else pass1_kernel<false><<<h->g1, THREADS, PASS1_SMEM, h->stream>>>(h->d_tgtP, (int)h->n, h->d_srcJ, h->d_work1, h->d_part1, h->d_sbox, nst1, nullptr);
     mark(h, 2);
     finalize1_kernel<<<blocks_for(h->npad), THREADS, 0, h->stream>>>(h->d_state, d_sigma2, d_w, h->d_part1, h->d_slots1, (int)h->n,
                                                                      h->d_tgtP, h->d_tgtQ, h->npad, h->d_pt1, h->d_mom_tgt);
     mark(h, 3);
     if (cull) {
         stage_omax_kernel<<<(unsigned)(h->npad / P2_STAGE), THREADS, 0, h->stream>>>(h->d_tgtQ, h->d_omax);
-        h->launches += 1;
+        sub_omax_kernel<<<(unsigned)((nsub2 + 7) / 8), THREADS, 0, h->stream>>>(h->d_tgtQ, nsub2, h->d_omax_sub);
+        h->launches += 2;
     }
-    if (cull) pass2_kernel<true><<<h->g2, THREADS, PASS2_SMEM, h->stream>>>(h->d_srcP, (int)h->m, h->d_tgtQ, h->d_work2, h->d_part2, h->d_tbox, h->d_omax);
-    else pass2_kernel<false><<<h->g2, THREADS, PASS2_SMEM, h->stream>>>(h->d_srcP, (int)h->m, h->d_tgtQ, h->d_work2, h->d_part2, nullptr, nullptr);
+    if (cull) pass2_kernel<true><<<h->g2, THREADS, PASS2_SMEM, h->stream>>>(h->d_srcP, (int)h->m, h->d_tgtQ, h->d_work2, h->d_part2, h->d_tbox, h->d_omax, h->d_tsub, h->d_omax_sub);
+    else pass2_kernel<false><<<h->g2, THREADS, PASS2_SMEM, h->stream>>>(h->d_srcP, (int)h->m, h->d_tgtQ, h->d_work2, h->d_part2, nullptr, nullptr, nullptr, nullptr);
     mark(h, 4);
     finalize2_kernel<<<blocks_for(h->m), THREADS, 0, h->stream>>>(h->d_state, d_sigma2, h->d_part2, h->d_slots2, (int)h->m, h->d_yc,
                                                                   d_ts, h->d_p1, h->d_pxc, h->d_mom_src);
@@ -414,7 +421,7 @@ int read_params(cpd_ctx* h, cpd_params* out) {
     out->scale = h->h_pin[12];
     out->sigma2 = h->h_pin[13];
     // a point reaches ~13.3 sigma (2^-127); culling can only pay once that is well inside the cloud
-    h->cull_active = h->extent > 0.0 && 13.3 * sqrt(out->sigma2) < 0.5 * h->extent;
+    h->cull_active = h->extent > 0.0 && 13.3 * sqrt(out->sigma2) < 0.25 * h->extent;
     out->q = h->h_pin[14];
     out->n_p = h->h_pin[15];
     return CPD_OK;
@@ -486,7 +493,7 @@ extern "C" void cpd_destroy(cpd_ctx* h) {
     if (!h) return;
     cudaSetDevice(h->device);
     cudaStreamSynchronize(h->stream);
-    void* wl[] = {h->d_work1, h->d_work2, h->d_slots1, h->d_slots2, h->d_sbox, h->d_tbox, h->d_omax};
+    void* wl[] = {h->d_work1, h->d_work2, h->d_slots1, h->d_slots2, h->d_sbox, h->d_tbox, h->d_omax, h->d_ssub, h->d_tsub, h->d_omax_sub};
     for (void* p : wl) if (p) cudaFree(p);
     void* srt[] = {h->d_perm_src, h->d_perm_tgt, h->d_idx_tmp, h->d_codes, h->d_codes_out, h->d_sort_tmp, h->d_outN, h->d_outM};
     for (void* p : srt) if (p) cudaFree(p);
@@ -614,7 +621,7 @@ extern "C" int cpd_set_state(cpd_ctx* h, int tf_kind, int update_scale, double w
     s.tf_kind = tf_kind;
     s.update_scale = update_scale ? 1 : 0;
     s.dim = d;
-    h->cull_active = h->extent > 0.0 && 13.3 * sqrt(init->sigma2) < 0.5 * h->extent;
+    h->cull_active = h->extent > 0.0 && 13.3 * sqrt(init->sigma2) < 0.25 * h->extent;
     h->have_state = true;
     return upload_state(h);
 }
@@ -673,7 +680,7 @@ extern "C" int cpd_estep(cpd_ctx* h, const double* t_source, double sigma2, doub
     TRY(upload_cloud(h, t_source, h->m, h->d_raw));
     gather3_kernel<<<blocks_for(h->m), THREADS, 0, h->stream>>>(h->d_raw, h->d_perm_src, h->m, 0.0, 0.0, 0.0, h->d_ts);
     h->launches += 1;
-    h->cull_active = h->extent > 0.0 && 13.3 * sqrt(sigma2) < 0.5 * h->extent;
+    h->cull_active = h->extent > 0.0 && 13.3 * sqrt(sigma2) < 0.25 * h->extent;
     h->h_pin[32] = sigma2;
     h->h_pin[33] = w;
     CU(cudaMemcpyAsync(&h->d_state->es_sigma2, h->h_pin + 32, 2 * sizeof(double), cudaMemcpyHostToDevice, h->stream));

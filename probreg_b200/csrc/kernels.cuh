@@ -323,6 +323,40 @@ stage_omax_kernel(const float4* __restrict__ tgtQ, float* __restrict__ omax) {
         omax[b] = -m;                                   // -inf when the whole stage is dead
     }
 }
+// the same two quantities per 64-record sub-chunk (one warp each): the second, finer level of the culling test
+__global__ void __launch_bounds__(THREADS)
+sub_bbox_kernel(const float4* __restrict__ pts, int n, int nsub, float4* __restrict__ box) {
+    const int b = blockIdx.x * (THREADS / 32) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (b >= nsub) return;
+    float lo[3] = {3.0e38f, 3.0e38f, 3.0e38f}, hi[3] = {-3.0e38f, -3.0e38f, -3.0e38f};
+    for (int i = b * SUB + lane; i < min(n, (b + 1) * SUB); i += 32) {
+        const float4 p = pts[i];
+        lo[0] = fminf(lo[0], p.x); lo[1] = fminf(lo[1], p.y); lo[2] = fminf(lo[2], p.z);
+        hi[0] = fmaxf(hi[0], p.x); hi[1] = fmaxf(hi[1], p.y); hi[2] = fmaxf(hi[2], p.z);
+    }
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            lo[a] = fminf(lo[a], __shfl_xor_sync(0xffffffffu, lo[a], o));
+            hi[a] = fmaxf(hi[a], __shfl_xor_sync(0xffffffffu, hi[a], o));
+        }
+    }
+    if (lane == 0) {
+        box[2 * b] = make_float4(lo[0], lo[1], lo[2], 0.f);
+        box[2 * b + 1] = make_float4(hi[0], hi[1], hi[2], 0.f);
+    }
+}
+__global__ void __launch_bounds__(THREADS)
+sub_omax_kernel(const float4* __restrict__ tgtQ, int nsub, float* __restrict__ omax) {
+    const int b = blockIdx.x * (THREADS / 32) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (b >= nsub) return;
+    float m = 3.0e38f;
+    for (int i = lane; i < SUB; i += 32) m = fminf(m, tgtQ[3 * ((size_t)b * SUB + i) + 1].z);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m = fminf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if (lane == 0) omax[b] = -m;
+}
 // bounding box of this warp's packed i-points -> wbox[0..6) (shared, one row per warp)
 template <int NP>
 __device__ __forceinline__ void warp_bbox(const u64 (&ax)[NP], const u64 (&ay)[NP], const u64 (&az)[NP], float* __restrict__ wbox) {
@@ -409,7 +443,7 @@ template <bool CULL>
 __global__ void __launch_bounds__(THREADS, CPD_MINB1)
 pass1_kernel(const float4* __restrict__ ipts, int ni, const float4* __restrict__ jrec, const int4* __restrict__ work,
              P1Part* __restrict__ part, const float4* __restrict__ sbox /* bounding boxes of the source stages */,
-             int nstages_total) {
+             int nstages_total, const float4* __restrict__ ssub /* ... and of their 64-record sub-chunks (CULL only) */) {
     __shared__ float wbox[THREADS / 32][8];
     extern __shared__ __align__(128) unsigned char smraw[];
     uint64_t* full = reinterpret_cast<uint64_t*>(smraw + NSTAGE * P1_STAGE_BYTES);
@@ -504,6 +538,10 @@ pass1_kernel(const float4* __restrict__ ipts, int ni, const float4* __restrict__
         }
 #pragma unroll 1
         for (int sc = 0; sc < (skip ? 0 : P1_STAGE / SUB); ++sc) {
+            if (CULL) {
+                const int sb = (st0 + it) * (P1_STAGE / SUB) + sc;
+                if (box_gap2(mybox, ssub[2 * sb], ssub[2 * sb + 1]) - omax_w >= CULL_GAP) continue;
+            }
             const ulonglong2* q = sp + sc * (2 * SUB);
             u64 Sc[NPAIR1], Uc[NPAIR1];          // Sc = sum e,  Uc = sum e * t'  with t' = u - o, e = 2^-t'
 #pragma unroll
@@ -669,7 +707,7 @@ template <bool CULL>
 __global__ void __launch_bounds__(THREADS, CPD_MINB2)
 pass2_kernel(const float4* __restrict__ ipts, int ni, const float4* __restrict__ jrec, const int4* __restrict__ work,
              double* __restrict__ part /* [slot][ni][4] */, const float4* __restrict__ tbox /* per target stage bbox or null */,
-             const float* __restrict__ omax_stage) {
+             const float* __restrict__ omax_stage, const float4* __restrict__ tsub, const float* __restrict__ omax_sub) {
     __shared__ float wbox[THREADS / 32][8];
     extern __shared__ __align__(128) unsigned char smraw[];
     uint64_t* full = reinterpret_cast<uint64_t*>(smraw + NSTAGE * P2_STAGE_BYTES);
@@ -714,6 +752,10 @@ pass2_kernel(const float4* __restrict__ ipts, int ni, const float4* __restrict__
         }
 #pragma unroll 1
         for (int sc = 0; sc < (skip ? 0 : P2_STAGE / SUB); ++sc) {
+            if (CULL) {
+                const int sb = (st0 + it) * (P2_STAGE / SUB) + sc;
+                if (box_gap2(mybox, tsub[2 * sb], tsub[2 * sb + 1]) - omax_sub[sb] >= CULL_GAP) continue;
+            }
             const ulonglong2* q = sp + sc * (3 * SUB);
             u64 s1[NPAIR2], sx[NPAIR2], sy[NPAIR2], sz[NPAIR2];
 #pragma unroll
