@@ -72,6 +72,16 @@ EXPORTED = tuple(_PROTOS)
 _lib = None
 
 
+def _load(path):
+    """dlopen `path` and attach the prototypes of include/cpd_b200.h."""
+    handle = ctypes.CDLL(path)
+    for name, (res, args) in _PROTOS.items():
+        fn = getattr(handle, name)
+        fn.restype = res
+        fn.argtypes = args
+    return handle
+
+
 def lib():
     """The loaded shared library (raises if it has not been built)."""
     global _lib
@@ -79,12 +89,7 @@ def lib():
         if not os.path.exists(LIB_PATH):
             raise CpdError("%s not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
                            "(or `make -C probreg_b200/csrc`); probreg_b200 has no CPU path" % LIB_PATH)
-        handle = ctypes.CDLL(LIB_PATH)
-        for name, (res, args) in _PROTOS.items():
-            fn = getattr(handle, name)
-            fn.restype = res
-            fn.argtypes = args
-        _lib = handle
+        _lib = _load(LIB_PATH)
     return _lib
 
 
@@ -115,13 +120,14 @@ class Handle(object):
         self._h = ctypes.c_void_p()
         self.dim = dim
         self.device = device
-        check(lib().cpd_create(ctypes.byref(self._h), device, dim, ctypes.c_void_p(stream) if stream else None))
+        self._lib = lib()          # a handle is destroyed by the library that created it
+        check(self._lib.cpd_create(ctypes.byref(self._h), device, dim, ctypes.c_void_p(stream) if stream else None))
         self.m = 0
         self.n = 0
 
     def close(self):
         if getattr(self, "_h", None) is not None and self._h.value:
-            lib().cpd_destroy(self._h)
+            self._lib.cpd_destroy(self._h)
             self._h = ctypes.c_void_p()
 
     def __del__(self):

@@ -5,6 +5,9 @@
 #include "kernels.cuh"
 
 #include <cub/device/device_radix_sort.cuh>
+#ifdef CPD_HOST_EMU
+#include "emu_solver.h"
+#endif
 
 #include <dlfcn.h>
 #include <math.h>
@@ -93,6 +96,13 @@ struct SolverApi {
 SolverApi g_sol;
 int load_cusolver() {
     if (g_sol.lib) return CPD_OK;
+#ifdef CPD_HOST_EMU   // CPU test build (tests/emu): documented-behaviour stand-ins instead of the real library
+    g_sol.Create = emu::solverCreate; g_sol.Destroy = emu::solverDestroy; g_sol.SetStream = emu::solverSetStream;
+    g_sol.CreateParams = emu::solverCreateParams; g_sol.DestroyParams = emu::solverDestroyParams;
+    g_sol.XgetrfBuf = emu::solverXgetrfBuf; g_sol.Xgetrf = emu::solverXgetrf; g_sol.Xgetrs = emu::solverXgetrs;
+    g_sol.lib = (void*)&g_sol;
+    return CPD_OK;
+#endif
     const char* names[] = {"libcusolver.so.11", "/usr/local/cuda/lib64/libcusolver.so.11", "libcusolver.so"};
     void* lib = nullptr;
     for (const char* nm : names) { lib = dlopen(nm, RTLD_NOW | RTLD_GLOBAL); if (lib) break; }

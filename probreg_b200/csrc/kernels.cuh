@@ -69,6 +69,13 @@ constexpr int SUB = CPD_SUB;           // j-points between offset checks / FP64 
 constexpr int GRP = CPD_GRP;           // j-points summed from zero before joining the sub-chunk sum (0: off)
 constexpr int PASS1_SMEM = NSTAGE * P1_STAGE_BYTES + 64, PASS2_SMEM = NSTAGE * P2_STAGE_BYTES + 64;
 
+// dynamic shared memory of the running CTA (the CPU test build of tests/emu substitutes its own buffer)
+#ifdef CPD_HOST_EMU
+#define CPD_DYN_SMEM(name) unsigned char* const name = emu::g_dyn_smem
+#else
+#define CPD_DYN_SMEM(name) extern __shared__ __align__(128) unsigned char name[]
+#endif
+
 constexpr float O_INIT = 1048576.0f;   // 2^20: "no source seen yet" offset; u above it is dead anyway
 constexpr float TWO100 = 1.2676506002282294e30f;
 constexpr float FAR_COORD = 1.0e18f;   // padding sources: u = 3e36, 2^(o-u) == 0
@@ -134,6 +141,11 @@ struct P2PInfo {
 // ---------------------------------------------------------------------------------------------
 // small PTX helpers
 // ---------------------------------------------------------------------------------------------
+#ifdef CPD_HOST_EMU
+}  // namespace cpd
+#include "emu_device.h"   // tests/emu: host stand-ins for the inline-PTX helpers below (CPU test build only)
+namespace cpd {
+#else
 __device__ __forceinline__ float ex2(float x) {
     float y;
     asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
@@ -149,6 +161,11 @@ __device__ __forceinline__ u64 fmul2(u64 a, u64 b) { u64 d; asm("mul.rn.f32x2 %0
 __device__ __forceinline__ u64 ffma2(u64 a, u64 b, u64 c) { u64 d; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c)); return d; }
 __device__ __forceinline__ u64 pack2(float lo, float hi) { u64 r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi)); return r; }
 __device__ __forceinline__ float2 unpack2(u64 v) { float2 r; asm("mov.b64 {%0, %1}, %2;" : "=f"(r.x), "=f"(r.y) : "l"(v)); return r; }
+__device__ __forceinline__ unsigned long long globaltimer_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
@@ -177,6 +194,7 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
         "r"(parity)
         : "memory");
 }
+#endif  // CPD_HOST_EMU
 __device__ __forceinline__ double warp_sum(double v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
@@ -445,7 +463,7 @@ pass1_kernel(const float4* __restrict__ ipts, int ni, const float4* __restrict__
              P1Part* __restrict__ part, const float4* __restrict__ sbox /* bounding boxes of the source stages */,
              int nstages_total, const float4* __restrict__ ssub /* ... and of their 64-record sub-chunks (CULL only) */) {
     __shared__ float wbox[THREADS / 32][8];
-    extern __shared__ __align__(128) unsigned char smraw[];
+    CPD_DYN_SMEM(smraw);
     uint64_t* full = reinterpret_cast<uint64_t*>(smraw + NSTAGE * P1_STAGE_BYTES);
     const int tid = threadIdx.x;
     const int4 wk = work[blockIdx.x];               // {i-tile, first stage, end stage, partial slot}: see build_work()
@@ -709,7 +727,7 @@ pass2_kernel(const float4* __restrict__ ipts, int ni, const float4* __restrict__
              double* __restrict__ part /* [slot][ni][4] */, const float4* __restrict__ tbox /* per target stage bbox or null */,
              const float* __restrict__ omax_stage, const float4* __restrict__ tsub, const float* __restrict__ omax_sub) {
     __shared__ float wbox[THREADS / 32][8];
-    extern __shared__ __align__(128) unsigned char smraw[];
+    CPD_DYN_SMEM(smraw);
     uint64_t* full = reinterpret_cast<uint64_t*>(smraw + NSTAGE * P2_STAGE_BYTES);
     const int tid = threadIdx.x;
     const int4 wk = work[blockIdx.x];
@@ -1207,6 +1225,7 @@ __global__ void mstep_api_kernel(DevState* st, const double* __restrict__ mom) {
 //   4. acquire-spin on my own mailbox's flags until every rank's sequence number has arrived (bounded)
 //   5. sum the slots in rank order (identical arithmetic on every rank), run the FP64 M-step
 // ---------------------------------------------------------------------------------------------
+#ifndef CPD_HOST_EMU
 __device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned long long v) {
     asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
@@ -1220,6 +1239,7 @@ __device__ __forceinline__ double ld_relaxed_sys(const double* p) {
     asm volatile("ld.relaxed.sys.global.f64 %0, [%1];" : "=d"(v) : "l"(p) : "memory");
     return v;
 }
+#endif
 __global__ void __launch_bounds__(256)
 moments_p2p_kernel(DevState* st, const double* __restrict__ part_a, int nb_a, int ka, const double* __restrict__ part_b,
                    int nb_b, int kb, double* __restrict__ mom, P2PInfo* info) {
@@ -1673,9 +1693,9 @@ probe_mix_kernel(float* out, int iters, float seed) {
 }
 __global__ void probe_clock_kernel(long long* out) {
     const long long c0 = clock64();
-    unsigned long long t0, t1;
-    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
-    do { asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1)); } while (t1 - t0 < 2000000ull);
+    const unsigned long long t0 = globaltimer_ns();
+    unsigned long long t1;
+    do { t1 = globaltimer_ns(); } while (t1 - t0 < 2000000ull);
     out[0] = clock64() - c0;
     out[1] = (long long)(t1 - t0);
 }
