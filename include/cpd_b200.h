@@ -107,6 +107,20 @@ int cpd_nonrigid_begin(cpd_ctx* h, double beta, double lmd, double sigma2, doubl
 int cpd_nonrigid_step(cpd_ctx* h, double* sigma2_out);
 int cpd_nonrigid_get(cpd_ctx* h, double* w_out, double* moved_out);
 
+/* NonRigidCPD with G replaced by a rank-K factorisation G ~= Q Bc Q^T (csrc/lowrank.cuh; BASELINE configuration 5, no
+ * reference counterpart: the reference only has the dense solve of cpd.py:296).  Same life cycle as the dense path:
+ * cpd_nonrigid_lowrank_begin instead of cpd_nonrigid_begin, then cpd_nonrigid_step / cpd_nonrigid_get.  Q comes from a
+ * randomised range finder (seeded, `power_iters` subspace iterations, 2 is plenty) on products G X formed on the fly, so
+ * nothing of size M x M is stored; each M-step is a K x K LU.  rank is clamped to M; rank <= 1024.
+ * cpd_nonrigid_lowrank_get: the rank in use, Q (m x rank row-major, caller's point order) and Bc (rank x rank); any may be NULL. */
+int cpd_nonrigid_lowrank_begin(cpd_ctx* h, double beta, double lmd, double sigma2, double w, int rank, int power_iters, uint64_t seed);
+int cpd_nonrigid_lowrank_get(cpd_ctx* h, int* rank_out, double* q_out, double* bcore_out);
+
+/* Correspondence priors of ConstrainedNonRigidCPD (cpd.py:364-374: p1_tilde = row sums of the indicator matrix, px_tilde =
+ * its product with the target; cpd.py:390-396: both enter the system and the right-hand side scaled by sigma2 / alpha).
+ * Call after cpd_nonrigid_begin / cpd_nonrigid_lowrank_begin; p1_tilde: m, px_tilde: m x D; both NULL switches priors off. */
+int cpd_nonrigid_set_prior(cpd_ctx* h, double alpha, const double* p1_tilde, const double* px_tilde);
+
 /* _math.rbf_kernel (cc/math_utils_py.cc:15 -> cc/math_utils.cc:17-19):
  * out[i*ny + j] = exp(-|x_i - y_j|^2 / (2*beta)) as float32, x: nx x D, y: ny x D.       */
 int cpd_rbf_kernel(int device, const double* x, int64_t nx, const double* y, int64_t ny, int dim,

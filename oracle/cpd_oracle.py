@@ -226,6 +226,45 @@ def mstep_nonrigid(source, target, es, sigma2_p, g, lmd, alpha=None, p1_tilde=No
     return Mstep((wmat,), float(sigma2), float(sigma2))
 
 
+def lowrank_factors(source, beta, rank, power_iters=2, seed=0):
+    """Rank-``rank`` factorisation G ~= Q Bc Q^T of the RBF Gram matrix by the randomised range finder the product uses
+    (probreg_b200/csrc/lowrank.cuh): Q = orth((G)^(power_iters+1) Omega), Bc = Q^T G Q.  No reference counterpart (the
+    reference only has the dense G); test infrastructure for the low-rank path.  numpy QR instead of Gram-Schmidt and
+    another random Omega, so only quantities that do not depend on the basis (Q Bc Q^T, the moved points, sigma2) are
+    comparable with the product."""
+    g = rbf_kernel_f32(source, source, beta).astype(np.float64)
+    m = source.shape[0]
+    rank = min(rank, m)
+    x = np.random.default_rng(seed).uniform(-1.0, 1.0, (m, rank))
+    for _ in range(power_iters + 1):
+        x, _r = np.linalg.qr(g.dot(x))
+    gq = g.dot(x)
+    bc = x.T.dot(gq)
+    return x, 0.5 * (bc + bc.T)
+
+
+def mstep_nonrigid_lowrank(source, target, es, sigma2_p, q_mat, bcore, lmd, alpha=None, p1_tilde=None, px_tilde=None):
+    """The M-step of cpd.py:284-303 (constrained: :376-404) with G = Q Bc Q^T, solved in the K x K form of lowrank.cuh:
+    (c I + Bc S) Z = Bc R,  S = Q^T diag(wgt) Q,  R = Q^T F,  W = (F - diag(wgt) Q Z) / c,  T = Y + Q Z."""
+    pt1, p1, px, n_p = es
+    dim = source.shape[1]
+    wgt, f = p1, px - (source.T * p1).T
+    if alpha is not None:
+        kk = sigma2_p / alpha
+        wgt = p1 + kk * p1_tilde
+        f = f + kk * (px_tilde - (source.T * p1_tilde).T)
+    c = lmd * sigma2_p
+    s_mat = (q_mat.T * wgt).dot(q_mat)
+    z = np.linalg.solve(c * np.identity(bcore.shape[0]) + bcore.dot(s_mat), bcore.dot(q_mat.T.dot(f)))
+    wmat = (f - (q_mat.T * wgt).T.dot(z)) / c
+    t = source + q_mat.dot(z)
+    tr_xp1x = np.trace((target.T * pt1).dot(target))
+    tr_pxt = np.trace(px.T.dot(t))
+    tr_tpt = np.trace((t.T * p1).dot(t))
+    sigma2 = (tr_xp1x - 2.0 * tr_pxt + tr_tpt) / (n_p * dim)
+    return Mstep((wmat, t), float(sigma2), float(sigma2))
+
+
 # ---------------------------------------------------------------------------
 # transforms (probreg/transformation.py)
 # ---------------------------------------------------------------------------
@@ -246,12 +285,14 @@ def apply_nonrigid(points, g, wmat):
 # ---------------------------------------------------------------------------
 def registration(source, target, tf_type="rigid", w=0.0, maxiter=50, tol=1e-3,
                  update_scale=True, beta=2.0, lmd=2.0, sigma2_0=None, init=None,
-                 block=None, trace=None, alpha=None, idx_source=None, idx_target=None):
+                 block=None, trace=None, alpha=None, idx_source=None, idx_target=None, g=None):
     """Runs the reference's loop.  Returns (Mstep, iterations_run).
 
     ``sigma2_0`` overrides the float32-emulated initial variance; ``init`` overrides
     the identity start ((rot, t, scale) or (b, t)); ``trace``, if a list, receives
-    (sigma2, q) after every iteration.
+    (sigma2, q) after every iteration; ``g`` replaces the RBF Gram matrix of the non-rigid
+    families (used to check the low-rank product path against the reference's dense
+    arithmetic on the SAME approximate G = Q Bc Q^T).
     """
     source = np.asarray(source, dtype=np.float64)
     target = np.asarray(target, dtype=np.float64)
@@ -259,13 +300,13 @@ def registration(source, target, tf_type="rigid", w=0.0, maxiter=50, tol=1e-3,
     n = target.shape[0]
     sigma2 = sigma2_init(source, target) if sigma2_0 is None else sigma2_0
     q = 1.0 + n * dim * 0.5 * np.log(sigma2)             # cpd.py:148
-    g = None
     if tf_type == "rigid":
         params = (np.identity(dim), np.zeros(dim), 1.0) if init is None else init
     elif tf_type == "affine":
         params = (np.identity(dim), np.zeros(dim)) if init is None else init
     elif tf_type in ("nonrigid", "nonrigid_constrained"):
-        g = rbf_kernel_f32(source, source, beta)          # transformation.py:91-99
+        if g is None:
+            g = rbf_kernel_f32(source, source, beta)      # transformation.py:91-99
         params = (np.zeros_like(source),)                 # cpd.py:281
         prior = {}
         if tf_type == "nonrigid_constrained":

@@ -43,6 +43,10 @@ _PROTOS = {
     "cpd_nonrigid_begin": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_double, ctypes.c_double, ctypes.c_double, ctypes.c_double]),
     "cpd_nonrigid_step": (ctypes.c_int, [ctypes.c_void_p, _c_dp]),
     "cpd_nonrigid_get": (ctypes.c_int, [ctypes.c_void_p, _c_dp, _c_dp]),
+    "cpd_nonrigid_lowrank_begin": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_double, ctypes.c_double, ctypes.c_double, ctypes.c_double,
+                                                  ctypes.c_int, ctypes.c_int, ctypes.c_uint64]),
+    "cpd_nonrigid_lowrank_get": (ctypes.c_int, [ctypes.c_void_p, ctypes.POINTER(ctypes.c_int), _c_dp, _c_dp]),
+    "cpd_nonrigid_set_prior": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_double, _c_dp, _c_dp]),
     "cpd_rbf_kernel": (ctypes.c_int, [ctypes.c_int, _c_dp, ctypes.c_int64, _c_dp, ctypes.c_int64, ctypes.c_int,
                                       ctypes.c_double, _c_fp]),
     "cpd_gauss_transform": (ctypes.c_int, [ctypes.c_int, _c_dp, ctypes.c_int64, _c_dp, ctypes.c_int64, ctypes.c_int, ctypes.c_double,
@@ -221,6 +225,33 @@ class Handle(object):
     # -- non-rigid (dense G on the device)
     def nonrigid_begin(self, beta, lmd, sigma2, w):
         check(lib().cpd_nonrigid_begin(self._h, float(beta), float(lmd), float(sigma2), float(w)))
+
+    def nonrigid_lowrank_begin(self, beta, lmd, sigma2, w, rank, power_iters=2, seed=0):
+        check(lib().cpd_nonrigid_lowrank_begin(self._h, float(beta), float(lmd), float(sigma2), float(w), int(rank), int(power_iters),
+                                               int(seed)))
+
+    def nonrigid_lowrank_factors(self):
+        """(Q (m x rank), Bc (rank x rank)) with G ~= Q Bc Q^T, Q in the caller's point order."""
+        k = ctypes.c_int()
+        check(lib().cpd_nonrigid_lowrank_get(self._h, ctypes.byref(k), None, None))
+        q, b = np.empty((self.m, k.value)), np.empty((k.value, k.value))
+        check(lib().cpd_nonrigid_lowrank_get(self._h, None, dptr(q), dptr(b)))
+        return q, b
+
+    def nonrigid_set_prior(self, alpha, p1_tilde, px_tilde):
+        if p1_tilde is None:
+            check(lib().cpd_nonrigid_set_prior(self._h, 1.0, None, None))
+            return
+        p1t = np.ascontiguousarray(p1_tilde, dtype=np.float64)
+        pxt = as_cloud(px_tilde, self.dim)
+        if p1t.shape != (self.m,) or pxt.shape[0] != self.m:
+            raise ValueError("prior shapes do not match the handle's source")
+        check(lib().cpd_nonrigid_set_prior(self._h, float(alpha), dptr(p1t), dptr(pxt)))
+
+    def nonrigid_moved(self):
+        t = np.empty((self.m, self.dim))
+        check(lib().cpd_nonrigid_get(self._h, None, dptr(t)))
+        return t
 
     def nonrigid_step(self):
         out = ctypes.c_double()

@@ -256,13 +256,22 @@ class NonRigidCPD(CoherentPointDrift):
 
     ``source``: (M, D) array or None; ``beta``: RBF width of G (denominator 2*beta, as in the reference);
     ``lmd``: weight of the smoothness term; ``use_cuda``: accepted, ignored.
+
+    Extension (no reference counterpart; BASELINE configuration 5): ``low_rank=K`` replaces G by a rank-K
+    factorisation Q Bc Q^T found on the device by a seeded randomised range finder (``low_rank_iters`` subspace
+    iterations); each M-step is then a K x K solve and nothing of size M x M exists anywhere.  The result carries a
+    ``LowRankNonRigidTransformation``.
     """
 
-    def __init__(self, source=None, beta=2.0, lmd=2.0, use_cuda=False, device=None, comm=None):
+    def __init__(self, source=None, beta=2.0, lmd=2.0, use_cuda=False, device=None, comm=None, low_rank=None,
+                 low_rank_iters=2, low_rank_seed=0):
         super(NonRigidCPD, self).__init__(source, use_cuda, device, comm)
         self._tf_type = tf.NonRigidTransformation
         self._beta = beta
         self._lmd = lmd
+        self._low_rank = low_rank
+        self._low_rank_iters = low_rank_iters
+        self._low_rank_seed = low_rank_seed
         self._tf_obj = None
         if not self._source is None:
             self._tf_obj = self._tf_type(None, self._source, self._beta, self.xp)
@@ -285,17 +294,33 @@ class NonRigidCPD(CoherentPointDrift):
     def _maximization_step(source, target, estep_res, sigma2_p, tf_obj, lmd, xp=np):
         return _nonrigid_mstep(source, target, estep_res, sigma2_p, tf_obj, lmd)
 
+    def _device_prior(self):
+        """(alpha, p1_tilde, px_tilde) for the device loop, or None (ConstrainedNonRigidCPD overrides)."""
+        return None
+
+    def _has_device_loop(self):
+        # a subclass that brings its own M-step is driven through expectation_step / maximization_step instead
+        return type(self).maximization_step in (NonRigidCPD.maximization_step, ConstrainedNonRigidCPD.maximization_step)
+
     def registration(self, target, w=0.0, maxiter=50, tol=0.001):
-        """The loop of probreg/cpd.py:106-120 with G, W, the M x M system and its LU resident on the GPU
-        (cpd_nonrigid_begin / cpd_nonrigid_step); per iteration only sigma2 (== q, cpd.py:303) comes back,
-        plus W when a callback wants the transformation."""
+        """The loop of probreg/cpd.py:106-120 with G (or its low-rank factors), W, the linear system and its LU
+        resident on the GPU (cpd_nonrigid_begin / cpd_nonrigid_lowrank_begin, cpd_nonrigid_step); per iteration only
+        sigma2 (== q, cpd.py:303) comes back, plus W when a callback wants the transformation."""
         assert not self._tf_type is None, "transformation type is None."
         target = _points(target)
         res = self._initialize(target)
-        if type(self).maximization_step is not NonRigidCPD.maximization_step:
-            return self._host_loop(target, res, w, maxiter, tol)       # subclasses with their own M-step
+        if not self._has_device_loop():
+            return self._host_loop(target, res, w, maxiter, tol)
         h = self._em
-        h.nonrigid_begin(self._beta, self._lmd, res.sigma2, w)
+        if self._low_rank:
+            h.nonrigid_lowrank_begin(self._beta, self._lmd, res.sigma2, w, self._low_rank, self._low_rank_iters, self._low_rank_seed)
+            q_mat, bcore = h.nonrigid_lowrank_factors()
+            self._tf_obj = tf.LowRankNonRigidTransformation(self._tf_obj.w, self._source, self._beta, q_mat, bcore)
+        else:
+            h.nonrigid_begin(self._beta, self._lmd, res.sigma2, w)
+        prior = self._device_prior()
+        if prior is not None:
+            h.nonrigid_set_prior(*prior)
         q = res.q
         want_tf = bool(self._callbacks)
         for i in range(maxiter):
@@ -309,8 +334,14 @@ class NonRigidCPD(CoherentPointDrift):
             if abs(res.q - q) < tol:
                 break
             q = res.q
-        self._tf_obj.w = h.nonrigid_w()
+        if maxiter > 0:
+            self._tf_obj.w = h.nonrigid_w()
         return res
+
+    def moved_source(self):
+        """The source after the last ``registration``, Y + G W, straight from the device (no M x M product)."""
+        assert self._em is not None, "registration has not been run."
+        return self._em.nonrigid_moved()
 
     def _host_loop(self, target, res, w, maxiter, tol):
         q = res.q
@@ -337,8 +368,8 @@ def _nonrigid_mstep(source, target, estep_res, sigma2_p, tf_obj, lmd, prior=None
     """Non-rigid M-step (probreg/cpd.py:284-303; with ``prior`` the constrained one, cpd.py:376-404).
 
     Solves (diag(p1 + k p1~) G + lmd sigma2 I) W = px + k px~ - diag(p1 + k p1~) Y with k = sigma2/alpha
-    (k = 0 without priors), then T = Y + G W and sigma2 from the three traces.  Host numpy for now
-    (the dense M x M solve is the next row to move onto the device).
+    (k = 0 without priors), then T = Y + G W and sigma2 from the three traces.  Host numpy: this is the
+    stand-alone ``maximization_step`` on a caller-supplied EstepResult; ``registration`` does not come here.
     """
     pt1, p1, px, n_p = estep_res
     m, dim = source.shape
@@ -371,8 +402,9 @@ class ConstrainedNonRigidCPD(NonRigidCPD):
     """
 
     def __init__(self, source=None, beta=2.0, lmd=2.0, alpha=1e-8, use_cuda=False, idx_source=None, idx_target=None,
-                 device=None, comm=None):
-        super(ConstrainedNonRigidCPD, self).__init__(source, beta, lmd, use_cuda, device, comm)
+                 device=None, comm=None, low_rank=None, low_rank_iters=2, low_rank_seed=0):
+        super(ConstrainedNonRigidCPD, self).__init__(source, beta, lmd, use_cuda, device, comm, low_rank, low_rank_iters,
+                                                     low_rank_seed)
         self.alpha = alpha
         self.idx_source, self.idx_target = idx_source, idx_target
         self.p1_tilde = None
@@ -392,6 +424,9 @@ class ConstrainedNonRigidCPD(NonRigidCPD):
     def maximization_step(self, target, estep_res, sigma2_p=None):
         return _nonrigid_mstep(self._source, target, estep_res, sigma2_p, self._tf_obj, self._lmd,
                                prior=(self.alpha, self.p1_tilde, self.px_tilde))
+
+    def _device_prior(self):
+        return (self.alpha, self.p1_tilde, self.px_tilde)
 
 
 def registration_cpd(source, target, tf_type_name="rigid", w=0.0, maxiter=50, tol=0.001, callbacks=(),

@@ -1436,8 +1436,8 @@ centre_px_kernel(const DevState* __restrict__ st, const double* __restrict__ p1,
 __global__ void __launch_bounds__(THREADS)
 rbf_kernel_kernel(const float* __restrict__ x, long long nx, const float* __restrict__ y, long long ny, int dim, float inv2beta,
                   float* __restrict__ out) {
-    const long long j = (long long)blockIdx.x * THREADS + threadIdx.x;
-    const long long i = blockIdx.y;
+    const long long j = (long long)blockIdx.y * THREADS + threadIdx.x;      // rows on grid.x: grid.y is limited to 65535
+    const long long i = blockIdx.x;
     if (j < ny) {
         float d2 = 0.f;
         for (int a = 0; a < dim; ++a) { const float d = x[i * dim + a] - y[j * dim + a]; d2 += d * d; }
@@ -1454,8 +1454,8 @@ rbf_kernel_kernel(const float* __restrict__ x, long long nx, const float* __rest
 __global__ void __launch_bounds__(THREADS)
 nr_gram_kernel(const double* __restrict__ yc, double c0, double c1, double c2, long long m, int dim, float inv2beta,
                float* __restrict__ G) {
-    const long long j = (long long)blockIdx.x * THREADS + threadIdx.x;
-    const long long i = blockIdx.y;
+    const long long j = (long long)blockIdx.y * THREADS + threadIdx.x;      // rows on grid.x: grid.y is limited to 65535
+    const long long i = blockIdx.x;
     if (j < m) {
         const double cc[3] = {c0, c1, c2};
         float d2 = 0.f;
@@ -1488,21 +1488,42 @@ nr_apply_kernel(const float* __restrict__ G, const double* __restrict__ W, const
 }
 // A = diag(p1) G + lmd sigma2 I, stored row-major (== column-major A^T for the LU; solved with op(T))   cpd.py:296
 __global__ void __launch_bounds__(THREADS)
-nr_system_kernel(const float* __restrict__ G, const double* __restrict__ p1, const double* __restrict__ sigma2_ptr, double lmd,
-                 long long m, double* __restrict__ A) {
-    const long long j = (long long)blockIdx.x * THREADS + threadIdx.x;
-    const long long i = blockIdx.y;
-    if (j < m) A[i * m + j] = p1[i] * (double)G[i * m + j] + (i == j ? lmd * *sigma2_ptr : 0.0);
+nr_system_kernel(const float* __restrict__ G, const double* __restrict__ wgt /* p1, or p1 + (sigma2/alpha) p1~ */,
+                 const double* __restrict__ sigma2_ptr, double lmd, long long m, double* __restrict__ A) {
+    const long long j = (long long)blockIdx.y * THREADS + threadIdx.x;      // rows on grid.x: grid.y is limited to 65535
+    const long long i = blockIdx.x;
+    if (j < m) A[i * m + j] = wgt[i] * (double)G[i * m + j] + (i == j ? lmd * *sigma2_ptr : 0.0);
 }
 // B[c*m + i] = px_ic - p1_i y_ic   (right-hand side of cpd.py:296; px = px~ + cx p1, y = y~ + cy)
+//               + k (px~prior_ic - p1~prior_i y_ic),  k = sigma2 / alpha   with correspondence priors (cpd.py:395)
 __global__ void __launch_bounds__(THREADS)
 nr_rhs_kernel(const DevState* __restrict__ st, const double* __restrict__ p1, const double* __restrict__ pxc,
-              const double* __restrict__ yc, long long m, double* __restrict__ B) {
+              const double* __restrict__ yc, const double* __restrict__ p1t, const double* __restrict__ pxt, double alpha, long long m,
+              double* __restrict__ B) {
     const long long i = (long long)blockIdx.x * THREADS + threadIdx.x;
     if (i < m) {
+        const double k = p1t ? st->sigma2 / alpha : 0.0;
 #pragma unroll
-        for (int c = 0; c < 3; ++c) B[c * m + i] = pxc[3 * i + c] + p1[i] * (st->cx[c] - yc[3 * i + c] - st->cy[c]);
+        for (int c = 0; c < 3; ++c) {
+            const double y = yc[3 * i + c] + st->cy[c];
+            double r = pxc[3 * i + c] + p1[i] * (st->cx[c] - y);
+            if (p1t) r += k * (pxt[3 * i + c] - p1t[i] * y);
+            B[c * m + i] = r;
+        }
     }
+}
+// wgt = p1 + (sigma2 / alpha) p1~   (cpd.py:391-392)
+__global__ void __launch_bounds__(THREADS)
+nr_weight_kernel(const double* __restrict__ p1, const double* __restrict__ p1t, const double* __restrict__ sigma2_ptr, double alpha,
+                 long long m, double* __restrict__ wgt) {
+    const long long i = (long long)blockIdx.x * THREADS + threadIdx.x;
+    if (i < m) wgt[i] = p1[i] + (*sigma2_ptr / alpha) * p1t[i];
+}
+// ts = y (the moved source before the first M-step: W = 0, cpd.py:281)
+__global__ void __launch_bounds__(THREADS)
+nr_identity_kernel(const double* __restrict__ yc, double c0, double c1, double c2, long long m, double* __restrict__ ts) {
+    const long long i = (long long)blockIdx.x * THREADS + threadIdx.x;
+    if (i < m) { ts[3 * i] = yc[3 * i] + c0; ts[3 * i + 1] = yc[3 * i + 1] + c1; ts[3 * i + 2] = yc[3 * i + 2] + c2; }
 }
 __global__ void __launch_bounds__(THREADS)
 nr_unpack_kernel(const double* __restrict__ B, long long m, double* __restrict__ W) {

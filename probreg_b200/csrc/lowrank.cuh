@@ -1,0 +1,256 @@
+// lowrank.cuh -- non-rigid CPD with a rank-K factorisation of the RBF Gram matrix (SURVEY section 8(f) row 1,
+// BASELINE configuration 5: N = M = 50k, K = 200).
+//
+// Reference: NonRigidCPD._maximization_step (probreg/cpd.py:284-303) solves the dense M x M system
+//     (diag(p1) G + lmd sigma2 I) W = px - diag(p1) Y,        G_ij = exp(-|y_i - y_j|^2 / (2 beta))   (cc/math_utils.cc:17-19)
+// -- 2/3 M^3 flops and 12 M^2 bytes per iteration (10^14 flops, 30 GB at M = 50k).  The reference has no low-rank path;
+// this one follows the construction of the CPD paper (Myronenko & Song 2010, section 6 "fast implementation"), with the
+// eigen-decomposition replaced by a randomised range finder that only needs products G X, which the pair kernel forms on
+// the fly (G is never stored):
+//     G ~= Q Bc Q^T,   Q (M x K) orthonormal columns,  Bc = Q^T G Q (K x K)
+//     W  = (F - diag(p1) Q Z) / c,     c = lmd sigma2,  F = px - diag(p1) Y
+//     Z  = Bc Q^T W  solves the K x K system  (c I + Bc S) Z = Bc R,   S = Q^T diag(p1) Q,  R = Q^T F
+//     T  = Y + G W ~= Y + Q Z
+// (Woodbury written without Bc^-1, so numerically rank-deficient Q -- zero columns -- is harmless.)
+// Parity: against the dense device path / the numpy oracle at small M (tests); at K = M the two coincide up to rounding.
+//
+// Layout: Q, X, GQ are FP64 "column-major" [K][ld]: row k holds column k of the matrix, i contiguous -- every kernel below
+// then reads them coalesced along i.  All arrays are in the library's internal (Z-order) source order.
+#pragma once
+#include "kernels.cuh"
+
+namespace cpd {
+
+constexpr int LR_COLS = 16;       // columns of X handled per CTA of lr_gram_apply_kernel
+constexpr int LR_JT = 256;        // j-points per shared-memory tile (== THREADS)
+constexpr int LR_SLICES = 8;      // i-slices of lr_inner_kernel (partials merged in fixed order)
+constexpr int LR_TILE = 32;       // output tile edge of lr_inner_kernel (2 x 2 outputs per thread)
+constexpr int LR_CHUNK = 64;      // i-points per shared-memory chunk of lr_inner_kernel
+constexpr int LR_MAX_RANK = 1024;
+
+// float32 coordinates scaled by sqrt(log2(e) / (2 beta)):  G_ij = 2^-(|a_i - a_j|^2).  The cast to float32 comes first,
+// like the pybind11/Eigen cast of the reference (cc/types.h:19); padding records are far away (G == 0).
+__global__ void __launch_bounds__(THREADS)
+lr_pack_kernel(const double* __restrict__ yc, double c0, double c1, double c2, long long m, long long mpad, float sb,
+               float4* __restrict__ pts) {
+    const long long i = (long long)blockIdx.x * THREADS + threadIdx.x;
+    if (i < m) pts[i] = make_float4(sb * (float)(yc[3 * i] + c0), sb * (float)(yc[3 * i + 1] + c1), sb * (float)(yc[3 * i + 2] + c2), 0.0f);
+    else if (i < mpad) pts[i] = make_float4(FAR_COORD, FAR_COORD, FAR_COORD, 0.0f);
+}
+
+// counter-based uniform(-1, 1) test matrix of the range finder: X[k][i] = u(seed, k, i)   (splitmix64 finaliser)
+__global__ void __launch_bounds__(THREADS)
+lr_random_kernel(double* __restrict__ X, long long m, long long ld, int rank, unsigned long long seed) {
+    const long long i = (long long)blockIdx.x * THREADS + threadIdx.x;
+    const int k = blockIdx.y;
+    if (i < m && k < rank) {
+        unsigned long long z = seed + 0x9e3779b97f4a7c15ull * (unsigned long long)((long long)k * m + i + 1);
+        z = (z ^ (z >> 30)) * 0xbf58476d1ce4e5b9ull;
+        z = (z ^ (z >> 27)) * 0x94d049bb133111ebull;
+        z ^= z >> 31;
+        X[(long long)k * ld + i] = (double)(z >> 11) * (2.0 / 9007199254740992.0) - 1.0;
+    }
+}
+
+// out[c][i] = sum_j G_ij X[c][j]  for the LR_COLS columns c0 .. c0+LR_COLS of this CTA's column group (blockIdx.y):
+// the pair kernel of the E-step with a weight per column instead of the normalisation.  One i-point per thread,
+// j-points and the X tile staged through shared memory, FP32 pair arithmetic and 32-term FP32 partial sums, FP64 beyond.
+__global__ void __launch_bounds__(THREADS)
+lr_gram_apply_kernel(const float4* __restrict__ pts, long long m, long long mpad, const double* __restrict__ X, long long ld, int rank,
+                     double* __restrict__ out) {
+    __shared__ float4 sp[LR_JT];
+    __shared__ __align__(16) float sx[LR_JT][LR_COLS];
+    const long long i = (long long)blockIdx.x * THREADS + threadIdx.x;
+    const int c0 = blockIdx.y * LR_COLS;
+    const float4 t = pts[i < m ? i : m - 1];
+    double acc[LR_COLS];
+#pragma unroll
+    for (int c = 0; c < LR_COLS; ++c) acc[c] = 0.0;
+    for (long long j0 = 0; j0 < mpad; j0 += LR_JT) {
+        __syncthreads();
+        const long long j = j0 + threadIdx.x;
+        sp[threadIdx.x] = pts[j];                                  // j < mpad always (mpad is a multiple of LR_JT)
+#pragma unroll
+        for (int c = 0; c < LR_COLS; ++c) sx[threadIdx.x][c] = (j < m && c0 + c < rank) ? (float)X[(long long)(c0 + c) * ld + j] : 0.0f;
+        __syncthreads();
+#pragma unroll 1
+        for (int g = 0; g < LR_JT; g += 32) {
+            float a[LR_COLS];
+#pragma unroll
+            for (int c = 0; c < LR_COLS; ++c) a[c] = 0.0f;
+#pragma unroll 4
+            for (int jj = 0; jj < 32; ++jj) {
+                const float4 b = sp[g + jj];
+                const float dx = t.x - b.x, dy = t.y - b.y, dz = t.z - b.z;
+                const float e = ex2(-fmaf(dz, dz, fmaf(dy, dy, dx * dx)));
+                const float4* xr = reinterpret_cast<const float4*>(sx[g + jj]);
+#pragma unroll
+                for (int q = 0; q < LR_COLS / 4; ++q) {
+                    const float4 xv = xr[q];
+                    a[4 * q] = fmaf(e, xv.x, a[4 * q]); a[4 * q + 1] = fmaf(e, xv.y, a[4 * q + 1]);
+                    a[4 * q + 2] = fmaf(e, xv.z, a[4 * q + 2]); a[4 * q + 3] = fmaf(e, xv.w, a[4 * q + 3]);
+                }
+            }
+#pragma unroll
+            for (int c = 0; c < LR_COLS; ++c) acc[c] += (double)a[c];
+        }
+    }
+    if (i < m) {
+#pragma unroll
+        for (int c = 0; c < LR_COLS; ++c)
+            if (c0 + c < rank) out[(long long)(c0 + c) * ld + i] = acc[c];
+    }
+}
+
+// ---- orthonormalisation of the columns of X (classical Gram-Schmidt, every column projected twice) ---------------------
+// coef[k] = <X_k, X_j>  for k = k_first .. j (the last one is |X_j|^2); one CTA per k, fixed-order reduction
+__global__ void __launch_bounds__(THREADS)
+lr_dots_kernel(const double* __restrict__ X, long long m, long long ld, int j, int k_first, double* __restrict__ coef) {
+    const int k = k_first + blockIdx.x;
+    const double* a = X + (long long)k * ld;
+    const double* b = X + (long long)j * ld;
+    double v[1] = {0.0};
+    for (long long i = threadIdx.x; i < m; i += THREADS) v[0] += a[i] * b[i];
+    block_reduce_store<1>(v, coef + k);
+}
+// X_j -= sum_{k<j} coef[k] X_k
+__global__ void __launch_bounds__(THREADS)
+lr_project_kernel(double* __restrict__ X, long long m, long long ld, int j, const double* __restrict__ coef) {
+    __shared__ double sc[LR_MAX_RANK];
+    for (int k = threadIdx.x; k < j; k += THREADS) sc[k] = coef[k];
+    __syncthreads();
+    const long long i = (long long)blockIdx.x * THREADS + threadIdx.x;
+    if (i < m) {
+        double x = X[(long long)j * ld + i];
+        for (int k = 0; k < j; ++k) x -= sc[k] * X[(long long)k * ld + i];
+        X[(long long)j * ld + i] = x;
+    }
+}
+// X_j *= 1/|X_j|; a column that has (numerically) nothing left outside the span of its predecessors becomes zero.
+// n0 = |X_j|^2 before the projections, n2 = after.
+__global__ void __launch_bounds__(THREADS)
+lr_scale_kernel(double* __restrict__ X, long long m, long long ld, int j, const double* __restrict__ n0_ptr, const double* __restrict__ n2_ptr) {
+    const long long i = (long long)blockIdx.x * THREADS + threadIdx.x;
+    const double n0 = *n0_ptr, n2 = *n2_ptr;
+    const double s = (n2 > 1e-280 && n2 > 1e-28 * n0) ? 1.0 / sqrt(n2) : 0.0;
+    if (i < m) X[(long long)j * ld + i] *= s;
+}
+
+// ---- out[a][b] = sum_i wt_i A[a][i] Bm[b][i]   (a < na, b < nb; wt may be null) -------------------------------------------
+// One CTA per {32 x 32 output tile, i-slice}; 2 x 2 outputs per thread; partial per slice, merged by lr_merge_kernel.
+__global__ void __launch_bounds__(THREADS)
+lr_inner_kernel(const double* __restrict__ A, int na, long long lda, const double* __restrict__ Bm, int nb, long long ldb,
+                const double* __restrict__ wt, long long m, double* __restrict__ part /* [LR_SLICES][na][nb] */) {
+    __shared__ double sa[LR_TILE][LR_CHUNK + 1], sb[LR_TILE][LR_CHUNK + 1];
+    const int tiles_b = (nb + LR_TILE - 1) / LR_TILE;
+    const int ta0 = (blockIdx.x / tiles_b) * LR_TILE, tb0 = (blockIdx.x % tiles_b) * LR_TILE;
+    const int slice = blockIdx.y;
+    const long long per = (m + LR_SLICES - 1) / LR_SLICES;
+    const long long i_lo = per * slice, i_hi = (i_lo + per < m) ? i_lo + per : m;
+    const int ty = threadIdx.x / 16, tx = threadIdx.x % 16;
+    double acc[2][2] = {{0.0, 0.0}, {0.0, 0.0}};
+    for (long long i0 = i_lo; i0 < i_hi; i0 += LR_CHUNK) {
+        __syncthreads();
+        for (int e = threadIdx.x; e < LR_TILE * LR_CHUNK; e += THREADS) {
+            const int r = e / LR_CHUNK, ii = e % LR_CHUNK;
+            const long long i = i0 + ii;
+            const bool in = i < i_hi;
+            const double w = in ? (wt ? wt[i] : 1.0) : 0.0;
+            sa[r][ii] = (in && ta0 + r < na) ? w * A[(long long)(ta0 + r) * lda + i] : 0.0;
+            sb[r][ii] = (in && tb0 + r < nb) ? Bm[(long long)(tb0 + r) * ldb + i] : 0.0;
+        }
+        __syncthreads();
+#pragma unroll 8
+        for (int ii = 0; ii < LR_CHUNK; ++ii) {
+            const double a0 = sa[ty][ii], a1 = sa[ty + 16][ii], b0 = sb[tx][ii], b1 = sb[tx + 16][ii];
+            acc[0][0] += a0 * b0; acc[0][1] += a0 * b1; acc[1][0] += a1 * b0; acc[1][1] += a1 * b1;
+        }
+    }
+    double* dst = part + (size_t)slice * na * nb;
+#pragma unroll
+    for (int u = 0; u < 2; ++u)
+#pragma unroll
+        for (int v = 0; v < 2; ++v) {
+            const int a = ta0 + ty + 16 * u, b = tb0 + tx + 16 * v;
+            if (a < na && b < nb) dst[(size_t)a * nb + b] = acc[u][v];
+        }
+}
+// out[e] = sum_slices part[s][e]  (fixed order); symmetrise != 0: out = (out + out^T) / 2 for a square n x n result
+__global__ void __launch_bounds__(THREADS)
+lr_merge_kernel(const double* __restrict__ part, int na, int nb, int symmetrise, double* __restrict__ out) {
+    const int e = blockIdx.x * THREADS + threadIdx.x;
+    if (e < na * nb) {
+        const int a = e / nb, b = e % nb;
+        double s = 0.0, t = 0.0;
+        for (int sl = 0; sl < LR_SLICES; ++sl) {
+            s += part[(size_t)sl * na * nb + e];
+            if (symmetrise) t += part[(size_t)sl * na * nb + (size_t)b * nb + a];
+        }
+        out[e] = symmetrise ? 0.5 * (s + t) : s;
+    }
+}
+
+// ---- the K x K system of one M-step:  Msys = c I + Bc S  (row-major),  rhs[d][a] = sum_k Bc[a][k] R[k][d],  c = lmd sigma2 ----
+__global__ void __launch_bounds__(THREADS)
+lr_system_kernel(const double* __restrict__ Bc, const double* __restrict__ S, const double* __restrict__ R /* [K][3] */, int rank,
+                 const double* __restrict__ sigma2_ptr, double lmd, double* __restrict__ Msys, double* __restrict__ rhs /* [3][K] */,
+                 double* __restrict__ c_out) {
+    const int e = blockIdx.x * THREADS + threadIdx.x;
+    const double c = lmd * *sigma2_ptr;
+    if (e == 0) *c_out = c;
+    if (e < rank * rank) {
+        const int a = e / rank, b = e % rank;
+        double s = (a == b) ? c : 0.0;
+        for (int k = 0; k < rank; ++k) s += Bc[(size_t)a * rank + k] * S[(size_t)k * rank + b];
+        Msys[e] = s;
+    } else if (e < rank * rank + 3 * rank) {
+        const int f = e - rank * rank, d = f / rank, a = f % rank;
+        double s = 0.0;
+        for (int k = 0; k < rank; ++k) s += Bc[(size_t)a * rank + k] * R[(size_t)k * 3 + d];
+        rhs[f] = s;
+    }
+}
+
+// T_i = y_i + sum_k Q[k][i] Z[k]   (Z arrives as the solution layout of the LU solve: Zt[d][k])
+__global__ void __launch_bounds__(THREADS)
+lr_apply_kernel(const double* __restrict__ Q, long long m, long long ld, int rank, const double* __restrict__ Zt, const double* __restrict__ yc,
+                double c0, double c1, double c2, double* __restrict__ ts) {
+    __shared__ double sz[3][LR_MAX_RANK];
+    for (int e = threadIdx.x; e < 3 * rank; e += THREADS) sz[e / rank][e % rank] = Zt[e];
+    __syncthreads();
+    const long long i = (long long)blockIdx.x * THREADS + threadIdx.x;
+    if (i < m) {
+        double a0 = 0.0, a1 = 0.0, a2 = 0.0;
+        for (int k = 0; k < rank; ++k) {
+            const double q = Q[(long long)k * ld + i];
+            a0 += q * sz[0][k]; a1 += q * sz[1][k]; a2 += q * sz[2][k];
+        }
+        ts[3 * i] = yc[3 * i] + c0 + a0;
+        ts[3 * i + 1] = yc[3 * i + 1] + c1 + a1;
+        ts[3 * i + 2] = yc[3 * i + 2] + c2 + a2;
+    }
+}
+
+// W_i = (F_i - p1_i (T_i - y_i)) / c      [T - Y = Q Z]      F arrives as [3][m] (nr_rhs_kernel)
+__global__ void __launch_bounds__(THREADS)
+lr_w_kernel(const double* __restrict__ F, const double* __restrict__ p1, const double* __restrict__ ts, const double* __restrict__ yc,
+            double c0, double c1, double c2, long long m, const double* __restrict__ c_ptr, double* __restrict__ W) {
+    const long long i = (long long)blockIdx.x * THREADS + threadIdx.x;
+    if (i < m) {
+        const double inv = 1.0 / *c_ptr, cc[3] = {c0, c1, c2};
+#pragma unroll
+        for (int d = 0; d < 3; ++d) W[3 * i + d] = (F[(long long)d * m + i] - p1[i] * (ts[3 * i + d] - yc[3 * i + d] - cc[d])) * inv;
+    }
+}
+
+// out[perm[i]][k] = Q[k][i]: the basis in the caller's point order, row-major M x K
+__global__ void __launch_bounds__(THREADS)
+lr_export_kernel(const double* __restrict__ Q, const int* __restrict__ perm, long long m, long long ld, int rank, double* __restrict__ out) {
+    const long long i = (long long)blockIdx.x * THREADS + threadIdx.x;
+    if (i < m) {
+        const long long r = perm[i];
+        for (int k = 0; k < rank; ++k) out[r * rank + k] = Q[(long long)k * ld + i];
+    }
+}
+
+}  // namespace cpd

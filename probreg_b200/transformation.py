@@ -73,13 +73,44 @@ class NonRigidTransformation(Transformation):
     """x_i -> x_i + (G w)_i with G the RBF Gram matrix of the source (transformation.py:81-102).
 
     ``g`` is built by the CUDA RBF kernel (math_utils.rbf_kernel -> cpd_rbf_kernel), float32 like
-    the reference's ``_math.rbf_kernel``.
+    the reference's ``_math.rbf_kernel`` -- on first use rather than in the constructor (the reference builds it
+    eagerly, transformation.py:96): the device-resident EM loop keeps its own G and a caller that only wants
+    ``w`` or the final moved points never pays for an M x M host array.
     """
 
     def __init__(self, w, points, beta=2.0, xp=np):
         super(NonRigidTransformation, self).__init__(xp)
-        self.g = mu.rbf_kernel(points, points, beta)
+        self._points = points
+        self._beta = beta
+        self._g = None
         self.w = w
+
+    @property
+    def g(self):
+        if self._g is None:
+            self._g = mu.rbf_kernel(self._points, self._points, self._beta)
+        return self._g
+
+    @g.setter
+    def g(self, value):
+        self._g = value
 
     def _transform(self, points):
         return points + np.dot(self.g, self.w)
+
+
+class LowRankNonRigidTransformation(NonRigidTransformation):
+    """The same map with G ~= q bcore q^T (rank K): x_i -> x_i + (q (bcore (q^T w)))_i.
+
+    Produced by ``NonRigidCPD(..., low_rank=K)``; no reference counterpart (the reference only has the dense G).
+    ``q`` (M x K, orthonormal columns) and ``bcore`` (K x K) come from the device (cpd_nonrigid_lowrank_get).
+    ``g`` stays available (dense, built on first use) for code written against the reference's attribute.
+    """
+
+    def __init__(self, w, points, beta, q, bcore, xp=np):
+        super(LowRankNonRigidTransformation, self).__init__(w, points, beta, xp)
+        self.q = q
+        self.bcore = bcore
+
+    def _transform(self, points):
+        return points + np.dot(self.q, np.dot(self.bcore, np.dot(self.q.T, self.w)))

@@ -1,0 +1,210 @@
+"""Low-rank non-rigid CPD (BASELINE configuration 5) and the device-side correspondence priors.
+
+There is no reference counterpart for the low-rank path (the reference solves the dense M x M system, cpd.py:296), so
+parity is anchored as SURVEY section 8(f) says: against the reference's dense arithmetic (the numpy oracle) at sizes where the
+dense solve is possible, with the truncation error of the factorisation as the tolerance, and -- tighter -- against the
+oracle run on the SAME approximate G = Q Bc Q^T, where only rounding separates the two.
+
+CPU tests run the library under the emulation of tests/emu; the gpu-marked ones call the real library.  The GPU budget
+of round 1 was spent before this path existed, so the gpu tests below have not run on hardware yet: they are marked
+xfail(strict=False) until the first hardware run confirms them (NEXT.md).
+"""
+import numpy as np
+import pytest
+
+from oracle import cpd_oracle as orc
+from probreg_b200 import _cabi, cpd
+
+UNVERIFIED = pytest.mark.xfail(reason="written after the round-1 GPU budget was spent: validated under the CPU emulation only, "
+                                      "first hardware run pending", strict=False)
+F = np.array([[1.0, 0.5, 0.0], [0.0, 1.0, 0.7], [0.3, 0.0, 1.0]])
+
+
+def _deformed_pair(m, seed=9):
+    src, _ = orc.synthetic_pair(m)
+    tgt = src + 0.03 * np.sin(2 * np.pi * src.dot(F)) + 0.002 * np.random.default_rng(seed).standard_normal(src.shape)
+    return src, tgt
+
+
+# ---- the algebra (numpy only) -----------------------------------------------------------------------------------------------
+def test_kxk_form_equals_the_dense_solve_on_the_same_low_rank_g():
+    src, tgt = _deformed_pair(300)
+    q, bc = orc.lowrank_factors(src, 2.0, 40)
+    g_lr = q.dot(bc).dot(q.T)
+    es = orc.expectation_step(src, tgt, 0.01, 0.05)
+    dense = orc.mstep_nonrigid(src, tgt, es, 0.01, g_lr, 1.5)
+    lr = orc.mstep_nonrigid_lowrank(src, tgt, es, 0.01, q, bc, 1.5)
+    np.testing.assert_allclose(lr.params[1], src + g_lr.dot(dense.params[0]), atol=1e-9)
+    assert lr.sigma2 == pytest.approx(dense.sigma2, rel=1e-9)
+    # W itself: T = Y + G W must hold for the low-rank W as well
+    np.testing.assert_allclose(src + g_lr.dot(lr.params[0]), lr.params[1], atol=1e-9)
+    # and with correspondence priors
+    p1t, pxt = orc.constraint_terms(300, tgt, np.arange(0, 300, 15), np.arange(0, 300, 15))
+    dense = orc.mstep_nonrigid(src, tgt, es, 0.01, g_lr, 1.5, alpha=1e-2, p1_tilde=p1t, px_tilde=pxt)
+    lr = orc.mstep_nonrigid_lowrank(src, tgt, es, 0.01, q, bc, 1.5, alpha=1e-2, p1_tilde=p1t, px_tilde=pxt)
+    np.testing.assert_allclose(lr.params[1], src + g_lr.dot(dense.params[0]), atol=1e-9)
+
+
+def test_range_finder_reaches_float32_noise_quickly():
+    src, _ = _deformed_pair(500)
+    g = orc.rbf_kernel_f32(src, src, 2.0).astype(np.float64)
+    for rank, bound in [(10, 1e-4), (40, 1e-7)]:
+        q, bc = orc.lowrank_factors(src, 2.0, rank)
+        assert np.linalg.norm(g - q.dot(bc).dot(q.T), 2) / np.linalg.norm(g, 2) < bound
+
+
+# ---- the library (bodies shared by the emulated CPU tests and the GPU tests) ---------------------------------------------------
+def _check_against_oracles(m, rank, iters, beta, lmd, w, tol_dense, constrained=False):
+    src, tgt = _deformed_pair(m)
+    kw = {}
+    okw = {}
+    if constrained:
+        idx = np.arange(0, m, 11)
+        kw = {"alpha": 1e-2, "idx_source": idx, "idx_target": idx}
+        okw = {"alpha": 1e-2, "idx_source": idx, "idx_target": idx}
+    cls = cpd.ConstrainedNonRigidCPD if constrained else cpd.NonRigidCPD
+    reg = cls(src, beta=beta, lmd=lmd, low_rank=rank, **kw)
+    res = reg.registration(tgt, w=w, maxiter=iters, tol=-1.0)
+    moved = reg.moved_source()
+    tfm = res.transformation
+    k = min(rank, m)
+    assert tfm.q.shape == (m, k) and tfm.bcore.shape == (k, k) and tfm.w.shape == (m, 3)
+    # the factors: orthonormal columns (or zero ones once the numerical rank is exhausted), symmetric core
+    gram = tfm.q.T.dot(tfm.q)
+    d = np.diag(gram)
+    assert np.all((np.abs(d - 1.0) < 1e-12) | (d == 0.0))
+    np.testing.assert_allclose(gram - np.diag(d), 0.0, atol=1e-12)
+    np.testing.assert_allclose(tfm.bcore, tfm.bcore.T, atol=0.0)
+    g_lr = tfm.q.dot(tfm.bcore).dot(tfm.q.T)
+    g = orc.rbf_kernel_f32(src, src, beta).astype(np.float64)
+    assert np.linalg.norm(g - g_lr, 2) / np.linalg.norm(g, 2) < (1e-6 if k >= 30 else 1e-3)
+    # the transformation object reproduces the device's moved points
+    np.testing.assert_allclose(tfm.transform(src), moved, atol=1e-10)
+    # 1. the reference's dense arithmetic on the SAME G: only rounding (and the FP32 pair maths of the E-step) differ
+    tf_name = "nonrigid_constrained" if constrained else "nonrigid"
+    same, _ = orc.registration(src, tgt, tf_name, maxiter=iters, tol=-1.0, beta=beta, lmd=lmd, w=w, g=g_lr, **okw)
+    assert res.sigma2 == pytest.approx(same.sigma2, rel=1e-5)
+    np.testing.assert_allclose(moved, src + g_lr.dot(same.params[0]), atol=2e-5)
+    # 2. the reference itself (exact G): the truncation error of the factorisation on top
+    ref, _ = orc.registration(src, tgt, tf_name, maxiter=iters, tol=-1.0, beta=beta, lmd=lmd, w=w, **okw)
+    assert res.sigma2 == pytest.approx(ref.sigma2, rel=tol_dense)
+    np.testing.assert_allclose(moved, src + g.dot(ref.params[0]), atol=max(2e-5, tol_dense))
+    return res
+
+
+def _check_full_rank_equals_dense(m):
+    """rank == M: the factorisation is exact up to rounding, so the low-rank loop must land on the dense device loop."""
+    src, tgt = _deformed_pair(m)
+    a = cpd.NonRigidCPD(src, beta=0.5, lmd=1.0)
+    ra = a.registration(tgt, w=0.0, maxiter=4, tol=-1.0)
+    b = cpd.NonRigidCPD(src, beta=0.5, lmd=1.0, low_rank=m + 50)          # clamped to M
+    rb = b.registration(tgt, w=0.0, maxiter=4, tol=-1.0)
+    assert rb.transformation.q.shape == (m, m)
+    assert rb.sigma2 == pytest.approx(ra.sigma2, rel=1e-6)
+    np.testing.assert_allclose(b.moved_source(), a.moved_source(), atol=1e-6)
+
+
+def _check_misc():
+    src, tgt = _deformed_pair(200)
+    a = cpd.NonRigidCPD(src, low_rank=20, low_rank_seed=3).registration(tgt, maxiter=3, tol=-1.0)
+    b = cpd.NonRigidCPD(src, low_rank=20, low_rank_seed=3).registration(tgt, maxiter=3, tol=-1.0)
+    assert a.sigma2 == b.sigma2 and np.array_equal(a.transformation.w, b.transformation.w)       # seeded, deterministic
+    c = cpd.NonRigidCPD(src, low_rank=20, low_rank_seed=4).registration(tgt, maxiter=3, tol=-1.0)
+    assert c.sigma2 == pytest.approx(a.sigma2, rel=1e-4)                   # another basis, (nearly) the same subspace
+    seen = []
+    r = cpd.registration_cpd(src, tgt, "nonrigid", maxiter=3, tol=-1.0, low_rank=20, callbacks=[lambda t: seen.append(t.w.copy())])
+    assert len(seen) == 3 and r.sigma2 == pytest.approx(a.sigma2, rel=1e-4) and not np.array_equal(seen[0], seen[2])
+    # default tolerance: stops like the dense loop does (q == sigma2, cpd.py:303)
+    d = cpd.NonRigidCPD(src, low_rank=20)
+    rd = d.registration(tgt)
+    assert 0.0 < rd.sigma2 < a.sigma2
+    # 2-D
+    s2 = np.random.default_rng(2).random((150, 2))
+    t2 = s2 + 0.02 * np.sin(6.0 * s2[:, ::-1])
+    r2 = cpd.NonRigidCPD(s2, beta=1.0, lmd=1.0, low_rank=30)
+    res2 = r2.registration(t2, maxiter=5, tol=-1.0)
+    o2, _ = orc.registration(s2, t2, "nonrigid", maxiter=5, tol=-1.0, beta=1.0, lmd=1.0)
+    assert res2.sigma2 == pytest.approx(o2.sigma2, rel=1e-4)
+    # argument errors
+    h = _cabi.Handle(3)
+    h.set_source(src)
+    h.set_target(tgt)
+    for bad in (0, -3, 5000):
+        with pytest.raises(_cabi.CpdError):
+            h.nonrigid_lowrank_begin(2.0, 2.0, 0.01, 0.0, bad)
+    with pytest.raises(_cabi.CpdError):
+        h.nonrigid_lowrank_factors()                                       # nothing begun
+    h.nonrigid_begin(2.0, 2.0, 0.01, 0.0)
+    with pytest.raises(_cabi.CpdError):
+        h.nonrigid_lowrank_factors()                                       # dense mode has no factors
+    with pytest.raises(ValueError):
+        h.nonrigid_set_prior(1e-2, np.zeros(5), np.zeros((5, 3)))
+
+
+def test_lowrank_vs_oracles_emulated(emulated):
+    _check_against_oracles(260, 36, 5, 2.0, 2.0, 0.05, 1e-4)
+
+
+def test_lowrank_constrained_emulated(emulated):
+    _check_against_oracles(220, 32, 4, 1.0, 1.5, 0.0, 1e-4, constrained=True)
+
+
+def test_lowrank_full_rank_equals_dense_emulated(emulated):
+    _check_full_rank_equals_dense(70)
+
+
+def test_lowrank_misc_emulated(emulated):
+    _check_misc()
+
+
+@pytest.mark.gpu
+@UNVERIFIED
+def test_lowrank_vs_oracles_gpu():
+    _check_against_oracles(2000, 100, 6, 2.0, 2.0, 0.05, 2e-5)
+    _check_against_oracles(1500, 60, 6, 0.3, 1.5, 0.0, 1e-3)               # narrow kernel: slower spectral decay
+
+
+@pytest.mark.gpu
+@UNVERIFIED
+def test_lowrank_constrained_gpu():
+    _check_against_oracles(1500, 80, 5, 1.0, 1.5, 0.0, 5e-5, constrained=True)
+
+
+@pytest.mark.gpu
+@UNVERIFIED
+def test_lowrank_full_rank_equals_dense_gpu():
+    _check_full_rank_equals_dense(400)
+
+
+@pytest.mark.gpu
+@UNVERIFIED
+def test_lowrank_misc_gpu():
+    _check_misc()
+
+
+@pytest.mark.gpu
+@UNVERIFIED
+def test_lowrank_baseline_config5_properties():
+    """BASELINE configuration 5 (N = M = 50k, K = 200): size-independent properties, and the dense device loop at 6k as
+    the cross-check the dense path can still afford."""
+    src, tgt = _deformed_pair(6000)
+    a = cpd.NonRigidCPD(src, beta=2.0, lmd=2.0)
+    ra = a.registration(tgt, maxiter=5, tol=-1.0)
+    b = cpd.NonRigidCPD(src, beta=2.0, lmd=2.0, low_rank=200)
+    rb = b.registration(tgt, maxiter=5, tol=-1.0)
+    assert rb.sigma2 == pytest.approx(ra.sigma2, rel=2e-5)
+    np.testing.assert_allclose(b.moved_source(), a.moved_source(), atol=2e-5)
+    src, tgt = _deformed_pair(50000)
+    trace = []
+    reg = cpd.NonRigidCPD(src, beta=2.0, lmd=2.0, low_rank=200)
+    reg.set_callbacks([lambda t: trace.append(1)])
+    res = reg.registration(tgt, maxiter=8, tol=-1.0)
+    q = res.transformation.q
+    assert q.shape == (50000, 200)
+    gram = q.T.dot(q)
+    d = np.diag(gram)
+    assert np.all((np.abs(d - 1.0) < 1e-11) | (d == 0.0))
+    moved = reg.moved_source()
+    assert np.isfinite(moved).all() and np.isfinite(res.sigma2) and res.sigma2 > 0
+    # the deformation is recovered: residual to the (unpermuted) target well below the 0.03 amplitude that was applied
+    assert np.sqrt(((moved - tgt) ** 2).sum(1)).mean() < 0.4 * np.sqrt(((src - tgt) ** 2).sum(1)).mean()
