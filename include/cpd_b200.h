@@ -95,6 +95,13 @@ int cpd_estep(cpd_ctx* h, const double* t_source, double sigma2, double w,
 int cpd_mstep(cpd_ctx* h, int tf_kind, int update_scale, const double* pt1, const double* p1,
               const double* px, double n_p, cpd_params* out);
 
+/* BayesianCoherentPointDrift.expectation_step(t_source, target, scale, alpha, sigma_mat, sigma2, w) (probreg/bcpd.py:53-72)
+ * against the handle's target shard: the same two passes with a per-source weight alpha_m exp(-scale^2 sigma_mm D / 2 sigma2)
+ * (1 - w) and the constant w / N.  alpha: m; sigma_diag: the m diagonal entries of sigma_mat (the only ones bcpd.py:61 reads).
+ * Out (any may be NULL): nu_d (n_local), nu (m), px (m x D), n_p; x_hat of the reference's EstepResult is px / nu.        */
+int cpd_bcpd_estep(cpd_ctx* h, const double* t_source, double scale, const double* alpha, const double* sigma_diag, double sigma2,
+                   double w, double* nu_d, double* nu, double* px, double* n_p);
+
 /* Copies of the last E-step's reductions (device -> host), valid after cpd_em_step/run. */
 int cpd_last_estep(cpd_ctx* h, double* pt1, double* p1, double* px, double* n_p);
 
@@ -125,6 +132,10 @@ int cpd_nonrigid_set_prior(cpd_ctx* h, double alpha, const double* p1_tilde, con
  * out[i*ny + j] = exp(-|x_i - y_j|^2 / (2*beta)) as float32, x: nx x D, y: ny x D.       */
 int cpd_rbf_kernel(int device, const double* x, int64_t nx, const double* y, int64_t ny, int dim,
                    double beta, float* out);
+
+/* _math.inverse_multiquadric_kernel (cc/math_utils_py.cc -> cc/math_utils.cc:37-39): out[i*ny + j] = (|x_i - y_j|^2 + c)^(-1/2),
+ * float32 (used by CombinedBCPD._initialize, bcpd.py:113).                                                                   */
+int cpd_imq_kernel(int device, const double* x, int64_t nx, const double* y, int64_t ny, int dim, double c, float* out);
 
 /* gauss_transform._gauss_transform_direct / GaussTransform.compute (gauss_transform.py:10-16, 47-60), evaluated
  * exactly (no IFGT): out[c*n + i] = sum_j weights[c*m + j] * exp(-|target_i - source_j|^2 / h^2).        */

@@ -265,6 +265,38 @@ def mstep_nonrigid_lowrank(source, target, es, sigma2_p, q_mat, bcore, lmd, alph
     return Mstep((wmat, t), float(sigma2), float(sigma2))
 
 
+BcpdEstep = namedtuple("BcpdEstep", ["nu_d", "nu", "n_p", "px", "x_hat"])
+
+
+def bcpd_expectation_step(t_source, target, scale, alpha, sigma_mat, sigma2, w=0.0):
+    """probreg/bcpd.py:53-72 (BayesianCoherentPointDrift.expectation_step), restated.
+
+    phi_mn = N(x_n; t_m, sigma2 I) * exp(-scale^2 D sigma_mm / (2 sigma2)) * (1 - w) * alpha_m      (bcpd.py:57-63)
+    den_n  = w / N + sum_m phi_mn, zero -> float32 eps                                            (bcpd.py:64-65)
+    P = phi / den;  nu_d = sum_m P (N);  nu = sum_n P (M);  px = P x (M x D);  x_hat = px / nu      (bcpd.py:66-72)
+    ``sigma_mat`` may be the M x M matrix (only its diagonal is read) or the diagonal itself.
+    """
+    t_source = np.asarray(t_source, dtype=np.float64)
+    target = np.asarray(target, dtype=np.float64)
+    m, dim = t_source.shape
+    n = target.shape[0]
+    sdiag = np.asarray(sigma_mat, dtype=np.float64)
+    if sdiag.ndim == 2:
+        sdiag = np.diag(sdiag)
+    d2 = ((t_source[:, None, :] - target[None, :, :]) ** 2).sum(-1)                  # (M, N)
+    phi = np.exp(-d2 / (2.0 * sigma2)) / (2.0 * np.pi * sigma2) ** (dim * 0.5)
+    phi = phi * (np.exp(-(scale ** 2) / (2.0 * sigma2) * sdiag * dim) * (1.0 - w) * np.asarray(alpha, dtype=np.float64))[:, None]
+    den = w / n + phi.sum(axis=0)
+    den[den == 0] = EPS32
+    p = phi / den
+    nu_d = p.sum(axis=0)
+    nu = p.sum(axis=1)
+    px = p.dot(target)
+    with np.errstate(divide="ignore", invalid="ignore"):
+        x_hat = px / nu[:, None]
+    return BcpdEstep(nu_d, nu, float(nu.sum()), px, x_hat)
+
+
 # ---------------------------------------------------------------------------
 # transforms (probreg/transformation.py)
 # ---------------------------------------------------------------------------

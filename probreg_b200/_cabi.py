@@ -39,6 +39,8 @@ _PROTOS = {
     "cpd_estep": (ctypes.c_int, [ctypes.c_void_p, _c_dp, ctypes.c_double, ctypes.c_double, _c_dp, _c_dp, _c_dp, _c_dp]),
     "cpd_mstep": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, _c_dp, _c_dp, _c_dp, ctypes.c_double,
                                  ctypes.POINTER(CpdParams)]),
+    "cpd_bcpd_estep": (ctypes.c_int, [ctypes.c_void_p, _c_dp, ctypes.c_double, _c_dp, _c_dp, ctypes.c_double, ctypes.c_double,
+                                      _c_dp, _c_dp, _c_dp, _c_dp]),
     "cpd_last_estep": (ctypes.c_int, [ctypes.c_void_p, _c_dp, _c_dp, _c_dp, _c_dp]),
     "cpd_nonrigid_begin": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_double, ctypes.c_double, ctypes.c_double, ctypes.c_double]),
     "cpd_nonrigid_step": (ctypes.c_int, [ctypes.c_void_p, _c_dp]),
@@ -48,6 +50,8 @@ _PROTOS = {
     "cpd_nonrigid_lowrank_get": (ctypes.c_int, [ctypes.c_void_p, ctypes.POINTER(ctypes.c_int), _c_dp, _c_dp]),
     "cpd_nonrigid_set_prior": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_double, _c_dp, _c_dp]),
     "cpd_rbf_kernel": (ctypes.c_int, [ctypes.c_int, _c_dp, ctypes.c_int64, _c_dp, ctypes.c_int64, ctypes.c_int,
+                                      ctypes.c_double, _c_fp]),
+    "cpd_imq_kernel": (ctypes.c_int, [ctypes.c_int, _c_dp, ctypes.c_int64, _c_dp, ctypes.c_int64, ctypes.c_int,
                                       ctypes.c_double, _c_fp]),
     "cpd_gauss_transform": (ctypes.c_int, [ctypes.c_int, _c_dp, ctypes.c_int64, _c_dp, ctypes.c_int64, ctypes.c_int, ctypes.c_double,
                                            _c_dp, ctypes.c_int, _c_dp]),
@@ -204,6 +208,19 @@ class Handle(object):
         n_p = ctypes.c_double()
         check(lib().cpd_estep(self._h, dptr(ts), float(sigma2), float(w), dptr(pt1), dptr(p1), dptr(px), ctypes.byref(n_p)))
         return pt1, p1, px, n_p.value
+
+    def bcpd_estep(self, t_source, scale, alpha, sigma_diag, sigma2, w):
+        """(nu_d, nu, px, n_p) of probreg/bcpd.py:53-72 for the handle's target."""
+        ts = as_cloud(t_source, self.dim)
+        al = np.ascontiguousarray(alpha, dtype=np.float64)
+        sd = np.ascontiguousarray(sigma_diag, dtype=np.float64)
+        if ts.shape[0] != self.m or al.shape != (self.m,) or sd.shape != (self.m,):
+            raise ValueError("t_source / alpha / sigma_diag do not match the handle's source count %d" % self.m)
+        nu_d, nu, px = np.empty(self.n), np.empty(self.m), np.empty((self.m, self.dim))
+        n_p = ctypes.c_double()
+        check(lib().cpd_bcpd_estep(self._h, dptr(ts), float(scale), dptr(al), dptr(sd), float(sigma2), float(w), dptr(nu_d), dptr(nu),
+                                   dptr(px), ctypes.byref(n_p)))
+        return nu_d, nu, px, n_p.value
 
     def last_estep(self):
         pt1, p1, px = np.empty(self.n), np.empty(self.m), np.empty((self.m, self.dim))

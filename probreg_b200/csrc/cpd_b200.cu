@@ -184,6 +184,10 @@ struct cpd_ctx {
     long long nr_m = 0;
     double nr_lmd = 0.0;
     bool nr_ready = false;
+    // weighted E-step (BCPD): per-source exponent offsets and the {log2 c, dead-column shift} pair for finalize 1
+    float* d_la = nullptr;
+    double* d_log2c = nullptr;
+    bool wgt_on = false;
     // correspondence priors of ConstrainedNonRigidCPD
     double *d_wgt = nullptr, *d_p1t = nullptr, *d_pxt = nullptr;
     long long prior_m = 0;
@@ -409,19 +413,29 @@ int launch_estep(cpd_ctx* h, const double* d_sigma2, const double* d_w, const do
         sub_bbox_kernel<<<(unsigned)((nsub2 + 7) / 8), THREADS, 0, h->stream>>>(h->d_tgtP, (int)h->n, nsub2, h->d_tsub);
         h->launches += 3;
     }
-    if (cull) pass1_kernel<true><<<h->g1, THREADS, PASS1_SMEM, h->stream>>>(h->d_tgtP, (int)h->n, h->d_srcJ, h->d_work1, h->d_part1, h->d_sbox, nst1, h->d_ssub);
-    else pass1_kernel<false><<<h->g1, THREADS, PASS1_SMEM, h->stream>>>(h->d_tgtP, (int)h->n, h->d_srcJ, h->d_work1, h->d_part1, h->d_sbox, nst1, nullptr);
+    const bool wgt = h->wgt_on;
+    if (wgt) {
+        weight_patch_kernel<<<blocks_for(h->m), THREADS, 0, h->stream>>>(h->d_la, h->m, h->d_srcP, h->d_srcJ);
+        h->launches += 1;
+    }
+#define CPD_PASS1(C, W) pass1_kernel<C, W><<<h->g1, THREADS, PASS1_SMEM, h->stream>>>(h->d_tgtP, (int)h->n, h->d_srcJ, h->d_work1, h->d_part1, h->d_sbox, nst1, (C) ? h->d_ssub : nullptr)
+    if (cull) { if (wgt) CPD_PASS1(true, true); else CPD_PASS1(true, false); }
+    else { if (wgt) CPD_PASS1(false, true); else CPD_PASS1(false, false); }
+#undef CPD_PASS1
     mark(h, 2);
     finalize1_kernel<<<blocks_for(h->npad), THREADS, 0, h->stream>>>(h->d_state, d_sigma2, d_w, h->d_part1, h->d_slots1, (int)h->n,
-                                                                     h->d_tgtP, h->d_tgtQ, h->npad, h->d_pt1, h->d_mom_tgt);
+                                                                     h->d_tgtP, h->d_tgtQ, h->npad, h->d_pt1, h->d_mom_tgt,
+                                                                     wgt ? h->d_log2c : nullptr);
     mark(h, 3);
     if (cull) {
         stage_omax_kernel<<<(unsigned)(h->npad / P2_STAGE), THREADS, 0, h->stream>>>(h->d_tgtQ, h->d_omax);
         sub_omax_kernel<<<(unsigned)((nsub2 + 7) / 8), THREADS, 0, h->stream>>>(h->d_tgtQ, nsub2, h->d_omax_sub);
         h->launches += 2;
     }
-    if (cull) pass2_kernel<true><<<h->g2, THREADS, PASS2_SMEM, h->stream>>>(h->d_srcP, (int)h->m, h->d_tgtQ, h->d_work2, h->d_part2, h->d_tbox, h->d_omax, h->d_tsub, h->d_omax_sub);
-    else pass2_kernel<false><<<h->g2, THREADS, PASS2_SMEM, h->stream>>>(h->d_srcP, (int)h->m, h->d_tgtQ, h->d_work2, h->d_part2, nullptr, nullptr, nullptr, nullptr);
+#define CPD_PASS2(C, W) pass2_kernel<C, W><<<h->g2, THREADS, PASS2_SMEM, h->stream>>>(h->d_srcP, (int)h->m, h->d_tgtQ, h->d_work2, h->d_part2, (C) ? h->d_tbox : nullptr, (C) ? h->d_omax : nullptr, (C) ? h->d_tsub : nullptr, (C) ? h->d_omax_sub : nullptr)
+    if (cull) { if (wgt) CPD_PASS2(true, true); else CPD_PASS2(true, false); }
+    else { if (wgt) CPD_PASS2(false, true); else CPD_PASS2(false, false); }
+#undef CPD_PASS2
     mark(h, 4);
     finalize2_kernel<<<blocks_for(h->m), THREADS, 0, h->stream>>>(h->d_state, d_sigma2, h->d_part2, h->d_slots2, (int)h->m, h->d_yc,
                                                                   d_ts, h->d_p1, h->d_pxc, h->d_mom_src);
@@ -488,13 +502,17 @@ extern "C" int cpd_create(cpd_ctx** out, int device, int dim, void* stream) {
     h->sm_count = prop.multiProcessorCount;
     if (stream) { h->stream = (cudaStream_t)stream; h->own_stream = false; }
     else { CU(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking)); h->own_stream = true; }
-    CU(cudaFuncSetAttribute(pass1_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, PASS1_SMEM));
-    CU(cudaFuncSetAttribute(pass2_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, PASS2_SMEM));
-    CU(cudaFuncSetAttribute(pass1_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, PASS1_SMEM));
-    CU(cudaFuncSetAttribute(pass2_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, PASS2_SMEM));
+    CU(cudaFuncSetAttribute(pass1_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, PASS1_SMEM));
+    CU(cudaFuncSetAttribute(pass2_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, PASS2_SMEM));
+    CU(cudaFuncSetAttribute(pass1_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, PASS1_SMEM));
+    CU(cudaFuncSetAttribute(pass2_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, PASS2_SMEM));
+    CU(cudaFuncSetAttribute(pass1_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, PASS1_SMEM));
+    CU(cudaFuncSetAttribute(pass2_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, PASS2_SMEM));
+    CU(cudaFuncSetAttribute(pass1_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, PASS1_SMEM));
+    CU(cudaFuncSetAttribute(pass2_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, PASS2_SMEM));
     int occ1 = 0, occ2 = 0;
-    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ1, pass1_kernel<false>, THREADS, PASS1_SMEM));
-    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ2, pass2_kernel<false>, THREADS, PASS2_SMEM));
+    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ1, pass1_kernel<false, false>, THREADS, PASS1_SMEM));
+    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ2, pass2_kernel<false, false>, THREADS, PASS2_SMEM));
     h->slots1 = h->sm_count * std::max(1, occ1);
     h->slots2 = h->sm_count * std::max(1, occ2);
     TRY(dev_alloc(&h->d_state, 1));
@@ -524,7 +542,7 @@ extern "C" void cpd_destroy(cpd_ctx* h) {
     void* nrp[] = {h->d_G, h->d_W, h->d_A, h->d_B, h->d_ts2, h->d_nrpart, h->d_ipiv, h->d_info, h->d_work};
     for (void* p : nrp) if (p) cudaFree(p);
     void* lrp[] = {h->d_lr_pts, h->d_lr_Q, h->d_lr_X, h->d_lr_coef, h->d_lr_part, h->d_lr_Bc, h->d_lr_S, h->d_lr_R, h->d_lr_sys, h->d_lr_rhs,
-                   h->d_lr_c, h->d_lr_out, h->d_wgt, h->d_p1t, h->d_pxt};
+                   h->d_lr_c, h->d_lr_out, h->d_wgt, h->d_p1t, h->d_pxt, h->d_la, h->d_log2c};
     for (void* p : lrp) if (p) cudaFree(p);
     if (h->h_work) free(h->h_work);
     if (h->sol_params && g_sol.DestroyParams) g_sol.DestroyParams(h->sol_params);
@@ -717,6 +735,58 @@ extern "C" int cpd_estep(cpd_ctx* h, const double* t_source, double sigma2, doub
         TRY(allreduce(h, h->d_pxc, (size_t)h->m * 3));
     }
     return cpd_last_estep(h, pt1, p1, px, n_p);
+}
+
+// BayesianCoherentPointDrift.expectation_step (probreg/bcpd.py:53-72): the CPD E-step with a weight per source,
+//   pmat_nm = exp(-|x_n - t_m|^2 / 2 sigma2) (2 pi sigma2)^(-D/2) * exp(-scale^2 / (2 sigma2) * sigma_mm * D) * (1 - w) * alpha_m,
+//   den_n = w / N + sum_m pmat_nm,  P = pmat / den,  nu_d = sum_m P (n),  nu = sum_n P (m),  px = P x (m x D),  n_p = sum nu.
+// The weights enter the exponent as la_m = -log2(weight_m) (FP64 here, minus their minimum so that la >= 0 and FP32 keeps
+// them to ~1e-7 absolute); the constant w / N moves to the same units.  x_hat = px / nu is left to the caller (bcpd.py:70-71).
+extern "C" int cpd_bcpd_estep(cpd_ctx* h, const double* t_source, double scale, const double* alpha, const double* sigma_diag,
+                              double sigma2, double w, double* nu_d, double* nu, double* px, double* n_p) {
+    if (!h || !t_source || !alpha || !sigma_diag) return fail(CPD_ERR_ARG, "null argument");
+    if (!(sigma2 > 0.0)) return fail(CPD_ERR_ARG, "sigma2 must be positive, got %g", sigma2);
+    if (!(w >= 0.0 && w < 1.0)) return fail(CPD_ERR_ARG, "w must be in [0, 1), got %g", w);
+    if (!h->have_source || !h->have_target) return fail(CPD_ERR_STATE, "source and target must both be set");
+    CU(cudaSetDevice(h->device));
+    const long long m = h->m;
+    std::vector<double> la((size_t)m);
+    const double kf = scale * scale / (2.0 * sigma2) * (double)h->dim * LOG2E, l1w = -log2(1.0 - w);
+    double la_min = INFINITY;
+    for (long long i = 0; i < m; ++i) {
+        if (!(alpha[i] >= 0.0) || !(sigma_diag[i] >= 0.0)) return fail(CPD_ERR_ARG, "alpha and diag(sigma_mat) must be non-negative");
+        la[(size_t)i] = (alpha[i] > 0.0 ? -log2(alpha[i]) : INFINITY) + l1w + kf * sigma_diag[i];
+        la_min = std::min(la_min, la[(size_t)i]);
+    }
+    if (!(la_min < INFINITY)) return fail(CPD_ERR_ARG, "every source has zero weight");
+    for (long long i = 0; i < m; ++i) la[(size_t)i] = std::min(la[(size_t)i] - la_min, 1.0e30);      // +inf -> a weight of exactly 0
+    TRY(dev_alloc(&h->d_la, (size_t)m));
+    if (!h->d_log2c) TRY(dev_alloc(&h->d_log2c, 2));
+    const double half_d_log2 = 0.5 * (double)h->dim * log2(2.0 * 3.14159265358979323846 * sigma2);
+    h->h_pin[34] = (w > 0.0) ? log2(w / (double)h->n_global) + la_min + half_d_log2 : -INFINITY;   // log2 of the constant, in kernel units
+    h->h_pin[35] = -la_min - half_d_log2;                                                          // kernel units -> log2 of the float64 sum
+    CU(cudaMemcpyAsync(h->d_log2c, h->h_pin + 34, 2 * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    CU(cudaMemcpyAsync(h->d_outM, la.data(), (size_t)m * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    gather_f32_kernel<<<blocks_for(m), THREADS, 0, h->stream>>>(h->d_outM, h->d_perm_src, m, h->d_la);
+    KCHECK();
+    CU(cudaStreamSynchronize(h->stream));          // `la` (pageable host memory) may go out of scope
+    if (h->raw_cap < (size_t)m * 3) { TRY(dev_alloc(&h->d_raw, (size_t)m * 3)); h->raw_cap = (size_t)m * 3; }
+    TRY(upload_cloud(h, t_source, m, h->d_raw));
+    gather3_kernel<<<blocks_for(m), THREADS, 0, h->stream>>>(h->d_raw, h->d_perm_src, m, 0.0, 0.0, 0.0, h->d_ts);
+    h->launches += 2;
+    h->cull_active = h->extent > 0.0 && 13.3 * sqrt(sigma2) < 0.25 * h->extent;
+    h->h_pin[32] = sigma2;
+    h->h_pin[33] = w;
+    CU(cudaMemcpyAsync(&h->d_state->es_sigma2, h->h_pin + 32, 2 * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    h->wgt_on = true;
+    const int r = launch_estep(h, &h->d_state->es_sigma2, &h->d_state->es_w, h->d_ts);
+    h->wgt_on = false;
+    TRY(r);
+    if (h->comm) {
+        TRY(allreduce(h, h->d_p1, (size_t)m));
+        TRY(allreduce(h, h->d_pxc, (size_t)m * 3));
+    }
+    return cpd_last_estep(h, nu_d, nu, px, n_p);
 }
 
 extern "C" int cpd_last_estep(cpd_ctx* h, double* pt1, double* p1, double* px, double* n_p) {
@@ -1106,7 +1176,9 @@ extern "C" int cpd_nonrigid_lowrank_get(cpd_ctx* h, int* rank_out, double* q_out
     return CPD_OK;
 }
 
-extern "C" int cpd_rbf_kernel(int device, const double* x, int64_t nx, const double* y, int64_t ny, int dim, double beta, float* out) {
+namespace {
+// float32 nx x ny kernel matrix of two host clouds; kind 0: rbf (param = beta), 1: inverse multiquadric (param = c)
+int pair_matrix(int kind, int device, const double* x, int64_t nx, const double* y, int64_t ny, int dim, double param, float* out) {
     if (!x || !y || !out || nx < 1 || ny < 1 || dim < 1 || dim > 16) return fail(CPD_ERR_ARG, "bad argument");
     if (cpd_device_count() == 0) return fail(CPD_ERR_CUDA, "no CUDA device: this library has no CPU path");
     CU(cudaSetDevice(device));
@@ -1120,11 +1192,20 @@ extern "C" int cpd_rbf_kernel(int device, const double* x, int64_t nx, const dou
     CU(cudaMemcpy(dx, xf.data(), xf.size() * sizeof(float), cudaMemcpyHostToDevice));
     CU(cudaMemcpy(dy, yf.data(), yf.size() * sizeof(float), cudaMemcpyHostToDevice));
     dim3 grid((unsigned)nx, blocks_for(ny));
-    rbf_kernel_kernel<<<grid, THREADS>>>(dx, nx, dy, ny, dim, (float)(1.0 / (2.0 * beta)), dout);
+    if (kind == 0) rbf_kernel_kernel<<<grid, THREADS>>>(dx, nx, dy, ny, dim, (float)(1.0 / (2.0 * param)), dout);
+    else imq_kernel_kernel<<<grid, THREADS>>>(dx, nx, dy, ny, dim, (float)param, dout);
     KCHECK();
     CU(cudaMemcpy(out, dout, (size_t)nx * ny * sizeof(float), cudaMemcpyDeviceToHost));
     cudaFree(dx); cudaFree(dy); cudaFree(dout);
     return CPD_OK;
+}
+}  // namespace
+
+extern "C" int cpd_rbf_kernel(int device, const double* x, int64_t nx, const double* y, int64_t ny, int dim, double beta, float* out) {
+    return pair_matrix(0, device, x, nx, y, ny, dim, beta, out);
+}
+extern "C" int cpd_imq_kernel(int device, const double* x, int64_t nx, const double* y, int64_t ny, int dim, double c, float* out) {
+    return pair_matrix(1, device, x, nx, y, ny, dim, c, out);
 }
 
 // Direct Gauss transform on host arrays (stateless).  weights: k x m row-major, out: k x n.

@@ -269,6 +269,20 @@ pack_kernel(const DevState* __restrict__ st, const double* __restrict__ sigma2_p
     }
 }
 
+// Per-source weights of a weighted E-step (BCPD): la_m = -log2(weight_m) - min(...) >= 0 goes into the spare lanes of the
+// records pack_kernel wrote: srcP[m].w (pass 2 i-points) and srcJ[2m+1].zw (pass 1 j-records).  Padding keeps 0.
+__global__ void __launch_bounds__(THREADS)
+weight_patch_kernel(const float* __restrict__ la, long long m, float4* __restrict__ srcP, float4* __restrict__ srcJ) {
+    const long long i = (long long)blockIdx.x * THREADS + threadIdx.x;
+    if (i < m) {
+        const float v = la[i];
+        srcP[i].w = v;
+        float4 r = srcJ[2 * i + 1];
+        r.z = v; r.w = v;
+        srcJ[2 * i + 1] = r;
+    }
+}
+
 // ---------------------------------------------------------------------------------------------
 // pass 1: per target n and split:  (o, S, SU) with  sum_m 2^(-u) = S 2^(-o),  sum_m 2^(-u) u = SU 2^(-o)
 // One CTA per work item {target tile, source-stage range, partial slot}; the host chooses the number of stage
@@ -412,6 +426,9 @@ __device__ __forceinline__ float box_gap2(const float* __restrict__ wbox, const 
 // Why: adding thousands of tiny terms one by one to a partial sum that already holds a dominant term drops
 // them (absorption), a SYSTEMATIC loss that does not average out -- measured -1.2e-6 on sigma2 with a flat
 // 64-term sum, -2e-6 with 128 (profiles/r1_precision_subchunk.txt).
+// WGT: every source carries a weight 2^-la (la >= 0) in the spare half of its z-record; t' = u - o + la, added LAST so that
+// pass 2 (which adds the same la after the same FMA chain) sees bit-identical exponents (the BCPD E-step, bcpd.py:53-66).
+template <bool WGT>
 __device__ __forceinline__ void pass1_sum(const ulonglong2* __restrict__ q, const u64 (&ax)[NPAIR1], const u64 (&ay)[NPAIR1],
                                           const u64 (&az)[NPAIR1], const u64 (&no)[NPAIR1], u64 (&Sc)[NPAIR1], u64 (&Uc)[NPAIR1]) {
     if (GRP > 0) {
@@ -422,12 +439,15 @@ __device__ __forceinline__ void pass1_sum(const ulonglong2* __restrict__ q, cons
             for (int jj = 0; jj < (GRP > 0 ? GRP : 1); ++jj) {
                 const ulonglong2 bxy = q[2 * (g0 + jj)];
                 const u64 bz = q[2 * (g0 + jj) + 1].x;
+                u64 la = 0ull;
+                if (WGT) la = q[2 * (g0 + jj) + 1].y;
 #pragma unroll
                 for (int p = 0; p < NPAIR1; ++p) {
                     const u64 dx = fsub2(ax[p], bxy.x), dy = fsub2(ay[p], bxy.y), dz = fsub2(az[p], bz);
                     u64 t = ffma2(dx, dx, no[p]);
                     t = ffma2(dy, dy, t);
                     t = ffma2(dz, dz, t);
+                    if (WGT) t = fadd2(t, la);
                     const float2 tt = unpack2(t);
                     const u64 e = pack2(ex2(-tt.x), ex2(-tt.y));
                     gs[p] = jj == 0 ? e : fadd2(gs[p], e);
@@ -442,12 +462,15 @@ __device__ __forceinline__ void pass1_sum(const ulonglong2* __restrict__ q, cons
         for (int jj = 0; jj < SUB; ++jj) {
             const ulonglong2 bxy = q[2 * jj];
             const u64 bz = q[2 * jj + 1].x;
+            u64 la = 0ull;
+            if (WGT) la = q[2 * jj + 1].y;
 #pragma unroll
             for (int p = 0; p < NPAIR1; ++p) {
                 const u64 dx = fsub2(ax[p], bxy.x), dy = fsub2(ay[p], bxy.y), dz = fsub2(az[p], bz);
                 u64 t = ffma2(dx, dx, no[p]);
                 t = ffma2(dy, dy, t);
                 t = ffma2(dz, dz, t);
+                if (WGT) t = fadd2(t, la);
                 const float2 tt = unpack2(t);
                 const u64 e = pack2(ex2(-tt.x), ex2(-tt.y));
                 Sc[p] = fadd2(Sc[p], e);
@@ -457,7 +480,7 @@ __device__ __forceinline__ void pass1_sum(const ulonglong2* __restrict__ q, cons
     }
 }
 
-template <bool CULL>
+template <bool CULL, bool WGT>
 __global__ void __launch_bounds__(THREADS, CPD_MINB1)
 pass1_kernel(const float4* __restrict__ ipts, int ni, const float4* __restrict__ jrec, const int4* __restrict__ work,
              P1Part* __restrict__ part, const float4* __restrict__ sbox /* bounding boxes of the source stages */,
@@ -522,10 +545,14 @@ pass1_kernel(const float4* __restrict__ ipts, int ni, const float4* __restrict__
         for (int jj = 0; jj < 128; ++jj) {
             const ulonglong2 bxy = near[2 * jj];
             const u64 bz = near[2 * jj + 1].x;
+            u64 la = 0ull;
+            if (WGT) la = near[2 * jj + 1].y;
 #pragma unroll
             for (int p = 0; p < NPAIR1; ++p) {
                 const u64 dx = fsub2(ax[p], bxy.x), dy = fsub2(ay[p], bxy.y), dz = fsub2(az[p], bz);
-                const float2 u = unpack2(ffma2(dz, dz, ffma2(dy, dy, fmul2(dx, dx))));
+                u64 uu = ffma2(dz, dz, ffma2(dy, dy, fmul2(dx, dx)));
+                if (WGT) uu = fadd2(uu, la);
+                const float2 u = unpack2(uu);
                 cm[2 * p] = fminf(cm[2 * p], u.x);
                 cm[2 * p + 1] = fminf(cm[2 * p + 1], u.y);
             }
@@ -564,7 +591,7 @@ pass1_kernel(const float4* __restrict__ ipts, int ni, const float4* __restrict__
             u64 Sc[NPAIR1], Uc[NPAIR1];          // Sc = sum e,  Uc = sum e * t'  with t' = u - o, e = 2^-t'
 #pragma unroll
             for (int p = 0; p < NPAIR1; ++p) { Sc[p] = 0ull; Uc[p] = 0ull; }
-            pass1_sum(q, ax, ay, az, no, Sc, Uc);
+            pass1_sum<WGT>(q, ax, ay, az, no, Sc, Uc);
             bool bad = false;
 #pragma unroll
             for (int p = 0; p < NPAIR1; ++p) {
@@ -579,10 +606,14 @@ pass1_kernel(const float4* __restrict__ ipts, int ni, const float4* __restrict__
                 for (int jj = 0; jj < SUB; ++jj) {
                     const ulonglong2 bxy = q[2 * jj];
                     const u64 bz = q[2 * jj + 1].x;
+                    u64 la = 0ull;
+                    if (WGT) la = q[2 * jj + 1].y;
 #pragma unroll
                     for (int p = 0; p < NPAIR1; ++p) {
                         const u64 dx = fsub2(ax[p], bxy.x), dy = fsub2(ay[p], bxy.y), dz = fsub2(az[p], bz);
-                        const float2 u = unpack2(ffma2(dz, dz, ffma2(dy, dy, fmul2(dx, dx))));
+                        u64 uu = ffma2(dz, dz, ffma2(dy, dy, fmul2(dx, dx)));
+                        if (WGT) uu = fadd2(uu, la);
+                        const float2 u = unpack2(uu);
                         cm[2 * p] = fminf(cm[2 * p], u.x);
                         cm[2 * p + 1] = fminf(cm[2 * p + 1], u.y);
                     }
@@ -606,7 +637,7 @@ pass1_kernel(const float4* __restrict__ ipts, int ni, const float4* __restrict__
                     for (int o = 16; o > 0; o >>= 1) om = fmaxf(om, __shfl_xor_sync(0xffffffffu, om, o));
                     omax_w = om;
                 }
-                pass1_sum(q, ax, ay, az, no, Sc, Uc);
+                pass1_sum<WGT>(q, ax, ay, az, no, Sc, Uc);
             }
 #pragma unroll
             for (int p = 0; p < NPAIR1; ++p) {
@@ -655,7 +686,8 @@ pass1_kernel(const float4* __restrict__ ipts, int ni, const float4* __restrict__
 __global__ void __launch_bounds__(THREADS)
 finalize1_kernel(const DevState* __restrict__ st, const double* __restrict__ sigma2_ptr, const double* __restrict__ w_ptr,
                  const P1Part* __restrict__ part, const int* __restrict__ tile_slots, int n, const float4* __restrict__ tgtP,
-                 float4* __restrict__ tgtQ, long long npad, double* __restrict__ pt1, double* __restrict__ mom_part) {
+                 float4* __restrict__ tgtQ, long long npad, double* __restrict__ pt1, double* __restrict__ mom_part,
+                 const double* __restrict__ log2c_ptr /* null: c from w (cpd.py:79); else log2 of the constant added to sum_m K (BCPD) */) {
     const int i = blockIdx.x * THREADS + threadIdx.x;
     double v[RM_TGT] = {0.0, 0.0};
     if (i < n) {
@@ -684,11 +716,12 @@ finalize1_kernel(const DevState* __restrict__ st, const double* __restrict__ sig
             const double tps = 2.0 * 3.14159265358979323846 * sigma2;
             c = (st->dim == 3 ? tps * sqrt(tps) : tps) * (w / (1.0 - w) * (double)st->m / (double)st->n_global);
         }
-        const bool dead = !(log2S >= DEAD_LOG2);
+        double lc = c > 0.0 ? log2(c) : -INFINITY, dead_shift = 0.0;
+        if (log2c_ptr != nullptr) { lc = log2c_ptr[0]; dead_shift = log2c_ptr[1]; c = (lc > -INFINITY) ? 1.0 : 0.0; }
+        const bool dead = !(log2S + dead_shift >= DEAD_LOG2);
         double L = 0.0, p1n = 0.0;
         if (!dead) {
             if (c > 0.0) {
-                const double lc = log2(c);
                 const double hi = fmax(log2S, lc), lo = fmin(log2S, lc);
                 L = hi + log2(1.0 + exp2(lo - hi));
                 p1n = exp2(log2S - L);
@@ -721,7 +754,7 @@ finalize1_kernel(const DevState* __restrict__ st, const double* __restrict__ sig
 // pass 2: per source m and split of the targets:  p1_m = sum_n P_mn,  sd_m = sum_n P_mn (a_m - b_n)
 // with P_mn = 2^(o_n - u_mn) * rn_n.  Per two pairs: 11 packed FP32 instructions + 2 MUFU.
 // ---------------------------------------------------------------------------------------------
-template <bool CULL>
+template <bool CULL, bool WGT>
 __global__ void __launch_bounds__(THREADS, CPD_MINB2)
 pass2_kernel(const float4* __restrict__ ipts, int ni, const float4* __restrict__ jrec, const int4* __restrict__ work,
              double* __restrict__ part /* [slot][ni][4] */, const float4* __restrict__ tbox /* per target stage bbox or null */,
@@ -745,7 +778,7 @@ pass2_kernel(const float4* __restrict__ ipts, int ni, const float4* __restrict__
             tma_load_1d(smraw + s * P2_STAGE_BYTES, jbytes + (size_t)(st0 + s) * P2_STAGE_BYTES, P2_STAGE_BYTES, &full[s]);
         }
     }
-    u64 ax[NPAIR2], ay[NPAIR2], az[NPAIR2];
+    u64 ax[NPAIR2], ay[NPAIR2], az[NPAIR2], al[NPAIR2];      // al = (la, la') of the two sources: WGT only
     double A1[RI2], AX[RI2], AY[RI2], AZ[RI2];
 #pragma unroll
     for (int p = 0; p < NPAIR2; ++p) {
@@ -754,6 +787,7 @@ pass2_kernel(const float4* __restrict__ ipts, int ni, const float4* __restrict__
         m1 = m1 < ni ? m1 : ni - 1;
         const float4 p0 = ipts[m0], p1 = ipts[m1];
         ax[p] = pack2(p0.x, p1.x); ay[p] = pack2(p0.y, p1.y); az[p] = pack2(p0.z, p1.z);
+        if (WGT) al[p] = pack2(p0.w, p1.w);
     }
     float* const mybox = wbox[tid >> 5];
     if (CULL) warp_bbox<NPAIR2>(ax, ay, az, mybox);
@@ -793,6 +827,7 @@ pass2_kernel(const float4* __restrict__ ipts, int ni, const float4* __restrict__
                             u64 t = ffma2(dx, dx, bzo.y);         // t' = u - o_n: the same FMA chain and offset as pass 1
                             t = ffma2(dy, dy, t);
                             t = ffma2(dz, dz, t);
+                            if (WGT) t = fadd2(t, al[p]);
                             const float2 tt = unpack2(t);
                             const u64 pr = fmul2(pack2(ex2(-tt.x), ex2(-tt.y)), rn);
                             g1[p] = jj == 0 ? pr : fadd2(g1[p], pr);
@@ -819,6 +854,7 @@ pass2_kernel(const float4* __restrict__ ipts, int ni, const float4* __restrict__
                         u64 t = ffma2(dx, dx, bzo.y);
                         t = ffma2(dy, dy, t);
                         t = ffma2(dz, dz, t);
+                        if (WGT) t = fadd2(t, al[p]);
                         const float2 tt = unpack2(t);
                         const u64 pr = fmul2(pack2(ex2(-tt.x), ex2(-tt.y)), rn);
                         s1[p] = fadd2(s1[p], pr);
@@ -1336,6 +1372,11 @@ gather1_kernel(const double* __restrict__ in, const int* __restrict__ perm, long
     const long long k = (long long)blockIdx.x * THREADS + threadIdx.x;
     if (k < n) out[k] = in[perm[k]];
 }
+__global__ void __launch_bounds__(THREADS)
+gather_f32_kernel(const double* __restrict__ in, const int* __restrict__ perm, long long n, float* __restrict__ out) {
+    const long long k = (long long)blockIdx.x * THREADS + threadIdx.x;
+    if (k < n) out[k] = (float)in[perm[k]];
+}
 // out[perm[k]] = in[k]   (n x ncomp): back to the caller's order
 __global__ void __launch_bounds__(THREADS)
 scatter_kernel(const double* __restrict__ in, const int* __restrict__ perm, long long n, int ncomp, double* __restrict__ out) {
@@ -1442,6 +1483,19 @@ rbf_kernel_kernel(const float* __restrict__ x, long long nx, const float* __rest
         float d2 = 0.f;
         for (int a = 0; a < dim; ++a) { const float d = x[i * dim + a] - y[j * dim + a]; d2 += d * d; }
         out[i * ny + j] = expf(-d2 * inv2beta);
+    }
+}
+
+// _math.inverse_multiquadric_kernel (cc/math_utils.cc:37-39): float32 (|x_i - y_j|^2 + c)^(-1/2)
+__global__ void __launch_bounds__(THREADS)
+imq_kernel_kernel(const float* __restrict__ x, long long nx, const float* __restrict__ y, long long ny, int dim, float c,
+                  float* __restrict__ out) {
+    const long long j = (long long)blockIdx.y * THREADS + threadIdx.x;
+    const long long i = blockIdx.x;
+    if (j < ny) {
+        float d2 = 0.f;
+        for (int a = 0; a < dim; ++a) { const float d = x[i * dim + a] - y[j * dim + a]; d2 += d * d; }
+        out[i * ny + j] = 1.0f / sqrtf(d2 + c);
     }
 }
 

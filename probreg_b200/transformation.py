@@ -114,3 +114,15 @@ class LowRankNonRigidTransformation(NonRigidTransformation):
 
     def _transform(self, points):
         return points + np.dot(self.q, np.dot(self.bcore, np.dot(self.q.T, self.w)))
+
+
+class CombinedTransformation(Transformation):
+    """x -> rigid(x + v): a per-point displacement followed by a similarity (transformation.py:105-121; BCPD)."""
+
+    def __init__(self, rot=None, t=None, scale=1.0, v=0.0):
+        super(CombinedTransformation, self).__init__()
+        self.rigid_trans = RigidTransformation(np.identity(3) if rot is None else rot, np.zeros(3) if t is None else t, scale)
+        self.v = v
+
+    def _transform(self, points):
+        return self.rigid_trans._transform(points + self.v)
