@@ -147,19 +147,19 @@ class Handle(object):
     # -- data
     def set_source(self, source):
         src = as_cloud(source, self.dim)
-        check(lib().cpd_set_source(self._h, dptr(src), src.shape[0]))
+        check(self._lib.cpd_set_source(self._h, dptr(src), src.shape[0]))
         self.m = src.shape[0]
 
     def set_target(self, target, n_global=None, frame_origin=None):
         tgt = as_cloud(target, self.dim)
         n_global = tgt.shape[0] if n_global is None else int(n_global)
         org = None if frame_origin is None else np.ascontiguousarray(frame_origin, dtype=np.float64)
-        check(lib().cpd_set_target(self._h, dptr(tgt), tgt.shape[0], n_global, dptr(org)))
+        check(self._lib.cpd_set_target(self._h, dptr(tgt), tgt.shape[0], n_global, dptr(org)))
         self.n = tgt.shape[0]
 
     def sigma2_init(self):
         out = ctypes.c_double()
-        check(lib().cpd_sigma2_init(self._h, ctypes.byref(out)))
+        check(self._lib.cpd_sigma2_init(self._h, ctypes.byref(out)))
         return out.value
 
     # -- EM
@@ -174,7 +174,7 @@ class Handle(object):
         for i in range(d):
             p.t[i] = tt[i]
         p.scale, p.sigma2, p.q = float(scale), float(sigma2), float(q)
-        check(lib().cpd_set_state(self._h, tf_kind, int(bool(update_scale)), float(w), ctypes.byref(p)))
+        check(self._lib.cpd_set_state(self._h, tf_kind, int(bool(update_scale)), float(w), ctypes.byref(p)))
 
     def _unpack(self, p):
         d = self.dim
@@ -184,17 +184,17 @@ class Handle(object):
 
     def em_step(self, read=True):
         if not read:
-            check(lib().cpd_em_step(self._h, None))
+            check(self._lib.cpd_em_step(self._h, None))
             return None
         p = CpdParams()
-        check(lib().cpd_em_step(self._h, ctypes.byref(p)))
+        check(self._lib.cpd_em_step(self._h, ctypes.byref(p)))
         return self._unpack(p)
 
     def em_run(self, maxiter, tol, trace=False):
         p = CpdParams()
         it = ctypes.c_int()
         tr = np.zeros((max(maxiter, 1), 2)) if trace else None
-        check(lib().cpd_em_run(self._h, int(maxiter), float(tol), ctypes.byref(p), ctypes.byref(it), dptr(tr)))
+        check(self._lib.cpd_em_run(self._h, int(maxiter), float(tol), ctypes.byref(p), ctypes.byref(it), dptr(tr)))
         out = self._unpack(p) + (it.value,)
         return out + (tr[: it.value],) if trace else out
 
@@ -206,7 +206,7 @@ class Handle(object):
         p1 = np.empty(self.m) if want_p1 else None
         px = np.empty((self.m, self.dim)) if want_px else None
         n_p = ctypes.c_double()
-        check(lib().cpd_estep(self._h, dptr(ts), float(sigma2), float(w), dptr(pt1), dptr(p1), dptr(px), ctypes.byref(n_p)))
+        check(self._lib.cpd_estep(self._h, dptr(ts), float(sigma2), float(w), dptr(pt1), dptr(p1), dptr(px), ctypes.byref(n_p)))
         return pt1, p1, px, n_p.value
 
     def bcpd_estep(self, t_source, scale, alpha, sigma_diag, sigma2, w):
@@ -218,14 +218,14 @@ class Handle(object):
             raise ValueError("t_source / alpha / sigma_diag do not match the handle's source count %d" % self.m)
         nu_d, nu, px = np.empty(self.n), np.empty(self.m), np.empty((self.m, self.dim))
         n_p = ctypes.c_double()
-        check(lib().cpd_bcpd_estep(self._h, dptr(ts), float(scale), dptr(al), dptr(sd), float(sigma2), float(w), dptr(nu_d), dptr(nu),
+        check(self._lib.cpd_bcpd_estep(self._h, dptr(ts), float(scale), dptr(al), dptr(sd), float(sigma2), float(w), dptr(nu_d), dptr(nu),
                                    dptr(px), ctypes.byref(n_p)))
         return nu_d, nu, px, n_p.value
 
     def last_estep(self):
         pt1, p1, px = np.empty(self.n), np.empty(self.m), np.empty((self.m, self.dim))
         n_p = ctypes.c_double()
-        check(lib().cpd_last_estep(self._h, dptr(pt1), dptr(p1), dptr(px), ctypes.byref(n_p)))
+        check(self._lib.cpd_last_estep(self._h, dptr(pt1), dptr(p1), dptr(px), ctypes.byref(n_p)))
         return pt1, p1, px, n_p.value
 
     def mstep(self, tf_kind, update_scale, pt1, p1, px, n_p):
@@ -235,102 +235,102 @@ class Handle(object):
         if pt1.shape[0] != self.n or p1.shape[0] != self.m or px.shape[0] != self.m:
             raise ValueError("EstepResult shapes do not match the handle's source/target")
         p = CpdParams()
-        check(lib().cpd_mstep(self._h, tf_kind, int(bool(update_scale)), dptr(pt1), dptr(p1), dptr(px), float(n_p),
+        check(self._lib.cpd_mstep(self._h, tf_kind, int(bool(update_scale)), dptr(pt1), dptr(p1), dptr(px), float(n_p),
                               ctypes.byref(p)))
         return self._unpack(p)
 
     # -- non-rigid (dense G on the device)
     def nonrigid_begin(self, beta, lmd, sigma2, w):
-        check(lib().cpd_nonrigid_begin(self._h, float(beta), float(lmd), float(sigma2), float(w)))
+        check(self._lib.cpd_nonrigid_begin(self._h, float(beta), float(lmd), float(sigma2), float(w)))
 
     def nonrigid_lowrank_begin(self, beta, lmd, sigma2, w, rank, power_iters=2, seed=0):
-        check(lib().cpd_nonrigid_lowrank_begin(self._h, float(beta), float(lmd), float(sigma2), float(w), int(rank), int(power_iters),
+        check(self._lib.cpd_nonrigid_lowrank_begin(self._h, float(beta), float(lmd), float(sigma2), float(w), int(rank), int(power_iters),
                                                int(seed)))
 
     def nonrigid_lowrank_factors(self):
         """(Q (m x rank), Bc (rank x rank)) with G ~= Q Bc Q^T, Q in the caller's point order."""
         k = ctypes.c_int()
-        check(lib().cpd_nonrigid_lowrank_get(self._h, ctypes.byref(k), None, None))
+        check(self._lib.cpd_nonrigid_lowrank_get(self._h, ctypes.byref(k), None, None))
         q, b = np.empty((self.m, k.value)), np.empty((k.value, k.value))
-        check(lib().cpd_nonrigid_lowrank_get(self._h, None, dptr(q), dptr(b)))
+        check(self._lib.cpd_nonrigid_lowrank_get(self._h, None, dptr(q), dptr(b)))
         return q, b
 
     def nonrigid_set_prior(self, alpha, p1_tilde, px_tilde):
         if p1_tilde is None:
-            check(lib().cpd_nonrigid_set_prior(self._h, 1.0, None, None))
+            check(self._lib.cpd_nonrigid_set_prior(self._h, 1.0, None, None))
             return
         p1t = np.ascontiguousarray(p1_tilde, dtype=np.float64)
         pxt = as_cloud(px_tilde, self.dim)
         if p1t.shape != (self.m,) or pxt.shape[0] != self.m:
             raise ValueError("prior shapes do not match the handle's source")
-        check(lib().cpd_nonrigid_set_prior(self._h, float(alpha), dptr(p1t), dptr(pxt)))
+        check(self._lib.cpd_nonrigid_set_prior(self._h, float(alpha), dptr(p1t), dptr(pxt)))
 
     def nonrigid_moved(self):
         t = np.empty((self.m, self.dim))
-        check(lib().cpd_nonrigid_get(self._h, None, dptr(t)))
+        check(self._lib.cpd_nonrigid_get(self._h, None, dptr(t)))
         return t
 
     def nonrigid_step(self):
         out = ctypes.c_double()
-        check(lib().cpd_nonrigid_step(self._h, ctypes.byref(out)))
+        check(self._lib.cpd_nonrigid_step(self._h, ctypes.byref(out)))
         return out.value
 
     def nonrigid_w(self):
         w = np.empty((self.m, self.dim))
-        check(lib().cpd_nonrigid_get(self._h, dptr(w), None))
+        check(self._lib.cpd_nonrigid_get(self._h, dptr(w), None))
         return w
 
     # -- multi-GPU
     def attach_comm(self, nccl_comm, world_size, rank):
         """nccl_comm: the value returned by comm_create (borrowed; it must outlive the handle)."""
-        check(lib().cpd_comm_attach(self._h, nccl_comm, world_size, rank))
+        check(self._lib.cpd_comm_attach(self._h, nccl_comm, world_size, rank))
 
     def p2p_local_handle(self):
         buf = ctypes.create_string_buffer(64)
-        check(lib().cpd_p2p_local_handle(self._h, buf))
+        check(self._lib.cpd_p2p_local_handle(self._h, buf))
         return buf.raw
 
     def p2p_attach(self, handles, world_size, rank):
         blob = b"".join(handles)
         assert len(blob) == 64 * world_size
-        check(lib().cpd_p2p_attach(self._h, blob, world_size, rank))
+        check(self._lib.cpd_p2p_attach(self._h, blob, world_size, rank))
 
     def p2p_detach(self):
-        check(lib().cpd_p2p_detach(self._h))
+        check(self._lib.cpd_p2p_detach(self._h))
 
     # -- measurement
     def timer_start(self):
-        check(lib().cpd_timer_start(self._h))
+        check(self._lib.cpd_timer_start(self._h))
 
     def timer_stop(self):
         ms = ctypes.c_float()
-        check(lib().cpd_timer_stop(self._h, ctypes.byref(ms)))
+        check(self._lib.cpd_timer_stop(self._h, ctypes.byref(ms)))
         return ms.value
 
     def sync(self):
-        check(lib().cpd_sync(self._h))
+        check(self._lib.cpd_sync(self._h))
 
     def event_record(self, idx):
-        check(lib().cpd_event_record(self._h, idx))
+        check(self._lib.cpd_event_record(self._h, idx))
 
     def event_elapsed(self, a, b):
         ms = ctypes.c_float()
-        check(lib().cpd_event_elapsed(self._h, a, b, ctypes.byref(ms)))
+        check(self._lib.cpd_event_elapsed(self._h, a, b, ctypes.byref(ms)))
         return ms.value
 
     def set_profiling(self, on):
-        check(lib().cpd_set_profiling(self._h, int(on)))
+        check(self._lib.cpd_set_profiling(self._h, int(on)))
 
     def stage_times(self):
         ms = (ctypes.c_float * 6)()
-        check(lib().cpd_stage_times(self._h, ms))
+        check(self._lib.cpd_stage_times(self._h, ms))
         return list(ms)
 
     def launch_count(self):
         return int(lib().cpd_launch_count(self._h))
 
     def flush_l2(self, nbytes=0):
-        check(lib().cpd_flush_l2(self._h, nbytes))
+        check(self._lib.cpd_flush_l2(self._h, nbytes))
 
 
 def unique_id():

@@ -186,6 +186,7 @@ struct cpd_ctx {
     bool nr_ready = false;
     // weighted E-step (BCPD): per-source exponent offsets and the {log2 c, dead-column shift} pair for finalize 1
     float* d_la = nullptr;
+    size_t la_cap = 0;
     double* d_log2c = nullptr;
     bool wgt_on = false;
     // correspondence priors of ConstrainedNonRigidCPD
@@ -221,6 +222,13 @@ int dev_alloc(T** p, size_t count) {
     return CPD_OK;
 }
 #define TRY(x) do { int r__ = (x); if (r__ != CPD_OK) return r__; } while (0)
+// device buffer of a stateless entry point: freed on every exit path
+template <typename T>
+struct DevBuf {
+    T* p = nullptr;
+    ~DevBuf() { if (p) cudaFree(p); }
+    int alloc(size_t count) { return dev_alloc(&p, count); }
+};
 
 inline unsigned blocks_for(long long n) { return (unsigned)((n + THREADS - 1) / THREADS); }
 
@@ -760,7 +768,7 @@ extern "C" int cpd_bcpd_estep(cpd_ctx* h, const double* t_source, double scale, 
     }
     if (!(la_min < INFINITY)) return fail(CPD_ERR_ARG, "every source has zero weight");
     for (long long i = 0; i < m; ++i) la[(size_t)i] = std::min(la[(size_t)i] - la_min, 1.0e30);      // +inf -> a weight of exactly 0
-    TRY(dev_alloc(&h->d_la, (size_t)m));
+    if (h->la_cap < (size_t)m) { TRY(dev_alloc(&h->d_la, (size_t)m)); h->la_cap = (size_t)m; }
     if (!h->d_log2c) TRY(dev_alloc(&h->d_log2c, 2));
     const double half_d_log2 = 0.5 * (double)h->dim * log2(2.0 * 3.14159265358979323846 * sigma2);
     h->h_pin[34] = (w > 0.0) ? log2(w / (double)h->n_global) + la_min + half_d_log2 : -INFINITY;   // log2 of the constant, in kernel units
@@ -1185,18 +1193,17 @@ int pair_matrix(int kind, int device, const double* x, int64_t nx, const double*
     std::vector<float> xf((size_t)nx * dim), yf((size_t)ny * dim);   // the pybind11/Eigen cast to float32 (cc/types.h:19)
     for (size_t i = 0; i < xf.size(); ++i) xf[i] = (float)x[i];
     for (size_t i = 0; i < yf.size(); ++i) yf[i] = (float)y[i];
-    float *dx = nullptr, *dy = nullptr, *dout = nullptr;
-    TRY(dev_alloc(&dx, xf.size()));
-    TRY(dev_alloc(&dy, yf.size()));
-    TRY(dev_alloc(&dout, (size_t)nx * ny));
-    CU(cudaMemcpy(dx, xf.data(), xf.size() * sizeof(float), cudaMemcpyHostToDevice));
-    CU(cudaMemcpy(dy, yf.data(), yf.size() * sizeof(float), cudaMemcpyHostToDevice));
+    DevBuf<float> dx, dy, dout;
+    TRY(dx.alloc(xf.size()));
+    TRY(dy.alloc(yf.size()));
+    TRY(dout.alloc((size_t)nx * ny));
+    CU(cudaMemcpy(dx.p, xf.data(), xf.size() * sizeof(float), cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(dy.p, yf.data(), yf.size() * sizeof(float), cudaMemcpyHostToDevice));
     dim3 grid((unsigned)nx, blocks_for(ny));
-    if (kind == 0) rbf_kernel_kernel<<<grid, THREADS>>>(dx, nx, dy, ny, dim, (float)(1.0 / (2.0 * param)), dout);
-    else imq_kernel_kernel<<<grid, THREADS>>>(dx, nx, dy, ny, dim, (float)param, dout);
+    if (kind == 0) rbf_kernel_kernel<<<grid, THREADS>>>(dx.p, nx, dy.p, ny, dim, (float)(1.0 / (2.0 * param)), dout.p);
+    else imq_kernel_kernel<<<grid, THREADS>>>(dx.p, nx, dy.p, ny, dim, (float)param, dout.p);
     KCHECK();
-    CU(cudaMemcpy(out, dout, (size_t)nx * ny * sizeof(float), cudaMemcpyDeviceToHost));
-    cudaFree(dx); cudaFree(dy); cudaFree(dout);
+    CU(cudaMemcpy(out, dout.p, (size_t)nx * ny * sizeof(float), cudaMemcpyDeviceToHost));
     return CPD_OK;
 }
 }  // namespace
@@ -1233,21 +1240,20 @@ extern "C" int cpd_gauss_transform(int device, const double* source, int64_t m, 
         ht[(size_t)i] = make_float4(v[0], v[1], v[2], 0.0f);
     }
     for (int cc = 0; cc < k; ++cc) for (int64_t j = 0; j < m; ++j) hw[(size_t)cc * mpad + j] = (float)weights[(size_t)cc * m + j];
-    float4 *ds = nullptr, *dt = nullptr;
-    float* dw = nullptr;
-    double* dout = nullptr;
-    TRY(dev_alloc(&ds, hs.size()));
-    TRY(dev_alloc(&dt, ht.size()));
-    TRY(dev_alloc(&dw, hw.size()));
-    TRY(dev_alloc(&dout, (size_t)k * n));
-    CU(cudaMemcpy(ds, hs.data(), hs.size() * sizeof(float4), cudaMemcpyHostToDevice));
-    CU(cudaMemcpy(dt, ht.data(), ht.size() * sizeof(float4), cudaMemcpyHostToDevice));
-    CU(cudaMemcpy(dw, hw.data(), hw.size() * sizeof(float), cudaMemcpyHostToDevice));
+    DevBuf<float4> ds, dt;
+    DevBuf<float> dw;
+    DevBuf<double> dout;
+    TRY(ds.alloc(hs.size()));
+    TRY(dt.alloc(ht.size()));
+    TRY(dw.alloc(hw.size()));
+    TRY(dout.alloc((size_t)k * n));
+    CU(cudaMemcpy(ds.p, hs.data(), hs.size() * sizeof(float4), cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(dt.p, ht.data(), ht.size() * sizeof(float4), cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(dw.p, hw.data(), hw.size() * sizeof(float), cudaMemcpyHostToDevice));
     for (int k0 = 0; k0 < k; k0 += GT_K)
-        gauss_transform_kernel<<<blocks_for(n), THREADS>>>(dt, (int)n, ds, dw, (int)mpad, k0, std::min(GT_K, k - k0), dout);
+        gauss_transform_kernel<<<blocks_for(n), THREADS>>>(dt.p, (int)n, ds.p, dw.p, (int)mpad, k0, std::min(GT_K, k - k0), dout.p);
     KCHECK();
-    CU(cudaMemcpy(out, dout, (size_t)k * n * sizeof(double), cudaMemcpyDeviceToHost));
-    cudaFree(ds); cudaFree(dt); cudaFree(dw); cudaFree(dout);
+    CU(cudaMemcpy(out, dout.p, (size_t)k * n * sizeof(double), cudaMemcpyDeviceToHost));
     return CPD_OK;
 }
 
