@@ -7,6 +7,7 @@
 #include <sys/mman.h>
 #include <ucontext.h>
 
+#include <algorithm>
 #include <chrono>
 #include <vector>
 
@@ -104,8 +105,31 @@ unsigned vote_any(bool pred) {
 }
 long long launches() { return g_launches; }
 
+// Order in which the runnable fibers of a block get the CPU in each scheduling round.  CPD_EMU_SCHED = "rr" (default:
+// thread 0, 1, 2, ...), "reverse", or "random[:seed]" (a fresh permutation every round).  A kernel whose result depends on
+// the order is missing a barrier; the test-suite runs under all three.
+static void next_order(std::vector<size_t>& order, size_t n) {
+    static int mode = -1;
+    static unsigned long long rng = 0x9e3779b97f4a7c15ull;
+    if (mode < 0) {
+        const char* e = getenv("CPD_EMU_SCHED");
+        mode = (!e || !strncmp(e, "rr", 2)) ? 0 : (!strncmp(e, "reverse", 7) ? 1 : 2);
+        if (mode == 2 && e[6] == ':') rng ^= strtoull(e + 7, nullptr, 10) * 0xbf58476d1ce4e5b9ull;
+    }
+    if (order.size() != n) {
+        order.resize(n);
+        for (size_t i = 0; i < n; ++i) order[i] = mode == 1 ? n - 1 - i : i;
+    }
+    if (mode == 2)
+        for (size_t i = n - 1; i > 0; --i) {
+            rng ^= rng << 13; rng ^= rng >> 7; rng ^= rng << 17;
+            std::swap(order[i], order[rng % (i + 1)]);
+        }
+}
+
 void launch(const char* name, dim3 grid, dim3 block, size_t smem, cudaStream_t, const std::function<void()>& body) {
     const size_t nthreads = (size_t)block.x * block.y * block.z;
+    static std::vector<size_t> order;
     // the hardware limits a blind launch would trip over
     if (nthreads == 0 || nthreads > 1024 || grid.x == 0 || grid.y == 0 || grid.z == 0 || grid.x > 2147483647u || grid.y > 65535u ||
         grid.z > 65535u || smem > 227u * 1024u) {
@@ -150,7 +174,9 @@ void launch(const char* name, dim3 grid, dim3 block, size_t smem, cudaStream_t, 
                 long long idle_rounds = 0;
                 while (remaining > 0) {
                     int progressed = 0;
-                    for (size_t t = 0; t < nthreads; ++t) {
+                    next_order(order, nthreads);
+                    for (size_t oi = 0; oi < nthreads; ++oi) {
+                        const size_t t = order[oi];
                         Fiber& f = g_fibers[t];
                         if (f.done) continue;
                         g_cur = (int)t;

@@ -104,6 +104,22 @@ def test_multi_wave_work_lists_under_emulation(emulated, monkeypatch, sms):
     np.testing.assert_allclose(es.px, ref.px, rtol=2e-5, atol=2e-5)
 
 
+def test_results_do_not_depend_on_the_thread_schedule(emu_lib_path):
+    """Same inputs under three fiber schedules (in order, reversed, a random permutation per round): bit-identical results."""
+    import os
+    import subprocess
+    import sys
+
+    probe = os.path.join(os.path.dirname(emu_lib_path), "..", "sched_probe.py")
+    digests = []
+    for mode in ("rr", "reverse", "random:11"):
+        env = dict(os.environ, CPD_EMU_SCHED=mode)
+        r = subprocess.run([sys.executable, probe, emu_lib_path], capture_output=True, text=True, env=env, timeout=900)
+        assert r.returncode == 0, r.stderr[-2000:]
+        digests.append(r.stdout.strip().splitlines()[-1])
+    assert digests[0] == digests[1] == digests[2], digests
+
+
 def test_emulation_is_not_reachable_from_the_package(emu_lib_path):
     """The package loads probreg_b200/libcpd_b200.so (or CPD_B200_LIB) and nothing else; the emulation lives under tests/."""
     import os

@@ -1,0 +1,53 @@
+"""BASELINE.json configurations 3 and 4 at full size through size-independent properties (no oracle can hold them):
+   3. affine CPD, N = M = 250k on one GPU;   4. rigid CPD, N = M = 1M sharded over 8 GPUs -> here ONE rank's shard
+   (1M sources x 125k targets, the global N in the outlier constant), which is what each of the 8 processes executes.
+Only kernels that have run on hardware are involved, but these sizes have not been run through pytest on hardware yet
+(tools/gpu_sizes.py exercised them in round 1): xfail(strict=False) until they have, and the file sorts last.
+"""
+import numpy as np
+import pytest
+
+from oracle import c_oracle
+from oracle import cpd_oracle as orc
+from probreg_b200 import _cabi, cpd
+
+pytestmark = [pytest.mark.gpu, pytest.mark.timeout(900),
+              pytest.mark.xfail(reason="size not yet run through pytest on hardware", strict=False)]
+
+
+def test_config3_affine_250k_properties():
+    n = 250000
+    src, tgt = orc.synthetic_pair(n, "affine")
+    seen = []
+    res = cpd.registration_cpd(src, tgt, "affine", maxiter=25, tol=-1.0, callbacks=[lambda t: seen.append(1)])
+    assert len(seen) == 25
+    lin = orc.rot_z(30.0).dot(np.diag([1.1, 0.9, 1.05]))
+    lin[0, 1] += 0.05
+    np.testing.assert_allclose(res.transformation.b, lin, atol=5e-3)
+    np.testing.assert_allclose(res.transformation.t, [0.1, -0.2, 0.3], atol=5e-3)
+    assert 5e-5 < res.sigma2 < 5e-3
+    # one E-step at the final transform: conservation laws + a column sample against the C oracle
+    ts = res.transformation.transform(src)
+    es = cpd.AffineCPD(src).expectation_step(ts, tgt, res.sigma2, 0.1)
+    assert es.n_p == pytest.approx(es.pt1.sum(), rel=1e-7)
+    np.testing.assert_allclose(es.px.sum(0), (es.pt1[:, None] * tgt).sum(0), rtol=1e-6)
+    sel = np.random.default_rng(2).choice(n, 600, replace=False)
+    ref = c_oracle.expectation_step(ts, tgt[sel], res.sigma2, 0.1, n_global=n)
+    np.testing.assert_allclose(es.pt1[sel], ref.pt1, rtol=5e-5, atol=1e-12)
+
+
+def test_config4_one_rank_shard_of_1m():
+    m, n_global, ranks = 1000000, 1000000, 8
+    src, tgt = orc.synthetic_pair(m)
+    lo, hi = 3 * (n_global // ranks), 4 * (n_global // ranks)               # the shard rank 3 would hold
+    h = _cabi.Handle(3)
+    h.set_source(src)
+    h.set_target(tgt[lo:hi], n_global=n_global, frame_origin=tgt.mean(0))
+    ts = orc.apply_rigid(src, orc.rot_z(29.5), np.array([0.1, -0.2, 0.3]))
+    pt1, p1, px, n_p = h.estep(ts, 3e-4, 0.1)
+    assert pt1.shape == (hi - lo,) and p1.shape == (m,)
+    assert n_p == pytest.approx(pt1.sum(), rel=1e-7)                          # sum_m p1 == sum_n pt1 over the shard
+    np.testing.assert_allclose(px.sum(0), (pt1[:, None] * tgt[lo:hi]).sum(0), rtol=1e-6)
+    sel = np.random.default_rng(3).choice(hi - lo, 300, replace=False)
+    ref = c_oracle.expectation_step(ts, tgt[lo:hi][sel], 3e-4, 0.1, n_global=n_global)
+    np.testing.assert_allclose(pt1[sel], ref.pt1, rtol=5e-5, atol=1e-12)
