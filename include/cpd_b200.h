@@ -113,6 +113,10 @@ int cpd_last_estep(cpd_ctx* h, double* pt1, double* p1, double* px, double* n_p)
 int cpd_nonrigid_begin(cpd_ctx* h, double beta, double lmd, double sigma2, double w);
 int cpd_nonrigid_step(cpd_ctx* h, double* sigma2_out);
 int cpd_nonrigid_get(cpd_ctx* h, double* w_out, double* moved_out);
+/* NonRigidCPD._maximization_step (cpd.py:284-303; with priors set: ConstrainedNonRigidCPD's, cpd.py:376-404) from a caller-supplied
+ * EstepResult (host arrays as cpd_estep returns them) and the sigma2 that E-step used; after a *_begin on this handle.  The
+ * new W / moved source are read with cpd_nonrigid_get; *sigma2_out == q (cpd.py:303).                                            */
+int cpd_nonrigid_mstep(cpd_ctx* h, const double* pt1, const double* p1, const double* px, double sigma2_p, double* sigma2_out);
 
 /* NonRigidCPD with G replaced by a rank-K factorisation G ~= Q Bc Q^T (csrc/lowrank.cuh; BASELINE configuration 5, no
  * reference counterpart: the reference only has the dense solve of cpd.py:296).  Same life cycle as the dense path:

@@ -45,6 +45,7 @@ _PROTOS = {
     "cpd_nonrigid_begin": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_double, ctypes.c_double, ctypes.c_double, ctypes.c_double]),
     "cpd_nonrigid_step": (ctypes.c_int, [ctypes.c_void_p, _c_dp]),
     "cpd_nonrigid_get": (ctypes.c_int, [ctypes.c_void_p, _c_dp, _c_dp]),
+    "cpd_nonrigid_mstep": (ctypes.c_int, [ctypes.c_void_p, _c_dp, _c_dp, _c_dp, ctypes.c_double, _c_dp]),
     "cpd_nonrigid_lowrank_begin": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_double, ctypes.c_double, ctypes.c_double, ctypes.c_double,
                                                   ctypes.c_int, ctypes.c_int, ctypes.c_uint64]),
     "cpd_nonrigid_lowrank_get": (ctypes.c_int, [ctypes.c_void_p, ctypes.POINTER(ctypes.c_int), _c_dp, _c_dp]),
@@ -269,6 +270,16 @@ class Handle(object):
         t = np.empty((self.m, self.dim))
         check(self._lib.cpd_nonrigid_get(self._h, None, dptr(t)))
         return t
+
+    def nonrigid_mstep(self, pt1, p1, px, sigma2_p):
+        pt1 = np.ascontiguousarray(pt1, dtype=np.float64)
+        p1 = np.ascontiguousarray(p1, dtype=np.float64)
+        px = as_cloud(px, self.dim)
+        if pt1.shape[0] != self.n or p1.shape[0] != self.m or px.shape[0] != self.m:
+            raise ValueError("EstepResult shapes do not match the handle's source/target")
+        out = ctypes.c_double()
+        check(self._lib.cpd_nonrigid_mstep(self._h, dptr(pt1), dptr(p1), dptr(px), float(sigma2_p), ctypes.byref(out)))
+        return out.value
 
     def nonrigid_step(self):
         out = ctypes.c_double()

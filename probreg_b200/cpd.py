@@ -251,8 +251,8 @@ class NonRigidCPD(CoherentPointDrift):
 
     SURVEY section 8(f) row 1: ``registration`` keeps G (float32, like ``_math.rbf_kernel``), W and the
     M x M system on the device -- E-step by the CPD kernels, the dense solve of cpd.py:296 by cuSOLVER's LU,
-    sigma2 in residual form.  ``maximization_step`` on a caller-supplied EstepResult stays a host numpy
-    solve (the reference's own arithmetic on host arrays).
+    sigma2 in residual form.  ``maximization_step`` on a caller-supplied EstepResult runs the same solve on the
+    device (cpd_nonrigid_mstep) with sigma2 from the reference's three traces.
 
     ``source``: (M, D) array or None; ``beta``: RBF width of G (denominator 2*beta, as in the reference);
     ``lmd``: weight of the smoothness term; ``use_cuda``: accepted, ignored.
@@ -281,7 +281,39 @@ class NonRigidCPD(CoherentPointDrift):
         self._tf_obj = self._tf_type(None, self._source, self._beta)
 
     def maximization_step(self, target, estep_res, sigma2_p=None):
-        return self._maximization_step(self._source, target, estep_res, sigma2_p, self._tf_obj, self._lmd, self.xp)
+        """Non-rigid M-step (probreg/cpd.py:284-303) from a caller-supplied EstepResult, on the device
+        (cpd_nonrigid_mstep): the M x M (or, with ``low_rank``, K x K) solve, T = Y + G W and sigma2 from the three traces.
+        G / its factors are rebuilt only when the source changed since the last call."""
+        target = _points(target)
+        h = self._nonrigid_handle(target, sigma2_p)
+        pt1, p1, px, n_p = estep_res
+        sigma2 = h.nonrigid_mstep(pt1, p1, px, sigma2_p)
+        self._tf_obj.w = h.nonrigid_w()
+        return MstepResult(self._tf_obj, sigma2, sigma2)
+
+    def _nonrigid_handle(self, target, sigma2):
+        """Handle with the current source's G (or factors) resident and, for the constrained variant, its priors set."""
+        assert self._source is not None, "source is None."
+        dim = self._source.shape[1]
+        key = (self._beta, self._low_rank, self._low_rank_iters, self._low_rank_seed)
+        fresh = (self._em is None or self._em.dim != dim or getattr(self, "_nr_key", None) != key or
+                 getattr(self, "_nr_src", None) is None or not np.array_equal(self._nr_src, self._source))
+        if fresh:
+            self._em_handle(target)                          # uploads source and target
+            h = self._em
+            if self._low_rank:
+                h.nonrigid_lowrank_begin(self._beta, self._lmd, sigma2, 0.0, self._low_rank, self._low_rank_iters, self._low_rank_seed)
+                q_mat, bcore = h.nonrigid_lowrank_factors()
+                self._tf_obj = tf.LowRankNonRigidTransformation(self._tf_obj.w, self._source, self._beta, q_mat, bcore)
+            else:
+                h.nonrigid_begin(self._beta, self._lmd, sigma2, 0.0)
+            self._nr_key, self._nr_src = key, np.array(self._source, copy=True)
+        else:
+            self._set_target(self._em, target)
+        prior = self._device_prior()
+        if prior is not None:
+            self._em.nonrigid_set_prior(*prior)
+        return self._em
 
     def _initialize(self, target):
         dim = self._source.shape[1]
@@ -292,7 +324,11 @@ class NonRigidCPD(CoherentPointDrift):
 
     @staticmethod
     def _maximization_step(source, target, estep_res, sigma2_p, tf_obj, lmd, xp=np):
-        return _nonrigid_mstep(source, target, estep_res, sigma2_p, tf_obj, lmd)
+        """Static form of probreg/cpd.py:284-303 (tf_obj supplies beta; its w is updated in place like the reference's)."""
+        obj = NonRigidCPD(source, beta=tf_obj._beta, lmd=lmd)
+        res = obj.maximization_step(target, estep_res, sigma2_p)
+        tf_obj.w = res.transformation.w
+        return MstepResult(tf_obj, res.sigma2, res.q)
 
     def _device_prior(self):
         """(alpha, p1_tilde, px_tilde) for the device loop, or None (ConstrainedNonRigidCPD overrides)."""
@@ -312,6 +348,7 @@ class NonRigidCPD(CoherentPointDrift):
         if not self._has_device_loop():
             return self._host_loop(target, res, w, maxiter, tol)
         h = self._em
+        self._nr_key = self._nr_src = None                   # registration() re-begins; the stand-alone M-step cache is stale
         if self._low_rank:
             h.nonrigid_lowrank_begin(self._beta, self._lmd, res.sigma2, w, self._low_rank, self._low_rank_iters, self._low_rank_seed)
             q_mat, bcore = h.nonrigid_lowrank_factors()
@@ -364,32 +401,6 @@ class NonRigidCPD(CoherentPointDrift):
         raise NotImplementedError
 
 
-def _nonrigid_mstep(source, target, estep_res, sigma2_p, tf_obj, lmd, prior=None):
-    """Non-rigid M-step (probreg/cpd.py:284-303; with ``prior`` the constrained one, cpd.py:376-404).
-
-    Solves (diag(p1 + k p1~) G + lmd sigma2 I) W = px + k px~ - diag(p1 + k p1~) Y with k = sigma2/alpha
-    (k = 0 without priors), then T = Y + G W and sigma2 from the three traces.  Host numpy: this is the
-    stand-alone ``maximization_step`` on a caller-supplied EstepResult; ``registration`` does not come here.
-    """
-    pt1, p1, px, n_p = estep_res
-    m, dim = source.shape
-    wgt, rhs = p1, px
-    if prior is not None:
-        k = sigma2_p / prior[0]
-        wgt = p1 + k * prior[1]
-        rhs = px + k * prior[2]
-    lhs = tf_obj.g * wgt[:, None]
-    lhs[np.diag_indices(m)] += lmd * sigma2_p
-    w = np.linalg.solve(lhs, rhs - source * wgt[:, None])
-    moved = source + np.dot(tf_obj.g, w)
-    tr_xp1x = float(np.dot(pt1, np.einsum("ij,ij->i", target, target)))
-    tr_pxt = float(np.einsum("ij,ij->", px, moved))
-    tr_tpt = float(np.dot(p1, np.einsum("ij,ij->i", moved, moved)))
-    sigma2 = (tr_xp1x - 2.0 * tr_pxt + tr_tpt) / (n_p * dim)
-    tf_obj.w = w
-    return MstepResult(tf_obj, sigma2, sigma2)
-
-
 class ConstrainedNonRigidCPD(NonRigidCPD):
     """Extended CPD with point-correspondence priors (probreg/cpd.py:306-404,
     https://people.mpi-inf.mpg.de/~golyanik/04_DRAFTS/ECPD2016.pdf).
@@ -412,6 +423,11 @@ class ConstrainedNonRigidCPD(NonRigidCPD):
 
     def _initialize(self, target):
         res = super(ConstrainedNonRigidCPD, self)._initialize(target)
+        self._prior_terms(target)
+        return res
+
+    def _prior_terms(self, target):
+        """p1_tilde / px_tilde of cpd.py:370-374 as a sparse gather (duplicates count once, like the 0/1 indicator matrix)."""
         m, dim = self._source.shape
         self.p1_tilde = np.zeros(m)
         self.px_tilde = np.zeros((m, dim))
@@ -419,11 +435,12 @@ class ConstrainedNonRigidCPD(NonRigidCPD):
             pairs = np.unique(np.c_[np.asarray(self.idx_source).ravel(), np.asarray(self.idx_target).ravel()], axis=0)
             np.add.at(self.p1_tilde, pairs[:, 0], 1.0)
             np.add.at(self.px_tilde, pairs[:, 0], np.asarray(target, dtype=np.float64)[pairs[:, 1]])
-        return res
 
     def maximization_step(self, target, estep_res, sigma2_p=None):
-        return _nonrigid_mstep(self._source, target, estep_res, sigma2_p, self._tf_obj, self._lmd,
-                               prior=(self.alpha, self.p1_tilde, self.px_tilde))
+        """cpd.py:376-404 on the device: NonRigidCPD.maximization_step with the two prior terms (``_device_prior``)."""
+        if self.p1_tilde is None:
+            self._prior_terms(_points(target))
+        return NonRigidCPD.maximization_step(self, target, estep_res, sigma2_p)
 
     def _device_prior(self):
         return (self.alpha, self.p1_tilde, self.px_tilde)

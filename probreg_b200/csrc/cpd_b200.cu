@@ -980,7 +980,7 @@ extern "C" int cpd_nonrigid_begin(cpd_ctx* h, double beta, double lmd, double si
     TRY(solver_workspace(h, m, h->d_A));
     const DevState& hs = h->h_state;
     dim3 grid((unsigned)m, blocks_for(m));
-    nr_gram_kernel<<<grid, THREADS, 0, h->stream>>>(h->d_yc, hs.cy[0], hs.cy[1], hs.cy[2], m, h->dim, (float)(1.0 / (2.0 * beta)),
+    nr_gram_kernel<<<grid, THREADS, 0, h->stream>>>(h->d_yc, hs.cy[0], hs.cy[1], hs.cy[2], m, h->dim, (float)(2.0 * beta),
                                                   h->d_G);
     KCHECK();
     h->launches += 1;
@@ -1071,22 +1071,13 @@ extern "C" int cpd_nonrigid_set_prior(cpd_ctx* h, double alpha, const double* p1
     return CPD_OK;
 }
 
-// one EM iteration of probreg/cpd.py:111-113 for NonRigidCPD: E-step on T = Y + G W, solve cpd.py:296, sigma2 cpd.py:298-301
-extern "C" int cpd_nonrigid_step(cpd_ctx* h, double* sigma2_out) {
-    if (!h) return fail(CPD_ERR_ARG, "null handle");
-    if (!h->nr_ready) return fail(CPD_ERR_STATE, "cpd_nonrigid_begin has not been called");
-    CU(cudaSetDevice(h->device));
+namespace {
+// From d_p1 / d_pxc (and the priors) to W and the moved source d_ts2 = Y + G W: the linear system of cpd.py:296, dense LU or
+// the K x K form of lowrank.cuh.  sigma2 of the PREVIOUS iteration is read from the device state.
+int nonrigid_solve(cpd_ctx* h) {
     const long long m = h->m;
     const DevState& hs = h->h_state;
-    TRY(launch_estep(h, &h->d_state->sigma2, &h->d_state->w, h->d_ts));
-    const int nbs = (int)blocks_for(m), nbt = (int)blocks_for(h->npad);
-    moments_kernel<0><<<1, 256, 0, h->stream>>>(h->d_state, h->d_mom_src, nbs, RM_SRC, h->d_mom_tgt, nbt, RM_TGT, h->d_mom);
-    h->launches += 1;
-    if (h->comm) {   // every rank solves the same (global) system
-        TRY(allreduce(h, h->d_p1, (size_t)m));
-        TRY(allreduce(h, h->d_pxc, (size_t)m * 3));
-        TRY(allreduce(h, h->d_mom, MOM_PAD));
-    }
+    const int nbs = (int)blocks_for(m);
     // weights and right-hand side of cpd.py:296 (with priors: cpd.py:390-396)
     const double* wgt = h->d_p1;
     if (h->prior_on) {
@@ -1126,6 +1117,26 @@ extern "C" int cpd_nonrigid_step(cpd_ctx* h, double* sigma2_out) {
         lr_w_kernel<<<nbs, THREADS, 0, h->stream>>>(h->d_B, wgt, h->d_ts2, h->d_yc, hs.cy[0], hs.cy[1], hs.cy[2], m, h->d_lr_c, h->d_W);
         h->launches += 3;
     }
+    return CPD_OK;
+}
+}  // namespace
+
+// one EM iteration of probreg/cpd.py:111-113 for NonRigidCPD: E-step on T = Y + G W, solve cpd.py:296, sigma2 cpd.py:298-301
+extern "C" int cpd_nonrigid_step(cpd_ctx* h, double* sigma2_out) {
+    if (!h) return fail(CPD_ERR_ARG, "null handle");
+    if (!h->nr_ready) return fail(CPD_ERR_STATE, "cpd_nonrigid_begin has not been called");
+    CU(cudaSetDevice(h->device));
+    const long long m = h->m;
+    TRY(launch_estep(h, &h->d_state->sigma2, &h->d_state->w, h->d_ts));
+    const int nbs = (int)blocks_for(m), nbt = (int)blocks_for(h->npad);
+    moments_kernel<0><<<1, 256, 0, h->stream>>>(h->d_state, h->d_mom_src, nbs, RM_SRC, h->d_mom_tgt, nbt, RM_TGT, h->d_mom);
+    h->launches += 1;
+    if (h->comm) {   // every rank solves the same (global) system
+        TRY(allreduce(h, h->d_p1, (size_t)m));
+        TRY(allreduce(h, h->d_pxc, (size_t)m * 3));
+        TRY(allreduce(h, h->d_mom, MOM_PAD));
+    }
+    TRY(nonrigid_solve(h));
     nr_resid_kernel<<<nbs, THREADS, 0, h->stream>>>(h->d_state, h->d_p1, h->d_pxc, h->d_ts, h->d_ts2, m, h->d_nrpart);
     nr_sigma_kernel<<<1, 32, 0, h->stream>>>(h->d_state, h->d_nrpart, nbs, h->d_mom);
     KCHECK();
@@ -1139,6 +1150,50 @@ extern "C" int cpd_nonrigid_step(cpd_ctx* h, double* sigma2_out) {
         if (info != 0) return fail(CPD_ERR_STATE, "LU factorisation of the non-rigid system failed (info = %d)", info);
         *sigma2_out = p.sigma2;
     }
+    return CPD_OK;
+}
+
+// NonRigidCPD._maximization_step / ConstrainedNonRigidCPD._maximization_step (cpd.py:284-303 / 376-404) from a caller-supplied
+// EstepResult: pt1 (n_local), p1 (m), px (m x D) as returned by cpd_estep, sigma2_p the variance the E-step was run with.
+// Needs cpd_nonrigid_begin / cpd_nonrigid_lowrank_begin (and optionally cpd_nonrigid_set_prior) on this handle.  The new W
+// and moved source are read with cpd_nonrigid_get.  sigma2 by the reference's three traces, FP64.
+extern "C" int cpd_nonrigid_mstep(cpd_ctx* h, const double* pt1, const double* p1, const double* px, double sigma2_p, double* sigma2_out) {
+    if (!h || !pt1 || !p1 || !px) return fail(CPD_ERR_ARG, "null argument");
+    if (!h->nr_ready) return fail(CPD_ERR_STATE, "cpd_nonrigid_begin has not been called");
+    if (!(sigma2_p > 0.0)) return fail(CPD_ERR_ARG, "sigma2_p must be positive, got %g", sigma2_p);
+    CU(cudaSetDevice(h->device));
+    TRY(prepare(h));
+    const long long m = h->m, n = h->n;
+    // caller's order -> internal (Morton) order, px -> centred px~ (as cpd_mstep does)
+    CU(cudaMemcpyAsync(h->d_outN, pt1, (size_t)n * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    gather1_kernel<<<blocks_for(n), THREADS, 0, h->stream>>>(h->d_outN, h->d_perm_tgt, n, h->d_pt1);
+    CU(cudaMemcpyAsync(h->d_outM, p1, (size_t)m * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    gather1_kernel<<<blocks_for(m), THREADS, 0, h->stream>>>(h->d_outM, h->d_perm_src, m, h->d_p1);
+    if (h->raw_cap < (size_t)m * 3) { TRY(dev_alloc(&h->d_raw, (size_t)m * 3)); h->raw_cap = (size_t)m * 3; }
+    TRY(upload_cloud(h, px, m, h->d_raw));
+    gather3_kernel<<<blocks_for(m), THREADS, 0, h->stream>>>(h->d_raw, h->d_perm_src, m, 0.0, 0.0, 0.0, h->d_px);
+    centre_px_kernel<<<blocks_for(m), THREADS, 0, h->stream>>>(h->d_state, h->d_p1, h->d_px, (int)m, h->d_pxc);
+    h->h_pin[36] = sigma2_p;
+    CU(cudaMemcpyAsync(&h->d_state->sigma2, h->h_pin + 36, sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    KCHECK();
+    h->launches += 4;
+    TRY(nonrigid_solve(h));
+    const unsigned nb = blocks_for(std::max(m, n));
+    if (h->sums_cap < (size_t)nb * 4 + 4) { TRY(dev_alloc(&h->d_sums, (size_t)nb * 4 + 4)); h->sums_cap = (size_t)nb * 4 + 4; }
+    nr_traces_kernel<<<nb, THREADS, 0, h->stream>>>(h->d_state, h->d_pt1, h->d_xc, n, h->d_p1, h->d_pxc, h->d_ts2, m, h->d_sums + 4);
+    reduce_cols_kernel<<<1, 32, 0, h->stream>>>(h->d_sums + 4, (int)nb, 4, h->d_sums);
+    KCHECK();
+    if (h->comm) TRY(allreduce(h, h->d_sums, 1));            // pt1 / x are per shard; p1, px, T are global already
+    nr_sigma_api_kernel<<<1, 32, 0, h->stream>>>(h->d_state, h->d_sums);
+    KCHECK();
+    h->launches += 3;
+    std::swap(h->d_ts, h->d_ts2);
+    CU(cudaMemcpyAsync(h->h_pin + 56, h->d_info, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    cpd_params p;
+    TRY(read_params(h, &p));
+    const int info = *reinterpret_cast<const int*>(h->h_pin + 56);
+    if (info != 0) return fail(CPD_ERR_STATE, "LU factorisation of the non-rigid system failed (info = %d)", info);
+    if (sigma2_out) *sigma2_out = p.sigma2;
     return CPD_OK;
 }
 
@@ -1200,7 +1255,7 @@ int pair_matrix(int kind, int device, const double* x, int64_t nx, const double*
     CU(cudaMemcpy(dx.p, xf.data(), xf.size() * sizeof(float), cudaMemcpyHostToDevice));
     CU(cudaMemcpy(dy.p, yf.data(), yf.size() * sizeof(float), cudaMemcpyHostToDevice));
     dim3 grid((unsigned)nx, blocks_for(ny));
-    if (kind == 0) rbf_kernel_kernel<<<grid, THREADS>>>(dx.p, nx, dy.p, ny, dim, (float)(1.0 / (2.0 * param)), dout.p);
+    if (kind == 0) rbf_kernel_kernel<<<grid, THREADS>>>(dx.p, nx, dy.p, ny, dim, (float)(2.0 * param), dout.p);
     else imq_kernel_kernel<<<grid, THREADS>>>(dx.p, nx, dy.p, ny, dim, (float)param, dout.p);
     KCHECK();
     CU(cudaMemcpy(out, dout.p, (size_t)nx * ny * sizeof(float), cudaMemcpyDeviceToHost));

@@ -1475,14 +1475,14 @@ centre_px_kernel(const DevState* __restrict__ st, const double* __restrict__ p1,
 }
 // _math.rbf_kernel (cc/math_utils.cc:17-19): float32 Gram matrix, 2*beta in the denominator
 __global__ void __launch_bounds__(THREADS)
-rbf_kernel_kernel(const float* __restrict__ x, long long nx, const float* __restrict__ y, long long ny, int dim, float inv2beta,
+rbf_kernel_kernel(const float* __restrict__ x, long long nx, const float* __restrict__ y, long long ny, int dim, float two_beta,
                   float* __restrict__ out) {
     const long long j = (long long)blockIdx.y * THREADS + threadIdx.x;      // rows on grid.x: grid.y is limited to 65535
     const long long i = blockIdx.x;
     if (j < ny) {
         float d2 = 0.f;
         for (int a = 0; a < dim; ++a) { const float d = x[i * dim + a] - y[j * dim + a]; d2 += d * d; }
-        out[i * ny + j] = expf(-d2 * inv2beta);
+        out[i * ny + j] = expf(-d2 / two_beta);          // a division, like (-diff2 / (2.0 * beta)).exp() in cc/math_utils.cc:18
     }
 }
 
@@ -1506,7 +1506,7 @@ imq_kernel_kernel(const float* __restrict__ x, long long nx, const float* __rest
 // ---------------------------------------------------------------------------------------------
 // G[i][j] = exp(-|y_i - y_j|^2 / (2 beta)) from the float32 casts of the ORIGINAL coordinates (cc/math_utils.cc:17-19)
 __global__ void __launch_bounds__(THREADS)
-nr_gram_kernel(const double* __restrict__ yc, double c0, double c1, double c2, long long m, int dim, float inv2beta,
+nr_gram_kernel(const double* __restrict__ yc, double c0, double c1, double c2, long long m, int dim, float two_beta,
                float* __restrict__ G) {
     const long long j = (long long)blockIdx.y * THREADS + threadIdx.x;      // rows on grid.x: grid.y is limited to 65535
     const long long i = blockIdx.x;
@@ -1517,7 +1517,7 @@ nr_gram_kernel(const double* __restrict__ yc, double c0, double c1, double c2, l
             const float d = (float)(yc[3 * i + a] + cc[a]) - (float)(yc[3 * j + a] + cc[a]);
             d2 += d * d;
         }
-        G[i * m + j] = expf(-d2 * inv2beta);
+        G[i * m + j] = expf(-d2 / two_beta);
     }
 }
 // ts_i = y_i + sum_j G_ij W_j   (transformation.py:101-102), one warp per row, FP64 accumulation
@@ -1603,6 +1603,41 @@ nr_resid_kernel(const DevState* __restrict__ st, const double* __restrict__ p1, 
         v[0] = acc; v[1] = p1[i];
     }
     block_reduce_store<2>(v, part + (size_t)blockIdx.x * 2);
+}
+// The three traces of cpd.py:298-300 from a caller-supplied EstepResult, in the caller's (uncentred) coordinates, FP64:
+// per-block partials {sum_n pt1 |x|^2, sum_m px . T, sum_m p1 |T|^2, sum_m p1}; blocks cover max(m, n) points.
+__global__ void __launch_bounds__(THREADS)
+nr_traces_kernel(const DevState* __restrict__ st, const double* __restrict__ pt1, const double* __restrict__ xc, long long n,
+                 const double* __restrict__ p1, const double* __restrict__ pxc, const double* __restrict__ ts, long long m,
+                 double* __restrict__ part) {
+    const long long i = (long long)blockIdx.x * THREADS + threadIdx.x;
+    double v[4] = {0.0, 0.0, 0.0, 0.0};
+    if (i < n) {
+        double x2 = 0.0;
+#pragma unroll
+        for (int c = 0; c < 3; ++c) { const double x = xc[3 * i + c] + st->cx[c]; x2 += x * x; }
+        v[0] = pt1[i] * x2;
+    }
+    if (i < m) {
+        double pt = 0.0, t2 = 0.0;
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            const double t = ts[3 * i + c];
+            pt += (pxc[3 * i + c] + st->cx[c] * p1[i]) * t;
+            t2 += t * t;
+        }
+        v[1] = pt; v[2] = p1[i] * t2; v[3] = p1[i];
+    }
+    block_reduce_store<4>(v, part + (size_t)blockIdx.x * 4);
+}
+// sigma2 = (tr_xp1x - 2 tr_pxt + tr_tpt) / (n_p D), q := sigma2   (cpd.py:301-303); tr[0] may have been all-reduced over ranks
+__global__ void __launch_bounds__(32)
+nr_sigma_api_kernel(DevState* st, const double* __restrict__ tr) {
+    if (threadIdx.x == 0) {
+        st->sigma2 = (tr[0] - 2.0 * tr[1] + tr[2]) / (tr[3] * st->dim);
+        st->q = st->sigma2;
+        st->n_p = tr[3];
+    }
 }
 // sigma2 = (Srr / sk^2 + sum part[.][0]) / (Np D);  q := sigma2 (cpd.py:303).  mom[RM_SRR] holds the (all-reduced) Srr.
 __global__ void __launch_bounds__(32)

@@ -142,6 +142,62 @@ def _check_misc():
         h.nonrigid_set_prior(1e-2, np.zeros(5), np.zeros((5, 3)))
 
 
+def _check_standalone_mstep():
+    """maximization_step on a caller-supplied EstepResult (cpd.py:284-303 / 376-404): dense, low-rank and constrained."""
+    # sigma2 at 2e-6: G is float32 and its entries differ from the reference's in the last bit (expf implementations)
+    src, tgt = _deformed_pair(240)
+    es = orc.expectation_step(src, tgt, 0.01, 0.05)
+    g = orc.rbf_kernel_f32(src, src, 0.7)
+    ref = orc.mstep_nonrigid(src, tgt, es, 0.01, g, 1.5)
+    reg = cpd.NonRigidCPD(src, beta=0.7, lmd=1.5)
+    res = reg.maximization_step(tgt, cpd.EstepResult(*es), 0.01)
+    assert res.sigma2 == pytest.approx(ref.sigma2, rel=2e-6) and res.q == res.sigma2
+    # (the M x M system is ill-conditioned: another pivot order moves G W by ~1e-6; sigma2 is far more stable)
+    np.testing.assert_allclose(reg.moved_source(), src + g.dot(ref.params[0]), atol=1e-5)
+    np.testing.assert_allclose(res.transformation.transform(src), src + g.dot(ref.params[0]), atol=2e-5)   # float32 g times an ill-conditioned w
+    # a second call with another EstepResult reuses G (source unchanged) ...
+    es2 = orc.expectation_step(src, tgt, 0.004, 0.0)
+    ref2 = orc.mstep_nonrigid(src, tgt, es2, 0.004, g, 1.5)
+    res2 = reg.maximization_step(tgt, cpd.EstepResult(*es2), 0.004)
+    assert res2.sigma2 == pytest.approx(ref2.sigma2, rel=2e-6)
+    # ... and notices an edited source
+    reg.set_source(src * 1.01)
+    g3 = orc.rbf_kernel_f32(src * 1.01, src * 1.01, 0.7)
+    ref3 = orc.mstep_nonrigid(src * 1.01, tgt, es2, 0.004, g3, 1.5)
+    assert reg.maximization_step(tgt, cpd.EstepResult(*es2), 0.004).sigma2 == pytest.approx(ref3.sigma2, rel=2e-6)
+    # the reference's static form
+    tfo = cpd.tf.NonRigidTransformation(None, src, 0.7)
+    st = cpd.NonRigidCPD._maximization_step(src, tgt, cpd.EstepResult(*es), 0.01, tfo, 1.5)
+    assert st.sigma2 == pytest.approx(ref.sigma2, rel=2e-6) and st.transformation is tfo and tfo.w.shape == src.shape
+    # constrained
+    idx = np.arange(0, 240, 9)
+    p1t, pxt = orc.constraint_terms(240, tgt, idx, idx)
+    refc = orc.mstep_nonrigid(src, tgt, es, 0.01, g, 1.5, alpha=1e-2, p1_tilde=p1t, px_tilde=pxt)
+    regc = cpd.ConstrainedNonRigidCPD(src, beta=0.7, lmd=1.5, alpha=1e-2, idx_source=idx, idx_target=idx)
+    resc = regc.maximization_step(tgt, cpd.EstepResult(*es), 0.01)
+    assert resc.sigma2 == pytest.approx(refc.sigma2, rel=2e-6)
+    np.testing.assert_allclose(regc.moved_source(), src + g.dot(refc.params[0]), atol=1e-5)
+    # low-rank: against the K x K oracle on the device's own factors
+    regl = cpd.NonRigidCPD(src, beta=0.7, lmd=1.5, low_rank=50)
+    resl = regl.maximization_step(tgt, cpd.EstepResult(*es), 0.01)
+    tfm = resl.transformation
+    refl = orc.mstep_nonrigid_lowrank(src, tgt, es, 0.01, tfm.q, tfm.bcore, 1.5)
+    assert resl.sigma2 == pytest.approx(refl.sigma2, rel=2e-6)
+    np.testing.assert_allclose(regl.moved_source(), refl.params[1], atol=1e-8)
+    np.testing.assert_allclose(tfm.w, refl.params[0], atol=1e-6 * np.abs(refl.params[0]).max())
+
+
+def test_standalone_mstep_emulated(emulated):
+    _check_standalone_mstep()
+
+
+@pytest.mark.gpu
+@pytest.mark.timeout(600)
+@UNVERIFIED
+def test_standalone_mstep_gpu():
+    _check_standalone_mstep()
+
+
 def test_lowrank_vs_oracles_emulated(emulated):
     _check_against_oracles(260, 36, 5, 2.0, 2.0, 0.05, 1e-4)
 
