@@ -7,6 +7,7 @@
 
 #include <cub/device/device_radix_sort.cuh>
 #ifdef CPD_HOST_EMU
+#include "emu_nccl.h"
 #include "emu_solver.h"
 #endif
 
@@ -66,6 +67,16 @@ struct NcclApi {
 NcclApi g_nccl;
 int load_nccl() {
     if (g_nccl.lib) return CPD_OK;
+#ifdef CPD_HOST_EMU   // CPU test build (tests/emu): ranks are threads of one process, the collective is a rendezvous
+    static_assert(sizeof(nccl_uid) == sizeof(emu::nccl_uid_t), "unique id layout");
+    g_nccl.GetUniqueId = reinterpret_cast<int (*)(nccl_uid*)>(emu::ncclGetUniqueId);
+    g_nccl.CommInitRank = reinterpret_cast<int (*)(nccl_comm*, int, nccl_uid, int)>(emu::ncclCommInitRank);
+    g_nccl.AllReduce = emu::ncclAllReduce;
+    g_nccl.CommDestroy = emu::ncclCommDestroy;
+    g_nccl.GetErrorString = emu::ncclGetErrorString;
+    g_nccl.lib = (void*)&g_nccl;
+    return CPD_OK;
+#endif
     const char* names[] = {"libnccl.so.2", "libnccl.so"};
     void* lib = nullptr;
     for (const char* nm : names) { lib = dlopen(nm, RTLD_NOW | RTLD_GLOBAL); if (lib) break; }

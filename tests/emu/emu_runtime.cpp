@@ -9,6 +9,7 @@
 
 #include <algorithm>
 #include <chrono>
+#include <mutex>
 #include <vector>
 
 #undef threadIdx
@@ -128,6 +129,10 @@ static void next_order(std::vector<size_t>& order, size_t n) {
 }
 
 void launch(const char* name, dim3 grid, dim3 block, size_t smem, cudaStream_t, const std::function<void()>& body) {
+    // one kernel at a time in the whole process: ranks of a multi-rank test are OS threads, and the scheduler state, the
+    // `static` stand-ins for __shared__ and the mbarrier table are process-wide
+    static std::mutex kernel_lock;
+    std::lock_guard<std::mutex> lk(kernel_lock);
     const size_t nthreads = (size_t)block.x * block.y * block.z;
     static std::vector<size_t> order;
     // the hardware limits a blind launch would trip over
@@ -208,10 +213,15 @@ static int emu_sms() {
     const int v = e ? atoi(e) : 0;
     return v > 0 ? v : 148;
 }
-cudaError_t cudaGetDeviceCount(int* n) { *n = 1; return cudaSuccess; }
+static int emu_devices() {
+    const char* e = getenv("CPD_EMU_DEVICES");
+    const int v = e ? atoi(e) : 0;
+    return v > 0 ? v : 1;
+}
+cudaError_t cudaGetDeviceCount(int* n) { *n = emu_devices(); return cudaSuccess; }
 cudaError_t cudaGetLastError() { return cudaSuccess; }
 const char* cudaGetErrorString(cudaError_t e) { return e == cudaSuccess ? "no error" : "emulated CUDA error"; }
-cudaError_t cudaSetDevice(int d) { return d == 0 ? cudaSuccess : cudaErrorInvalidValue; }
+cudaError_t cudaSetDevice(int d) { return (d >= 0 && d < emu_devices()) ? cudaSuccess : cudaErrorInvalidValue; }
 cudaError_t cudaGetDeviceProperties(cudaDeviceProp* p, int) {
     memset(p, 0, sizeof(*p));
     p->major = 10; p->minor = 0; p->multiProcessorCount = emu_sms();
