@@ -95,7 +95,7 @@ def test_sharded_estep_and_registration(emulated, monkeypatch, world):
     assert all(r == results[0] for r in results), "ranks disagree"
 
 
-def test_sharded_nonrigid_lowrank_and_bcpd(emulated, monkeypatch):
+def test_sharded_nonrigid_dense_lowrank_constrained(emulated, monkeypatch):
     monkeypatch.setenv("CPD_EMU_DEVICES", "2")
     src, _ = orc.synthetic_pair(260)
     f = np.array([[1.0, 0.5, 0.0], [0.0, 1.0, 0.7], [0.3, 0.0, 1.0]])
