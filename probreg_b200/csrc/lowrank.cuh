@@ -4,7 +4,7 @@
 // Reference: NonRigidCPD._maximization_step (probreg/cpd.py:284-303) solves the dense M x M system
 //     (diag(p1) G + lmd sigma2 I) W = px - diag(p1) Y,        G_ij = exp(-|y_i - y_j|^2 / (2 beta))   (cc/math_utils.cc:17-19)
 // -- 2/3 M^3 flops and 12 M^2 bytes per iteration (10^14 flops, 30 GB at M = 50k).  The reference has no low-rank path;
-// this one follows the construction of the CPD paper (Myronenko & Song 2010, section 6 "fast implementation"), with the
+// this one follows the low-rank construction of the CPD paper (Myronenko & Song 2010, "fast implementation"), with the
 // eigen-decomposition replaced by a randomised range finder that only needs products G X, which the pair kernel forms on
 // the fly (G is never stored):
 //     G ~= Q Bc Q^T,   Q (M x K) orthonormal columns,  Bc = Q^T G Q (K x K)

@@ -15,8 +15,16 @@
 namespace cpd {
 typedef unsigned long long u64;
 
+// CPD_EMU_EX2=mufu: perturb the result by a smooth function of the argument's fractional part, up to 2^-22 relative -- the
+// size and kind of error MUFU.EX2 has.  The library's parity must not depend on ex2 being exact (it relies on both passes
+// seeing the SAME argument so that the error cancels in K / sum K); the test-suite also runs in this mode.
 static inline float ex2(float x) {
-    const float r = exp2f(x);
+    static const int mode = [] { const char* e = getenv("CPD_EMU_EX2"); return (e && !strcmp(e, "mufu")) ? 1 : 0; }();
+    float r = exp2f(x);
+    if (mode == 1 && x > -1000.0f && x < 1000.0f) {
+        const float fr = x - floorf(x);
+        r *= 1.0f + 2.3841858e-07f * sinf(6.2831853f * (3.0f * fr + 0.17f));
+    }
     return (r < FLT_MIN) ? 0.0f : r;
 }
 static inline u64 pack2(float lo, float hi) {

@@ -120,6 +120,24 @@ def test_results_do_not_depend_on_the_thread_schedule(emu_lib_path):
     assert digests[0] == digests[1] == digests[2], digests
 
 
+def test_parity_survives_a_mufu_like_ex2(emu_lib_path):
+    """Re-run a slice of the emulated tests with ex2 perturbed by up to 2^-22 relative, smoothly in the fractional part of its
+    argument (CPD_EMU_EX2=mufu): parity must not hinge on an exact exp2 -- the two passes see identical arguments, so the error
+    cancels in K / sum K (decision 2; section 4d for the weighted instantiations)."""
+    import os
+    import subprocess
+    import sys
+
+    here = os.path.dirname(os.path.abspath(__file__))
+    env = dict(os.environ, CPD_EMU_EX2="mufu")
+    sel = "estep_bunny or registration_vs_reference or default_tolerance or bcpd_estep_vs_reference or lowrank_vs_oracles"
+    r = subprocess.run([sys.executable, "-m", "pytest", "-q", "-x", "-m", "not gpu", "-p", "no:cacheprovider", "-k", sel,
+                        os.path.join(here, "test_emulated_library.py"), os.path.join(here, "test_zz_bcpd.py"),
+                        os.path.join(here, "test_zz_lowrank.py")], capture_output=True, text=True, env=env, timeout=1500, cwd=here)
+    assert r.returncode == 0, r.stdout[-3000:]
+    assert " passed" in r.stdout and "failed" not in r.stdout
+
+
 def test_emulation_is_not_reachable_from_the_package(emu_lib_path):
     """The package loads probreg_b200/libcpd_b200.so (or CPD_B200_LIB) and nothing else; the emulation lives under tests/."""
     import os

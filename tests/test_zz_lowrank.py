@@ -101,8 +101,10 @@ def _check_full_rank_equals_dense(m):
     b = cpd.NonRigidCPD(src, beta=0.5, lmd=1.0, low_rank=m + 50)          # clamped to M
     rb = b.registration(tgt, w=0.0, maxiter=4, tol=-1.0)
     assert rb.transformation.q.shape == (m, m)
-    assert rb.sigma2 == pytest.approx(ra.sigma2, rel=5e-6)          # G by MUFU.EX2 on scaled coordinates vs expf: ~3e-7 per entry
-    np.testing.assert_allclose(b.moved_source(), a.moved_source(), atol=2e-6)
+    # G by MUFU.EX2 on scaled coordinates vs expf: ~3e-7 per entry, amplified by the ill-conditioned solve (4e-6 on the moved
+    # points when the emulation perturbs ex2 like MUFU does, CPD_EMU_EX2=mufu)
+    assert rb.sigma2 == pytest.approx(ra.sigma2, rel=5e-6)
+    np.testing.assert_allclose(b.moved_source(), a.moved_source(), atol=1e-5)
 
 
 def _check_misc():
