@@ -127,6 +127,11 @@ int cpd_nonrigid_mstep(cpd_ctx* h, const double* pt1, const double* p1, const do
 int cpd_nonrigid_lowrank_begin(cpd_ctx* h, double beta, double lmd, double sigma2, double w, int rank, int power_iters, uint64_t seed);
 int cpd_nonrigid_lowrank_get(cpd_ctx* h, int* rank_out, double* q_out, double* bcore_out);
 
+/* Another registration with the same source (one template, many targets): resets W = 0 (cpd.py:281), the moved source, sigma2, w,
+ * lmd and the priors, and keeps G / the low-rank factors of the last cpd_nonrigid_*begin.  The caller vouches that the source
+ * coordinates on the handle are the ones that begin saw.                                                                      */
+int cpd_nonrigid_restart(cpd_ctx* h, double lmd, double sigma2, double w);
+
 /* Correspondence priors of ConstrainedNonRigidCPD (cpd.py:364-374: p1_tilde = row sums of the indicator matrix, px_tilde =
  * its product with the target; cpd.py:390-396: both enter the system and the right-hand side scaled by sigma2 / alpha).
  * Call after cpd_nonrigid_begin / cpd_nonrigid_lowrank_begin; p1_tilde: m, px_tilde: m x D; both NULL switches priors off. */

@@ -45,6 +45,7 @@ _PROTOS = {
     "cpd_nonrigid_begin": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_double, ctypes.c_double, ctypes.c_double, ctypes.c_double]),
     "cpd_nonrigid_step": (ctypes.c_int, [ctypes.c_void_p, _c_dp]),
     "cpd_nonrigid_get": (ctypes.c_int, [ctypes.c_void_p, _c_dp, _c_dp]),
+    "cpd_nonrigid_restart": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_double, ctypes.c_double, ctypes.c_double]),
     "cpd_nonrigid_mstep": (ctypes.c_int, [ctypes.c_void_p, _c_dp, _c_dp, _c_dp, ctypes.c_double, _c_dp]),
     "cpd_nonrigid_lowrank_begin": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_double, ctypes.c_double, ctypes.c_double, ctypes.c_double,
                                                   ctypes.c_int, ctypes.c_int, ctypes.c_uint64]),
@@ -270,6 +271,9 @@ class Handle(object):
         t = np.empty((self.m, self.dim))
         check(self._lib.cpd_nonrigid_get(self._h, None, dptr(t)))
         return t
+
+    def nonrigid_restart(self, lmd, sigma2, w):
+        check(self._lib.cpd_nonrigid_restart(self._h, float(lmd), float(sigma2), float(w)))
 
     def nonrigid_mstep(self, pt1, p1, px, sigma2_p):
         pt1 = np.ascontiguousarray(pt1, dtype=np.float64)

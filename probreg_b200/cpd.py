@@ -273,6 +273,7 @@ class NonRigidCPD(CoherentPointDrift):
         self._low_rank_iters = low_rank_iters
         self._low_rank_seed = low_rank_seed
         self._tf_obj = None
+        self._nr_key = self._nr_src = self._nr_handle = self._nr_factors = None      # what the handle's G / factors were built for
         if not self._source is None:
             self._tf_obj = self._tf_type(None, self._source, self._beta, self.xp)
 
@@ -297,19 +298,21 @@ class NonRigidCPD(CoherentPointDrift):
         dim = self._source.shape[1]
         key = (self._beta, self._low_rank, self._low_rank_iters, self._low_rank_seed)
         fresh = (self._em is None or self._em.dim != dim or getattr(self, "_nr_key", None) != key or
-                 getattr(self, "_nr_src", None) is None or not np.array_equal(self._nr_src, self._source))
+                 getattr(self, "_nr_src", None) is None or getattr(self, "_nr_handle", None) is not self._em or
+                 not np.array_equal(self._nr_src, self._source))
+        self._em_handle(target)                              # uploads source (deterministic internal order) and target
+        h = self._em
         if fresh:
-            self._em_handle(target)                          # uploads source and target
-            h = self._em
             if self._low_rank:
                 h.nonrigid_lowrank_begin(self._beta, self._lmd, sigma2, 0.0, self._low_rank, self._low_rank_iters, self._low_rank_seed)
-                q_mat, bcore = h.nonrigid_lowrank_factors()
-                self._tf_obj = tf.LowRankNonRigidTransformation(self._tf_obj.w, self._source, self._beta, q_mat, bcore)
+                self._nr_factors = h.nonrigid_lowrank_factors()
+                self._tf_obj = tf.LowRankNonRigidTransformation(self._tf_obj.w, self._source, self._beta, self._nr_factors[0],
+                                                                self._nr_factors[1])
             else:
                 h.nonrigid_begin(self._beta, self._lmd, sigma2, 0.0)
-            self._nr_key, self._nr_src = key, np.array(self._source, copy=True)
+            self._nr_key, self._nr_src, self._nr_handle = key, np.array(self._source, copy=True), h
         else:
-            self._set_target(self._em, target)
+            h.nonrigid_restart(self._lmd, sigma2, 0.0)
         prior = self._device_prior()
         if prior is not None:
             self._em.nonrigid_set_prior(*prior)
@@ -348,13 +351,23 @@ class NonRigidCPD(CoherentPointDrift):
         if not self._has_device_loop():
             return self._host_loop(target, res, w, maxiter, tol)
         h = self._em
-        self._nr_key = self._nr_src = None                   # registration() re-begins; the stand-alone M-step cache is stale
-        if self._low_rank:
-            h.nonrigid_lowrank_begin(self._beta, self._lmd, res.sigma2, w, self._low_rank, self._low_rank_iters, self._low_rank_seed)
-            q_mat, bcore = h.nonrigid_lowrank_factors()
-            self._tf_obj = tf.LowRankNonRigidTransformation(self._tf_obj.w, self._source, self._beta, q_mat, bcore)
+        key = (self._beta, self._low_rank, self._low_rank_iters, self._low_rank_seed)
+        if (getattr(self, "_nr_key", None) == key and getattr(self, "_nr_src", None) is not None and self._nr_handle is h
+                and np.array_equal(self._nr_src, self._source)):
+            h.nonrigid_restart(self._lmd, res.sigma2, w)          # same source as last time: G / the factors are still valid
+            if self._low_rank:
+                self._tf_obj = tf.LowRankNonRigidTransformation(self._tf_obj.w, self._source, self._beta, self._nr_factors[0],
+                                                                self._nr_factors[1])
         else:
-            h.nonrigid_begin(self._beta, self._lmd, res.sigma2, w)
+            self._nr_key = self._nr_src = None
+            if self._low_rank:
+                h.nonrigid_lowrank_begin(self._beta, self._lmd, res.sigma2, w, self._low_rank, self._low_rank_iters, self._low_rank_seed)
+                self._nr_factors = h.nonrigid_lowrank_factors()
+                self._tf_obj = tf.LowRankNonRigidTransformation(self._tf_obj.w, self._source, self._beta, self._nr_factors[0],
+                                                                self._nr_factors[1])
+            else:
+                h.nonrigid_begin(self._beta, self._lmd, res.sigma2, w)
+            self._nr_key, self._nr_src, self._nr_handle = key, np.array(self._source, copy=True), h
         prior = self._device_prior()
         if prior is not None:
             h.nonrigid_set_prior(*prior)

@@ -1057,6 +1057,19 @@ extern "C" int cpd_nonrigid_lowrank_begin(cpd_ctx* h, double beta, double lmd, d
     return CPD_OK;
 }
 
+// Start another registration with the SAME source (one template, many targets): W = 0, T = Y, new sigma2 / w / lmd, priors off --
+// G (or its low-rank factors) stays.  The caller guarantees that the source set on this handle is the one the last
+// cpd_nonrigid_*begin saw (cpd_set_source with identical coordinates is fine: the internal order is deterministic).
+extern "C" int cpd_nonrigid_restart(cpd_ctx* h, double lmd, double sigma2, double w) {
+    if (!h) return fail(CPD_ERR_ARG, "null handle");
+    if (!h->nr_ready) return fail(CPD_ERR_STATE, "cpd_nonrigid_begin has not been called");
+    if (!h->have_source || !h->have_target) return fail(CPD_ERR_STATE, "source and target must both be set");
+    if (!(sigma2 > 0.0) || !(w >= 0.0 && w < 1.0)) return fail(CPD_ERR_ARG, "bad sigma2/w");
+    if (h->nr_m != h->m || (h->lr_rank > 0 && h->lr_m != h->m)) return fail(CPD_ERR_STATE, "the source size changed since cpd_nonrigid_begin");
+    CU(cudaSetDevice(h->device));
+    return nonrigid_common_begin(h, lmd, sigma2, w);
+}
+
 // Correspondence priors of ConstrainedNonRigidCPD (cpd.py:364-374, 390-396): p1_tilde (m) and px_tilde (m x D) in the caller's
 // order, alpha > 0.  Both NULL: priors off.  Valid until the next cpd_nonrigid_*begin with another source size.
 extern "C" int cpd_nonrigid_set_prior(cpd_ctx* h, double alpha, const double* p1_tilde, const double* px_tilde) {

@@ -117,6 +117,20 @@ def _check_misc():
     seen = []
     r = cpd.registration_cpd(src, tgt, "nonrigid", maxiter=3, tol=-1.0, low_rank=20, callbacks=[lambda t: seen.append(t.w.copy())])
     assert len(seen) == 3 and r.sigma2 == pytest.approx(a.sigma2, rel=1e-4) and not np.array_equal(seen[0], seen[2])
+    # one template, several targets: the second registration keeps G / the factors (cpd_nonrigid_restart) and must give exactly
+    # what a fresh object gives
+    tgt2 = tgt + 0.01
+    for kw in ({"low_rank": 20}, {}):
+        reuse = cpd.NonRigidCPD(src, **kw)
+        reuse.registration(tgt, maxiter=2, tol=-1.0)
+        r2 = reuse.registration(tgt2, maxiter=3, tol=-1.0, w=0.1)
+        f2 = cpd.NonRigidCPD(src, **kw).registration(tgt2, maxiter=3, tol=-1.0, w=0.1)
+        assert r2.sigma2 == f2.sigma2 and np.array_equal(r2.transformation.w, f2.transformation.w)
+        src_b = src + 0.5                                                   # ... and an edited source rebuilds them
+        reuse.set_source(src_b)
+        r3 = reuse.registration(tgt2 + 0.5, maxiter=2, tol=-1.0)
+        f3 = cpd.NonRigidCPD(src_b, **kw).registration(tgt2 + 0.5, maxiter=2, tol=-1.0)
+        assert r3.sigma2 == f3.sigma2
     # default tolerance: stops like the dense loop does (q == sigma2, cpd.py:303)
     d = cpd.NonRigidCPD(src, low_rank=20)
     rd = d.registration(tgt)
