@@ -24,8 +24,29 @@ unsigned char* g_dyn_smem = nullptr;
 
 namespace {
 constexpr size_t STACK = 512 << 10;
+// Context switch between the scheduler and a fiber.  On x86-64 a hand-written switch of the callee-saved registers and the stack
+// pointer (no system call; glibc's swapcontext saves the signal mask on every switch, which is most of the cost of a warp
+// shuffle here); elsewhere, or with -DEMU_UCONTEXT (AddressSanitizer understands that one better), plain ucontext.
+#if defined(__x86_64__) && !defined(EMU_UCONTEXT)
+#define EMU_FAST_SWITCH 1
+struct Ctx { void* sp; };
+extern "C" void emu_switch(Ctx* from, Ctx* to);
+asm(".text\n"
+    ".globl emu_switch\n"
+    ".type emu_switch,@function\n"
+    "emu_switch:\n"
+    "    pushq %rbp\n    pushq %rbx\n    pushq %r12\n    pushq %r13\n    pushq %r14\n    pushq %r15\n"
+    "    movq %rsp, (%rdi)\n"
+    "    movq (%rsi), %rsp\n"
+    "    popq %r15\n    popq %r14\n    popq %r13\n    popq %r12\n    popq %rbx\n    popq %rbp\n"
+    "    ret\n"
+    ".size emu_switch, .-emu_switch\n");
+#else
+struct Ctx { ucontext_t uc; };
+static void emu_switch(Ctx* from, Ctx* to) { swapcontext(&from->uc, &to->uc); }
+#endif
 struct Fiber {
-    ucontext_t ctx;
+    Ctx ctx;
     bool done = false;
 };
 struct Warp {
@@ -35,7 +56,7 @@ struct Warp {
     bool pred[32];
     bool present[32];
 };
-ucontext_t g_sched;
+Ctx g_sched;
 std::vector<Fiber> g_fibers;
 std::vector<Warp> g_warps;
 char* g_stacks = nullptr;
@@ -62,7 +83,8 @@ void trampoline() {
     w.present[g_cur & 31] = false;
     release_block_barrier_if_complete();     // exited threads count as arrived (CUDA semantics)
     release_warp_barrier_if_complete(w);
-    swapcontext(&f.ctx, &g_sched);
+    emu_switch(&f.ctx, &g_sched);
+    abort();                                  // a finished fiber is never resumed
 }
 void warp_barrier() {
     Warp& w = g_warps[g_cur >> 5];
@@ -75,7 +97,7 @@ void warp_barrier() {
 
 void yield() {
     Fiber& f = g_fibers[g_cur];
-    swapcontext(&f.ctx, &g_sched);
+    emu_switch(&f.ctx, &g_sched);
 }
 void syncthreads() {
     const unsigned gen = g_bar_gen;
@@ -167,11 +189,20 @@ void launch(const char* name, dim3 grid, dim3 block, size_t smem, cudaStream_t, 
                 for (size_t t = 0; t < nthreads; ++t) {
                     Fiber& f = g_fibers[t];
                     f.done = false;
-                    getcontext(&f.ctx);
-                    f.ctx.uc_stack.ss_sp = g_stacks + t * STACK;
-                    f.ctx.uc_stack.ss_size = STACK;
-                    f.ctx.uc_link = &g_sched;
-                    makecontext(&f.ctx, trampoline, 0);
+#ifdef EMU_FAST_SWITCH
+                    {   // first switch "returns" into trampoline with the stack aligned as after a call
+                        void** top = reinterpret_cast<void**>(g_stacks + (t + 1) * STACK);
+                        top[-2] = reinterpret_cast<void*>(&trampoline);
+                        for (int r = 3; r <= 8; ++r) top[-r] = nullptr;      // rbp, rbx, r12..r15
+                        f.ctx.sp = &top[-8];
+                    }
+#else
+                    getcontext(&f.ctx.uc);
+                    f.ctx.uc.uc_stack.ss_sp = g_stacks + t * STACK;
+                    f.ctx.uc.uc_stack.ss_size = STACK;
+                    f.ctx.uc.uc_link = &g_sched.uc;
+                    makecontext(&f.ctx.uc, trampoline, 0);
+#endif
                     g_warps[t >> 5].alive++;
                     g_warps[t >> 5].present[t & 31] = true;
                 }
@@ -186,7 +217,7 @@ void launch(const char* name, dim3 grid, dim3 block, size_t smem, cudaStream_t, 
                         if (f.done) continue;
                         g_cur = (int)t;
                         g_threadIdx = uint3{(unsigned)(t % block.x), (unsigned)((t / block.x) % block.y), (unsigned)(t / ((size_t)block.x * block.y))};
-                        swapcontext(&g_sched, &f.ctx);
+                        emu_switch(&g_sched, &f.ctx);
                         if (f.done) { --remaining; ++progressed; }
                     }
                     // a round in which nobody finished is normal (barriers); a very long run of them is a deadlock

@@ -33,12 +33,15 @@ CASES = [
     (P.test_mstep_from_oracle_estep, {"kind": "rigid_noscale"}),
     (P.test_mstep_from_oracle_estep, {"kind": "affine"}),
     (P.test_mstep_2d_and_reflection, {}),
-    (P.test_registration_vs_reference, dict(zip("fname,tag,tf_type,iters,w,kw,sk,tk".split(","), P.CASES[0]), callbacks=True)),
-    (P.test_registration_vs_reference, dict(zip("fname,tag,tf_type,iters,w,kw,sk,tk".split(","), P.CASES[2]), callbacks=False)),
-    (P.test_registration_vs_reference, dict(zip("fname,tag,tf_type,iters,w,kw,sk,tk".split(","), P.CASES[3]), callbacks=False)),
-    (P.test_registration_vs_reference, dict(zip("fname,tag,tf_type,iters,w,kw,sk,tk".split(","), P.CASES[5]), callbacks=False)),
-    (P.test_registration_vs_reference, dict(zip("fname,tag,tf_type,iters,w,kw,sk,tk".split(","), P.CASES[8]), callbacks=True)),
+] + [
+    (P.test_registration_vs_reference, dict(zip("fname,tag,tf_type,iters,w,kw,sk,tk".split(","), c), callbacks=(i % 2 == 0)))
+    for i, c in enumerate(P.CASES)
+] + [
+    (P.test_estep_outliers_vs_reference, {"syn1500": "fixture", "tag": "mid"}),
+    (P.test_estep_ragged_sizes, {"m": 2049, "n": 4097, "dim": 3, "w": 0.2}),
     (P.test_default_tolerance_stops_where_the_reference_does, {"bunny": "fixture", "tag": "rigid_default", "tf_type": "rigid"}),
+    (P.test_default_tolerance_stops_where_the_reference_does, {"bunny": "fixture", "tag": "affine_default", "tf_type": "affine"}),
+    (P.test_nonrigid_device_loop_2000_vs_oracle, {}),
     (P.test_tf_init_params_and_reference_test_recipe, {}),
     (P.test_nonrigid_vs_reference, {"nonrigid_golden": "fixture"}),
     (P.test_constrained_nonrigid_vs_reference, {"nonrigid_golden": "fixture"}),
@@ -72,7 +75,7 @@ def test_culling_is_bit_exact_under_emulation(emulated, monkeypatch):
     from oracle import cpd_oracle as orc
     from probreg_b200 import _cabi
 
-    src, tgt = orc.synthetic_pair(3000)
+    src, tgt = orc.synthetic_pair(6000)
     ts = orc.apply_rigid(src, orc.rot_z(30.0), np.array([0.1, -0.2, 0.3]))
 
     def run(no_cull):

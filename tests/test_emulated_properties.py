@@ -10,7 +10,7 @@ from oracle import cpd_oracle as orc
 from probreg_b200 import _cabi, cpd
 
 SIZES = st.sampled_from([1, 2, 31, 63, 64, 65, 127, 255, 256, 257, 511, 512, 513, 640, 1023, 1024, 1025, 1100])
-COMMON = dict(max_examples=25, deadline=None, suppress_health_check=[HealthCheck.function_scoped_fixture, HealthCheck.too_slow],
+COMMON = dict(max_examples=60, deadline=None, suppress_health_check=[HealthCheck.function_scoped_fixture, HealthCheck.too_slow],
               derandomize=True)
 
 
@@ -46,7 +46,7 @@ def test_estep_matches_oracle_on_random_inputs(emulated, m, n, dim, log_s2, w, s
     assert es.n_p == pytest.approx(ref.n_p, rel=rtol, abs=1e-9)     # a sum of few pairs when sigma << spacing: no averaging
 
 
-@settings(**dict(COMMON, max_examples=10))
+@settings(**dict(COMMON, max_examples=25))
 @given(m=st.sampled_from([60, 300, 700]), n=st.sampled_from([50, 333, 900]), kind=st.sampled_from(["rigid", "rigid_noscale", "affine"]),
        w=st.sampled_from([0.0, 0.1]), seed=st.integers(0, 10 ** 6), dim=st.sampled_from([2, 3]))
 def test_registration_matches_oracle_on_random_inputs(emulated, m, n, kind, w, seed, dim):
@@ -69,7 +69,7 @@ def test_registration_matches_oracle_on_random_inputs(emulated, m, n, kind, w, s
         assert res.transformation.scale == pytest.approx(ref.params[2], rel=1e-5)
 
 
-@settings(**dict(COMMON, max_examples=8))
+@settings(**dict(COMMON, max_examples=12))
 @given(m=st.sampled_from([700, 1500, 2600]), n=st.sampled_from([600, 1300, 2100]), log_s2=st.floats(-6.5, -3.3), w=st.sampled_from([0.0, 0.1]),
        seed=st.integers(0, 10 ** 6), clusters=st.booleans())
 def test_culled_estep_is_bit_identical_on_random_inputs(emulated, monkeypatch, m, n, log_s2, w, seed, clusters):
@@ -94,7 +94,7 @@ def test_culled_estep_is_bit_identical_on_random_inputs(emulated, monkeypatch, m
     assert outs[0][3] == outs[1][3]
 
 
-@settings(**dict(COMMON, max_examples=12))
+@settings(**dict(COMMON, max_examples=40))
 @given(m=SIZES, n=SIZES, dim=st.sampled_from([2, 3]), log_s2=st.floats(-5.0, 1.0), w=st.sampled_from([0.0, 0.1, 0.6]),
        seed=st.integers(0, 10 ** 6), conc=st.sampled_from([0.2, 1.0, 50.0]), smax=st.sampled_from([0.0, 1e-3, 1.0]))
 def test_bcpd_estep_matches_oracle_on_random_inputs(emulated, m, n, dim, log_s2, w, seed, conc, smax):
