@@ -42,6 +42,7 @@ CASES = [
     (P.test_default_tolerance_stops_where_the_reference_does, {"bunny": "fixture", "tag": "rigid_default", "tf_type": "rigid"}),
     (P.test_default_tolerance_stops_where_the_reference_does, {"bunny": "fixture", "tag": "affine_default", "tf_type": "affine"}),
     (P.test_nonrigid_device_loop_2000_vs_oracle, {}),
+    (P.test_estep_sigma_sweep_20k, {"s2": 1e-4}),                  # 20 tiles x 40 stages, culling instantiations, vs the C oracle
     (P.test_tf_init_params_and_reference_test_recipe, {}),
     (P.test_nonrigid_vs_reference, {"nonrigid_golden": "fixture"}),
     (P.test_constrained_nonrigid_vs_reference, {"nonrigid_golden": "fixture"}),
