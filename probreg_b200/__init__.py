@@ -5,5 +5,5 @@
 
 See DESIGN.md for the kernels and INTEGRATION.md for how a probreg checkout binds to them.
 """
-from . import cpd, gauss_transform, math_utils, transformation  # noqa: F401
+from . import bcpd, cpd, gauss_transform, io, log, math_utils, transformation  # noqa: F401
 from .version import __version__  # noqa: F401
