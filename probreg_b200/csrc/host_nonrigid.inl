@@ -1,0 +1,386 @@
+// host_nonrigid.inl: the non-rigid entry points of include/cpd_b200.h (dense G, low-rank factors, correspondence priors) -- part of the single translation unit cpd_b200.cu (included at its end; uses its handle type, error
+// macros and helpers).  Split out for readability only.
+// ---------------------------------------------------------------------------------------------
+// non-rigid CPD with a dense G, resident on the device
+// ---------------------------------------------------------------------------------------------
+namespace {
+// state shared by the dense and the low-rank non-rigid loops: W = 0 (cpd.py:281), T = Y, sigma2, w
+int nonrigid_common_begin(cpd_ctx* h, double lmd, double sigma2, double w) {
+    const long long m = h->m;
+    if (h->nr_m != m) {
+        TRY(dev_alloc(&h->d_W, (size_t)m * 3));
+        TRY(dev_alloc(&h->d_B, (size_t)m * 3));
+        TRY(dev_alloc(&h->d_ts2, (size_t)m * 3));
+        TRY(dev_alloc(&h->d_wgt, (size_t)m));
+        TRY(dev_alloc(&h->d_nrpart, (size_t)blocks_for(m) * 2));
+        TRY(dev_alloc(&h->d_ipiv, (size_t)m));
+        TRY(dev_alloc(&h->d_info, 1));
+        if (h->d_G) { cudaFree(h->d_G); h->d_G = nullptr; }
+        if (h->d_A) { cudaFree(h->d_A); h->d_A = nullptr; }
+        h->nr_m = m;
+        h->work_dev = 0;
+    }
+    h->prior_on = false;                         // priors are set after begin (cpd_nonrigid_set_prior)
+    if (!h->sol) {
+        SOLV(g_sol.Create(&h->sol));
+        SOLV(g_sol.SetStream(h->sol, h->stream));
+        SOLV(g_sol.CreateParams(&h->sol_params));
+    }
+    const DevState& hs = h->h_state;
+    CU(cudaMemsetAsync(h->d_W, 0, (size_t)m * 3 * sizeof(double), h->stream));                       // cpd.py:281
+    CU(cudaMemsetAsync(h->d_info, 0, sizeof(int), h->stream));
+    nr_identity_kernel<<<blocks_for(m), THREADS, 0, h->stream>>>(h->d_yc, hs.cy[0], hs.cy[1], hs.cy[2], m, h->d_ts);   // T = Y + G 0
+    KCHECK();
+    h->launches += 1;
+    h->nr_lmd = lmd;
+    h->h_state.sigma2 = sigma2;
+    h->h_state.q = 0.0;
+    h->h_state.w = w;
+    h->h_state.tf_kind = CPD_TF_NONRIGID;
+    h->h_state.err = 0;
+    return upload_state(h);
+}
+// workspace of the LU of an n x n system stored at `a`
+int solver_workspace(cpd_ctx* h, long long n, double* a) {
+    size_t wd = 0, wh = 0;
+    SOLV(g_sol.XgetrfBuf(h->sol, h->sol_params, n, n, CUDA_R_64F_, a, n, CUDA_R_64F_, &wd, &wh));
+    if (wd > h->work_dev || !h->d_work) {
+        if (h->d_work) cudaFree(h->d_work);
+        h->d_work = nullptr;
+        CU(cudaMalloc(&h->d_work, std::max<size_t>(wd, 16)));
+        h->work_dev = std::max<size_t>(wd, 16);
+    }
+    if (wh > h->work_host || !h->h_work) {
+        free(h->h_work);
+        h->h_work = malloc(std::max<size_t>(wh, 16));
+        h->work_host = std::max<size_t>(wh, 16);
+    }
+    return CPD_OK;
+}
+// Orthonormalise the `rank` columns of X ([rank][ld]) in place: classical Gram-Schmidt, each column projected twice
+int lr_orthonormalise(cpd_ctx* h, double* X, int rank) {
+    const long long m = h->m, ld = h->mpad;
+    const unsigned nb = blocks_for(m);
+    double* coef = h->d_lr_coef;             // [3][rank + 1]: one row per projection round, so that |x|^2 of each survives
+    for (int j = 0; j < rank; ++j) {
+        for (int round = 0; round < 2; ++round) {
+            double* c = coef + (size_t)round * (rank + 1);
+            lr_dots_kernel<<<(unsigned)(j + 1), THREADS, 0, h->stream>>>(X, m, ld, j, 0, c);
+            if (j > 0) lr_project_kernel<<<nb, THREADS, 0, h->stream>>>(X, m, ld, j, c);
+            h->launches += j > 0 ? 2 : 1;
+        }
+        double* c2 = coef + (size_t)2 * (rank + 1);
+        lr_dots_kernel<<<1, THREADS, 0, h->stream>>>(X, m, ld, j, j, c2);
+        lr_scale_kernel<<<nb, THREADS, 0, h->stream>>>(X, m, ld, j, coef + j, c2 + j);
+        h->launches += 2;
+    }
+    KCHECK();
+    return CPD_OK;
+}
+// dst[c][i] = sum_j G_ij src[c][j] for all `rank` columns
+int lr_gram_apply(cpd_ctx* h, const double* src, double* dst, int rank) {
+    dim3 grid(blocks_for(h->m), (unsigned)((rank + LR_COLS - 1) / LR_COLS));
+    lr_gram_apply_kernel<<<grid, THREADS, 0, h->stream>>>(h->d_lr_pts, h->m, h->mpad, src, h->mpad, rank, dst);
+    KCHECK();
+    h->launches += 1;
+    return CPD_OK;
+}
+// out[na][nb] = A diag(wt) Bm^T over the points
+int lr_inner(cpd_ctx* h, const double* A, int na, long long lda, const double* Bm, int nb, long long ldb, const double* wt, int symmetrise,
+             double* out) {
+    const int tiles = ((na + LR_TILE - 1) / LR_TILE) * ((nb + LR_TILE - 1) / LR_TILE);
+    dim3 grid((unsigned)tiles, LR_SLICES);
+    lr_inner_kernel<<<grid, THREADS, 0, h->stream>>>(A, na, lda, Bm, nb, ldb, wt, h->m, h->d_lr_part);
+    lr_merge_kernel<<<blocks_for((long long)na * nb), THREADS, 0, h->stream>>>(h->d_lr_part, na, nb, symmetrise, out);
+    KCHECK();
+    h->launches += 2;
+    return CPD_OK;
+}
+}  // namespace
+
+extern "C" int cpd_nonrigid_begin(cpd_ctx* h, double beta, double lmd, double sigma2, double w) {
+    if (!h) return fail(CPD_ERR_ARG, "null handle");
+    if (!h->have_source || !h->have_target) return fail(CPD_ERR_STATE, "source and target must both be set");
+    if (!(beta > 0.0) || !(sigma2 > 0.0) || !(w >= 0.0 && w < 1.0)) return fail(CPD_ERR_ARG, "bad beta/sigma2/w");
+    CU(cudaSetDevice(h->device));
+    TRY(load_cusolver());
+    h->nr_ready = false;
+    const long long m = h->m;
+    TRY(nonrigid_common_begin(h, lmd, sigma2, w));
+    if (!h->d_G) TRY(dev_alloc(&h->d_G, (size_t)m * m));
+    if (!h->d_A) TRY(dev_alloc(&h->d_A, (size_t)m * m));
+    TRY(solver_workspace(h, m, h->d_A));
+    const DevState& hs = h->h_state;
+    dim3 grid((unsigned)m, blocks_for(m));
+    nr_gram_kernel<<<grid, THREADS, 0, h->stream>>>(h->d_yc, hs.cy[0], hs.cy[1], hs.cy[2], m, h->dim, (float)(2.0 * beta),
+                                                  h->d_G);
+    KCHECK();
+    h->launches += 1;
+    h->lr_rank = 0;
+    h->nr_ready = true;
+    return CPD_OK;
+}
+
+// NonRigidCPD with G ~= Q Bc Q^T of rank `rank` (lowrank.cuh): randomised range finder with `power_iters` subspace
+// iterations on products G X formed by the pair kernel; nothing of size M x M is ever stored.
+extern "C" int cpd_nonrigid_lowrank_begin(cpd_ctx* h, double beta, double lmd, double sigma2, double w, int rank, int power_iters,
+                                          uint64_t seed) {
+    if (!h) return fail(CPD_ERR_ARG, "null handle");
+    if (!h->have_source || !h->have_target) return fail(CPD_ERR_STATE, "source and target must both be set");
+    if (!(beta > 0.0) || !(sigma2 > 0.0) || !(w >= 0.0 && w < 1.0)) return fail(CPD_ERR_ARG, "bad beta/sigma2/w");
+    if (rank < 1 || rank > LR_MAX_RANK) return fail(CPD_ERR_ARG, "rank must be in 1..%d, got %d", LR_MAX_RANK, rank);
+    if (power_iters < 0 || power_iters > 8) return fail(CPD_ERR_ARG, "power_iters must be in 0..8, got %d", power_iters);
+    CU(cudaSetDevice(h->device));
+    TRY(load_cusolver());
+    h->nr_ready = false;
+    const long long m = h->m, ld = h->mpad;
+    if (rank > m) rank = (int)m;
+    TRY(nonrigid_common_begin(h, lmd, sigma2, w));
+    if (h->lr_m != m || h->lr_cap < rank) {
+        TRY(dev_alloc(&h->d_lr_pts, (size_t)ld));
+        TRY(dev_alloc(&h->d_lr_Q, (size_t)rank * ld));
+        TRY(dev_alloc(&h->d_lr_X, (size_t)rank * ld));
+        TRY(dev_alloc(&h->d_lr_coef, (size_t)3 * (rank + 1)));
+        TRY(dev_alloc(&h->d_lr_part, (size_t)LR_SLICES * rank * rank));
+        TRY(dev_alloc(&h->d_lr_Bc, (size_t)rank * rank));
+        TRY(dev_alloc(&h->d_lr_S, (size_t)rank * rank));
+        TRY(dev_alloc(&h->d_lr_R, (size_t)rank * 3));
+        TRY(dev_alloc(&h->d_lr_sys, (size_t)rank * rank));
+        TRY(dev_alloc(&h->d_lr_rhs, (size_t)rank * 3));
+        TRY(dev_alloc(&h->d_lr_c, 1));
+        h->lr_m = m;
+        h->lr_cap = rank;
+    }
+    TRY(solver_workspace(h, rank, h->d_lr_sys));
+    const DevState& hs = h->h_state;
+    lr_pack_kernel<<<blocks_for(ld), THREADS, 0, h->stream>>>(h->d_yc, hs.cy[0], hs.cy[1], hs.cy[2], m, ld,
+                                                              (float)sqrt(LOG2E / (2.0 * beta)), h->d_lr_pts);
+    dim3 rgrid(blocks_for(m), (unsigned)rank);
+    lr_random_kernel<<<rgrid, THREADS, 0, h->stream>>>(h->d_lr_X, m, ld, rank, (unsigned long long)seed);
+    KCHECK();
+    h->launches += 2;
+    // Q <- orth(G Omega); then `power_iters` times Q <- orth(G Q); finally X = G Q and Bc = Q^T X (symmetrised)
+    TRY(lr_gram_apply(h, h->d_lr_X, h->d_lr_Q, rank));
+    TRY(lr_orthonormalise(h, h->d_lr_Q, rank));
+    for (int it = 0; it < power_iters; ++it) {
+        TRY(lr_gram_apply(h, h->d_lr_Q, h->d_lr_X, rank));
+        std::swap(h->d_lr_Q, h->d_lr_X);
+        TRY(lr_orthonormalise(h, h->d_lr_Q, rank));
+    }
+    TRY(lr_gram_apply(h, h->d_lr_Q, h->d_lr_X, rank));
+    TRY(lr_inner(h, h->d_lr_Q, rank, ld, h->d_lr_X, rank, ld, nullptr, 1, h->d_lr_Bc));
+    h->lr_rank = rank;
+    h->nr_ready = true;
+    return CPD_OK;
+}
+
+// Start another registration with the SAME source (one template, many targets): W = 0, T = Y, new sigma2 / w / lmd, priors off --
+// G (or its low-rank factors) stays.  The caller guarantees that the source set on this handle is the one the last
+// cpd_nonrigid_*begin saw (cpd_set_source with identical coordinates is fine: the internal order is deterministic).
+extern "C" int cpd_nonrigid_restart(cpd_ctx* h, double lmd, double sigma2, double w) {
+    if (!h) return fail(CPD_ERR_ARG, "null handle");
+    if (!h->nr_ready) return fail(CPD_ERR_STATE, "cpd_nonrigid_begin has not been called");
+    if (!h->have_source || !h->have_target) return fail(CPD_ERR_STATE, "source and target must both be set");
+    if (!(sigma2 > 0.0) || !(w >= 0.0 && w < 1.0)) return fail(CPD_ERR_ARG, "bad sigma2/w");
+    if (h->nr_m != h->m || (h->lr_rank > 0 && h->lr_m != h->m)) return fail(CPD_ERR_STATE, "the source size changed since cpd_nonrigid_begin");
+    CU(cudaSetDevice(h->device));
+    return nonrigid_common_begin(h, lmd, sigma2, w);
+}
+
+// Correspondence priors of ConstrainedNonRigidCPD (cpd.py:364-374, 390-396): p1_tilde (m) and px_tilde (m x D) in the caller's
+// order, alpha > 0.  Both NULL: priors off.  Valid until the next cpd_nonrigid_*begin with another source size.
+extern "C" int cpd_nonrigid_set_prior(cpd_ctx* h, double alpha, const double* p1_tilde, const double* px_tilde) {
+    if (!h) return fail(CPD_ERR_ARG, "null handle");
+    if (!h->nr_ready) return fail(CPD_ERR_STATE, "cpd_nonrigid_begin has not been called");
+    CU(cudaSetDevice(h->device));
+    if (!p1_tilde && !px_tilde) { h->prior_on = false; return CPD_OK; }
+    if (!p1_tilde || !px_tilde) return fail(CPD_ERR_ARG, "p1_tilde and px_tilde must be given together");
+    if (!(alpha > 0.0)) return fail(CPD_ERR_ARG, "alpha must be positive, got %g", alpha);
+    const long long m = h->m;
+    if (!h->d_p1t || h->prior_m != m) {
+        TRY(dev_alloc(&h->d_p1t, (size_t)m));
+        TRY(dev_alloc(&h->d_pxt, (size_t)m * 3));
+        h->prior_m = m;
+    }
+    // caller's order -> internal (Morton) order
+    CU(cudaMemcpyAsync(h->d_outM, p1_tilde, (size_t)m * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    gather1_kernel<<<blocks_for(m), THREADS, 0, h->stream>>>(h->d_outM, h->d_perm_src, m, h->d_p1t);
+    if (h->raw_cap < (size_t)m * 3) { TRY(dev_alloc(&h->d_raw, (size_t)m * 3)); h->raw_cap = (size_t)m * 3; }
+    TRY(upload_cloud(h, px_tilde, m, h->d_raw));
+    gather3_kernel<<<blocks_for(m), THREADS, 0, h->stream>>>(h->d_raw, h->d_perm_src, m, 0.0, 0.0, 0.0, h->d_pxt);
+    KCHECK();
+    CU(cudaStreamSynchronize(h->stream));
+    h->launches += 2;
+    h->prior_alpha = alpha;
+    h->prior_on = true;
+    return CPD_OK;
+}
+
+namespace {
+// From d_p1 / d_pxc (and the priors) to W and the moved source d_ts2 = Y + G W: the linear system of cpd.py:296, dense LU or
+// the K x K form of lowrank.cuh.  sigma2 of the PREVIOUS iteration is read from the device state.
+int nonrigid_solve(cpd_ctx* h) {
+    const long long m = h->m;
+    const DevState& hs = h->h_state;
+    const int nbs = (int)blocks_for(m);
+    // weights and right-hand side of cpd.py:296 (with priors: cpd.py:390-396)
+    const double* wgt = h->d_p1;
+    if (h->prior_on) {
+        nr_weight_kernel<<<nbs, THREADS, 0, h->stream>>>(h->d_p1, h->d_p1t, &h->d_state->sigma2, h->prior_alpha, m, h->d_wgt);
+        h->launches += 1;
+        wgt = h->d_wgt;
+    }
+    nr_rhs_kernel<<<nbs, THREADS, 0, h->stream>>>(h->d_state, h->d_p1, h->d_pxc, h->d_yc, h->prior_on ? h->d_p1t : nullptr,
+                                                  h->prior_on ? h->d_pxt : nullptr, h->prior_alpha, m, h->d_B);
+    KCHECK();
+    h->launches += 1;
+    if (h->lr_rank == 0) {
+        dim3 grid((unsigned)m, blocks_for(m));
+        nr_system_kernel<<<grid, THREADS, 0, h->stream>>>(h->d_G, wgt, &h->d_state->sigma2, h->nr_lmd, m, h->d_A);
+        KCHECK();
+        SOLV(g_sol.Xgetrf(h->sol, h->sol_params, m, m, CUDA_R_64F_, h->d_A, m, h->d_ipiv, CUDA_R_64F_, h->d_work, h->work_dev, h->h_work,
+                          h->work_host, h->d_info));
+        SOLV(g_sol.Xgetrs(h->sol, h->sol_params, CUBLAS_OP_T_, m, 3, CUDA_R_64F_, h->d_A, m, h->d_ipiv, CUDA_R_64F_, h->d_B, m, h->d_info));
+        nr_unpack_kernel<<<nbs, THREADS, 0, h->stream>>>(h->d_B, m, h->d_W);
+        nr_apply_kernel<<<(unsigned)((m + 7) / 8), THREADS, 0, h->stream>>>(h->d_G, h->d_W, h->d_yc, hs.cy[0], hs.cy[1], hs.cy[2], m,
+                                                                            h->d_ts2);
+        h->launches += 3;
+    } else {
+        const int k = h->lr_rank;
+        const long long ld = h->mpad;
+        TRY(lr_inner(h, h->d_lr_Q, k, ld, h->d_lr_Q, k, ld, wgt, 1, h->d_lr_S));                 // S = Q^T diag(wgt) Q
+        TRY(lr_inner(h, h->d_lr_Q, k, ld, h->d_B, 3, m, nullptr, 0, h->d_lr_R));              // R = Q^T F (F is [3][m])
+        lr_system_kernel<<<blocks_for((long long)k * k + 3 * k), THREADS, 0, h->stream>>>(h->d_lr_Bc, h->d_lr_S, h->d_lr_R, k,
+                                                                                          &h->d_state->sigma2, h->nr_lmd, h->d_lr_sys,
+                                                                                          h->d_lr_rhs, h->d_lr_c);
+        KCHECK();
+        SOLV(g_sol.Xgetrf(h->sol, h->sol_params, k, k, CUDA_R_64F_, h->d_lr_sys, k, h->d_ipiv, CUDA_R_64F_, h->d_work, h->work_dev,
+                          h->h_work, h->work_host, h->d_info));
+        SOLV(g_sol.Xgetrs(h->sol, h->sol_params, CUBLAS_OP_T_, k, 3, CUDA_R_64F_, h->d_lr_sys, k, h->d_ipiv, CUDA_R_64F_, h->d_lr_rhs, k,
+                          h->d_info));
+        lr_apply_kernel<<<nbs, THREADS, 0, h->stream>>>(h->d_lr_Q, m, ld, k, h->d_lr_rhs, h->d_yc, hs.cy[0], hs.cy[1], hs.cy[2], h->d_ts2);
+        lr_w_kernel<<<nbs, THREADS, 0, h->stream>>>(h->d_B, wgt, h->d_ts2, h->d_yc, hs.cy[0], hs.cy[1], hs.cy[2], m, h->d_lr_c, h->d_W);
+        h->launches += 3;
+    }
+    return CPD_OK;
+}
+}  // namespace
+
+// one EM iteration of probreg/cpd.py:111-113 for NonRigidCPD: E-step on T = Y + G W, solve cpd.py:296, sigma2 cpd.py:298-301
+extern "C" int cpd_nonrigid_step(cpd_ctx* h, double* sigma2_out) {
+    if (!h) return fail(CPD_ERR_ARG, "null handle");
+    if (!h->nr_ready) return fail(CPD_ERR_STATE, "cpd_nonrigid_begin has not been called");
+    CU(cudaSetDevice(h->device));
+    const long long m = h->m;
+    TRY(launch_estep(h, &h->d_state->sigma2, &h->d_state->w, h->d_ts));
+    const int nbs = (int)blocks_for(m), nbt = (int)blocks_for(h->npad);
+    moments_kernel<0><<<1, 256, 0, h->stream>>>(h->d_state, h->d_mom_src, nbs, RM_SRC, h->d_mom_tgt, nbt, RM_TGT, h->d_mom);
+    h->launches += 1;
+    if (h->comm) {   // every rank solves the same (global) system
+        TRY(allreduce(h, h->d_p1, (size_t)m));
+        TRY(allreduce(h, h->d_pxc, (size_t)m * 3));
+        TRY(allreduce(h, h->d_mom, MOM_PAD));
+    }
+    TRY(nonrigid_solve(h));
+    nr_resid_kernel<<<nbs, THREADS, 0, h->stream>>>(h->d_state, h->d_p1, h->d_pxc, h->d_ts, h->d_ts2, m, h->d_nrpart);
+    nr_sigma_kernel<<<1, 32, 0, h->stream>>>(h->d_state, h->d_nrpart, nbs, h->d_mom);
+    KCHECK();
+    h->launches += 2;
+    std::swap(h->d_ts, h->d_ts2);
+    if (sigma2_out) {
+        CU(cudaMemcpyAsync(h->h_pin + 56, h->d_info, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+        cpd_params p;
+        TRY(read_params(h, &p));
+        const int info = *reinterpret_cast<const int*>(h->h_pin + 56);
+        if (info != 0) return fail(CPD_ERR_STATE, "LU factorisation of the non-rigid system failed (info = %d)", info);
+        *sigma2_out = p.sigma2;
+    }
+    return CPD_OK;
+}
+
+// NonRigidCPD._maximization_step / ConstrainedNonRigidCPD._maximization_step (cpd.py:284-303 / 376-404) from a caller-supplied
+// EstepResult: pt1 (n_local), p1 (m), px (m x D) as returned by cpd_estep, sigma2_p the variance the E-step was run with.
+// Needs cpd_nonrigid_begin / cpd_nonrigid_lowrank_begin (and optionally cpd_nonrigid_set_prior) on this handle.  The new W
+// and moved source are read with cpd_nonrigid_get.  sigma2 by the reference's three traces, FP64.
+extern "C" int cpd_nonrigid_mstep(cpd_ctx* h, const double* pt1, const double* p1, const double* px, double sigma2_p, double* sigma2_out) {
+    if (!h || !pt1 || !p1 || !px) return fail(CPD_ERR_ARG, "null argument");
+    if (!h->nr_ready) return fail(CPD_ERR_STATE, "cpd_nonrigid_begin has not been called");
+    if (!(sigma2_p > 0.0)) return fail(CPD_ERR_ARG, "sigma2_p must be positive, got %g", sigma2_p);
+    CU(cudaSetDevice(h->device));
+    TRY(prepare(h));
+    const long long m = h->m, n = h->n;
+    // caller's order -> internal (Morton) order, px -> centred px~ (as cpd_mstep does)
+    CU(cudaMemcpyAsync(h->d_outN, pt1, (size_t)n * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    gather1_kernel<<<blocks_for(n), THREADS, 0, h->stream>>>(h->d_outN, h->d_perm_tgt, n, h->d_pt1);
+    CU(cudaMemcpyAsync(h->d_outM, p1, (size_t)m * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    gather1_kernel<<<blocks_for(m), THREADS, 0, h->stream>>>(h->d_outM, h->d_perm_src, m, h->d_p1);
+    if (h->raw_cap < (size_t)m * 3) { TRY(dev_alloc(&h->d_raw, (size_t)m * 3)); h->raw_cap = (size_t)m * 3; }
+    TRY(upload_cloud(h, px, m, h->d_raw));
+    gather3_kernel<<<blocks_for(m), THREADS, 0, h->stream>>>(h->d_raw, h->d_perm_src, m, 0.0, 0.0, 0.0, h->d_px);
+    centre_px_kernel<<<blocks_for(m), THREADS, 0, h->stream>>>(h->d_state, h->d_p1, h->d_px, (int)m, h->d_pxc);
+    h->h_pin[36] = sigma2_p;
+    CU(cudaMemcpyAsync(&h->d_state->sigma2, h->h_pin + 36, sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    KCHECK();
+    h->launches += 4;
+    TRY(nonrigid_solve(h));
+    const unsigned nb = blocks_for(std::max(m, n));
+    if (h->sums_cap < (size_t)nb * 4 + 4) { TRY(dev_alloc(&h->d_sums, (size_t)nb * 4 + 4)); h->sums_cap = (size_t)nb * 4 + 4; }
+    nr_traces_kernel<<<nb, THREADS, 0, h->stream>>>(h->d_state, h->d_pt1, h->d_xc, n, h->d_p1, h->d_pxc, h->d_ts2, m, h->d_sums + 4);
+    reduce_cols_kernel<<<1, 32, 0, h->stream>>>(h->d_sums + 4, (int)nb, 4, h->d_sums);
+    KCHECK();
+    if (h->comm) TRY(allreduce(h, h->d_sums, 1));            // pt1 / x are per shard; p1, px, T are global already
+    nr_sigma_api_kernel<<<1, 32, 0, h->stream>>>(h->d_state, h->d_sums);
+    KCHECK();
+    h->launches += 3;
+    std::swap(h->d_ts, h->d_ts2);
+    CU(cudaMemcpyAsync(h->h_pin + 56, h->d_info, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    cpd_params p;
+    TRY(read_params(h, &p));
+    const int info = *reinterpret_cast<const int*>(h->h_pin + 56);
+    if (info != 0) return fail(CPD_ERR_STATE, "LU factorisation of the non-rigid system failed (info = %d)", info);
+    if (sigma2_out) *sigma2_out = p.sigma2;
+    return CPD_OK;
+}
+
+// W (m x D) of the current NonRigidTransformation, and optionally the moved source T = Y + G W (m x D)
+extern "C" int cpd_nonrigid_get(cpd_ctx* h, double* w_out, double* moved_out) {
+    if (!h) return fail(CPD_ERR_ARG, "null handle");
+    if (!h->nr_ready) return fail(CPD_ERR_STATE, "cpd_nonrigid_begin has not been called");
+    CU(cudaSetDevice(h->device));
+    if (w_out) {
+        scatter_kernel<<<blocks_for(h->m), THREADS, 0, h->stream>>>(h->d_W, h->d_perm_src, h->m, 3, h->d_outM);
+        TRY(download_cloud(h, h->d_outM, h->m, w_out));
+        CU(cudaStreamSynchronize(h->stream));
+        h->launches += 1;
+    }
+    if (moved_out) {
+        scatter_kernel<<<blocks_for(h->m), THREADS, 0, h->stream>>>(h->d_ts, h->d_perm_src, h->m, 3, h->d_outM);
+        TRY(download_cloud(h, h->d_outM, h->m, moved_out));
+        CU(cudaStreamSynchronize(h->stream));
+        h->launches += 1;
+    }
+    KCHECK();
+    return CPD_OK;
+}
+
+// The factors of the low-rank path in the caller's point order: q_out (m x rank, row-major, orthonormal columns) and
+// bcore_out (rank x rank, symmetric) with G ~= q bcore q^T; rank_out receives the rank in use (<= the one asked for).
+extern "C" int cpd_nonrigid_lowrank_get(cpd_ctx* h, int* rank_out, double* q_out, double* bcore_out) {
+    if (!h) return fail(CPD_ERR_ARG, "null handle");
+    if (!h->nr_ready || h->lr_rank == 0) return fail(CPD_ERR_STATE, "cpd_nonrigid_lowrank_begin has not been called");
+    CU(cudaSetDevice(h->device));
+    const int k = h->lr_rank;
+    if (rank_out) *rank_out = k;
+    if (q_out) {
+        const size_t need = (size_t)h->m * k;
+        if (h->lr_out_cap < need) { TRY(dev_alloc(&h->d_lr_out, need)); h->lr_out_cap = need; }
+        lr_export_kernel<<<blocks_for(h->m), THREADS, 0, h->stream>>>(h->d_lr_Q, h->d_perm_src, h->m, h->mpad, k, h->d_lr_out);
+        KCHECK();
+        h->launches += 1;
+        CU(cudaMemcpyAsync(q_out, h->d_lr_out, need * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    }
+    if (bcore_out) CU(cudaMemcpyAsync(bcore_out, h->d_lr_Bc, (size_t)k * k * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    return CPD_OK;
+}
+

@@ -107,7 +107,7 @@ def build(force=False, verbose=False):
     srcs = [os.path.join(CSRC, "cpd_b200.cu"), os.path.join(CSRC, "kernels.cuh"), os.path.join(ROOT, "include", "cpd_b200.h")]
     srcs += [os.path.join(HERE, f) for f in ("cuda_runtime.h", "emu_device.h", "emu_runtime.cpp", "emu_solver.h", "emu_nccl.h", "build.py",
                                              os.path.join("cub", "device", "device_radix_sort.cuh"))]
-    srcs += sorted(os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cuh", ".h", ".cu")))
+    srcs += sorted(os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cuh", ".h", ".cu", ".inl")))
     h = hashlib.sha256()
     for s in sorted(set(srcs)):
         with open(s, "rb") as f:
@@ -116,13 +116,19 @@ def build(force=False, verbose=False):
     os.makedirs(BUILD, exist_ok=True)
     if not force and os.path.exists(OUT) and os.path.exists(stamp) and open(stamp).read() == h.hexdigest():
         return OUT
-    with open(os.path.join(CSRC, "cpd_b200.cu")) as f:
-        cu = f.read()
+    # host sources (the .cu and the .inl files it includes) get their launches rewritten into _build/, which precedes csrc/ on the
+    # include path; device headers (.cuh) are compiled as they are
     gen = os.path.join(BUILD, "cpd_b200_emu.cpp")
-    with open(gen, "w") as f:
-        f.write("// GENERATED by tests/emu/build.py from probreg_b200/csrc/cpd_b200.cu -- do not edit\n" + translate(cu))
+    for name in sorted(os.listdir(CSRC)):
+        if name.endswith((".cu", ".inl")):
+            with open(os.path.join(CSRC, name)) as f:
+                text = f.read()
+            dst = gen if name == "cpd_b200.cu" else os.path.join(BUILD, name)
+            with open(dst, "w") as f:
+                f.write("// GENERATED by tests/emu/build.py from probreg_b200/csrc/%s -- do not edit\n" % name + translate(text))
     cmd = ["g++", "-O2", "-g", "-std=c++17", "-fPIC", "-shared", "-ffp-contract=off", "-fno-strict-aliasing", "-w",
-           "-I" + HERE, "-I" + os.path.join(ROOT, "include"), "-I" + CSRC, "-o", OUT, gen, os.path.join(HERE, "emu_runtime.cpp"), "-ldl", "-lpthread"]
+           "-I" + HERE, "-I" + BUILD, "-I" + os.path.join(ROOT, "include"), "-I" + CSRC, "-o", OUT, gen, os.path.join(HERE, "emu_runtime.cpp"),
+           "-ldl", "-lpthread"]
     if verbose:
         print(" ".join(cmd))
     subprocess.check_call(cmd)

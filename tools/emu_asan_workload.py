@@ -1,7 +1,7 @@
 """AddressSanitizer sweep of the emulated library (test infrastructure).
 
 Build:  g++ -O1 -g -std=c++17 -fPIC -shared -ffp-contract=off -fno-strict-aliasing -w -fsanitize=address -fno-omit-frame-pointer -DEMU_UCONTEXT \
-        -Itests/emu -Iinclude -Iprobreg_b200/csrc -o tests/emu/_build/libcpd_b200_emu_asan.so \
+        -Itests/emu -Itests/emu/_build -Iinclude -Iprobreg_b200/csrc -o tests/emu/_build/libcpd_b200_emu_asan.so \
         tests/emu/_build/cpd_b200_emu.cpp tests/emu/emu_runtime.cpp -ldl        (after python tests/emu/build.py)
 Run:    ASAN_OPTIONS=detect_leaks=0:detect_stack_use_after_return=0 LD_PRELOAD=$(gcc -print-file-name=libasan.so) \
         python tools/emu_asan_workload.py
