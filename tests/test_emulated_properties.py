@@ -125,3 +125,29 @@ def test_bcpd_estep_matches_oracle_on_random_inputs(emulated, m, n, dim, log_s2,
     np.testing.assert_allclose(es.nu_d[live], ref.nu_d[live], rtol=rtol, atol=1e-12)
     np.testing.assert_allclose(es.nu, ref.nu, rtol=rtol, atol=1e-9 + rtol * ref.nu.max())
     np.testing.assert_allclose(es.px, ref.px, rtol=rtol, atol=1e-9 + rtol * np.abs(ref.px).max())
+
+
+@settings(**dict(COMMON, max_examples=8))
+@given(m=st.sampled_from([40, 97, 150]), beta=st.sampled_from([0.3, 1.0, 2.0, 5.0]), lmd=st.sampled_from([0.5, 2.0, 8.0]),
+       w=st.sampled_from([0.0, 0.1]), rank_frac=st.sampled_from([0.15, 0.4, 1.0]), seed=st.integers(0, 10 ** 6), dim=st.sampled_from([2, 3]))
+def test_nonrigid_dense_and_lowrank_on_random_inputs(emulated, m, beta, lmd, w, rank_frac, seed, dim):
+    """Dense device loop vs the reference arithmetic; low-rank loop vs the reference arithmetic on the SAME G = Q Bc Q^T."""
+    rng = np.random.default_rng(seed)
+    src = rng.random((m, dim))
+    n = m + int(rng.integers(-m // 4, m // 4))
+    tgt = src[rng.integers(0, m, n)] + 0.04 * np.sin(5.0 * src[rng.integers(0, m, n)][:, ::-1]) + 0.003 * rng.standard_normal((n, dim))
+    dense = cpd.NonRigidCPD(src, beta=beta, lmd=lmd)
+    rd = dense.registration(tgt, w=w, maxiter=3, tol=-1.0)
+    od, _ = orc.registration(src, tgt, "nonrigid", maxiter=3, tol=-1.0, beta=beta, lmd=lmd, w=w)
+    g = orc.rbf_kernel_f32(src, src, beta)
+    assert rd.sigma2 == pytest.approx(od.sigma2, rel=2e-5)
+    np.testing.assert_allclose(dense.moved_source(), src + g.dot(od.params[0]), atol=5e-5)
+    rank = max(2, int(rank_frac * m)) if m <= 97 else max(2, int(min(rank_frac, 0.4) * m))      # keep the emulation quick
+    low = cpd.NonRigidCPD(src, beta=beta, lmd=lmd, low_rank=rank)
+    rl = low.registration(tgt, w=w, maxiter=3, tol=-1.0)
+    g_lr = rl.transformation.q.dot(rl.transformation.bcore).dot(rl.transformation.q.T)
+    ol, _ = orc.registration(src, tgt, "nonrigid", maxiter=3, tol=-1.0, beta=beta, lmd=lmd, w=w, g=g_lr)
+    assert rl.sigma2 == pytest.approx(ol.sigma2, rel=2e-5)
+    np.testing.assert_allclose(low.moved_source(), src + g_lr.dot(ol.params[0]), atol=5e-5)
+    if rank == m:                                            # nothing truncated: the two device loops agree as well
+        assert rl.sigma2 == pytest.approx(rd.sigma2, rel=2e-5)
