@@ -77,12 +77,24 @@ int lr_orthonormalise(cpd_ctx* h, double* X, int rank) {
     KCHECK();
     return CPD_OK;
 }
-// dst[c][i] = sum_j G_ij src[c][j] for all `rank` columns
+// dst[c][i] = sum_j G_ij src[c][j] for all `rank` columns.  The product shards over rows with one exchange: in a multi-rank
+// handle (sources replicated, identically ordered on every rank) each rank forms its contiguous share of the rows into a zeroed
+// buffer and one all-reduce -- a sum of one value and zeros, hence exact and identical everywhere -- gathers them.
 int lr_gram_apply(cpd_ctx* h, const double* src, double* dst, int rank) {
-    dim3 grid(blocks_for(h->m), (unsigned)((rank + LR_COLS - 1) / LR_COLS));
-    lr_gram_apply_kernel<<<grid, THREADS, 0, h->stream>>>(h->d_lr_pts, h->m, h->mpad, src, h->mpad, rank, dst);
-    KCHECK();
-    h->launches += 1;
+    long long i_lo = 0, i_hi = h->m;
+    const bool shard = h->comm != nullptr && h->world > 1;
+    if (shard) {
+        i_lo = h->m * h->rank / h->world;
+        i_hi = h->m * (h->rank + 1) / h->world;
+        CU(cudaMemsetAsync(dst, 0, (size_t)rank * h->mpad * sizeof(double), h->stream));
+    }
+    if (i_hi > i_lo) {
+        dim3 grid(blocks_for(i_hi - i_lo), (unsigned)((rank + LR_COLS - 1) / LR_COLS));
+        lr_gram_apply_kernel<<<grid, THREADS, 0, h->stream>>>(h->d_lr_pts, h->m, h->mpad, src, h->mpad, rank, dst, i_lo, i_hi);
+        KCHECK();
+        h->launches += 1;
+    }
+    if (shard) TRY(allreduce(h, dst, (size_t)rank * h->mpad));
     return CPD_OK;
 }
 // out[na][nb] = A diag(wt) Bm^T over the points

@@ -57,12 +57,12 @@ lr_random_kernel(double* __restrict__ X, long long m, long long ld, int rank, un
 // j-points and the X tile staged through shared memory, FP32 pair arithmetic and 32-term FP32 partial sums, FP64 beyond.
 __global__ void __launch_bounds__(THREADS)
 lr_gram_apply_kernel(const float4* __restrict__ pts, long long m, long long mpad, const double* __restrict__ X, long long ld, int rank,
-                     double* __restrict__ out) {
+                     double* __restrict__ out, long long i_begin, long long i_end /* rows of this launch: all, or one rank's share */) {
     __shared__ float4 sp[LR_JT];
     __shared__ __align__(16) float sx[LR_JT][LR_COLS];
-    const long long i = (long long)blockIdx.x * THREADS + threadIdx.x;
+    const long long i = i_begin + (long long)blockIdx.x * THREADS + threadIdx.x;
     const int c0 = blockIdx.y * LR_COLS;
-    const float4 t = pts[i < m ? i : m - 1];
+    const float4 t = pts[i < i_end ? i : i_end - 1];
     double acc[LR_COLS];
 #pragma unroll
     for (int c = 0; c < LR_COLS; ++c) acc[c] = 0.0;
@@ -95,7 +95,7 @@ lr_gram_apply_kernel(const float4* __restrict__ pts, long long m, long long mpad
             for (int c = 0; c < LR_COLS; ++c) acc[c] += (double)a[c];
         }
     }
-    if (i < m) {
+    if (i < i_end) {
 #pragma unroll
         for (int c = 0; c < LR_COLS; ++c)
             if (c0 + c < rank) out[(long long)(c0 + c) * ld + i] = acc[c];

@@ -122,3 +122,21 @@ def test_sharded_nonrigid_dense_lowrank_constrained(emulated, monkeypatch):
 
     results = _run_ranks(2, body)
     assert results[0] == results[1], "ranks disagree"
+
+
+def test_sharded_range_finder_gives_the_single_rank_factors(emulated, monkeypatch):
+    """The G X products are split over the ranks' row shares and gathered by an all-reduce of value + zeros: the factors must be
+    bit-identical to the single-rank ones."""
+    monkeypatch.setenv("CPD_EMU_DEVICES", "3")
+    src, tgt = orc.synthetic_pair(333)
+    single = cpd.NonRigidCPD(src, beta=1.5, low_rank=30)
+    single.registration(tgt, maxiter=1, tol=-1.0)
+    q1, b1 = single._nr_factors
+
+    def body(comm):
+        reg = cpd.NonRigidCPD(src, beta=1.5, low_rank=30, comm=comm)
+        reg.registration(tgt, maxiter=1, tol=-1.0)
+        return reg._nr_factors[0].tobytes(), reg._nr_factors[1].tobytes()
+
+    for q, b in _run_ranks(3, body):
+        assert q == q1.tobytes() and b == b1.tobytes()
