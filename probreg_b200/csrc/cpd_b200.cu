@@ -207,6 +207,7 @@ struct cpd_ctx {
     bool prior_on = false;
     // non-rigid CPD, rank-K G ~= Q Bc Q^T (lowrank.cuh)
     int lr_rank = 0;                      // > 0: cpd_nonrigid_step takes the low-rank M-step
+    bool lr_w_stale = false;              // W of the low-rank path is formed on demand
     long long lr_m = 0;
     int lr_cap = 0;
     float4* d_lr_pts = nullptr;

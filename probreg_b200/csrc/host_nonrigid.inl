@@ -28,6 +28,7 @@ int nonrigid_common_begin(cpd_ctx* h, double lmd, double sigma2, double w) {
     }
     const DevState& hs = h->h_state;
     CU(cudaMemsetAsync(h->d_W, 0, (size_t)m * 3 * sizeof(double), h->stream));                       // cpd.py:281
+    h->lr_w_stale = false;
     CU(cudaMemsetAsync(h->d_info, 0, sizeof(int), h->stream));
     nr_identity_kernel<<<blocks_for(m), THREADS, 0, h->stream>>>(h->d_yc, hs.cy[0], hs.cy[1], hs.cy[2], m, h->d_ts);   // T = Y + G 0
     KCHECK();
@@ -271,8 +272,8 @@ int nonrigid_solve(cpd_ctx* h) {
         SOLV(g_sol.Xgetrs(h->sol, h->sol_params, CUBLAS_OP_T_, k, 3, CUDA_R_64F_, h->d_lr_sys, k, h->d_ipiv, CUDA_R_64F_, h->d_lr_rhs, k,
                           h->d_info));
         lr_apply_kernel<<<nbs, THREADS, 0, h->stream>>>(h->d_lr_Q, m, ld, k, h->d_lr_rhs, h->d_yc, hs.cy[0], hs.cy[1], hs.cy[2], h->d_ts2);
-        lr_w_kernel<<<nbs, THREADS, 0, h->stream>>>(h->d_B, wgt, h->d_ts2, h->d_yc, hs.cy[0], hs.cy[1], hs.cy[2], m, h->d_lr_c, h->d_W);
-        h->launches += 3;
+        h->lr_w_stale = true;          // W = (F - diag(wgt) Q Z) / c is formed when somebody asks for it (cpd_nonrigid_get)
+        h->launches += 2;
     }
     return CPD_OK;
 }
@@ -360,6 +361,13 @@ extern "C" int cpd_nonrigid_get(cpd_ctx* h, double* w_out, double* moved_out) {
     if (!h->nr_ready) return fail(CPD_ERR_STATE, "cpd_nonrigid_begin has not been called");
     CU(cudaSetDevice(h->device));
     if (w_out) {
+        if (h->lr_rank > 0 && h->lr_w_stale) {      // d_B still holds F, d_ts the moved source and d_lr_c the c of the last solve
+            const DevState& hs = h->h_state;
+            lr_w_kernel<<<blocks_for(h->m), THREADS, 0, h->stream>>>(h->d_B, h->prior_on ? h->d_wgt : h->d_p1, h->d_ts, h->d_yc, hs.cy[0],
+                                                                     hs.cy[1], hs.cy[2], h->m, h->d_lr_c, h->d_W);
+            h->lr_w_stale = false;
+            h->launches += 1;
+        }
         scatter_kernel<<<blocks_for(h->m), THREADS, 0, h->stream>>>(h->d_W, h->d_perm_src, h->m, 3, h->d_outM);
         TRY(download_cloud(h, h->d_outM, h->m, w_out));
         CU(cudaStreamSynchronize(h->stream));
