@@ -62,17 +62,21 @@ int solver_workspace(cpd_ctx* h, long long n, double* a) {
 int lr_orthonormalise(cpd_ctx* h, double* X, int rank) {
     const long long m = h->m, ld = h->mpad;
     const unsigned nb = blocks_for(m);
-    double* coef = h->d_lr_coef;             // [3][rank + 1]: one row per projection round, so that |x|^2 of each survives
+    const int stride = rank + 1;
+    long long per_slice = 8192;                              // points per slice of a dot product (tests lower it to reach nsl > 1)
+    if (const char* e = getenv("CPD_B200_LR_SLICE_POINTS")) per_slice = std::max<long long>(32, atoll(e));
+    const unsigned nsl = (unsigned)std::min<long long>(LR_SLICES, std::max<long long>(1, (m + per_slice - 1) / per_slice));
+    const size_t round_sz = (size_t)LR_SLICES * stride;     // d_lr_coef: [3 rounds][LR_SLICES][rank + 1] slice partials
     for (int j = 0; j < rank; ++j) {
         for (int round = 0; round < 2; ++round) {
-            double* c = coef + (size_t)round * (rank + 1);
-            lr_dots_kernel<<<(unsigned)(j + 1), THREADS, 0, h->stream>>>(X, m, ld, j, 0, c);
-            if (j > 0) lr_project_kernel<<<nb, THREADS, 0, h->stream>>>(X, m, ld, j, c);
+            double* part = h->d_lr_coef + round * round_sz;
+            lr_dots_kernel<<<dim3((unsigned)(j + 1), nsl), THREADS, 0, h->stream>>>(X, m, ld, j, 0, stride, part);
+            if (j > 0) lr_project_kernel<<<nb, THREADS, 0, h->stream>>>(X, m, ld, j, stride, (int)nsl, part);
             h->launches += j > 0 ? 2 : 1;
         }
-        double* c2 = coef + (size_t)2 * (rank + 1);
-        lr_dots_kernel<<<1, THREADS, 0, h->stream>>>(X, m, ld, j, j, c2);
-        lr_scale_kernel<<<nb, THREADS, 0, h->stream>>>(X, m, ld, j, coef + j, c2 + j);
+        double* part2 = h->d_lr_coef + 2 * round_sz;
+        lr_dots_kernel<<<dim3(1, nsl), THREADS, 0, h->stream>>>(X, m, ld, j, j, stride, part2);
+        lr_scale_kernel<<<nb, THREADS, 0, h->stream>>>(X, m, ld, j, stride, (int)nsl, h->d_lr_coef, part2);
         h->launches += 2;
     }
     KCHECK();
@@ -153,7 +157,7 @@ extern "C" int cpd_nonrigid_lowrank_begin(cpd_ctx* h, double beta, double lmd, d
         TRY(dev_alloc(&h->d_lr_pts, (size_t)ld));
         TRY(dev_alloc(&h->d_lr_Q, (size_t)rank * ld));
         TRY(dev_alloc(&h->d_lr_X, (size_t)rank * ld));
-        TRY(dev_alloc(&h->d_lr_coef, (size_t)3 * (rank + 1)));
+        TRY(dev_alloc(&h->d_lr_coef, (size_t)3 * LR_SLICES * (rank + 1)));
         TRY(dev_alloc(&h->d_lr_part, (size_t)LR_SLICES * rank * rank));
         TRY(dev_alloc(&h->d_lr_Bc, (size_t)rank * rank));
         TRY(dev_alloc(&h->d_lr_S, (size_t)rank * rank));

@@ -103,21 +103,31 @@ lr_gram_apply_kernel(const float4* __restrict__ pts, long long m, long long mpad
 }
 
 // ---- orthonormalisation of the columns of X (classical Gram-Schmidt, every column projected twice) ---------------------
-// coef[k] = <X_k, X_j>  for k = k_first .. j (the last one is |X_j|^2); one CTA per k, fixed-order reduction
+// part[s][k] = <X_k, X_j> over the s-th of LR_SLICES point slices, for k = k_first .. j (the last one is |X_j|^2).
+// One CTA per {k, slice}: a single CTA per k would stream 2 M doubles through one SM (~20 us at M = 50k, whatever j is);
+// consumers add the slices in a fixed order, so the result is reproducible.
 __global__ void __launch_bounds__(THREADS)
-lr_dots_kernel(const double* __restrict__ X, long long m, long long ld, int j, int k_first, double* __restrict__ coef) {
-    const int k = k_first + blockIdx.x;
+lr_dots_kernel(const double* __restrict__ X, long long m, long long ld, int j, int k_first, int stride /* rank + 1 */,
+               double* __restrict__ part) {
+    const int k = k_first + blockIdx.x, slice = blockIdx.y, nsl = gridDim.y;      // nsl <= LR_SLICES, chosen by the host from m
+    const long long per = (m + nsl - 1) / nsl;
+    const long long i_lo = per * slice, i_hi = (i_lo + per < m) ? i_lo + per : m;
     const double* a = X + (long long)k * ld;
     const double* b = X + (long long)j * ld;
     double v[1] = {0.0};
-    for (long long i = threadIdx.x; i < m; i += THREADS) v[0] += a[i] * b[i];
-    block_reduce_store<1>(v, coef + k);
+    for (long long i = i_lo + threadIdx.x; i < i_hi; i += THREADS) v[0] += a[i] * b[i];
+    block_reduce_store<1>(v, part + (size_t)slice * stride + k);
 }
-// X_j -= sum_{k<j} coef[k] X_k
+__device__ __forceinline__ double lr_sum_slices(const double* __restrict__ part, int stride, int nsl, int k) {
+    double s = 0.0;
+    for (int sl = 0; sl < nsl; ++sl) s += part[(size_t)sl * stride + k];
+    return s;
+}
+// X_j -= sum_{k<j} coef[k] X_k,   coef[k] = sum over slices of part[.][k]
 __global__ void __launch_bounds__(THREADS)
-lr_project_kernel(double* __restrict__ X, long long m, long long ld, int j, const double* __restrict__ coef) {
+lr_project_kernel(double* __restrict__ X, long long m, long long ld, int j, int stride, int nsl, const double* __restrict__ part) {
     __shared__ double sc[LR_MAX_RANK];
-    for (int k = threadIdx.x; k < j; k += THREADS) sc[k] = coef[k];
+    for (int k = threadIdx.x; k < j; k += THREADS) sc[k] = lr_sum_slices(part, stride, nsl, k);
     __syncthreads();
     const long long i = (long long)blockIdx.x * THREADS + threadIdx.x;
     if (i < m) {
@@ -127,11 +137,12 @@ lr_project_kernel(double* __restrict__ X, long long m, long long ld, int j, cons
     }
 }
 // X_j *= 1/|X_j|; a column that has (numerically) nothing left outside the span of its predecessors becomes zero.
-// n0 = |X_j|^2 before the projections, n2 = after.
+// n0 = |X_j|^2 before the projections (slices of part0), n2 = after (slices of part2).
 __global__ void __launch_bounds__(THREADS)
-lr_scale_kernel(double* __restrict__ X, long long m, long long ld, int j, const double* __restrict__ n0_ptr, const double* __restrict__ n2_ptr) {
+lr_scale_kernel(double* __restrict__ X, long long m, long long ld, int j, int stride, int nsl, const double* __restrict__ part0,
+                const double* __restrict__ part2) {
     const long long i = (long long)blockIdx.x * THREADS + threadIdx.x;
-    const double n0 = *n0_ptr, n2 = *n2_ptr;
+    const double n0 = lr_sum_slices(part0, stride, nsl, j), n2 = lr_sum_slices(part2, stride, nsl, j);
     const double s = (n2 > 1e-280 && n2 > 1e-28 * n0) ? 1.0 / sqrt(n2) : 0.0;
     if (i < m) X[(long long)j * ld + i] *= s;
 }

@@ -233,6 +233,19 @@ def test_lowrank_misc_emulated(emulated):
     _check_misc()
 
 
+def test_sliced_dot_products_give_the_same_basis_emulated(emulated, monkeypatch):
+    """The Gram-Schmidt dot products are split into up to 8 point slices once M is large; force that at a small M and
+    compare with the unsliced run (same arithmetic up to the order of a handful of FP64 additions)."""
+    src, tgt = _deformed_pair(300)
+    base = cpd.NonRigidCPD(src, low_rank=24).registration(tgt, maxiter=2, tol=-1.0)
+    monkeypatch.setenv("CPD_B200_LR_SLICE_POINTS", "48")                      # 300 points -> 7 slices
+    sliced = cpd.NonRigidCPD(src, low_rank=24).registration(tgt, maxiter=2, tol=-1.0)
+    qb, qs = base.transformation.q, sliced.transformation.q
+    np.testing.assert_allclose(qs.T.dot(qs), np.identity(24), atol=1e-12)
+    np.testing.assert_allclose(qs.dot(sliced.transformation.bcore).dot(qs.T), qb.dot(base.transformation.bcore).dot(qb.T), atol=2e-6)
+    assert sliced.sigma2 == pytest.approx(base.sigma2, rel=1e-6)       # the trailing columns are rounding noise: another summation order, another noise basis
+
+
 @pytest.mark.gpu
 @pytest.mark.timeout(600)
 @UNVERIFIED
