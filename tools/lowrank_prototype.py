@@ -1,5 +1,6 @@
 #!/usr/bin/env python
-"""Round-2 groundwork (CPU prototype, not product code): non-rigid CPD with a rank-K G = Q L Q^T.
+"""[historical: the CPU prototype that preceded csrc/lowrank.cuh; the product solves the K x K system without the eigen-decomposition]
+CPU prototype (not product code): non-rigid CPD with a rank-K G = Q L Q^T.
 
 Checks, against the dense oracle at small M, (i) how fast the spectrum of the RBF Gram matrix decays for the reference's
 default beta, (ii) that the Woodbury form of the M-step (cpd.py:296)
