@@ -107,7 +107,7 @@ int lr_inner(cpd_ctx* h, const double* A, int na, long long lda, const double* B
              double* out) {
     const int tiles = ((na + LR_TILE - 1) / LR_TILE) * ((nb + LR_TILE - 1) / LR_TILE);
     dim3 grid((unsigned)tiles, LR_SLICES);
-    lr_inner_kernel<<<grid, THREADS, 0, h->stream>>>(A, na, lda, Bm, nb, ldb, wt, h->m, h->d_lr_part);
+    lr_inner_kernel<<<grid, THREADS, 0, h->stream>>>(A, na, lda, Bm, nb, ldb, wt, h->m, symmetrise, h->d_lr_part);
     lr_merge_kernel<<<blocks_for((long long)na * nb), THREADS, 0, h->stream>>>(h->d_lr_part, na, nb, symmetrise, out);
     KCHECK();
     h->launches += 2;

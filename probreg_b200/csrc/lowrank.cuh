@@ -151,10 +151,12 @@ lr_scale_kernel(double* __restrict__ X, long long m, long long ld, int j, int st
 // One CTA per {32 x 32 output tile, i-slice}; 2 x 2 outputs per thread; partial per slice, merged by lr_merge_kernel.
 __global__ void __launch_bounds__(THREADS)
 lr_inner_kernel(const double* __restrict__ A, int na, long long lda, const double* __restrict__ Bm, int nb, long long ldb,
-                const double* __restrict__ wt, long long m, double* __restrict__ part /* [LR_SLICES][na][nb] */) {
+                const double* __restrict__ wt, long long m, int upper_only /* symmetric result: tiles below the diagonal are skipped */,
+                double* __restrict__ part /* [LR_SLICES][na][nb] */) {
     __shared__ double sa[LR_TILE][LR_CHUNK + 1], sb[LR_TILE][LR_CHUNK + 1];
     const int tiles_b = (nb + LR_TILE - 1) / LR_TILE;
     const int ta0 = (blockIdx.x / tiles_b) * LR_TILE, tb0 = (blockIdx.x % tiles_b) * LR_TILE;
+    if (upper_only && ta0 > tb0) return;            // the whole CTA, before any barrier; lr_merge_kernel mirrors the upper tiles
     const int slice = blockIdx.y;
     const long long per = (m + LR_SLICES - 1) / LR_SLICES;
     const long long i_lo = per * slice, i_hi = (i_lo + per < m) ? i_lo + per : m;
@@ -186,18 +188,22 @@ lr_inner_kernel(const double* __restrict__ A, int na, long long lda, const doubl
             if (a < na && b < nb) dst[(size_t)a * nb + b] = acc[u][v];
         }
 }
-// out[e] = sum_slices part[s][e]  (fixed order); symmetrise != 0: out = (out + out^T) / 2 for a square n x n result
+// out[e] = sum_slices part[s][e]  (fixed order).  symmetrise != 0 (square, mathematically symmetric result whose tiles below
+// the diagonal were not computed): diagonal tiles give (x + x^T) / 2, the others are mirrored from the upper triangle.
 __global__ void __launch_bounds__(THREADS)
 lr_merge_kernel(const double* __restrict__ part, int na, int nb, int symmetrise, double* __restrict__ out) {
     const int e = blockIdx.x * THREADS + threadIdx.x;
     if (e < na * nb) {
         const int a = e / nb, b = e % nb;
+        const int ta = a / LR_TILE, tb = b / LR_TILE;
+        const size_t e_ab = (size_t)a * nb + b, e_ba = (size_t)b * nb + a;
         double s = 0.0, t = 0.0;
         for (int sl = 0; sl < LR_SLICES; ++sl) {
-            s += part[(size_t)sl * na * nb + e];
-            if (symmetrise) t += part[(size_t)sl * na * nb + (size_t)b * nb + a];
+            const double* p = part + (size_t)sl * na * nb;
+            if (!symmetrise || ta <= tb) s += p[e_ab];
+            if (symmetrise && ta >= tb) t += p[e_ba];
         }
-        out[e] = symmetrise ? 0.5 * (s + t) : s;
+        out[e] = !symmetrise ? s : (ta == tb ? 0.5 * (s + t) : (ta < tb ? s : t));
     }
 }
 
