@@ -134,6 +134,23 @@ def _check_misc():
         r3 = reuse.registration(tgt2 + 0.5, maxiter=2, tol=-1.0)
         f3 = cpd.NonRigidCPD(src_b, **kw).registration(tgt2 + 0.5, maxiter=2, tol=-1.0)
         assert r3.sigma2 == f3.sigma2
+    # one HANDLE through changing sizes and modes (buffers are re-used / re-allocated inside the library): every run must
+    # equal the same run on a fresh handle
+    def run_on(h, m, rank):
+        s_, t_ = _deformed_pair(m, seed=m)
+        h.set_source(s_)
+        h.set_target(t_)
+        s2 = h.sigma2_init()
+        if rank:
+            h.nonrigid_lowrank_begin(1.0, 2.0, s2, 0.05, rank, 1, 5)
+        else:
+            h.nonrigid_begin(1.0, 2.0, s2, 0.05)
+        return [h.nonrigid_step() for _ in range(2)], h.nonrigid_w(), h.nonrigid_moved()
+
+    shared = _cabi.Handle(3)
+    for m, rank in [(150, 20), (90, 0), (210, 33), (210, 0), (60, 60), (150, 8)]:
+        got, want = run_on(shared, m, rank), run_on(_cabi.Handle(3), m, rank)
+        assert got[0] == want[0] and np.array_equal(got[1], want[1]) and np.array_equal(got[2], want[2]), (m, rank)
     # default tolerance: stops like the dense loop does (q == sigma2, cpd.py:303)
     d = cpd.NonRigidCPD(src, low_rank=20)
     rd = d.registration(tgt)
