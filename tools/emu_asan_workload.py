@@ -32,6 +32,11 @@ a = cpd.NonRigidCPD(src[:300], low_rank=40); a.registration(tgt[:310], maxiter=2
 b = cpd.NonRigidCPD(src[:300]); b.registration(tgt[:310], maxiter=2, tol=-1)
 idx = np.arange(0, 300, 10)
 c = cpd.ConstrainedNonRigidCPD(src[:300], idx_source=idx, idx_target=idx, alpha=1e-2, low_rank=30); c.registration(tgt[:310], maxiter=2, tol=-1)
+es_ = orc.expectation_step(src[:300], tgt[:310], 0.01, 0.05)
+b.maximization_step(tgt[:310], cpd.EstepResult(*es_), 0.01); a.maximization_step(tgt[:310], cpd.EstepResult(*es_), 0.01)
+c.maximization_step(tgt[:310], cpd.EstepResult(*es_), 0.01)
+a.registration(tgt[:290] + 0.01, maxiter=2, tol=-1)            # restart path: factors kept
+d = cpd.NonRigidCPD(src[:120], low_rank=120); d.registration(tgt[:100], maxiter=1, tol=-1)   # rank == M
 print("nonrigid ok")
 bcpd.CombinedBCPD(src[:257]).expectation_step(src[:257], tgt[:513], 1.0, 1.0 / 257, np.ones(257), 0.02, 0.1)
 gt.GaussTransform(src[:300], 0.3).compute(tgt[:100], rng.standard_normal((5, 300)))
