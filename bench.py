@@ -351,6 +351,7 @@ def run_ours(args):
                 "materialised_equiv_frac": 8.0 * n_local * n / (t_estep_ms * 1e-3) / 1e9 / hbm_peak},
     }
     cpu = cpu_sample(n, args.cpu_cols) if world == 1 and not args.no_cpu else None
+    extras = run_extras() if world == 1 and not args.no_extras and n == 100000 else None
     out = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
         "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
@@ -375,10 +376,28 @@ def run_ours(args):
         "clocks": clocks,
         "probe": probe,
         "result_check": {"sigma2_after_run": final[3], "scale": final[2]},
+        "extras": extras,
     }
     emit(out)
     if world > 1:
         tdist.destroy_process_group()
+
+
+def run_extras():
+    """Side measurements (BASELINE configs 3 and 5, first-hardware-run probes of the newest paths) in a SUBPROCESS, after the bench
+    line's own numbers are final: whatever happens there -- an exception, a CUDA fault, a time-out -- costs the bench line
+    nothing but this key.  tools/bench_extras.py prints one JSON object."""
+    import subprocess
+
+    try:
+        r = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "bench_extras.py")], capture_output=True, text=True, timeout=420,
+                           cwd=ROOT)
+        lines = [l for l in r.stdout.splitlines() if l.strip().startswith("{")]
+        if r.returncode != 0 or not lines:
+            return {"error": "exit %d: %s" % (r.returncode, (r.stderr or r.stdout)[-400:])}
+        return json.loads(lines[-1])
+    except Exception as e:                      # noqa: BLE001
+        return {"error": "%s: %s" % (type(e).__name__, str(e)[:300])}
 
 
 def emit(obj):
@@ -400,6 +419,7 @@ def main():
     ap.add_argument("--points", type=int, default=100000)
     ap.add_argument("--cpu-cols", type=int, default=2000, help="target columns in the CPU sample")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-extras", action="store_true", help="skip the side measurements of tools/bench_extras.py (key \"extras\")")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
