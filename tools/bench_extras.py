@@ -54,9 +54,14 @@ def affine_250k():
         h.event_record(2 * i + 1)
     h.sync()
     ms = float(np.mean([h.event_elapsed(2 * i, 2 * i + 1) for i in range(steps)]))
+    h.set_profiling(True)
+    h.em_step(read=False)
+    stages = h.stage_times()
+    h.set_profiling(False)
     out = h.em_step()
     return {"workload": "affine CPD, synthetic 3-D N=M=%d (BASELINE config 3)" % n, "ms_per_iteration": ms, "it_per_s": 1e3 / ms,
-            "gpair_per_s": 2.0 * n * n / (ms * 1e-3) / 1e9, "sigma2_after_12": out[3]}
+            "gpair_per_s": 2.0 * n * n / (ms * 1e-3) / 1e9, "sigma2_after_13": out[3],
+            "stage_ms": dict(zip(["pack", "pass1", "finalize1", "pass2", "finalize2", "moments_mstep"], [float(x) for x in stages]))}
 
 
 def lowrank_50k():
@@ -68,11 +73,14 @@ def lowrank_50k():
     h.set_source(src)
     h.set_target(tgt)
     s2 = h.sigma2_init()
-    h.sync()
-    t0 = time.perf_counter()
-    h.nonrigid_lowrank_begin(2.0, 2.0, s2, 0.0, rank, 2, 0)
-    h.sync()
-    setup_ms = (time.perf_counter() - t0) * 1e3
+    setup = {}
+    for piters in (0, 2):                       # set-up = (piters + 2) products G X + (piters + 1) orthonormalisations + Bc
+        h.sync()
+        t0 = time.perf_counter()
+        h.nonrigid_lowrank_begin(2.0, 2.0, s2, 0.0, rank, piters, 0)
+        h.sync()
+        setup["power_iters=%d" % piters] = (time.perf_counter() - t0) * 1e3
+    setup_ms = setup["power_iters=2"]
     trace = [h.nonrigid_step()]
     l0 = h.launch_count()
     steps = 8
@@ -86,7 +94,7 @@ def lowrank_50k():
     trace.append(h.nonrigid_step())
     moved = h.nonrigid_moved()
     return {"workload": "non-rigid CPD, rank-%d G, synthetic 3-D N=M=%d, beta=lmd=2 (BASELINE config 5)" % (rank, n),
-            "setup_ms": setup_ms, "ms_per_iteration": ms, "it_per_s": 1e3 / ms, "launches_per_iteration": launches,
+            "setup_ms": setup_ms, "setup_ms_by_power_iters": setup, "ms_per_iteration": ms, "it_per_s": 1e3 / ms, "launches_per_iteration": launches,
             "sigma2_first_and_10th": trace,
             "mean_residual_before_after": [float(np.linalg.norm(src - tgt, axis=1).mean()), float(np.linalg.norm(moved - tgt, axis=1).mean())]}
 
