@@ -99,6 +99,31 @@ def lowrank_50k():
             "mean_residual_before_after": [float(np.linalg.norm(src - tgt, axis=1).mean()), float(np.linalg.norm(moved - tgt, axis=1).mean())]}
 
 
+def bcpd_estep_100k():
+    """The weighted (WGT) instantiations of pass 1 / pass 2 at the bench size: stage times of one BCPD E-step."""
+    from probreg_b200 import _cabi
+    from probreg_b200.synthetic import synthetic_pair
+
+    n = 3000 if QUICK else 100000
+    src, tgt = synthetic_pair(n)
+    rng = np.random.default_rng(1)
+    alpha, sdiag = rng.dirichlet(np.ones(n)), rng.uniform(0.0, 1e-3, n)
+    h = _cabi.Handle(3)
+    h.set_source(src)
+    h.set_target(tgt)
+    h.bcpd_estep(src, 1.0, alpha, sdiag, 0.02, 0.1)
+    h.set_profiling(True)
+    # cpd_stage_times reads seven events; the last one is only recorded by cpd_em_step, so run one first
+    h.set_state(_cabi.TF_RIGID, True, 0.0, np.identity(3), np.zeros(3), 1.0, 0.02, 0.0)
+    h.em_step(read=False)
+    nu_d, nu, px, n_p = h.bcpd_estep(src, 1.0, alpha, sdiag, 0.02, 0.1)
+    stages = h.stage_times()
+    h.set_profiling(False)
+    return {"workload": "BCPD E-step, synthetic 3-D N=M=%d, sigma2 0.02, w 0.1" % n,
+            "stage_ms": dict(zip(["pack", "pass1_wgt", "finalize1", "pass2_wgt", "finalize2"], [float(x) for x in stages[:5]])),
+            "conservation": {"n_p": n_p, "sum_nu_d": float(nu_d.sum()), "sum_nu": float(nu.sum())}}
+
+
 def parity_probes():
     from probreg_b200 import bcpd, cpd
 
@@ -144,7 +169,7 @@ def parity_probes():
 
 def main():
     t0 = time.perf_counter()
-    res = {"affine_250k": guarded(affine_250k), "lowrank_50k": guarded(lowrank_50k)}
+    res = {"affine_250k": guarded(affine_250k), "lowrank_50k": guarded(lowrank_50k), "bcpd_estep_100k": guarded(bcpd_estep_100k)}
     res["first_hardware_run_probes"] = guarded(parity_probes)
     res["seconds"] = time.perf_counter() - t0
     print(json.dumps(res))
