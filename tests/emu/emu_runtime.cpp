@@ -238,7 +238,7 @@ unsigned long long globaltimer_ns() { return (unsigned long long)clock64(); }
 
 // ---- runtime API ---------------------------------------------------------------------------
 struct emu_stream { int unused; };
-struct emu_event { double t_ms; };
+struct emu_event { double t_ms; bool recorded; };
 static int emu_sms() {
     const char* e = getenv("CPD_EMU_SMS");
     const int v = e ? atoi(e) : 0;
@@ -281,11 +281,15 @@ cudaError_t cudaStreamCreateWithFlags(cudaStream_t* s, unsigned) { *s = new emu_
 cudaError_t cudaStreamDestroy(cudaStream_t s) { delete s; return cudaSuccess; }
 cudaError_t cudaStreamSynchronize(cudaStream_t) { return cudaSuccess; }
 cudaError_t cudaDeviceSynchronize() { return cudaSuccess; }
-cudaError_t cudaEventCreate(cudaEvent_t* e) { *e = new emu_event(); (*e)->t_ms = 0.0; return cudaSuccess; }
+cudaError_t cudaEventCreate(cudaEvent_t* e) { *e = new emu_event(); (*e)->t_ms = 0.0; (*e)->recorded = false; return cudaSuccess; }
 cudaError_t cudaEventDestroy(cudaEvent_t e) { delete e; return cudaSuccess; }
-cudaError_t cudaEventRecord(cudaEvent_t e, cudaStream_t) { e->t_ms = (double)clock64() * 1e-6; return cudaSuccess; }
+cudaError_t cudaEventRecord(cudaEvent_t e, cudaStream_t) { e->t_ms = (double)clock64() * 1e-6; e->recorded = true; return cudaSuccess; }
 cudaError_t cudaEventSynchronize(cudaEvent_t) { return cudaSuccess; }
-cudaError_t cudaEventElapsedTime(float* ms, cudaEvent_t a, cudaEvent_t b) { *ms = (float)(b->t_ms - a->t_ms); return cudaSuccess; }
+cudaError_t cudaEventElapsedTime(float* ms, cudaEvent_t a, cudaEvent_t b) {
+    if (!a->recorded || !b->recorded) return cudaErrorInvalidValue;      // the real runtime refuses events that were never recorded
+    *ms = (float)(b->t_ms - a->t_ms);
+    return cudaSuccess;
+}
 cudaError_t cudaIpcGetMemHandle(cudaIpcMemHandle_t*, void*) { return cudaErrorNotSupported; }
 cudaError_t cudaIpcOpenMemHandle(void**, cudaIpcMemHandle_t, unsigned) { return cudaErrorNotSupported; }
 cudaError_t cudaIpcCloseMemHandle(void*) { return cudaSuccess; }
