@@ -58,3 +58,30 @@ def test_reference_fixtures_load():
     assert abs(pio.voxel_down_sample(horse, 0.01).shape[0] - 480) <= 40       # tests/test_cpd.py recipe: ~480 points
     assert pio.read_points(os.path.join(REF, "examples", "cloud_0.pcd")).shape == (6535, 3)
     assert pio.read_points(os.path.join(REF, "examples", "fish_source.txt")).shape == (91, 2)
+
+
+def test_example_utils_follow_the_reference_recipes():
+    """examples/utils.py: numpy counterparts of the reference's examples/utils.py (rigid recipe: voxel filter, shuffle, noise,
+    outliers, 30 degrees about z; non-rigid: the two text clouds, voxel-filtered)."""
+    import os
+    import sys
+
+    import numpy as np
+
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "examples"))
+    import utils as ex
+
+    r = ex.euler2mat(0.1, -0.2, 0.3)
+    np.testing.assert_allclose(r.dot(r.T), np.identity(3), atol=1e-15)
+    np.testing.assert_allclose(ex.euler2mat(0.0, 0.0, np.deg2rad(30.0))[:2, :2], [[np.cos(np.pi / 6), -0.5], [0.5, np.cos(np.pi / 6)]], atol=1e-15)
+    bunny = ex.reference_file("bunny.pcd")
+    if bunny is None:
+        return                                                          # the reference's data files are not around (GPU box)
+    src, tgt = ex.prepare_source_and_target_rigid_3d(bunny, rng=np.random.default_rng(0))
+    assert src.shape[1] == 3 and tgt.shape == (src.shape[0] + 500, 3)
+    # undo the known transform: the inliers are the (shuffled, slightly noised) source
+    back = tgt[: src.shape[0]].dot(ex.euler2mat(0.0, 0.0, np.deg2rad(30.0)))
+    d = np.sqrt(((back[:, None, :] - src[None, :, :]) ** 2).sum(-1)).min(axis=1)
+    assert d.max() < 0.01
+    fish = ex.prepare_source_and_target_nonrigid_2d(ex.reference_file("fish_source.txt"), ex.reference_file("fish_target.txt"))
+    assert fish[0].shape == (91, 2) and fish[1].shape == (91, 2)
