@@ -11,33 +11,27 @@ from oracle import c_oracle
 from oracle import cpd_oracle as orc
 from probreg_b200 import _cabi, cpd
 
-pytestmark = [pytest.mark.gpu, pytest.mark.timeout(900),
-              pytest.mark.xfail(reason="size not yet run through pytest on hardware", strict=False)]
-
-
-def test_config3_affine_250k_properties():
-    n = 250000
+def _config3(n, iters, sample):
     src, tgt = orc.synthetic_pair(n, "affine")
     seen = []
-    res = cpd.registration_cpd(src, tgt, "affine", maxiter=25, tol=-1.0, callbacks=[lambda t: seen.append(1)])
-    assert len(seen) == 25
+    res = cpd.registration_cpd(src, tgt, "affine", maxiter=iters, tol=-1.0, callbacks=[lambda t: seen.append(1)])
+    assert len(seen) == iters
     lin = orc.rot_z(30.0).dot(np.diag([1.1, 0.9, 1.05]))
     lin[0, 1] += 0.05
-    np.testing.assert_allclose(res.transformation.b, lin, atol=5e-3)
-    np.testing.assert_allclose(res.transformation.t, [0.1, -0.2, 0.3], atol=5e-3)
+    np.testing.assert_allclose(res.transformation.b, lin, atol=1e-2)
+    np.testing.assert_allclose(res.transformation.t, [0.1, -0.2, 0.3], atol=1e-2)
     assert 5e-5 < res.sigma2 < 5e-3
     # one E-step at the final transform: conservation laws + a column sample against the C oracle
     ts = res.transformation.transform(src)
     es = cpd.AffineCPD(src).expectation_step(ts, tgt, res.sigma2, 0.1)
     assert es.n_p == pytest.approx(es.pt1.sum(), rel=1e-7)
     np.testing.assert_allclose(es.px.sum(0), (es.pt1[:, None] * tgt).sum(0), rtol=1e-6)
-    sel = np.random.default_rng(2).choice(n, 600, replace=False)
+    sel = np.random.default_rng(2).choice(n, sample, replace=False)
     ref = c_oracle.expectation_step(ts, tgt[sel], res.sigma2, 0.1, n_global=n)
     np.testing.assert_allclose(es.pt1[sel], ref.pt1, rtol=5e-5, atol=1e-12)
 
 
-def test_config4_one_rank_shard_of_1m():
-    m, n_global, ranks = 1000000, 1000000, 8
+def _config4(m, n_global, ranks, sample):
     src, tgt = orc.synthetic_pair(m)
     lo, hi = 3 * (n_global // ranks), 4 * (n_global // ranks)               # the shard rank 3 would hold
     h = _cabi.Handle(3)
@@ -48,6 +42,26 @@ def test_config4_one_rank_shard_of_1m():
     assert pt1.shape == (hi - lo,) and p1.shape == (m,)
     assert n_p == pytest.approx(pt1.sum(), rel=1e-7)                          # sum_m p1 == sum_n pt1 over the shard
     np.testing.assert_allclose(px.sum(0), (pt1[:, None] * tgt[lo:hi]).sum(0), rtol=1e-6)
-    sel = np.random.default_rng(3).choice(hi - lo, 300, replace=False)
+    sel = np.random.default_rng(3).choice(hi - lo, sample, replace=False)
     ref = c_oracle.expectation_step(ts, tgt[lo:hi][sel], 3e-4, 0.1, n_global=n_global)
     np.testing.assert_allclose(pt1[sel], ref.pt1, rtol=5e-5, atol=1e-12)
+
+
+@pytest.mark.gpu
+@pytest.mark.timeout(900)
+@pytest.mark.xfail(reason="size not yet run through pytest on hardware", strict=False)
+def test_config3_affine_250k_properties():
+    _config3(250000, 100, 600)           # the reference's affine loop needs ~100 iterations on this pair (oracle at 3000 points)
+
+
+@pytest.mark.gpu
+@pytest.mark.timeout(900)
+@pytest.mark.xfail(reason="size not yet run through pytest on hardware", strict=False)
+def test_config4_one_rank_shard_of_1m():
+    _config4(1000000, 1000000, 8, 300)
+
+
+def test_config3_and_config4_bodies_at_emulation_size(emulated):
+    """The same two test bodies at sizes the CPU emulation can run: checks the test logic itself before its first hardware run."""
+    _config3(2000, 100, 150)
+    _config4(4000, 4000, 8, 80)
