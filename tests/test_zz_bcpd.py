@@ -163,13 +163,9 @@ def test_bcpd_registration_gpu():
     _check_imq_and_registration()
 
 
-@pytest.mark.gpu
-@pytest.mark.timeout(600)
-@UNVERIFIED
-def test_bcpd_estep_full_size_properties():
-    """N = M = 100k: size-independent properties (sum nu == sum nu_d, sum_m px_m == sum_n nu_d_n x_n) and a column sample
-    against the C oracle-free numpy restatement."""
-    n = 100000
+def _check_full_size(n, sample):
+    """Size-independent properties (sum nu == sum nu_d, sum_m px_m == sum_n nu_d_n x_n) and a column sample against the numpy
+    restatement (the constant w / N and the (1 - w) alpha factor of the sample run are matched to the full run's)."""
     src, tgt = orc.synthetic_pair(n)
     rng = np.random.default_rng(1)
     alpha, sdiag = rng.dirichlet(np.ones(n)), rng.uniform(0.0, 1e-3, n)
@@ -179,7 +175,18 @@ def test_bcpd_estep_full_size_properties():
     nu_d, nu, px, n_p = h.bcpd_estep(src, 1.0, alpha, sdiag, 2e-3, 0.1)
     assert n_p == pytest.approx(nu_d.sum(), rel=1e-7) and n_p == pytest.approx(nu.sum(), rel=1e-9)
     np.testing.assert_allclose(px.sum(0), (nu_d[:, None] * tgt).sum(0), rtol=1e-6)
-    sel = rng.choice(n, 400, replace=False)
-    w_s = 0.1 * 400 / n                                              # w / N is what enters the denominator: keep it equal ...
-    ref = orc.bcpd_expectation_step(src, tgt[sel], 1.0, alpha * (1.0 - 0.1) / (1.0 - w_s), sdiag, 2e-3, w_s)   # ... and (1 - w) alpha
+    sel = rng.choice(n, sample, replace=False)
+    w_s = 0.1 * sample / n
+    ref = orc.bcpd_expectation_step(src, tgt[sel], 1.0, alpha * (1.0 - 0.1) / (1.0 - w_s), sdiag, 2e-3, w_s)
     np.testing.assert_allclose(nu_d[sel], ref.nu_d, rtol=5e-5, atol=1e-12)
+
+
+def test_bcpd_full_size_body_at_emulation_size(emulated):
+    _check_full_size(2500, 200)
+
+
+@pytest.mark.gpu
+@pytest.mark.timeout(600)
+@UNVERIFIED
+def test_bcpd_estep_full_size_properties():
+    _check_full_size(100000, 400)

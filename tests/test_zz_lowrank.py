@@ -292,30 +292,40 @@ def test_lowrank_misc_gpu():
     _check_misc()
 
 
-@pytest.mark.gpu
-@pytest.mark.timeout(600)
-@UNVERIFIED
-def test_lowrank_baseline_config5_properties():
-    """BASELINE configuration 5 (N = M = 50k, K = 200): size-independent properties, and the dense device loop at 6k as
-    the cross-check the dense path can still afford."""
-    src, tgt = _deformed_pair(6000)
+def _check_config5(m_cross, m_big, rank, iters):
+    """BASELINE configuration 5 (N = M = 50k, K = 200): size-independent properties, and the dense device loop at a size it
+    can still afford as the cross-check."""
+    src, tgt = _deformed_pair(m_cross)
     a = cpd.NonRigidCPD(src, beta=2.0, lmd=2.0)
     ra = a.registration(tgt, maxiter=5, tol=-1.0)
-    b = cpd.NonRigidCPD(src, beta=2.0, lmd=2.0, low_rank=200)
+    b = cpd.NonRigidCPD(src, beta=2.0, lmd=2.0, low_rank=rank)
     rb = b.registration(tgt, maxiter=5, tol=-1.0)
-    assert rb.sigma2 == pytest.approx(ra.sigma2, rel=5e-5)              # emulation with a MUFU-like ex2: 1.2e-5 / 5.1e-5
+    assert rb.sigma2 == pytest.approx(ra.sigma2, rel=5e-5)              # emulation with a MUFU-like ex2 at 6k: 1.2e-5 / 5.1e-5
     np.testing.assert_allclose(b.moved_source(), a.moved_source(), atol=2e-4)
-    src, tgt = _deformed_pair(50000)
+    src, tgt = _deformed_pair(m_big)
     trace = []
-    reg = cpd.NonRigidCPD(src, beta=2.0, lmd=2.0, low_rank=200)
-    reg.set_callbacks([lambda t: trace.append(1)])
-    res = reg.registration(tgt, maxiter=8, tol=-1.0)
+    reg = cpd.NonRigidCPD(src, beta=2.0, lmd=2.0, low_rank=rank)
+    reg.set_callbacks([lambda t: trace.append(t.w is not None)])
+    res = reg.registration(tgt, maxiter=iters, tol=-1.0)
+    assert len(trace) == iters and all(trace)
     q = res.transformation.q
-    assert q.shape == (50000, 200)
+    assert q.shape == (m_big, min(rank, m_big))
     gram = q.T.dot(q)
     d = np.diag(gram)
     assert np.all((np.abs(d - 1.0) < 1e-11) | (d == 0.0))
     moved = reg.moved_source()
     assert np.isfinite(moved).all() and np.isfinite(res.sigma2) and res.sigma2 > 0
-    # the deformation is recovered: residual to the (unpermuted) target well below the 0.03 amplitude that was applied
+    # the deformation is recovered: residual to the (unpermuted) target well below the 0.03 amplitude that was applied.  Non-rigid
+    # CPD first SHRINKS the cloud while sigma2 is large (after 8-10 iterations the residual has doubled) and needs ~30 to come back
     assert np.sqrt(((moved - tgt) ** 2).sum(1)).mean() < 0.4 * np.sqrt(((src - tgt) ** 2).sum(1)).mean()
+
+
+def test_config5_body_at_emulation_size(emulated):
+    _check_config5(260, 500, 40, 40)
+
+
+@pytest.mark.gpu
+@pytest.mark.timeout(600)
+@UNVERIFIED
+def test_lowrank_baseline_config5_properties():
+    _check_config5(6000, 50000, 200, 40)
