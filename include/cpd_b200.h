@@ -190,6 +190,8 @@ int cpd_event_elapsed(cpd_ctx* h, int idx_start, int idx_stop, float* ms);
  * [0] pack [1] pass1 [2] finalize1 [3] pass2 [4] finalize2 [5] moments+mstep (+allreduce)  */
 int cpd_set_profiling(cpd_ctx* h, int on);
 int cpd_stage_times(cpd_ctx* h, float ms[6]);
+/* the last cpd_nonrigid_lowrank_begin run with profiling on: ms of [0] the G X products [1] the orthonormalisations [2] Bc       */
+int cpd_lowrank_setup_times(cpd_ctx* h, float ms[3]);
 /* launches issued by this handle since creation (kernels only).                         */
 int64_t cpd_launch_count(cpd_ctx* h);
 /* overwrite `bytes` of scratch to evict L2 (bench hygiene); 0 => default 256 MiB.        */

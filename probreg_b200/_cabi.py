@@ -74,6 +74,7 @@ _PROTOS = {
     "cpd_event_elapsed": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, _c_fp]),
     "cpd_set_profiling": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int]),
     "cpd_stage_times": (ctypes.c_int, [ctypes.c_void_p, _c_fp]),
+    "cpd_lowrank_setup_times": (ctypes.c_int, [ctypes.c_void_p, _c_fp]),
     "cpd_launch_count": (ctypes.c_int64, [ctypes.c_void_p]),
     "cpd_flush_l2": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int64]),
     "cpd_microbench": (ctypes.c_int, [ctypes.c_int, _c_dp]),
@@ -340,6 +341,11 @@ class Handle(object):
         ms = (ctypes.c_float * 6)()
         check(self._lib.cpd_stage_times(self._h, ms))
         return list(ms)
+
+    def lowrank_setup_times(self):
+        ms = (ctypes.c_float * 3)()
+        check(self._lib.cpd_lowrank_setup_times(self._h, ms))
+        return {"gram_products_ms": ms[0], "orthonormalisation_ms": ms[1], "core_ms": ms[2]}
 
     def launch_count(self):
         return int(lib().cpd_launch_count(self._h))

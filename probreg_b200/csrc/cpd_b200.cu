@@ -208,6 +208,7 @@ struct cpd_ctx {
     // non-rigid CPD, rank-K G ~= Q Bc Q^T (lowrank.cuh)
     int lr_rank = 0;                      // > 0: cpd_nonrigid_step takes the low-rank M-step
     bool lr_w_stale = false;              // W of the low-rank path is formed on demand
+    float lr_setup_ms[3] = {0.f, 0.f, 0.f};   // products / orthonormalisations / core of the last profiled set-up
     long long lr_m = 0;
     int lr_cap = 0;
     float4* d_lr_pts = nullptr;

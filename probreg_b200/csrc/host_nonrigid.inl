@@ -176,16 +176,43 @@ extern "C" int cpd_nonrigid_lowrank_begin(cpd_ctx* h, double beta, double lmd, d
     lr_random_kernel<<<rgrid, THREADS, 0, h->stream>>>(h->d_lr_X, m, ld, rank, (unsigned long long)seed);
     KCHECK();
     h->launches += 2;
-    // Q <- orth(G Omega); then `power_iters` times Q <- orth(G Q); finally X = G Q and Bc = Q^T X (symmetrised)
+    // Q <- orth(G Omega); then `power_iters` times Q <- orth(G Q); finally X = G Q and Bc = Q^T X (symmetrised).
+    // With profiling on (cpd_set_profiling) the three phases are timed with events: cpd_lowrank_setup_times.
+    std::vector<cudaEvent_t> ev;
+    std::vector<int> phase;                  // phase of the interval that ENDS at the matching event: 0 products, 1 orth, 2 core
+    auto tick = [&](int ph) {
+        if (!h->profiling) return;
+        cudaEvent_t e = nullptr;
+        if (cudaEventCreate(&e) != cudaSuccess) return;
+        cudaEventRecord(e, h->stream);
+        ev.push_back(e);
+        phase.push_back(ph);
+    };
+    tick(-1);
     TRY(lr_gram_apply(h, h->d_lr_X, h->d_lr_Q, rank));
+    tick(0);
     TRY(lr_orthonormalise(h, h->d_lr_Q, rank));
+    tick(1);
     for (int it = 0; it < power_iters; ++it) {
         TRY(lr_gram_apply(h, h->d_lr_Q, h->d_lr_X, rank));
+        tick(0);
         std::swap(h->d_lr_Q, h->d_lr_X);
         TRY(lr_orthonormalise(h, h->d_lr_Q, rank));
+        tick(1);
     }
     TRY(lr_gram_apply(h, h->d_lr_Q, h->d_lr_X, rank));
+    tick(0);
     TRY(lr_inner(h, h->d_lr_Q, rank, ld, h->d_lr_X, rank, ld, nullptr, 1, h->d_lr_Bc));
+    tick(2);
+    if (!ev.empty()) {
+        h->lr_setup_ms[0] = h->lr_setup_ms[1] = h->lr_setup_ms[2] = 0.0f;
+        cudaEventSynchronize(ev.back());
+        for (size_t i = 1; i < ev.size(); ++i) {
+            float ms = 0.0f;
+            if (cudaEventElapsedTime(&ms, ev[i - 1], ev[i]) == cudaSuccess) h->lr_setup_ms[phase[i]] += ms;
+        }
+        for (cudaEvent_t e : ev) cudaEventDestroy(e);
+    }
     h->lr_rank = rank;
     h->nr_ready = true;
     return CPD_OK;
@@ -384,6 +411,14 @@ extern "C" int cpd_nonrigid_get(cpd_ctx* h, double* w_out, double* moved_out) {
         h->launches += 1;
     }
     KCHECK();
+    return CPD_OK;
+}
+
+// Duration of the last cpd_nonrigid_lowrank_begin that ran with profiling on, by phase: [0] the G X products, [1] the
+// orthonormalisations, [2] Bc = Q^T (G Q).
+extern "C" int cpd_lowrank_setup_times(cpd_ctx* h, float ms[3]) {
+    if (!h || !ms) return fail(CPD_ERR_ARG, "null argument");
+    for (int k = 0; k < 3; ++k) ms[k] = h->lr_setup_ms[k];
     return CPD_OK;
 }
 
