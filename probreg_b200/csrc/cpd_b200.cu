@@ -461,6 +461,7 @@ int launch_estep(cpd_ctx* h, const double* d_sigma2, const double* d_w, const do
     finalize2_kernel<<<blocks_for(h->m), THREADS, 0, h->stream>>>(h->d_state, d_sigma2, h->d_part2, h->d_slots2, (int)h->m, h->d_yc,
                                                                   d_ts, h->d_p1, h->d_pxc, h->d_mom_src);
     mark(h, 5);
+    mark(h, 6);          // E-step-only callers end here; cpd_em_step / cpd_nonrigid_step record event 6 again after their M-step
     KCHECK();
     h->launches += 5;
     return CPD_OK;

@@ -328,6 +328,7 @@ extern "C" int cpd_nonrigid_step(cpd_ctx* h, double* sigma2_out) {
     TRY(nonrigid_solve(h));
     nr_resid_kernel<<<nbs, THREADS, 0, h->stream>>>(h->d_state, h->d_p1, h->d_pxc, h->d_ts, h->d_ts2, m, h->d_nrpart);
     nr_sigma_kernel<<<1, 32, 0, h->stream>>>(h->d_state, h->d_nrpart, nbs, h->d_mom);
+    mark(h, 6);          // cpd_stage_times: [5] is the whole M-step (moments, system, LU / K x K solve, T, sigma2)
     KCHECK();
     h->launches += 2;
     std::swap(h->d_ts, h->d_ts2);
