@@ -21,7 +21,10 @@
 
 namespace cpd {
 
-constexpr int LR_COLS = 16;       // columns of X handled per CTA of lr_gram_apply_kernel
+#ifndef CPD_LR_COLS
+#define CPD_LR_COLS 16
+#endif
+constexpr int LR_COLS = CPD_LR_COLS;   // columns of X handled per CTA of lr_gram_apply_kernel (tunable: -DCPD_LR_COLS=...)
 constexpr int LR_JT = 256;        // j-points per shared-memory tile (== THREADS)
 constexpr int LR_SLICES = 8;      // i-slices of lr_inner_kernel (partials merged in fixed order)
 constexpr int LR_TILE = 32;       // output tile edge of lr_inner_kernel (2 x 2 outputs per thread)

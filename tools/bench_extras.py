@@ -130,6 +130,39 @@ def bcpd_estep_100k():
             "conservation": {"n_p": n_p, "sum_nu_d": float(nu_d.sum()), "sum_nu": float(nu.sum())}}
 
 
+def variants():
+    """build/variants/lib_*.so (tools/variants.txt, built by __graft_entry__.build): the low-rank set-up phases with each variant
+    library next to the product one -- tuning data for the kernels the variants change (LR_COLS of lr_gram_apply_kernel)."""
+    import glob
+
+    from probreg_b200 import _cabi
+
+    n, rank = (3000, 48) if QUICK else (50000, 200)
+    src, tgt = deformed(n)
+    out = {}
+    product = _cabi.lib()
+    libs = [("product", product)] + [(os.path.basename(p)[4:-3], p) for p in sorted(glob.glob(os.path.join(ROOT, "build", "variants", "lib_*.so")))]
+    for name, lib in libs:
+        def run(lib=lib):
+            saved = _cabi._lib
+            _cabi._lib = lib if not isinstance(lib, str) else _cabi._load(lib)
+            try:
+                h = _cabi.Handle(3)
+            finally:
+                _cabi._lib = saved
+            h.set_source(src)
+            h.set_target(tgt)
+            s2 = h.sigma2_init()
+            h.nonrigid_lowrank_begin(2.0, 2.0, s2, 0.0, rank, 0, 0)          # warm
+            h.set_profiling(True)
+            h.nonrigid_lowrank_begin(2.0, 2.0, s2, 0.0, rank, 0, 0)          # 2 products, 1 orthonormalisation
+            ph = h.lowrank_setup_times()
+            sig = h.nonrigid_step()
+            return {"gram_product_ms_each": ph["gram_products_ms"] / 2.0, "orthonormalisation_ms": ph["orthonormalisation_ms"], "sigma2_1": sig}
+        out[name] = guarded(run)
+    return out
+
+
 def parity_probes():
     from probreg_b200 import bcpd, cpd
 
@@ -177,6 +210,7 @@ def main():
     t0 = time.perf_counter()
     res = {"affine_250k": guarded(affine_250k), "lowrank_50k": guarded(lowrank_50k), "bcpd_estep_100k": guarded(bcpd_estep_100k)}
     res["first_hardware_run_probes"] = guarded(parity_probes)
+    res["variants"] = guarded(variants)
     res["seconds"] = time.perf_counter() - t0
     print(json.dumps(res))
 
