@@ -60,8 +60,15 @@ constexpr int THREADS = 256;           // threads per CTA in both passes
 constexpr int RI1 = CPD_RI1, RI2 = CPD_RI2;            // i-points held in registers per thread (pass 1 / pass 2)
 constexpr int ITILE1 = THREADS * RI1, ITILE2 = THREADS * RI2;   // i-points per CTA
 constexpr int NPAIR1 = RI1 / 2, NPAIR2 = RI2 / 2;      // i-points are processed as packed f32x2 pairs (FADD2 / FFMA2)
-constexpr int P1_STAGE = 512;          // sources per TMA stage in pass 1 (32 B records -> 16 KB)
-constexpr int P2_STAGE = 512;          // targets per TMA stage in pass 2 (48 B records -> 24 KB)
+#ifndef CPD_P1_STAGE
+#define CPD_P1_STAGE 512
+#endif
+#ifndef CPD_P2_STAGE
+#define CPD_P2_STAGE 512
+#endif
+constexpr int P1_STAGE = CPD_P1_STAGE;   // sources per TMA stage in pass 1 (32 B records -> 16 KB); a multiple of 256
+constexpr int P2_STAGE = CPD_P2_STAGE;   // targets per TMA stage in pass 2 (48 B records -> 24 KB); a multiple of 256
+static_assert(P1_STAGE % 256 == 0 && P2_STAGE % 256 == 0 && P1_STAGE >= 256 && P2_STAGE >= 256, "stage sizes are multiples of 256");
 constexpr int P1_REC = 32, P2_REC = 48;    // bytes per streamed j-record (coordinates duplicated for f32x2)
 constexpr int NSTAGE = 3;              // TMA pipeline depth
 constexpr int P1_STAGE_BYTES = P1_STAGE * P1_REC, P2_STAGE_BYTES = P2_STAGE * P2_REC;

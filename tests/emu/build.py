@@ -108,7 +108,7 @@ def build(force=False, verbose=False):
     srcs += [os.path.join(HERE, f) for f in ("cuda_runtime.h", "emu_device.h", "emu_runtime.cpp", "emu_solver.h", "emu_nccl.h", "build.py",
                                              os.path.join("cub", "device", "device_radix_sort.cuh"))]
     srcs += sorted(os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cuh", ".h", ".cu", ".inl")))
-    h = hashlib.sha256()
+    h = hashlib.sha256(os.environ.get("CPD_EMU_CXXFLAGS", "").encode())
     for s in sorted(set(srcs)):
         with open(s, "rb") as f:
             h.update(f.read())
@@ -126,7 +126,8 @@ def build(force=False, verbose=False):
             dst = gen if name == "cpd_b200.cu" else os.path.join(BUILD, name)
             with open(dst, "w") as f:
                 f.write("// GENERATED by tests/emu/build.py from probreg_b200/csrc/%s -- do not edit\n" % name + translate(text))
-    cmd = ["g++", "-O2", "-g", "-std=c++17", "-fPIC", "-shared", "-ffp-contract=off", "-fno-strict-aliasing", "-w",
+    extra = os.environ.get("CPD_EMU_CXXFLAGS", "").split()        # e.g. -DCPD_P1_STAGE=256: emulate a tuning variant
+    cmd = ["g++", "-O2", "-g", "-std=c++17", "-fPIC", "-shared", "-ffp-contract=off", "-fno-strict-aliasing", "-w"] + extra + [
            "-I" + HERE, "-I" + BUILD, "-I" + os.path.join(ROOT, "include"), "-I" + CSRC, "-o", OUT, gen, os.path.join(HERE, "emu_runtime.cpp"),
            "-ldl", "-lpthread"]
     if verbose:

@@ -131,34 +131,54 @@ def bcpd_estep_100k():
 
 
 def variants():
-    """build/variants/lib_*.so (tools/variants.txt, built by __graft_entry__.build): the low-rank set-up phases with each variant
-    library next to the product one -- tuning data for the kernels the variants change (LR_COLS of lr_gram_apply_kernel)."""
+    """build/variants/lib_*.so (tools/variants.txt, built by __graft_entry__.build) next to the product library: E-step stage
+    times at the bench shape and at the shard one rank of an 8-GPU run holds, and the low-rank set-up phases -- tuning data for
+    the kernels the variants change (TMA stage size of the two passes; LR_COLS of lr_gram_apply_kernel)."""
     import glob
 
     from probreg_b200 import _cabi
+    from probreg_b200.synthetic import synthetic_pair
 
-    n, rank = (3000, 48) if QUICK else (50000, 200)
-    src, tgt = deformed(n)
+    n, rank, nl = (3000, 48, 2000) if QUICK else (100000, 200, 50000)
+    src, tgt = synthetic_pair(n)
+    lsrc, ltgt = deformed(nl)
     out = {}
-    product = _cabi.lib()
-    libs = [("product", product)] + [(os.path.basename(p)[4:-3], p) for p in sorted(glob.glob(os.path.join(ROOT, "build", "variants", "lib_*.so")))]
+    libs = [("product", _cabi.lib())] + [(os.path.basename(p)[4:-3], p) for p in sorted(glob.glob(os.path.join(ROOT, "build", "variants", "lib_*.so")))]
+    names = ["pack", "pass1", "finalize1", "pass2", "finalize2", "moments_mstep"]
     for name, lib in libs:
         def run(lib=lib):
             saved = _cabi._lib
             _cabi._lib = lib if not isinstance(lib, str) else _cabi._load(lib)
             try:
-                h = _cabi.Handle(3)
+                h, hl = _cabi.Handle(3), _cabi.Handle(3)
             finally:
                 _cabi._lib = saved
-            h.set_source(src)
-            h.set_target(tgt)
-            s2 = h.sigma2_init()
-            h.nonrigid_lowrank_begin(2.0, 2.0, s2, 0.0, rank, 0, 0)          # warm
-            h.set_profiling(True)
-            h.nonrigid_lowrank_begin(2.0, 2.0, s2, 0.0, rank, 0, 0)          # 2 products, 1 orthonormalisation
-            ph = h.lowrank_setup_times()
-            sig = h.nonrigid_step()
-            return {"gram_product_ms_each": ph["gram_products_ms"] / 2.0, "orthonormalisation_ms": ph["orthonormalisation_ms"], "sigma2_1": sig}
+            res = {}
+            for tag, lo, hi in (("full", 0, n), ("shard_1_of_8", 3 * (n // 8), 4 * (n // 8))):
+                h.set_source(src)
+                h.set_target(tgt[lo:hi], n_global=n, frame_origin=tgt.mean(axis=0))
+                h.set_state(_cabi.TF_RIGID, True, 0.0, np.identity(3), np.zeros(3), 1.0, 0.05, 0.0)
+                for _ in range(3):
+                    h.em_step(read=False)
+                h.set_profiling(True)
+                st = []
+                for _ in range(5):
+                    h.flush_l2()
+                    h.em_step(read=False)
+                    st.append(h.stage_times())
+                h.set_profiling(False)
+                res["stage_ms_" + tag] = dict(zip(names, [float(x) for x in np.median(np.array(st), axis=0)]))
+                res["sigma2_" + tag] = h.em_step()[3]
+            hl.set_source(lsrc)
+            hl.set_target(ltgt)
+            s2 = hl.sigma2_init()
+            hl.nonrigid_lowrank_begin(2.0, 2.0, s2, 0.0, rank, 0, 0)         # warm
+            hl.set_profiling(True)
+            hl.nonrigid_lowrank_begin(2.0, 2.0, s2, 0.0, rank, 0, 0)         # 2 products, 1 orthonormalisation
+            ph = hl.lowrank_setup_times()
+            res["lowrank"] = {"gram_product_ms_each": ph["gram_products_ms"] / 2.0, "orthonormalisation_ms": ph["orthonormalisation_ms"],
+                              "sigma2_1": hl.nonrigid_step()}
+            return res
         out[name] = guarded(run)
     return out
 
