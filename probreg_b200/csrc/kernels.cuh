@@ -70,7 +70,10 @@ constexpr int P1_STAGE = CPD_P1_STAGE;   // sources per TMA stage in pass 1 (32 
 constexpr int P2_STAGE = CPD_P2_STAGE;   // targets per TMA stage in pass 2 (48 B records -> 24 KB); a multiple of 256
 static_assert(P1_STAGE % 256 == 0 && P2_STAGE % 256 == 0 && P1_STAGE >= 256 && P2_STAGE >= 256, "stage sizes are multiples of 256");
 constexpr int P1_REC = 32, P2_REC = 48;    // bytes per streamed j-record (coordinates duplicated for f32x2)
-constexpr int NSTAGE = 3;              // TMA pipeline depth
+#ifndef CPD_NSTAGE
+#define CPD_NSTAGE 3
+#endif
+constexpr int NSTAGE = CPD_NSTAGE;     // TMA pipeline depth
 constexpr int P1_STAGE_BYTES = P1_STAGE * P1_REC, P2_STAGE_BYTES = P2_STAGE * P2_REC;
 constexpr int SUB = CPD_SUB;           // j-points between offset checks / FP64 flushes
 constexpr int GRP = CPD_GRP;           // j-points summed from zero before joining the sub-chunk sum (0: off)
