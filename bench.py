@@ -111,67 +111,141 @@ class ClockSampler(object):
                 "samples_in_timed_region": timed, "reasons": sorted(reasons)}
 
 
-def workload(points):
+def workload(points, kind="rigid"):
     from probreg_b200.synthetic import synthetic_pair
-    return synthetic_pair(points, "rigid")
+    if kind == "nonrigid":                      # the rigid generator's source + a smooth displacement
+        src, _ = synthetic_pair(points, "rigid")
+        f = np.array([[1.0, 0.5, 0.0], [0.0, 1.0, 0.7], [0.3, 0.0, 1.0]])
+        tgt = src + 0.03 * np.sin(2 * np.pi * src.dot(f)) + 0.002 * np.random.default_rng(9).standard_normal(src.shape)
+        return src, np.ascontiguousarray(tgt)
+    return synthetic_pair(points, kind)
 
 
 # ---------------------------------------------------------------------------------------------
-# CPU arm: the oracle port of the reference's numpy path on a bounded sample
+# CPU arm: the UNMODIFIED reference (baseline/_ref/probreg, see baseline/install_ref.py) on a bounded sample;
+# the oracle port beside it as a second figure
 # ---------------------------------------------------------------------------------------------
-def cpu_sample(points, cols, repeats=1):
-    """One EM iteration of the reference algorithm, E-step on `cols` of the `points` target columns
-    (exact per column, cpd.py:80-87), extrapolated to all columns; M-step timed at full size."""
+WORKLOADS = {
+    2: ("rigid", 100000, "rigid CPD, synthetic 3-D N=M=%d, sigma2 auto, w=0, update_scale"),
+    3: ("affine", 250000, "affine CPD, synthetic 3-D N=M=%d, sigma2 auto, w=0"),
+    4: ("rigid", 1000000, "rigid CPD, synthetic 3-D N=M=%d, sigma2 auto, w=0, update_scale"),
+    5: ("nonrigid", 50000, "non-rigid CPD (low-rank G, K=200, beta=2, lmd=2), synthetic 3-D N=M=%d, sigma2 auto, w=0"),
+}
+
+
+def workload_string(config, points):
+    return WORKLOADS[config][2] % points
+
+
+def blas_threads():
+    try:
+        import threadpoolctl
+        return int(max([p.get("num_threads", 1) for p in threadpoolctl.threadpool_info()] + [1]))
+    except Exception:
+        return int(os.cpu_count() or 1)
+
+
+def reference_sample(kind, points, cols, chunk=250):
+    """One EM iteration of the reference's own code (probreg/cpd.py:111-113) on `cols` of the `points` target columns:
+    Transformation.transform on all sources, CoherentPointDrift.expectation_step (cpd.py:71-88) column-chunked -- exact for
+    w = 0 because `den` is per column -- and the class's _maximization_step (cpd.py:160-192 / 219-244) on the sampled
+    columns' EstepResult.  The E-step time is extrapolated to all columns; the M-step and the transform are not (they cost
+    O(M + N), < 0.1 % of the iteration)."""
+    from baseline import ref_loader
+    rcpd, rtf = ref_loader.load()
+    from probreg_b200.synthetic import synthetic_pair
+    src, tgt = synthetic_pair(points, "affine" if kind == "affine" else "rigid")
+    cols = min(cols, points)
+    sub = tgt[:cols]
+    # sigma2_0 in closed form (the reference's _initialize would allocate an M x N float32 matrix: 40 GB at 100k)
+    s2 = float(((src * src).sum() / points + (tgt * tgt).sum() / points - 2.0 * src.mean(0).dot(tgt.mean(0))) / 3.0)
+    reg = rcpd.AffineCPD(src) if kind == "affine" else rcpd.RigidCPD(src, update_scale=True)
+    tfm = rtf.AffineTransformation(np.identity(3), np.zeros(3)) if kind == "affine" else rtf.RigidTransformation(np.identity(3), np.zeros(3))
+    # one untimed chunk first: the first M x chunk float64 temporaries of a process are page-faulted in (seconds in this
+    # image's sandbox), after which the allocator re-uses them -- the reference's steady state is what is timed
+    reg.expectation_step(src, sub[:chunk], s2, 0.0)
+    t0 = time.perf_counter()
+    ts = tfm.transform(src)
+    t_tf = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    pt1, p1, px = [], np.zeros(points), np.zeros((points, 3))
+    for lo in range(0, cols, chunk):
+        es = reg.expectation_step(ts, sub[lo:lo + chunk], s2, 0.0)
+        pt1.append(es.pt1); p1 += es.p1; px += es.px
+    t_e = time.perf_counter() - t0
+    es = rcpd.EstepResult(np.concatenate(pt1), p1, px, float(p1.sum()))
+    t0 = time.perf_counter()
+    res = reg.maximization_step(sub, es, s2)
+    t_m = time.perf_counter() - t0
+    t_iter = t_e * (points / float(cols)) + t_m + t_tf
+    return {"value": 1.0 / t_iter, "unit": UNIT, "cores": blas_threads(), "host_cpus": os.cpu_count(), "kind": "reference",
+            "sample": "unmodified probreg/cpd.py (baseline/_ref): expectation_step on %d of %d target columns x all %d sources in "
+                      "chunks of %d (%.2f s, extrapolated x%.0f) + transform (%.3f s) + _maximization_step on the sampled "
+                      "columns (%.3f s); numpy/scipy as the reference uses them (~90%% single-threaded, BLAS threads = %d)"
+                      % (cols, points, points, chunk, t_e, points / float(cols), t_tf, t_m, blas_threads()),
+            "sec_per_iter_extrapolated": t_iter, "ns_per_pair": t_e / (cols * float(points)) * 1e9,
+            "sigma2_after": float(res.sigma2)}
+
+
+def port_sample(points, cols):
+    """The same iteration through the oracle port (oracle/cpd_oracle.py): a second CPU figure (about 3x faster than the reference)."""
     from oracle import cpd_oracle as orc
     src, tgt = workload(points)
     s2 = float(orc.sigma2_init_exact(src, tgt))
     cols = min(cols, points)
-    best = None
-    for _ in range(repeats):
-        t0 = time.perf_counter()
-        ts = orc.apply_rigid(src, np.identity(3), np.zeros(3))
-        es = orc.expectation_step(ts, tgt[:cols], s2, 0.0, n_global=points)
-        t_e = time.perf_counter() - t0
-        best = t_e if best is None else min(best, t_e)
-    rng = np.random.default_rng(0)
-    fake = orc.Estep(np.ones(points), rng.random(points) + 0.5, rng.random((points, 3)), float(points))
-    fake = orc.Estep(fake.pt1, fake.p1, fake.px, float(fake.p1.sum()))
+    chunk = 250
+    orc.expectation_step(src, tgt[:chunk], s2, 0.0, n_global=points)          # untimed: see reference_sample
     t0 = time.perf_counter()
-    orc.mstep_rigid(src, tgt, fake)
+    ts = orc.apply_rigid(src, np.identity(3), np.zeros(3))
+    parts = [orc.expectation_step(ts, tgt[lo:lo + chunk], s2, 0.0, n_global=points) for lo in range(0, cols, chunk)]
+    es = orc.Estep(np.concatenate([e.pt1 for e in parts]), sum(e.p1 for e in parts), sum(e.px for e in parts),
+                   float(sum(e.p1.sum() for e in parts)))
+    t_e = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    orc.mstep_rigid(src, tgt[:cols], es)
     t_m = time.perf_counter() - t0
-    t_iter = best * (points / float(cols)) + t_m
-    try:
-        import threadpoolctl
-        blas = max([p.get("num_threads", 1) for p in threadpoolctl.threadpool_info()] + [1])
-    except Exception:
-        blas = os.cpu_count()
-    return {"value": 1.0 / t_iter, "unit": UNIT, "cores": int(blas), "host_cpus": os.cpu_count(), "kind": "port",
-            "sample": "E-step on %d of %d target columns x all %d sources (%.2f s), extrapolated x%.0f; "
-                      "+ full-size M-step (%.3f s); numpy/scipy port of probreg/cpd.py:71-88,160-192 "
-                      "(~90%% single-threaded like the reference, BLAS threads = %d)"
-                      % (cols, points, points, best, points / float(cols), t_m, blas),
-            "sec_per_iter_extrapolated": t_iter, "ns_per_pair": best / (cols * float(points)) * 1e9}
+    t_iter = t_e * (points / float(cols)) + t_m
+    return {"value": 1.0 / t_iter, "unit": UNIT, "kind": "port", "sec_per_iter_extrapolated": t_iter,
+            "ns_per_pair": t_e / (cols * float(points)) * 1e9,
+            "sample": "oracle port, E-step on %d of %d columns (%.2f s) extrapolated + M-step on the sample (%.3f s)" % (cols, points, t_e, t_m)}
+
+
+def cpu_sample(kind, points, cols):
+    """cpu_baseline of the bench line: the reference when baseline/_ref travelled with the repo, else the oracle port."""
+    from baseline import ref_loader
+    if ref_loader.available() and kind in ("rigid", "affine"):
+        out = reference_sample(kind, points, cols)
+        if kind == "rigid":
+            try:
+                out["port"] = port_sample(points, cols)
+            except Exception as e:          # noqa: BLE001
+                out["port"] = {"error": str(e)[:200]}
+        return out
+    out = port_sample(points, cols)
+    out["cores"], out["host_cpus"] = blas_threads(), os.cpu_count()
+    return out
 
 
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    kind, points = args.kind, args.points
+    if kind == "nonrigid":
+        emit({"impl": "reference", "unavailable": "the reference has no low-rank non-rigid path (dense M x M solve: 30 GB and 1e14 flop per "
+                                                  "iteration at 50k); config 5 has no CPU arm"})
+        return
     cols = args.cpu_cols
-    vals = []
-    for _ in range(max(1, args.warmup > 0)):
-        cpu_sample(args.points, min(cols, 200))
-    last = None
+    vals, last = [], None
     for _ in range(args.steps):
-        last = cpu_sample(args.points, cols)
+        last = cpu_sample(kind, points, cols)
         vals.append(last["sec_per_iter_extrapolated"])
     t = float(np.mean(vals))
     last["value"] = 1.0 / t
     out = {"impl": "reference", "metric": METRIC, "value": 1.0 / t, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
            "warmup": args.warmup, "ms_per_step": t * 1e3, "higher_is_better": True, "scaling": "strong",
            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-           "config": {"workload": "rigid CPD, synthetic 3-D N=M=%d, sigma2 auto, w=0" % args.points,
-                      "extrapolated_from_columns": cols},
+           "config": {"workload": workload_string(args.config, points)},
            "cpu_baseline": last,
            "e2e": {"value": 1.0 / t, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
            "gpu_launches": 0}
@@ -203,7 +277,11 @@ def run_ours(args):
         torch.cuda.synchronize()
 
     n = args.points
-    src, tgt = workload(n)
+    kind = args.kind
+    if kind == "nonrigid":
+        return run_nonrigid(args, torch, _cabi, cpd, barrier, local_rank, world)
+    tf_kind = _cabi.TF_AFFINE if kind == "affine" else _cabi.TF_RIGID
+    src, tgt = workload(n, kind)
     lo, hi = pdist.shard_bounds(n, rank, world)
     origin = tgt.mean(axis=0)
 
@@ -217,7 +295,7 @@ def run_ours(args):
     q0 = 1.0 + n * 3 * 0.5 * np.log(s2)
 
     def reset():
-        h.set_state(_cabi.TF_RIGID, True, 0.0, np.identity(3), np.zeros(3), 1.0, s2, q0)
+        h.set_state(tf_kind, True, 0.0, np.identity(3), np.zeros(3), 1.0, s2, q0)
 
     reset()
     sampler = ClockSampler(world) if rank == 0 else None
@@ -287,7 +365,7 @@ def run_ours(args):
         return t.numpy()
 
     src_p, tgt_p = pinned(src), pinned(tgt)
-    r = cpd.RigidCPD(src_p, device=local_rank, comm=comm)
+    r = (cpd.AffineCPD if kind == "affine" else cpd.RigidCPD)(src_p, device=local_rank, comm=comm)
     r.registration(tgt_p, maxiter=1, tol=-1.0)
     barrier()
     e2e_steps = max(3, min(args.steps, 10))
@@ -350,14 +428,15 @@ def run_ours(args):
                 "materialised_equiv_gbs": 8.0 * n_local * n / (t_estep_ms * 1e-3) / 1e9,
                 "materialised_equiv_frac": 8.0 * n_local * n / (t_estep_ms * 1e-3) / 1e9 / hbm_peak},
     }
-    cpu = cpu_sample(n, args.cpu_cols) if world == 1 and not args.no_cpu else None
-    extras = run_extras() if world == 1 and not args.no_extras and n == 100000 else None
+    cpu = cpu_sample(kind, n, 4 * args.cpu_cols) if world == 1 and not args.no_cpu else None      # ~10-20 s of CPU work
+    extras = run_extras() if world == 1 and args.extras and args.config == 2 else None
+    also = run_also(args) if world == 1 and args.config == 2 and not args.no_also else None
     out = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
         "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
         "dtype": "f32", "dtype_note": "pair arithmetic f32 (packed f32x2); every sum beyond 64 terms, the moments and the M-step f64",
         "data": "synthetic",
-        "config": {"workload": "rigid CPD, synthetic 3-D N=M=%d, sigma2 auto, w=0, update_scale" % n,
+        "config": {"workload": workload_string(args.config, n), "baseline_config": args.config, "also": also,
                    "parallelism": "target-sharded x%d, sources replicated, one 32-double all-reduce per iteration (%s)"
                                   % (world, "fused into the M-step kernel over NVLink peer memory" if (comm is not None and comm.use_p2p)
                                      else ("ncclAllReduce" if world > 1 else "none needed")),
@@ -365,8 +444,8 @@ def run_ours(args):
                    "timing": "CUDA event pair per iteration on the library stream, summed, max over ranks"},
         "wall_ms_per_step_incl_flush": t_wall * 1e3 / args.steps,
         "e2e": {"value": 1.0 / e2e_s, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-                "what": "RigidCPD.registration(target, maxiter=1) per step: H2D both clouds (pinned), sigma2 init, "
-                        "1 EM iteration, D2H MstepResult",
+                "what": "%sCPD.registration(target, maxiter=1) per step: H2D both clouds (pinned), sigma2 init, "
+                        "1 EM iteration, D2H MstepResult" % ("Affine" if kind == "affine" else "Rigid"),
                 "amortised_value": 1.0 / e2e_amort_s,
                 "amortised_what": "registration(maxiter=%d): one upload, per-iteration D2H of the MstepResult" % args.steps},
         "gpu_launches": int(launches),
@@ -375,12 +454,139 @@ def run_ours(args):
         "cpu_baseline": cpu,
         "clocks": clocks,
         "probe": probe,
-        "result_check": {"sigma2_after_run": final[3], "scale": final[2]},
+        "result_check": {"sigma2_after_run": final[3], "scale": final[2], "lin": [float(x) for x in np.ravel(final[0])]},
         "extras": extras,
     }
     emit(out)
     if world > 1:
         tdist.destroy_process_group()
+
+
+def run_also(args):
+    """Short runs of BASELINE configurations 3 and 5 in SUBPROCESSES (a fault there costs the main line nothing but this key);
+    the compact summaries travel inside `config`, which the driver's record keeps."""
+    out = {}
+    for cfg, steps in ((3, 5), (5, 10)):
+        try:
+            r = subprocess.run([sys.executable, os.path.abspath(__file__), "--config", str(cfg), "--steps", str(steps), "--warmup", "3",
+                                "--no-cpu", "--no-also"], capture_output=True, text=True, timeout=300, cwd=ROOT)
+            lines = [l for l in r.stdout.splitlines() if l.strip().startswith("{")]
+            if r.returncode != 0 or not lines:
+                out["config%d" % cfg] = {"error": "exit %d: %s" % (r.returncode, (r.stderr or r.stdout)[-300:])}
+                continue
+            j = json.loads(lines[-1])
+            out["config%d" % cfg] = {"workload": j["config"]["workload"], "value": j["value"], "unit": j["unit"], "ms_per_step": j["ms_per_step"],
+                                    "e2e": j["e2e"]["value"], "roofline_frac": j["roofline"]["frac"],
+                                    "roofline_achieved": j["roofline"]["achieved"], "roofline_unit": j["roofline"]["unit"],
+                                    "setup_ms": j.get("setup_ms"), "setup": j.get("setup")}
+        except Exception as e:                  # noqa: BLE001
+            out["config%d" % cfg] = {"error": "%s: %s" % (type(e).__name__, str(e)[:200])}
+    return out
+
+
+def run_nonrigid(args, torch, _cabi, cpd, barrier, local_rank, world):
+    """BASELINE configuration 5: non-rigid CPD with G ~= Q Bc Q^T of rank 200 (no reference counterpart: the reference solves the
+    dense M x M system, cpd.py:296).  A step = one EM iteration (E-step + low-rank M-step, cpd_nonrigid_step); the one-off
+    factorisation (range finder on tcgen05 G X products + blocked orthonormalisation) is reported as `setup_ms`."""
+    rank = int(os.environ.get("RANK", "0"))
+    n, K = args.points, 200
+    src, tgt = workload(n, "nonrigid")
+    h = _cabi.Handle(3, device=local_rank)
+    h.set_source(src)
+    h.set_target(tgt)
+    s2 = h.sigma2_init()
+    h.set_profiling(True)
+    h.sync()
+    t0 = time.perf_counter()
+    h.nonrigid_lowrank_begin(2.0, 2.0, s2, 0.0, K, 2, 0)
+    h.sync()
+    setup_wall_ms = (time.perf_counter() - t0) * 1e3
+    setup = dict(zip(["gram_products_ms", "orthonormalisation_ms", "core_ms"], [float(x) for x in h.lowrank_setup_times()]))
+    h.set_profiling(False)
+    sampler = ClockSampler(world) if rank == 0 else None
+    if sampler:
+        sampler.start()
+    t_up = time.perf_counter()
+    while True:
+        for _ in range(10):
+            h.nonrigid_step()
+        if sampler is None or sampler.count() >= 2 or time.perf_counter() - t_up > 3.0:
+            break
+    h.nonrigid_restart(2.0, s2, 0.0)
+    for _ in range(max(args.warmup, 3)):
+        h.nonrigid_step()
+    h.sync()
+    launches0 = h.launch_count()
+    t_wall0 = time.perf_counter()
+    for i in range(args.steps):
+        h.flush_l2()
+        h.event_record(2 * i)
+        sig = h.nonrigid_step()
+        h.event_record(2 * i + 1)
+    h.sync()
+    t_wall1 = time.perf_counter()
+    launches = h.launch_count() - launches0
+    clocks = sampler.stop(t_wall0, t_wall1) if sampler else None
+    per_step = np.array([h.event_elapsed(2 * i, 2 * i + 1) for i in range(args.steps)])
+    ms_per_step = float(per_step.sum()) / args.steps
+    h.set_profiling(True)
+    stages = []
+    for _ in range(5):
+        h.flush_l2()
+        h.nonrigid_step()
+        stages.append(h.stage_times())
+    h.set_profiling(False)
+    st = np.median(np.array(stages), axis=0)
+    names = ["pack", "pass1", "finalize1", "pass2", "finalize2", "moments_mstep"]
+    t_estep_ms = float(st[1] + st[3])
+
+    def pinned(a):
+        t = torch.empty(a.shape, dtype=torch.float64, pin_memory=True)
+        t.numpy()[...] = a
+        return t.numpy()
+
+    src_p, tgt_p = pinned(src), pinned(tgt)
+    r = cpd.NonRigidCPD(src_p, beta=2.0, lmd=2.0, low_rank=K, device=local_rank)
+    t0 = time.perf_counter()
+    r.registration(tgt_p, maxiter=1, tol=-1.0)
+    cold_s = time.perf_counter() - t0
+    e2e_steps = max(3, min(args.steps, 10))
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        r.registration(tgt_p, maxiter=1, tol=-1.0)
+    e2e_s = (time.perf_counter() - t0) / e2e_steps
+    probe = _cabi.microbench(local_rank)
+    flops = FLOP_PER_PAIR_ITER * float(n) * float(n)
+    ach_tf = flops / (t_estep_ms * 1e-3) / 1e12
+    gram_flop = 2.0 * float(n) * float(n) * K
+    out = {
+        "metric": METRIC, "value": 1e3 / ms_per_step, "unit": UNIT, "n_gpus": 1, "steps": args.steps, "warmup": max(args.warmup, 3),
+        "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
+        "dtype_note": "pair arithmetic f32; G X products TF32 x3 (hi/lo split) on tcgen05 with FP32 TMEM accumulation per 2048-point chunk, "
+                      "FP64 across chunks; factors, K x K system and its LU f64",
+        "data": "synthetic",
+        "config": {"workload": workload_string(args.config, n), "baseline_config": args.config,
+                   "parallelism": "single GPU", "l2": "flushed (256 MiB memset) between timed iterations, outside the event pairs",
+                   "timing": "CUDA event pair per iteration on the library stream, summed"},
+        "setup_ms": setup_wall_ms,
+        "setup": dict(setup, what="one-off per source: 4 products G X (K = 200, tcgen05) + 3 orthonormalisations + Q^T G Q",
+                      gram_tflops_useful=(4 * gram_flop / (setup["gram_products_ms"] * 1e-3) / 1e12) if setup["gram_products_ms"] > 0 else None),
+        "e2e": {"value": 1.0 / e2e_s, "unit": UNIT, "h2d_bytes_per_step": int(src.nbytes + tgt.nbytes), "d2h_bytes_per_step": int(8 + src.nbytes),
+                "what": "NonRigidCPD(low_rank=200).registration(target, maxiter=1) per step: H2D both clouds (pinned), sigma2 init, restart on "
+                        "the cached factors of the unchanged source, 1 EM iteration, D2H sigma2 + W",
+                "cold_first_call_s": cold_s},
+        "gpu_launches": int(launches),
+        "stage_ms": dict(zip(names, [float(x) for x in st])),
+        "roofline": {"bound": "fp32", "kernel": "pass1_kernel + pass2_kernel (fused E-step of the non-rigid iteration)",
+                     "achieved": ach_tf, "peak": probe["ffma_tflops"], "unit": "TFLOP/s", "frac": ach_tf / probe["ffma_tflops"],
+                     "peak_source": "FFMA issue-rate probe run in this process (cpd_microbench)",
+                     "flop_per_pair": FLOP_PER_PAIR_ITER, "pairs_per_launch": float(n) * float(n), "traffic": None,
+                     "estep_share_of_step": t_estep_ms / ms_per_step},
+        "cpu_baseline": None,
+        "clocks": clocks,
+        "result_check": {"sigma2_after_run": float(sig)},
+    }
+    emit(out)
 
 
 def run_extras():
@@ -416,11 +622,17 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--points", type=int, default=100000)
+    ap.add_argument("--config", type=int, default=2, choices=[2, 3, 4, 5],
+                    help="BASELINE.json configuration: 2 rigid 100k (the metric's), 3 affine 250k, 4 rigid 1M (8 GPUs), 5 non-rigid low-rank 50k")
+    ap.add_argument("--points", type=int, default=0, help="override the configuration's point count")
     ap.add_argument("--cpu-cols", type=int, default=2000, help="target columns in the CPU sample")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
-    ap.add_argument("--no-extras", action="store_true", help="skip the side measurements of tools/bench_extras.py (key \"extras\")")
+    ap.add_argument("--no-also", action="store_true", help="skip the short runs of configurations 3 and 5 reported under config.also")
+    ap.add_argument("--extras", action="store_true", help="add the side measurements of tools/bench_extras.py (key \"extras\")")
     args = ap.parse_args()
+    args.kind = WORKLOADS[args.config][0]
+    if args.points <= 0:
+        args.points = WORKLOADS[args.config][1]
     if args.impl == "reference":
         run_reference(args)
     else:

@@ -70,6 +70,17 @@ def rbf_kernel_f32(x, y, beta):
     return np.exp(-k / np.float32(2.0 * beta)).astype(np.float32)
 
 
+def imq_kernel_f32(x, y, c=1.0):
+    """probreg/cc/math_utils.cc:37-39 -- (|x_i - y_j|^2 + c)^(-1/2) in float32, every operation rounded on its own
+    (squares summed coordinate by coordinate, like Eigen's squaredNorm without FMA contraction)."""
+    x32, y32 = np.asarray(x, dtype=np.float32), np.asarray(y, dtype=np.float32)
+    d = x32[:, None, :] - y32[None, :, :]
+    acc = d[:, :, 0] * d[:, :, 0]
+    for a in range(1, x32.shape[1]):
+        acc = acc + d[:, :, a] * d[:, :, a]
+    return (np.float32(1.0) / np.sqrt(acc + np.float32(c))).astype(np.float32)
+
+
 def sigma2_init(source, target, max_dense=int(4e7)):
     """probreg/math_utils.py:28-29: mean squared pair distance / D, in float32.
 

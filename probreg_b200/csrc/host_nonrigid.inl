@@ -58,8 +58,9 @@ int solver_workspace(cpd_ctx* h, long long n, double* a) {
     }
     return CPD_OK;
 }
-// Orthonormalise the `rank` columns of X ([rank][ld]) in place: classical Gram-Schmidt, each column projected twice
-int lr_orthonormalise(cpd_ctx* h, double* X, int rank) {
+// Orthonormalise the `rank` columns of X ([rank][ld]) in place, column by column: classical Gram-Schmidt, each column projected
+// twice (6 launches per column; kept as the cross-check of the blocked version below: CPD_B200_LR_ORTH=columnwise)
+int lr_orthonormalise_columnwise(cpd_ctx* h, double* X, int rank) {
     const long long m = h->m, ld = h->mpad;
     const unsigned nb = blocks_for(m);
     const int stride = rank + 1;
@@ -102,15 +103,47 @@ int lr_gram_apply(cpd_ctx* h, const double* src, double* dst, int rank) {
     if (shard) TRY(allreduce(h, dst, (size_t)rank * h->mpad));
     return CPD_OK;
 }
-// out[na][nb] = A diag(wt) Bm^T over the points
+// out[na][nb] = A diag(wt) Bm^T over the points.  The point range is cut into as many slices as the partial buffer holds
+// (at most 64, at least 1024 points each); lr_merge_kernel adds them in slice order.
 int lr_inner(cpd_ctx* h, const double* A, int na, long long lda, const double* Bm, int nb, long long ldb, const double* wt, int symmetrise,
              double* out) {
     const int tiles = ((na + LR_TILE - 1) / LR_TILE) * ((nb + LR_TILE - 1) / LR_TILE);
-    dim3 grid((unsigned)tiles, LR_SLICES);
+    const long long by_cap = (long long)(h->lr_part_cap / ((size_t)na * nb));
+    const int nsl = (int)std::max<long long>(1, std::min<long long>(std::min<long long>(64, by_cap), h->m / 1024));
+    dim3 grid((unsigned)tiles, (unsigned)nsl);
     lr_inner_kernel<<<grid, THREADS, 0, h->stream>>>(A, na, lda, Bm, nb, ldb, wt, h->m, symmetrise, h->d_lr_part);
-    lr_merge_kernel<<<blocks_for((long long)na * nb), THREADS, 0, h->stream>>>(h->d_lr_part, na, nb, symmetrise, out);
+    lr_merge_kernel<<<blocks_for((long long)na * nb), THREADS, 0, h->stream>>>(h->d_lr_part, nsl, na, nb, symmetrise, out);
     KCHECK();
     h->launches += 2;
+    return CPD_OK;
+}
+// Orthonormalise the `rank` columns of X ([rank][ld]) in place: block Gram-Schmidt with re-orthogonalisation over panels of
+// LR_PANEL columns (lowrank.cuh); numerically dependent columns become exactly zero.
+int lr_orthonormalise(cpd_ctx* h, double* X, int rank) {
+    if (const char* e = getenv("CPD_B200_LR_ORTH")) if (!strcmp(e, "columnwise")) return lr_orthonormalise_columnwise(h, X, rank);
+    const long long m = h->m, ld = h->mpad;
+    const unsigned nb = blocks_for(m);
+    double* C = h->d_lr_panel;                              // [rank][np] projection coefficients
+    double* W0 = C + (size_t)LR_MAX_RANK * LR_PANEL;        // Gram matrix of the panel as it arrived (its diagonal: arrival norms)
+    double* W = W0 + LR_PANEL * LR_PANEL;
+    double* T = W + LR_PANEL * LR_PANEL;
+    for (int j0 = 0; j0 < rank; j0 += LR_PANEL) {
+        const int np = std::min(LR_PANEL, rank - j0);
+        double* P = X + (size_t)j0 * ld;
+        TRY(lr_inner(h, P, np, ld, P, np, ld, nullptr, 1, W0));
+        for (int pass = 0; pass < 2; ++pass) {
+            if (j0 > 0) {
+                TRY(lr_inner(h, X, j0, ld, P, np, ld, nullptr, 0, C));
+                lr_panel_update_kernel<<<nb, THREADS, 0, h->stream>>>(X, m, ld, j0, np, j0, C);
+                h->launches += 1;
+            }
+            TRY(lr_inner(h, P, np, ld, P, np, ld, nullptr, 1, W));
+            lr_panel_chol_kernel<<<1, 32, 0, h->stream>>>(W, np, pass == 0 ? W0 : nullptr, np + 1, T);
+            lr_panel_apply_kernel<<<nb, THREADS, 0, h->stream>>>(X, m, ld, j0, np, T);
+            h->launches += 2;
+        }
+    }
+    KCHECK();
     return CPD_OK;
 }
 }  // namespace
@@ -158,7 +191,9 @@ extern "C" int cpd_nonrigid_lowrank_begin(cpd_ctx* h, double beta, double lmd, d
         TRY(dev_alloc(&h->d_lr_Q, (size_t)rank * ld));
         TRY(dev_alloc(&h->d_lr_X, (size_t)rank * ld));
         TRY(dev_alloc(&h->d_lr_coef, (size_t)3 * LR_SLICES * (rank + 1)));
-        TRY(dev_alloc(&h->d_lr_part, (size_t)LR_SLICES * rank * rank));
+        h->lr_part_cap = std::max<size_t>((size_t)LR_SLICES * rank * rank, (size_t)64 * LR_PANEL * LR_MAX_RANK / 8);
+        TRY(dev_alloc(&h->d_lr_part, h->lr_part_cap));
+        TRY(dev_alloc(&h->d_lr_panel, (size_t)LR_MAX_RANK * LR_PANEL + 3 * LR_PANEL * LR_PANEL));
         TRY(dev_alloc(&h->d_lr_Bc, (size_t)rank * rank));
         TRY(dev_alloc(&h->d_lr_S, (size_t)rank * rank));
         TRY(dev_alloc(&h->d_lr_R, (size_t)rank * 3));

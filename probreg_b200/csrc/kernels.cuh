@@ -1503,9 +1503,12 @@ imq_kernel_kernel(const float* __restrict__ x, long long nx, const float* __rest
     const long long j = (long long)blockIdx.y * THREADS + threadIdx.x;
     const long long i = blockIdx.x;
     if (j < ny) {
+        // every operation rounded on its own (no FMA contraction), like Eigen's squaredNorm built without -mfma and the float32
+        // numpy restatement the fixtures come from: BCPD inverts this matrix (bcpd.py:117), and the inverse of an inverse
+        // multiquadric Gram matrix amplifies a last-bit difference of its entries to the first digits of the M-step
         float d2 = 0.f;
-        for (int a = 0; a < dim; ++a) { const float d = x[i * dim + a] - y[j * dim + a]; d2 += d * d; }
-        out[i * ny + j] = 1.0f / sqrtf(d2 + c);
+        for (int a = 0; a < dim; ++a) { const float d = __fsub_rn(x[i * dim + a], y[j * dim + a]); d2 = __fadd_rn(d2, __fmul_rn(d, d)); }
+        out[i * ny + j] = __fdiv_rn(1.0f, __fsqrt_rn(__fadd_rn(d2, c)));
     }
 }
 

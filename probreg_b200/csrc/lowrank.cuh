@@ -150,19 +150,131 @@ lr_scale_kernel(double* __restrict__ X, long long m, long long ld, int j, int st
     if (i < m) X[(long long)j * ld + i] *= s;
 }
 
+// ---- blocked orthonormalisation (block classical Gram-Schmidt with re-orthogonalisation, panels of LR_PANEL columns) --------------
+// Per panel P = X[j0 .. j0+np):   (a) P -= Q Q^T P  against the finished columns Q = X[0 .. j0)      (lr_panel_* below)
+//                                 (b) P <- P T, T = R^-1 from the Cholesky factor of the panel's Gram matrix  (lr_panel_chol / _apply)
+//                                 (c), (d): both once more.
+// (b) leaves the columns normalised and orthogonal to ~eps / (relative pivot); (c) removes what (b) amplified along Q, at unit
+// scale; (d) starts from a Gram matrix I + O(1e-6) and ends at rounding level -- the same O(eps) orthogonality as projecting every
+// column twice on its own (lr_orthonormalise_columnwise), with 16 launches per 16 columns instead of 96 and each finished column
+// read 4 times per PANEL instead of 4 times per COLUMN (the column-wise version moved 32 GB at M = 50k, K = 200).
+// Rank decisions (a dropped column becomes exactly zero and stays zero in every later product, like before):
+//   * nothing left after (a): norm^2 <= 1e-28 of the norm^2 the column arrived with -- the column-wise rule;
+//   * nearly dependent INSIDE its panel: Cholesky pivot <= 1e-10 of the column's own norm^2 after (a).  A direction of relative weight
+//     < 1e-5 next to its panel neighbours; G itself is only float32-accurate (cc/math_utils.cc:17-19), so nothing real is lost.
+constexpr int LR_PANEL = 16;
+constexpr int LR_UPD_KC = 128;     // finished columns per shared-memory chunk of lr_panel_update_kernel
+
+// X[j0+p][i] -= sum_{k<nk} C[k][p] X[k][i]      (C row-major [nk][np]: the merged output of lr_inner_kernel)
+__global__ void __launch_bounds__(THREADS)
+lr_panel_update_kernel(double* __restrict__ X, long long m, long long ld, int j0, int np, int nk, const double* __restrict__ C /* [nk][np] */) {
+    __shared__ double sc[LR_UPD_KC][LR_PANEL];
+    const long long i = (long long)blockIdx.x * THREADS + threadIdx.x;
+    double acc[LR_PANEL];
+#pragma unroll
+    for (int p = 0; p < LR_PANEL; ++p) acc[p] = 0.0;
+    for (int k0 = 0; k0 < nk; k0 += LR_UPD_KC) {
+        const int kc = (nk - k0 < LR_UPD_KC) ? nk - k0 : LR_UPD_KC;
+        __syncthreads();
+        for (int e = threadIdx.x; e < kc * LR_PANEL; e += THREADS) {
+            const int k = e / LR_PANEL, pp = e % LR_PANEL;
+            sc[k][pp] = pp < np ? C[(size_t)(k0 + k) * np + pp] : 0.0;
+        }
+        __syncthreads();
+        if (i < m) {
+#pragma unroll 4
+            for (int k = 0; k < kc; ++k) {
+                const double q = X[(long long)(k0 + k) * ld + i];
+#pragma unroll
+                for (int p = 0; p < LR_PANEL; ++p) acc[p] = fma(sc[k][p], q, acc[p]);
+            }
+        }
+    }
+    if (i < m) {
+#pragma unroll
+        for (int p = 0; p < LR_PANEL; ++p)
+            if (p < np) X[(long long)(j0 + p) * ld + i] -= acc[p];
+    }
+}
+
+// One CTA: T = R^-1 (upper triangular, row-major [LR_PANEL][LR_PANEL]) with W = R^T R the panel's Gram matrix (row-major
+// [np][np]); n0 = the norm^2 each column arrived with (null: use W's own diagonal).  Dropped columns get a zero column in T.
+__global__ void __launch_bounds__(32)
+lr_panel_chol_kernel(const double* __restrict__ W, int np, const double* __restrict__ n0, int n0_stride, double* __restrict__ T) {
+    __shared__ double R[LR_PANEL][LR_PANEL], Ti[LR_PANEL][LR_PANEL];
+    __shared__ int live[LR_PANEL];
+    const int t = threadIdx.x;
+    if (t == 0) {
+        for (int a = 0; a < LR_PANEL; ++a)
+            for (int b = 0; b < LR_PANEL; ++b) { R[a][b] = 0.0; Ti[a][b] = 0.0; }
+        for (int p = 0; p < np; ++p) {
+            const double wpp = W[(size_t)p * np + p];
+            const double arrived = n0 ? n0[(size_t)p * n0_stride] : wpp;
+            double piv = wpp;
+            for (int q = 0; q < p; ++q) piv -= R[q][p] * R[q][p];
+            const bool ok = wpp > 1e-280 && wpp > 1e-28 * arrived && piv > 1e-10 * wpp;
+            live[p] = ok ? 1 : 0;
+            if (!ok) continue;
+            const double rpp = sqrt(piv);
+            R[p][p] = rpp;
+            for (int b = p + 1; b < np; ++b) {
+                double v = W[(size_t)p * np + b];
+                for (int q = 0; q < p; ++q) v -= R[q][p] * R[q][b];
+                R[p][b] = v / rpp;
+            }
+        }
+        // T = R^-1 restricted to the live columns: back substitution column by column
+        for (int b = 0; b < np; ++b) {
+            if (!live[b]) continue;
+            Ti[b][b] = 1.0 / R[b][b];
+            for (int a = b - 1; a >= 0; --a) {
+                if (!live[a]) continue;
+                double v = 0.0;
+                for (int q = a + 1; q <= b; ++q) v -= R[a][q] * Ti[q][b];
+                Ti[a][b] = v / R[a][a];
+            }
+        }
+    }
+    __syncthreads();
+    for (int e = t; e < LR_PANEL * LR_PANEL; e += 32) T[e] = Ti[e / LR_PANEL][e % LR_PANEL];
+}
+
+// X[j0+p][i] <- sum_{q<=p} X[j0+q][i] T[q][p]
+__global__ void __launch_bounds__(THREADS)
+lr_panel_apply_kernel(double* __restrict__ X, long long m, long long ld, int j0, int np, const double* __restrict__ T) {
+    __shared__ double st[LR_PANEL][LR_PANEL];
+    for (int e = threadIdx.x; e < LR_PANEL * LR_PANEL; e += THREADS) st[e / LR_PANEL][e % LR_PANEL] = T[e];
+    __syncthreads();
+    const long long i = (long long)blockIdx.x * THREADS + threadIdx.x;
+    if (i < m) {
+        double x[LR_PANEL];
+#pragma unroll
+        for (int p = 0; p < LR_PANEL; ++p) x[p] = p < np ? X[(long long)(j0 + p) * ld + i] : 0.0;
+#pragma unroll
+        for (int p = 0; p < LR_PANEL; ++p) {
+            if (p < np) {
+                double v = 0.0;
+#pragma unroll
+                for (int q = 0; q <= p; ++q) v = fma(x[q], st[q][p], v);
+                X[(long long)(j0 + p) * ld + i] = v;
+            }
+        }
+    }
+}
+
 // ---- out[a][b] = sum_i wt_i A[a][i] Bm[b][i]   (a < na, b < nb; wt may be null) -------------------------------------------
 // One CTA per {32 x 32 output tile, i-slice}; 2 x 2 outputs per thread; partial per slice, merged by lr_merge_kernel.
 __global__ void __launch_bounds__(THREADS)
 lr_inner_kernel(const double* __restrict__ A, int na, long long lda, const double* __restrict__ Bm, int nb, long long ldb,
                 const double* __restrict__ wt, long long m, int upper_only /* symmetric result: tiles below the diagonal are skipped */,
-                double* __restrict__ part /* [LR_SLICES][na][nb] */) {
+                double* __restrict__ part /* [gridDim.y][na][nb] */) {
     __shared__ double sa[LR_TILE][LR_CHUNK + 1], sb[LR_TILE][LR_CHUNK + 1];
     const int tiles_b = (nb + LR_TILE - 1) / LR_TILE;
     const int ta0 = (blockIdx.x / tiles_b) * LR_TILE, tb0 = (blockIdx.x % tiles_b) * LR_TILE;
     if (upper_only && ta0 > tb0) return;            // the whole CTA, before any barrier; lr_merge_kernel mirrors the upper tiles
-    const int slice = blockIdx.y;
-    const long long per = (m + LR_SLICES - 1) / LR_SLICES;
-    const long long i_lo = per * slice, i_hi = (i_lo + per < m) ? i_lo + per : m;
+    const int slice = blockIdx.y, nsl = gridDim.y;
+    const long long per = (m + nsl - 1) / nsl;
+    const long long i_lo = (per * slice < m) ? per * slice : m, i_hi = (i_lo + per < m) ? i_lo + per : m;
     const int ty = threadIdx.x / 16, tx = threadIdx.x % 16;
     double acc[2][2] = {{0.0, 0.0}, {0.0, 0.0}};
     for (long long i0 = i_lo; i0 < i_hi; i0 += LR_CHUNK) {
@@ -194,14 +306,14 @@ lr_inner_kernel(const double* __restrict__ A, int na, long long lda, const doubl
 // out[e] = sum_slices part[s][e]  (fixed order).  symmetrise != 0 (square, mathematically symmetric result whose tiles below
 // the diagonal were not computed): diagonal tiles give (x + x^T) / 2, the others are mirrored from the upper triangle.
 __global__ void __launch_bounds__(THREADS)
-lr_merge_kernel(const double* __restrict__ part, int na, int nb, int symmetrise, double* __restrict__ out) {
+lr_merge_kernel(const double* __restrict__ part, int nsl, int na, int nb, int symmetrise, double* __restrict__ out) {
     const int e = blockIdx.x * THREADS + threadIdx.x;
     if (e < na * nb) {
         const int a = e / nb, b = e % nb;
         const int ta = a / LR_TILE, tb = b / LR_TILE;
         const size_t e_ab = (size_t)a * nb + b, e_ba = (size_t)b * nb + a;
         double s = 0.0, t = 0.0;
-        for (int sl = 0; sl < LR_SLICES; ++sl) {
+        for (int sl = 0; sl < nsl; ++sl) {
             const double* p = part + (size_t)sl * na * nb;
             if (!symmetrise || ta <= tb) s += p[e_ab];
             if (symmetrise && ta >= tb) t += p[e_ba];

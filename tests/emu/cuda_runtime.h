@@ -141,4 +141,10 @@ static inline double __longlong_as_double(long long v) { double d; memcpy(&d, &v
 static inline float __int_as_float(int v) { float f; memcpy(&f, &v, 4); return f; }
 static inline int __float_as_int(float f) { int v; memcpy(&v, &f, 4); return v; }
 static inline float __fmaf_rn(float a, float b, float c) { return fmaf(a, b, c); }
+// individually rounded float32 operations (the host build of the emulation is compiled without FMA contraction: -ffp-contract=off)
+static inline float __fadd_rn(float a, float b) { volatile float r = a + b; return r; }
+static inline float __fsub_rn(float a, float b) { volatile float r = a - b; return r; }
+static inline float __fmul_rn(float a, float b) { volatile float r = a * b; return r; }
+static inline float __fdiv_rn(float a, float b) { volatile float r = a / b; return r; }
+static inline float __fsqrt_rn(float a) { volatile float r = sqrtf(a); return r; }
 static inline double __fma_rn(double a, double b, double c) { return fma(a, b, c); }

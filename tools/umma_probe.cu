@@ -1,0 +1,204 @@
+// tools/umma_probe.cu -- hardware bring-up of csrc/gram_umma.cuh (tcgen05 cannot be emulated on the CPU):
+//   1. layout probe: one [128 x 16] x [16 x N] TF32 MMA pair through the kernel's descriptor / swizzle / TMA / TMEM conventions
+//      against the CPU; on a mismatch, identity patterns decode which element the tensor core actually read where;
+//   2. the full product G X against an FP64 CPU sum on sampled rows and against the CUDA-core kernel, with timings.
+// build: nvcc -O3 -std=c++17 -gencode arch=compute_100a,code=sm_100a -DGU_DEBUG_WAIT -Iprobreg_b200/csrc -Iinclude -o build/umma_probe tools/umma_probe.cu
+// run:   timeout 300 build/umma_probe [points=50000] [rank=200] [chunk=2048]
+#include <math.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <vector>
+
+#include "lowrank.cuh"
+#include "gram_umma.cuh"
+
+using namespace cpd;
+
+#define CK(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { printf("CUDA error %s at line %d: %s\n", #x, __LINE__, cudaGetErrorString(e_)); return 1; } } while (0)
+
+static float tf32_trunc(float v) { uint32_t u; memcpy(&u, &v, 4); u &= 0xffffe000u; memcpy(&v, &u, 4); return v; }
+static float tf32_round(float v) { uint32_t u; memcpy(&u, &v, 4); u += 0x1000u; u &= 0xffffe000u; memcpy(&v, &u, 4); return v; }
+static double urand(unsigned long long& s) { s = s * 6364136223846793005ull + 1442695040888963407ull; return (double)(s >> 11) / 9007199254740992.0; }
+
+static int timeout_code() { int c = 0; cudaMemcpyFromSymbol(&c, gu_timeout_code, sizeof(int)); return c; }
+
+static int run_layout(int n16, const std::vector<float>& A, const std::vector<float>& B, std::vector<float>& D) {
+    float *dA, *dB, *dD;
+    CK(cudaMalloc(&dA, 128 * 16 * 4)); CK(cudaMalloc(&dB, (size_t)n16 * 16 * 4)); CK(cudaMalloc(&dD, (size_t)128 * n16 * 4));
+    CK(cudaMemcpy(dA, A.data(), 128 * 16 * 4, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(dB, B.data(), (size_t)n16 * 16 * 4, cudaMemcpyHostToDevice));
+    CK(cudaMemset(dD, 0xff, (size_t)128 * n16 * 4));
+    CUtensorMap map;
+    const int mr = gu_make_map(&map, dB, 16, n16, n16);
+    if (mr != 0) { printf("cuTensorMapEncodeTiled failed: %d\n", mr); return 1; }
+    CK(cudaFuncSetAttribute(gu_layout_probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 40000));
+    gu_layout_probe_kernel<<<1, 128, 40000>>>(map, dA, n16, dD);
+    CK(cudaGetLastError());
+    CK(cudaDeviceSynchronize());
+    D.resize((size_t)128 * n16);
+    CK(cudaMemcpy(D.data(), dD, D.size() * 4, cudaMemcpyDeviceToHost));
+    cudaFree(dA); cudaFree(dB); cudaFree(dD);
+    const int tc = timeout_code();
+    if (tc) { printf("layout probe: wait %d timed out\n", tc); return 2; }
+    return 0;
+}
+
+static int layout_tests() {
+    unsigned long long seed = 12345;
+    int bad = 0;
+    for (int n16 : {16, 64, 208, 256}) {
+        std::vector<float> A(128 * 16), B((size_t)n16 * 16), D;
+        for (auto& v : A) v = (float)(2.0 * urand(seed) - 1.0);
+        for (auto& v : B) v = (float)(2.0 * urand(seed) - 1.0);
+        const int rc = run_layout(n16, A, B, D);
+        if (rc) return rc;
+        double et = 0.0, er = 0.0;
+        for (int r = 0; r < 128; ++r)
+            for (int n = 0; n < n16; ++n) {
+                double st = 0.0, sr = 0.0;
+                for (int k = 0; k < 16; ++k) {
+                    st += (double)tf32_trunc(A[r * 16 + k]) * (double)tf32_trunc(B[n * 16 + k]);
+                    sr += (double)tf32_round(A[r * 16 + k]) * (double)tf32_round(B[n * 16 + k]);
+                }
+                et = fmax(et, fabs(st - D[(size_t)r * n16 + n]));
+                er = fmax(er, fabs(sr - D[(size_t)r * n16 + n]));
+            }
+        printf("layout n=%3d: max |D - ref|  truncating-TF32 ref %.3e   rounding-TF32 ref %.3e   %s\n", n16, et, er,
+               (et < 2e-5 || er < 2e-5) ? "OK" : "MISMATCH");
+        if (!(et < 2e-5 || er < 2e-5)) bad = 1;
+    }
+    if (bad) {
+        // decode: B = identity (row n has a one at k = n, n < 16), A[r][k] = 16 r + k  ->  D[r][n] = the A element read at (r, k = n)
+        const int n16 = 16;
+        std::vector<float> A(128 * 16), B((size_t)n16 * 16, 0.f), D;
+        for (int r = 0; r < 128; ++r) for (int k = 0; k < 16; ++k) A[r * 16 + k] = (float)(16 * r + k);
+        for (int n = 0; n < 16; ++n) B[n * 16 + n] = 1.f;
+        if (run_layout(n16, A, B, D) == 0) {
+            printf("decode A (identity B): D[r][n] should be 16 r + n; rows 0..15 and 126..127, as (row,k) read:\n");
+            for (int r : {0, 1, 2, 3, 4, 5, 6, 7, 8, 9, 15, 16, 64, 127}) {
+                printf("  r=%3d:", r);
+                for (int n = 0; n < 16; ++n) { const int v = (int)D[(size_t)r * n16 + n]; printf(" (%d,%d)", v / 16, v % 16); }
+                printf("\n");
+            }
+        }
+        // decode B: A = identity pattern (row r has a one at k = r % 16), B[n][k] = 16 n + k  ->  D[r][n] = B[n][r % 16]
+        for (int r = 0; r < 128; ++r) for (int k = 0; k < 16; ++k) A[r * 16 + k] = (r % 16 == k) ? 1.f : 0.f;
+        for (int n = 0; n < 16; ++n) for (int k = 0; k < 16; ++k) B[n * 16 + k] = (float)(16 * n + k);
+        if (run_layout(n16, A, B, D) == 0) {
+            printf("decode B (identity-pattern A): D[r][n] should be 16 n + r %% 16; rows 0..15, as (n,k) read:\n");
+            for (int r = 0; r < 16; ++r) {
+                printf("  r=%3d:", r);
+                for (int n = 0; n < 16; ++n) { const int v = (int)D[(size_t)r * n16 + n]; printf(" (%d,%d)", v / 16, v % 16); }
+                printf("\n");
+            }
+        }
+    }
+    return bad ? 3 : 0;
+}
+
+static int full_test(long long m, int rank, int chunk, double beta, bool time_old) {
+    const long long mpad = (m + 511) / 512 * 512;
+    const int n16 = (rank + 15) / 16 * 16;
+    unsigned long long seed = 777;
+    std::vector<double> Y((size_t)m * 3), X((size_t)rank * mpad, 0.0);
+    for (long long i = 0; i < m; ++i) { Y[3 * i] = urand(seed); Y[3 * i + 1] = 0.6 * urand(seed); Y[3 * i + 2] = 0.3 * urand(seed); }
+    for (int c = 0; c < rank; ++c) for (long long j = 0; j < m; ++j) X[(size_t)c * mpad + j] = 2.0 * urand(seed) - 1.0;
+    double *dY, *dX, *dOutNew, *dOutOld;
+    float4* dPts;
+    float *dPlanes, *dPart;
+    CK(cudaMalloc(&dY, (size_t)m * 3 * 8)); CK(cudaMalloc(&dX, (size_t)rank * mpad * 8));
+    CK(cudaMalloc(&dOutNew, (size_t)rank * mpad * 8)); CK(cudaMalloc(&dOutOld, (size_t)rank * mpad * 8));
+    CK(cudaMalloc(&dPts, (size_t)mpad * 16));
+    CK(cudaMalloc(&dPlanes, (size_t)2 * n16 * mpad * 4));
+    const int ntiles = (int)((m + GU_ROWS - 1) / GU_ROWS), nq = (int)((mpad + chunk - 1) / chunk);
+    const long long ldp = (long long)ntiles * GU_ROWS;
+    CK(cudaMalloc(&dPart, (size_t)nq * n16 * ldp * 4));
+    CK(cudaMemcpy(dY, Y.data(), (size_t)m * 3 * 8, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(dX, X.data(), (size_t)rank * mpad * 8, cudaMemcpyHostToDevice));
+    const float sb = (float)sqrt(LOG2E / (2.0 * beta));
+    lr_pack_kernel<<<(unsigned)((mpad + THREADS - 1) / THREADS), THREADS>>>(dY, 0.0, 0.0, 0.0, m, mpad, sb, dPts);
+    CK(cudaGetLastError());
+    CUtensorMap map;
+    if (gu_make_map(&map, dPlanes, mpad, 2 * n16, n16) != 0) { printf("tensor map encode failed\n"); return 1; }
+    CK(cudaFuncSetAttribute(gu_gram_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GU_SMEM));
+    int sms = 148;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, 0);
+    cudaEvent_t e0, e1, e2, e3;
+    cudaEventCreate(&e0); cudaEventCreate(&e1); cudaEventCreate(&e2); cudaEventCreate(&e3);
+    float t_split = 0, t_gram = 0, t_red = 0;
+    for (int rep = 0; rep < 3; ++rep) {
+        cudaEventRecord(e0);
+        gu_split_kernel<<<dim3((unsigned)((mpad + THREADS - 1) / THREADS), n16), THREADS>>>(dX, m, mpad, rank, n16, mpad, dPlanes);
+        cudaEventRecord(e1);
+        gu_gram_kernel<<<sms, GU_THREADS, GU_SMEM>>>(map, dPts, mpad, chunk, 0, m, n16, dPart, ldp);
+        cudaEventRecord(e2);
+        gu_reduce_kernel<<<dim3((unsigned)((m + THREADS - 1) / THREADS), rank), THREADS>>>(dPart, nq, n16, ldp, rank, m, 0, mpad, dOutNew);
+        cudaEventRecord(e3);
+        CK(cudaGetLastError());
+        CK(cudaDeviceSynchronize());
+        cudaEventElapsedTime(&t_split, e0, e1); cudaEventElapsedTime(&t_gram, e1, e2); cudaEventElapsedTime(&t_red, e2, e3);
+        const int tc = timeout_code();
+        if (tc) { printf("full kernel: wait %d timed out\n", tc); return 2; }
+    }
+    printf("m=%lld rank=%d (N=%d) chunk=%d beta=%g: split %.3f ms, gram (tcgen05) %.3f ms, reduce %.3f ms  => %.3f ms per product; "
+           "%.1f TFLOP/s useful (2 M^2 K), tensor work 3x\n", m, rank, n16, chunk, beta, t_split, t_gram, t_red, t_split + t_gram + t_red,
+           2.0 * m * m * rank / ((t_split + t_gram + t_red) * 1e-3) / 1e12);
+    float t_old = 0;
+    if (time_old) {
+        cudaEventRecord(e0);
+        lr_gram_apply_kernel<<<dim3((unsigned)((m + THREADS - 1) / THREADS), (unsigned)((rank + LR_COLS - 1) / LR_COLS)), THREADS>>>(
+            dPts, m, mpad, dX, mpad, rank, dOutOld, 0, m);
+        cudaEventRecord(e1);
+        CK(cudaGetLastError());
+        CK(cudaDeviceSynchronize());
+        cudaEventElapsedTime(&t_old, e0, e1);
+        printf("   CUDA-core kernel: %.3f ms\n", t_old);
+    }
+    // accuracy on sampled rows against an FP64 sum over the float32 G the kernels use
+    std::vector<double> on((size_t)rank * mpad), oo((size_t)rank * mpad);
+    CK(cudaMemcpy(on.data(), dOutNew, on.size() * 8, cudaMemcpyDeviceToHost));
+    if (time_old) CK(cudaMemcpy(oo.data(), dOutOld, oo.size() * 8, cudaMemcpyDeviceToHost));
+    std::vector<float4> P(mpad);
+    CK(cudaMemcpy(P.data(), dPts, (size_t)mpad * 16, cudaMemcpyDeviceToHost));
+    const int nsample = 48;
+    double en = 0, eo = 0, eno = 0, scale = 0;
+    std::vector<double> ref(rank);
+    for (int s = 0; s < nsample; ++s) {
+        const long long i = (s == 0) ? 0 : (s == 1 ? m - 1 : (long long)(urand(seed) * m));
+        for (int c = 0; c < rank; ++c) ref[c] = 0.0;
+        for (long long j = 0; j < m; ++j) {
+            const float dx = P[i].x - P[j].x, dy = P[i].y - P[j].y, dz = P[i].z - P[j].z;
+            const float u = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
+            const double g = exp2(-(double)u);
+            for (int c = 0; c < rank; ++c) ref[c] += g * X[(size_t)c * mpad + j];
+        }
+        for (int c = 0; c < rank; ++c) {
+            scale = fmax(scale, fabs(ref[c]));
+            en = fmax(en, fabs(on[(size_t)c * mpad + i] - ref[c]));
+            if (time_old) { eo = fmax(eo, fabs(oo[(size_t)c * mpad + i] - ref[c])); eno = fmax(eno, fabs(oo[(size_t)c * mpad + i] - on[(size_t)c * mpad + i])); }
+        }
+    }
+    printf("   accuracy on %d rows (max |err| / max |value| = %.3e): tcgen05 %.3e   CUDA-core %.3e   tcgen05 vs CUDA-core %.3e\n", nsample, scale,
+           en / scale, eo / scale, eno / scale);
+    cudaFree(dY); cudaFree(dX); cudaFree(dOutNew); cudaFree(dOutOld); cudaFree(dPts); cudaFree(dPlanes); cudaFree(dPart);
+    return (en / scale < 2e-5) ? 0 : 4;
+}
+
+int main(int argc, char** argv) {
+    const long long m = argc > 1 ? atoll(argv[1]) : 50000;
+    const int rank = argc > 2 ? atoi(argv[2]) : 200;
+    const int chunk = argc > 3 ? atoi(argv[3]) : 2048;
+    int rc = layout_tests();
+    printf("layout tests: %s\n", rc == 0 ? "PASS" : "FAIL");
+    if (rc == 2) return rc;                 // a wait timed out: the context is suspect
+    int rc2 = full_test(3000, 200, 512, 2.0, true);
+    if (rc2 == 2) return rc2;
+    rc2 |= full_test(5000, 37, 2048, 0.05, true);
+    rc2 |= full_test(m, rank, chunk, 2.0, true);
+    rc2 |= full_test(m, rank, 2 * chunk, 2.0, false);
+    rc2 |= full_test(m, rank, chunk / 2, 2.0, false);
+    printf("full tests: %s\n", rc2 == 0 ? "PASS" : "FAIL");
+    return rc | rc2;
+}
