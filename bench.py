@@ -345,6 +345,35 @@ def run_ours(args):
     value = 1e3 / ms_per_step
     final = h.em_step(read=True)            # the loop did real work: parameters moved towards the truth
 
+    # ---- multi-rank runs: the sharded loop against the same iterations on ONE GPU (asserted, rank 0) ---------------
+    shard_check = None
+    if world > 1:
+        reset()
+        for _ in range(2):
+            h.em_step(read=False)
+        sharded = h.em_step(read=True)
+        barrier()
+        if rank == 0:
+            h1 = _cabi.Handle(3, device=local_rank)
+            h1.set_source(src)
+            h1.set_target(tgt)
+            s2_1 = h1.sigma2_init()
+            h1.set_state(tf_kind, True, 0.0, np.identity(3), np.zeros(3), 1.0, s2_1, 1.0 + n * 3 * 0.5 * np.log(s2_1))
+            for _ in range(2):
+                h1.em_step(read=False)
+            single = h1.em_step(read=True)
+            h1.close()
+            shard_check = {"iterations": 3, "sigma2_sharded": sharded[3], "sigma2_single_gpu": single[3],
+                           "sigma2_rel_diff": abs(sharded[3] - single[3]) / single[3],
+                           "lin_max_abs_diff": float(np.abs(sharded[0] - single[0]).max()),
+                           "t_max_abs_diff": float(np.abs(sharded[1] - single[1]).max()),
+                           "sigma2_0_rel_diff": abs(s2 - s2_1) / s2_1}
+            shard_check["agree"] = bool(shard_check["sigma2_rel_diff"] < 1e-7 and shard_check["lin_max_abs_diff"] < 1e-7
+                                        and shard_check["t_max_abs_diff"] < 1e-7)
+            if not shard_check["agree"]:
+                raise SystemExit("sharded run disagrees with the single-GPU run: %r" % (shard_check,))
+        barrier()
+
     # ---- stage breakdown (profiling events, one sync per step; not part of `value`) -----------------
     h.set_profiling(True)
     stages = []
@@ -437,6 +466,7 @@ def run_ours(args):
         "dtype": "f32", "dtype_note": "pair arithmetic f32 (packed f32x2); every sum beyond 64 terms, the moments and the M-step f64",
         "data": "synthetic",
         "config": {"workload": workload_string(args.config, n), "baseline_config": args.config, "also": also,
+                   "sharded_equals_single_gpu": (shard_check or {}).get("agree"),
                    "parallelism": "target-sharded x%d, sources replicated, one 32-double all-reduce per iteration (%s)"
                                   % (world, "fused into the M-step kernel over NVLink peer memory" if (comm is not None and comm.use_p2p)
                                      else ("ncclAllReduce" if world > 1 else "none needed")),
@@ -454,7 +484,8 @@ def run_ours(args):
         "cpu_baseline": cpu,
         "clocks": clocks,
         "probe": probe,
-        "result_check": {"sigma2_after_run": final[3], "scale": final[2], "lin": [float(x) for x in np.ravel(final[0])]},
+        "result_check": {"sigma2_after_run": final[3], "scale": final[2], "lin": [float(x) for x in np.ravel(final[0])],
+                         "sharded_vs_single_gpu": shard_check},
         "extras": extras,
     }
     emit(out)
@@ -501,7 +532,7 @@ def run_nonrigid(args, torch, _cabi, cpd, barrier, local_rank, world):
     h.nonrigid_lowrank_begin(2.0, 2.0, s2, 0.0, K, 2, 0)
     h.sync()
     setup_wall_ms = (time.perf_counter() - t0) * 1e3
-    setup = dict(zip(["gram_products_ms", "orthonormalisation_ms", "core_ms"], [float(x) for x in h.lowrank_setup_times()]))
+    setup = {k: float(v) for k, v in dict(h.lowrank_setup_times()).items()}
     h.set_profiling(False)
     sampler = ClockSampler(world) if rank == 0 else None
     if sampler:

@@ -6,7 +6,8 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-# CPD_B200_LIB: load another build of the same library (tools/tune.sh variants); never a different implementation
+# CPD_B200_LIB: load another build of the same library (tools/tune.sh variants); never a different implementation -- lib() refuses
+# anything that exports cpd_is_emulation (the CPU build the test-suite keeps for itself), so the package cannot be given a CPU path this way
 LIB_PATH = os.environ.get("CPD_B200_LIB") or os.path.join(_HERE, "libcpd_b200.so")
 
 TF_RIGID, TF_AFFINE, TF_NONRIGID = 0, 1, 2
@@ -100,7 +101,11 @@ def lib():
         if not os.path.exists(LIB_PATH):
             raise CpdError("%s not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
                            "(or `make -C probreg_b200/csrc`); probreg_b200 has no CPU path" % LIB_PATH)
-        _lib = _load(LIB_PATH)
+        loaded = _load(LIB_PATH)
+        if hasattr(loaded, "cpd_is_emulation"):
+            raise CpdError("%s is the CPU emulation used by the tests (it exports cpd_is_emulation): probreg_b200 has no CPU path "
+                           "and will not load it as the product library" % LIB_PATH)
+        _lib = loaded
     return _lib
 
 

@@ -4,6 +4,8 @@
 #include "cpd_b200.h"
 #include "kernels.cuh"
 #include "lowrank.cuh"
+#include "gram_umma.cuh"
+#include "gram_i8.cuh"
 
 #include <cub/device/device_radix_sort.cuh>
 #ifdef CPD_HOST_EMU
@@ -215,6 +217,11 @@ struct cpd_ctx {
     double *d_lr_Q = nullptr, *d_lr_X = nullptr, *d_lr_coef = nullptr, *d_lr_part = nullptr, *d_lr_Bc = nullptr, *d_lr_S = nullptr,
            *d_lr_R = nullptr, *d_lr_sys = nullptr, *d_lr_rhs = nullptr, *d_lr_c = nullptr, *d_lr_out = nullptr, *d_lr_panel = nullptr;
     size_t lr_part_cap = 0;               // doubles in d_lr_part (slice partials of lr_inner)
+    float *d_gu_planes = nullptr, *d_gu_part = nullptr;      // tcgen05 G X product: TF32 hi / lo planes of X, chunk partials
+    size_t gu_planes_cap = 0, gu_part_cap = 0;
+    signed char* d_gi_planes = nullptr;                      // exact int8-digit product: digit planes of X, FP64 chunk partials, column maxima
+    double *d_gi_part = nullptr, *d_gi_colmax = nullptr;
+    size_t gi_planes_cap = 0, gi_part_cap = 0, gi_colmax_cap = 0;
     size_t lr_out_cap = 0;
     P2PMailbox* d_box = nullptr;          // this rank's mailbox (peers write into it)
     P2PInfo* d_p2p = nullptr;             // device copy of the peer table; non-null => fused P2P exchange
@@ -222,12 +229,20 @@ struct cpd_ctx {
     cudaEvent_t ev0 = nullptr, ev1 = nullptr, sev[7] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     bool profiling = false;
     int64_t launches = 0;
+    // the fused EM iteration as a CUDA graph (cpd_em_step): one graph launch instead of 7-12 kernel launches per iteration
+    DevState* h_state_ring = nullptr;     // pinned staging slots of upload_state
+    cudaEvent_t state_ev[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    int state_slot = 0;
+    bool graph_on = true;
+    cudaGraphExec_t em_graph = nullptr;
+    int em_graph_key = -1, em_graph_launches = 0, prepare_gen = 0;
     void* d_flush = nullptr;
     size_t flush_cap = 0;
     std::vector<cudaEvent_t> pool;
 };
 
 namespace {
+constexpr int STATE_RING = 8;
 template <typename T>
 int dev_alloc(T** p, size_t count) {
     if (*p) { cudaFree(*p); *p = nullptr; }
@@ -282,9 +297,19 @@ WorkList build_work(int ntiles, int nstages, int slots) {
     return w;
 }
 
+// Stream-ordered, no synchronise: the state goes through a small ring of pinned staging slots (a cudaMemcpyAsync from pageable
+// memory would synchronise the stream first); a slot is re-used only after the copy that last read it has completed.
 int upload_state(cpd_ctx* h) {
-    CU(cudaMemcpyAsync(h->d_state, &h->h_state, sizeof(DevState), cudaMemcpyHostToDevice, h->stream));
-    CU(cudaStreamSynchronize(h->stream));
+    if (!h->h_state_ring) {
+        CU(cudaMallocHost((void**)&h->h_state_ring, STATE_RING * sizeof(DevState)));
+        for (int k = 0; k < STATE_RING; ++k) CU(cudaEventCreateWithFlags(&h->state_ev[k], cudaEventDisableTiming));
+    }
+    const int k = h->state_slot;
+    h->state_slot = (k + 1) % STATE_RING;
+    CU(cudaEventSynchronize(h->state_ev[k]));                  // never recorded: returns at once
+    h->h_state_ring[k] = h->h_state;
+    CU(cudaMemcpyAsync(h->d_state, &h->h_state_ring[k], sizeof(DevState), cudaMemcpyHostToDevice, h->stream));
+    CU(cudaEventRecord(h->state_ev[k], h->stream));
     return CPD_OK;
 }
 
@@ -386,10 +411,12 @@ int prepare(cpd_ctx* h) {
     TRY(dev_alloc(&h->d_work2, w2.items.size()));
     TRY(dev_alloc(&h->d_slots1, w1.tile_slots.size()));
     TRY(dev_alloc(&h->d_slots2, w2.tile_slots.size()));
-    CU(cudaMemcpy(h->d_work1, w1.items.data(), w1.items.size() * sizeof(int4), cudaMemcpyHostToDevice));
-    CU(cudaMemcpy(h->d_work2, w2.items.data(), w2.items.size() * sizeof(int4), cudaMemcpyHostToDevice));
-    CU(cudaMemcpy(h->d_slots1, w1.tile_slots.data(), w1.tile_slots.size() * sizeof(int), cudaMemcpyHostToDevice));
-    CU(cudaMemcpy(h->d_slots2, w2.tile_slots.data(), w2.tile_slots.size() * sizeof(int), cudaMemcpyHostToDevice));
+    // on the handle's (non-blocking) stream, which the consuming kernels run on; the vectors live until the synchronise below
+    CU(cudaMemcpyAsync(h->d_work1, w1.items.data(), w1.items.size() * sizeof(int4), cudaMemcpyHostToDevice, h->stream));
+    CU(cudaMemcpyAsync(h->d_work2, w2.items.data(), w2.items.size() * sizeof(int4), cudaMemcpyHostToDevice, h->stream));
+    CU(cudaMemcpyAsync(h->d_slots1, w1.tile_slots.data(), w1.tile_slots.size() * sizeof(int), cudaMemcpyHostToDevice, h->stream));
+    CU(cudaMemcpyAsync(h->d_slots2, w2.tile_slots.data(), w2.tile_slots.size() * sizeof(int), cudaMemcpyHostToDevice, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
     TRY(dev_alloc(&h->d_sbox, (size_t)(h->mpad / P1_STAGE) * 2));
     TRY(dev_alloc(&h->d_tbox, (size_t)(h->npad / P2_STAGE) * 2));
     TRY(dev_alloc(&h->d_omax, (size_t)(h->npad / P2_STAGE)));
@@ -403,6 +430,7 @@ int prepare(cpd_ctx* h) {
     if (ms > h->mom_src_cap) { TRY(dev_alloc(&h->d_mom_src, ms)); h->mom_src_cap = ms; }
     if (mt > h->mom_tgt_cap) { TRY(dev_alloc(&h->d_mom_tgt, mt)); h->mom_tgt_cap = mt; }
     h->prepared = true;
+    h->prepare_gen += 1;                 // buffers / work lists changed: a captured EM graph is stale
     return CPD_OK;
 }
 
@@ -545,6 +573,7 @@ extern "C" int cpd_create(cpd_ctx** out, int device, int dim, void* stream) {
     CU(cudaEventCreate(&h->ev1));
     for (int k = 0; k < 7; ++k) CU(cudaEventCreate(&h->sev[k]));
     { const char* e = getenv("CPD_B200_NO_CULL"); h->cull_on = !(e && e[0] == '1'); }
+    { const char* e = getenv("CPD_B200_NO_GRAPH"); h->graph_on = !(e && e[0] == '1'); }
     memset(&h->h_state, 0, sizeof(DevState));
     h->h_state.dim = dim;
     h->h_state.scale = 1.0;
@@ -565,7 +594,7 @@ extern "C" void cpd_destroy(cpd_ctx* h) {
     void* nrp[] = {h->d_G, h->d_W, h->d_A, h->d_B, h->d_ts2, h->d_nrpart, h->d_ipiv, h->d_info, h->d_work};
     for (void* p : nrp) if (p) cudaFree(p);
     void* lrp[] = {h->d_lr_pts, h->d_lr_Q, h->d_lr_X, h->d_lr_coef, h->d_lr_part, h->d_lr_Bc, h->d_lr_S, h->d_lr_R, h->d_lr_sys, h->d_lr_rhs,
-                   h->d_lr_c, h->d_lr_out, h->d_lr_panel, h->d_wgt, h->d_p1t, h->d_pxt, h->d_la, h->d_log2c};
+                   h->d_lr_c, h->d_lr_out, h->d_lr_panel, h->d_gu_planes, h->d_gu_part, h->d_gi_planes, h->d_gi_part, h->d_gi_colmax, h->d_wgt, h->d_p1t, h->d_pxt, h->d_la, h->d_log2c};
     for (void* p : lrp) if (p) cudaFree(p);
     if (h->h_work) free(h->h_work);
     if (h->sol_params && g_sol.DestroyParams) g_sol.DestroyParams(h->sol_params);
@@ -577,6 +606,11 @@ extern "C" void cpd_destroy(cpd_ctx* h) {
                     h->d_pxc, h->d_px, h->d_mom_src, h->d_mom_tgt, h->d_mom, h->d_sums, h->d_state, h->d_flush};
     for (void* p : ptrs) if (p) cudaFree(p);
     if (h->h_pin) cudaFreeHost(h->h_pin);
+#ifndef CPD_HOST_EMU
+    if (h->em_graph) cudaGraphExecDestroy(h->em_graph);
+#endif
+    if (h->h_state_ring) cudaFreeHost(h->h_state_ring);
+    for (int k = 0; k < 8; ++k) if (h->state_ev[k]) cudaEventDestroy(h->state_ev[k]);
     if (h->ev0) cudaEventDestroy(h->ev0);
     if (h->ev1) cudaEventDestroy(h->ev1);
     for (int k = 0; k < 7; ++k) if (h->sev[k]) cudaEventDestroy(h->sev[k]);
@@ -694,10 +728,9 @@ extern "C" int cpd_set_state(cpd_ctx* h, int tf_kind, int update_scale, double w
     return upload_state(h);
 }
 
-extern "C" int cpd_em_step(cpd_ctx* h, cpd_params* out) {
-    if (!h) return fail(CPD_ERR_ARG, "null handle");
-    if (!h->have_state) return fail(CPD_ERR_STATE, "cpd_set_state has not been called");
-    CU(cudaSetDevice(h->device));
+namespace {
+// the launches of one fused EM iteration, in stream order (also what a graph capture records)
+int em_step_launches(cpd_ctx* h) {
     TRY(launch_estep(h, &h->d_state->sigma2, &h->d_state->w, nullptr));
     const int nbs = (int)blocks_for(h->m), nbt = (int)blocks_for(h->npad);
     if (h->d_p2p) {
@@ -715,6 +748,49 @@ extern "C" int cpd_em_step(cpd_ctx* h, cpd_params* out) {
     }
     mark(h, 6);
     KCHECK();
+    return CPD_OK;
+}
+}  // namespace
+
+// One EM iteration (probreg/cpd.py:111-113).  The launch sequence is fixed per {culling on/off, buffer generation}, so it is
+// captured once into a CUDA graph and replayed: one graph launch per iteration.  Not captured: profiling runs (events between
+// the kernels) and the ncclAllReduce variant of the multi-rank exchange (CPD_B200_NO_P2P=1); CPD_B200_NO_GRAPH=1 turns it off.
+extern "C" int cpd_em_step(cpd_ctx* h, cpd_params* out) {
+    if (!h) return fail(CPD_ERR_ARG, "null handle");
+    if (!h->have_state) return fail(CPD_ERR_STATE, "cpd_set_state has not been called");
+    CU(cudaSetDevice(h->device));
+#ifndef CPD_HOST_EMU
+    const bool use_graph = h->graph_on && !h->profiling && !(h->comm && !h->d_p2p) && !h->wgt_on;
+#else
+    const bool use_graph = false;
+#endif
+    if (!use_graph) {
+        TRY(em_step_launches(h));
+    }
+#ifndef CPD_HOST_EMU
+    else {
+        TRY(prepare(h));                                    // allocations and uploads happen outside the capture
+        const int key = h->prepare_gen * 2 + ((h->cull_on && h->cull_active) ? 1 : 0);
+        if (!h->em_graph || h->em_graph_key != key) {
+            if (h->em_graph) { cudaGraphExecDestroy(h->em_graph); h->em_graph = nullptr; }
+            const int64_t before = h->launches;
+            cudaGraph_t g = nullptr;
+            CU(cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal));
+            const int rc = em_step_launches(h);
+            const cudaError_t ce = cudaStreamEndCapture(h->stream, &g);
+            h->em_graph_launches = (int)(h->launches - before);
+            h->launches = before;
+            if (rc != CPD_OK) { if (g) cudaGraphDestroy(g); return rc; }
+            if (ce != cudaSuccess) return fail(CPD_ERR_CUDA, "cudaStreamEndCapture failed: %s", cudaGetErrorString(ce));
+            const cudaError_t ie = cudaGraphInstantiate(&h->em_graph, g, 0);
+            cudaGraphDestroy(g);
+            if (ie != cudaSuccess) { h->em_graph = nullptr; return fail(CPD_ERR_CUDA, "cudaGraphInstantiate failed: %s", cudaGetErrorString(ie)); }
+            h->em_graph_key = key;
+        }
+        CU(cudaGraphLaunch(h->em_graph, h->stream));
+        h->launches += h->em_graph_launches;                // kernels executed, whatever carried them to the device
+    }
+#endif
     if (out) return read_params(h, out);
     return CPD_OK;
 }

@@ -147,16 +147,47 @@ gu_split_kernel(const double* __restrict__ X, long long m, long long ld, int ran
     }
 }
 
-// out[c][i_begin + ii] = sum over the j-chunks of part[q][c][ii], in chunk order, FP64
+// out[c][i_begin + ii] = sum over the j-chunks of part[q][c][ii], in chunk order, FP64.  Four rows per thread (one 16-byte load
+// per chunk, four independent sums): the kernel is a pure stream over the partials (nq x n16 x ldp floats, read once).
 __global__ void __launch_bounds__(THREADS)
 gu_reduce_kernel(const float* __restrict__ part, int nq, int n16, long long ldp, int rank, long long rows, long long i_begin, long long ld,
                  double* __restrict__ out) {
-    const long long ii = (long long)blockIdx.x * THREADS + threadIdx.x;
+    const long long ii = ((long long)blockIdx.x * THREADS + threadIdx.x) * 4;      // ldp is a multiple of 256: 16-byte aligned
     const int c = blockIdx.y;
     if (ii < rows && c < rank) {
-        double s = 0.0;
-        for (int q = 0; q < nq; ++q) s += (double)part[((long long)q * n16 + c) * ldp + ii];
-        out[(long long)c * ld + i_begin + ii] = s;
+        double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+        const float* p = part + (long long)c * ldp + ii;
+        const long long step = (long long)n16 * ldp;
+#pragma unroll 4
+        for (int q = 0; q < nq; ++q) {
+            const float4 v = __ldg(reinterpret_cast<const float4*>(p + (long long)q * step));
+            s0 += (double)v.x; s1 += (double)v.y; s2 += (double)v.z; s3 += (double)v.w;
+        }
+        double* o = out + (long long)c * ld + i_begin + ii;
+        o[0] = s0;
+        if (ii + 1 < rows) o[1] = s1;
+        if (ii + 2 < rows) o[2] = s2;
+        if (ii + 3 < rows) o[3] = s3;
+    }
+}
+
+// first-use self-check: the largest |a - b| and |b| over rows [0, rows) of `cols` columns  ->  res[0], res[1] (one CTA)
+__global__ void __launch_bounds__(THREADS)
+gu_compare_kernel(const double* __restrict__ a, const double* __restrict__ b, long long ld, long long i_begin, long long rows, int cols,
+                  double* __restrict__ res) {
+    __shared__ double sd[THREADS], sv[THREADS];
+    double d = 0.0, v = 0.0;
+    for (int c = 0; c < cols; ++c)
+        for (long long i = threadIdx.x; i < rows; i += THREADS) {
+            const double x = a[(long long)c * ld + i_begin + i], y = b[(long long)c * ld + i_begin + i];
+            d = fmax(d, fabs(x - y)); v = fmax(v, fabs(y));
+            if (!(x == x)) d = 1e300;                      // NaN in the tensor-core result
+        }
+    sd[threadIdx.x] = d; sv[threadIdx.x] = v;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int t = 1; t < THREADS; ++t) { d = fmax(d, sd[t]); v = fmax(v, sv[t]); }
+        res[0] = d; res[1] = v;
     }
 }
 
@@ -335,7 +366,7 @@ gu_layout_probe_kernel(const __grid_constant__ CUtensorMap bmap, const float* __
     unsigned char* sb = smem + 8192;                       // n16 rows x 64 B
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 8192 + GU_B_BYTES);
     uint32_t* slot = reinterpret_cast<uint32_t*>(bars + 2);
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, r = threadIdx.x;
+    const int warp = threadIdx.x >> 5, r = threadIdx.x;
     if (threadIdx.x == 0) { mbar_init(&bars[0], 1); mbar_init(&bars[1], 1); mbar_fence_init(); }
     if (warp == 0) gu_tmem_alloc(slot, 256);
     gu_tc_fence_before();

@@ -15,6 +15,12 @@ extern "C" int cpd_timer_stop(cpd_ctx* h, float* ms) {
 extern "C" int cpd_sync(cpd_ctx* h) {
     if (!h) return fail(CPD_ERR_ARG, "null handle");
     CU(cudaStreamSynchronize(h->stream));
+    if (h->d_p2p) {          // a fused P2P exchange may have given up on a peer since the last read of the state
+        CU(cudaMemcpyAsync(h->h_pin + 40, &h->d_state->err, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+        CU(cudaStreamSynchronize(h->stream));
+        if (*reinterpret_cast<const int*>(h->h_pin + 40))
+            return fail(CPD_ERR_STATE, "a peer rank did not deliver its moments within the P2P exchange timeout");
+    }
     return CPD_OK;
 }
 extern "C" int cpd_event_record(cpd_ctx* h, int idx) {

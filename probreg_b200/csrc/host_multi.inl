@@ -63,6 +63,12 @@ extern "C" int cpd_p2p_attach(cpd_ctx* h, const char* handles, int world_size, i
     memset(&info, 0, sizeof(info));
     info.world = world_size;
     info.rank = rank;
+    // A rank waits this long for its peers' moments before it gives up (then DevState.err is set, the M-step is skipped and the
+    // next read of the state -- cpd_em_step(out), cpd_em_run, cpd_sync -- returns CPD_ERR_STATE).  Ranks running uneven host work
+    // between iterations (a slow callback on one rank) need either a bound above that or CPD_B200_NO_P2P=1 (ncclAllReduce).
+    double timeout_s = 120.0;
+    if (const char* e = getenv("CPD_B200_P2P_TIMEOUT_S")) { const double v = atof(e); if (v > 0.0) timeout_s = v; }
+    info.timeout_ns = (unsigned long long)(timeout_s * 1e9);
     for (int r = 0; r < world_size; ++r) {
         if (r == rank) { info.box[r] = h->d_box; continue; }
         cudaIpcMemHandle_t mh;

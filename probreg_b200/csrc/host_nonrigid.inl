@@ -86,6 +86,82 @@ int lr_orthonormalise_columnwise(cpd_ctx* h, double* X, int rank) {
 // dst[c][i] = sum_j G_ij src[c][j] for all `rank` columns.  The product shards over rows with one exchange: in a multi-rank
 // handle (sources replicated, identically ordered on every rank) each rank forms its contiguous share of the rows into a zeroed
 // buffer and one all-reduce -- a sum of one value and zeros, hence exact and identical everywhere -- gathers them.
+// The rows are formed on the tensor cores (gram_umma.cuh: tcgen05, TF32 x 3); CPD_B200_LR_GRAM=simt selects the CUDA-core
+// kernel the tensor-core path is checked against on its first use in a process (and which the CPU emulation build uses).
+#ifndef CPD_HOST_EMU
+int lr_gram_rows_umma(cpd_ctx* h, const double* src, double* dst, int rank, long long i_lo, long long i_hi) {
+    const long long ld = h->mpad, rows = i_hi - i_lo;
+    long long chunk = 1024;                                   // points per FP32 TMEM accumulation (error ~7e-9 per point, see DESIGN)
+    if (const char* e = getenv("CPD_B200_LR_CHUNK")) chunk = std::max<long long>(GU_KS, atoll(e) / GU_KS * GU_KS);
+    chunk = std::max(chunk, (ld / 128 + GU_KS - 1) / GU_KS * GU_KS);                // at most 128 chunk partials
+    const int nq = (int)((ld + chunk - 1) / chunk);
+    const int ntiles = (int)((rows + GU_ROWS - 1) / GU_ROWS);
+    const long long ldp = (long long)ntiles * GU_ROWS;
+    static bool attr_set = false;
+    if (!attr_set) {
+        CU(cudaFuncSetAttribute(gu_gram_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GU_SMEM));
+        attr_set = true;
+    }
+    for (int c0 = 0; c0 < rank; c0 += GU_NMAX) {
+        const int nc = std::min(GU_NMAX, rank - c0), n16 = (nc + 15) / 16 * 16;
+        const size_t need_planes = (size_t)2 * n16 * ld, need_part = (size_t)nq * n16 * ldp;
+        if (need_planes > h->gu_planes_cap) { TRY(dev_alloc(&h->d_gu_planes, need_planes)); h->gu_planes_cap = need_planes; }
+        if (need_part > h->gu_part_cap) { TRY(dev_alloc(&h->d_gu_part, need_part)); h->gu_part_cap = need_part; }
+        gu_split_kernel<<<dim3(blocks_for(ld), (unsigned)n16), THREADS, 0, h->stream>>>(src + (size_t)c0 * ld, h->m, ld, nc, n16, ld, h->d_gu_planes);
+        CUtensorMap map;
+        if (gu_make_map(&map, h->d_gu_planes, ld, 2 * n16, n16) != 0) return fail(CPD_ERR_CUDA, "cuTensorMapEncodeTiled failed");
+        gu_gram_kernel<<<h->sm_count, GU_THREADS, GU_SMEM, h->stream>>>(map, h->d_lr_pts, ld, (int)chunk, i_lo, i_hi, n16, h->d_gu_part, ldp);
+        gu_reduce_kernel<<<dim3((unsigned)((rows + 4 * THREADS - 1) / (4 * THREADS)), (unsigned)nc), THREADS, 0, h->stream>>>(
+            h->d_gu_part, nq, n16, ldp, nc, rows, i_lo, ld, dst + (size_t)c0 * ld);
+        KCHECK();
+        h->launches += 3;
+    }
+    return CPD_OK;
+}
+// exact integer-digit product (gram_i8.cuh): the default
+int lr_gram_rows_i8(cpd_ctx* h, const double* src, double* dst, int rank, long long i_lo, long long i_hi) {
+    const long long ld = h->mpad, rows = i_hi - i_lo;
+    const long long chunk = std::min<long long>(GI_MAX_CHUNK, ld);          // ld is a multiple of 512, hence of GI_KS
+    const int nq = (int)((ld + chunk - 1) / chunk);
+    const int ntiles = (int)((rows + GI_ROWS - 1) / GI_ROWS);
+    const long long ldp = (long long)ntiles * GI_ROWS;
+    static bool attr_set = false;
+    if (!attr_set) {
+        CU(cudaFuncSetAttribute(gi_gram_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GI_SMEM));
+        attr_set = true;
+    }
+    const int passes = (rank + GI_NMAX - 1) / GI_NMAX, per = (rank + passes - 1) / passes;
+    const size_t ncm = (size_t)rank + GI_NMAX + 16;
+    if (ncm > h->gi_colmax_cap) { TRY(dev_alloc(&h->d_gi_colmax, ncm)); h->gi_colmax_cap = ncm; }
+    CU(cudaMemsetAsync(h->d_gi_colmax, 0, ncm * sizeof(double), h->stream));
+    gi_colmax_kernel<<<(unsigned)rank, THREADS, 0, h->stream>>>(src, h->m, ld, h->d_gi_colmax);
+    h->launches += 1;
+    for (int c0 = 0; c0 < rank; c0 += per) {
+        const int nc = std::min(per, rank - c0), n16 = (nc + 15) / 16 * 16;
+        const size_t need_planes = (size_t)3 * n16 * ld, need_part = (size_t)nq * n16 * ldp;
+        if (need_planes > h->gi_planes_cap) { TRY(dev_alloc(&h->d_gi_planes, need_planes)); h->gi_planes_cap = need_planes; }
+        if (need_part > h->gi_part_cap) { TRY(dev_alloc(&h->d_gi_part, need_part)); h->gi_part_cap = need_part; }
+        gi_split_kernel<<<dim3(blocks_for(ld), (unsigned)n16), THREADS, 0, h->stream>>>(src + (size_t)c0 * ld, h->m, ld, nc, n16, ld,
+                                                                                     h->d_gi_colmax + c0, h->d_gi_planes);
+        CUtensorMap map;
+        if (gi_make_map(&map, h->d_gi_planes, ld, 3 * n16, n16) != 0) return fail(CPD_ERR_CUDA, "cuTensorMapEncodeTiled failed");
+        gi_gram_kernel<<<h->sm_count, GI_THREADS, GI_SMEM, h->stream>>>(map, h->d_lr_pts, ld, (int)chunk, i_lo, i_hi, n16, h->d_gi_colmax + c0,
+                                                                       h->d_gi_part, ldp);
+        gi_reduce_kernel<<<dim3(blocks_for(rows), (unsigned)nc), THREADS, 0, h->stream>>>(h->d_gi_part, nq, n16, ldp, nc, rows, i_lo, ld,
+                                                                                           dst + (size_t)c0 * ld);
+        KCHECK();
+        h->launches += 3;
+    }
+    return CPD_OK;
+}
+#endif
+int lr_gram_rows_simt(cpd_ctx* h, const double* src, double* dst, int rank, long long i_lo, long long i_hi) {
+    dim3 grid(blocks_for(i_hi - i_lo), (unsigned)((rank + LR_COLS - 1) / LR_COLS));
+    lr_gram_apply_kernel<<<grid, THREADS, 0, h->stream>>>(h->d_lr_pts, h->m, h->mpad, src, h->mpad, rank, dst, i_lo, i_hi);
+    KCHECK();
+    h->launches += 1;
+    return CPD_OK;
+}
 int lr_gram_apply(cpd_ctx* h, const double* src, double* dst, int rank) {
     long long i_lo = 0, i_hi = h->m;
     const bool shard = h->comm != nullptr && h->world > 1;
@@ -95,10 +171,43 @@ int lr_gram_apply(cpd_ctx* h, const double* src, double* dst, int rank) {
         CU(cudaMemsetAsync(dst, 0, (size_t)rank * h->mpad * sizeof(double), h->stream));
     }
     if (i_hi > i_lo) {
-        dim3 grid(blocks_for(i_hi - i_lo), (unsigned)((rank + LR_COLS - 1) / LR_COLS));
-        lr_gram_apply_kernel<<<grid, THREADS, 0, h->stream>>>(h->d_lr_pts, h->m, h->mpad, src, h->mpad, rank, dst, i_lo, i_hi);
-        KCHECK();
-        h->launches += 1;
+#ifdef CPD_HOST_EMU
+        TRY(lr_gram_rows_simt(h, src, dst, rank, i_lo, i_hi));
+#else
+        // 0: tensor cores, exact integer digits (default); 1: CUDA cores (FP32); 2: tensor cores, TF32 x 3 (FP32 TMEM accumulation:
+        // ~1e-5 relative, measured -- kept for comparison, profiles/r2_umma_*)
+        static int mode = -1;
+        static bool checked = false;
+        if (mode < 0) {
+            const char* e = getenv("CPD_B200_LR_GRAM");
+            mode = (e && !strcmp(e, "simt")) ? 1 : ((e && !strcmp(e, "tf32")) ? 2 : 0);
+        }
+        if (mode == 1) {
+            TRY(lr_gram_rows_simt(h, src, dst, rank, i_lo, i_hi));
+        } else {
+            if (mode == 2) TRY(lr_gram_rows_umma(h, src, dst, rank, i_lo, i_hi));
+            else TRY(lr_gram_rows_i8(h, src, dst, rank, i_lo, i_hi));
+            if (!checked) {
+                // first use in this process: the first rows of the first <= 16 columns once more on the CUDA cores.  A mismatch
+                // is an error (a wrong descriptor or swizzle shows as O(1) differences), never a silent change of path.
+                const long long rows = std::min<long long>(i_hi - i_lo, 256);
+                const int cols = std::min(rank, LR_COLS);
+                DevBuf<double> ref, res;
+                TRY(ref.alloc((size_t)cols * h->mpad));
+                TRY(res.alloc(2));
+                TRY(lr_gram_rows_simt(h, src, ref.p, cols, i_lo, i_lo + rows));
+                gu_compare_kernel<<<1, THREADS, 0, h->stream>>>(dst, ref.p, h->mpad, i_lo, rows, cols, res.p);
+                KCHECK();
+                double r[2] = {0.0, 0.0};
+                CU(cudaMemcpyAsync(r, res.p, sizeof(r), cudaMemcpyDeviceToHost, h->stream));
+                CU(cudaStreamSynchronize(h->stream));
+                h->launches += 1;
+                if (!(r[0] <= (mode == 2 ? 1e-4 : 5e-6) * r[1] + 1e-300))
+                    return fail(CPD_ERR_CUDA, "tensor-core G X product disagrees with the CUDA-core kernel: max |diff| %.3e, max |value| %.3e", r[0], r[1]);
+                checked = true;
+            }
+        }
+#endif
     }
     if (shard) TRY(allreduce(h, dst, (size_t)rank * h->mpad));
     return CPD_OK;
@@ -127,6 +236,7 @@ int lr_orthonormalise(cpd_ctx* h, double* X, int rank) {
     double* W0 = C + (size_t)LR_MAX_RANK * LR_PANEL;        // Gram matrix of the panel as it arrived (its diagonal: arrival norms)
     double* W = W0 + LR_PANEL * LR_PANEL;
     double* T = W + LR_PANEL * LR_PANEL;
+    double* scale2 = T + LR_PANEL * LR_PANEL;               // [LR_PANEL]: see lr_panel_chol_kernel
     for (int j0 = 0; j0 < rank; j0 += LR_PANEL) {
         const int np = std::min(LR_PANEL, rank - j0);
         double* P = X + (size_t)j0 * ld;
@@ -138,7 +248,7 @@ int lr_orthonormalise(cpd_ctx* h, double* X, int rank) {
                 h->launches += 1;
             }
             TRY(lr_inner(h, P, np, ld, P, np, ld, nullptr, 1, W));
-            lr_panel_chol_kernel<<<1, 32, 0, h->stream>>>(W, np, pass == 0 ? W0 : nullptr, np + 1, T);
+            lr_panel_chol_kernel<<<1, 32, 0, h->stream>>>(W, np, W0, np + 1, pass == 0 ? 1 : 0, scale2, T);
             lr_panel_apply_kernel<<<nb, THREADS, 0, h->stream>>>(X, m, ld, j0, np, T);
             h->launches += 2;
         }
@@ -193,7 +303,7 @@ extern "C" int cpd_nonrigid_lowrank_begin(cpd_ctx* h, double beta, double lmd, d
         TRY(dev_alloc(&h->d_lr_coef, (size_t)3 * LR_SLICES * (rank + 1)));
         h->lr_part_cap = std::max<size_t>((size_t)LR_SLICES * rank * rank, (size_t)64 * LR_PANEL * LR_MAX_RANK / 8);
         TRY(dev_alloc(&h->d_lr_part, h->lr_part_cap));
-        TRY(dev_alloc(&h->d_lr_panel, (size_t)LR_MAX_RANK * LR_PANEL + 3 * LR_PANEL * LR_PANEL));
+        TRY(dev_alloc(&h->d_lr_panel, (size_t)LR_MAX_RANK * LR_PANEL + 3 * LR_PANEL * LR_PANEL + LR_PANEL));
         TRY(dev_alloc(&h->d_lr_Bc, (size_t)rank * rank));
         TRY(dev_alloc(&h->d_lr_S, (size_t)rank * rank));
         TRY(dev_alloc(&h->d_lr_R, (size_t)rank * 3));

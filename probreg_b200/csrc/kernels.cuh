@@ -146,6 +146,7 @@ struct P2PInfo {
     P2PMailbox* box[P2P_MAX];     // box[r]: rank r's mailbox mapped into this process (box[rank] is local memory)
     int world, rank;
     unsigned long long seq;       // exchanges completed
+    unsigned long long timeout_ns;   // how long a rank waits for its peers' moments (wall clock, %globaltimer); see cpd_p2p_attach
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -1237,8 +1238,10 @@ moments_kernel(DevState* st, const double* __restrict__ part_a, int nb_a, int ka
     const int k = threadIdx.x & 31, w = threadIdx.x >> 5;
     double s = 0.0;
     if (k < ka) {
-        for (int b = w; b < nb_a; b += 8) s += part_a[(size_t)b * ka + k];
+#pragma unroll 8
+        for (int b = w; b < nb_a; b += 8) s += part_a[(size_t)b * ka + k];      // unrolled: 8 loads in flight, summed in the same order
     } else if (k < ka + kb) {
+#pragma unroll 8
         for (int b = w; b < nb_b; b += 8) s += part_b[(size_t)b * kb + (k - ka)];
     }
     sh[w][k] = s;
@@ -1295,8 +1298,10 @@ moments_p2p_kernel(DevState* st, const double* __restrict__ part_a, int nb_a, in
     const int k = threadIdx.x & 31, w = threadIdx.x >> 5;
     double s = 0.0;
     if (k < ka) {
-        for (int b = w; b < nb_a; b += 8) s += part_a[(size_t)b * ka + k];
+#pragma unroll 8
+        for (int b = w; b < nb_a; b += 8) s += part_a[(size_t)b * ka + k];      // unrolled: 8 loads in flight, summed in the same order
     } else if (k < ka + kb) {
+#pragma unroll 8
         for (int b = w; b < nb_b; b += 8) s += part_b[(size_t)b * kb + (k - ka)];
     }
     sh[w][k] = s;
@@ -1318,10 +1323,12 @@ moments_p2p_kernel(DevState* st, const double* __restrict__ part_a, int nb_a, in
     if ((int)threadIdx.x < world) {
         st_release_sys(&info->box[threadIdx.x]->flags[par][rank], seq);
         const unsigned long long* f = &info->box[rank]->flags[par][threadIdx.x];
-        long long spins = 0;
+        // wall-clock bound (a spin count would depend on the clock and on time slicing): ranks are only loosely synchronised by
+        // their host loops, so a peer may legitimately be late by as long as its slowest per-iteration callback
+        const unsigned long long t0 = globaltimer_ns(), limit = info->timeout_ns;
         while (ld_acquire_sys(f) < seq) {
             __nanosleep(64);
-            if (++spins > 4000000ll) { timeout = 1; break; }        // seconds: a peer is gone; fail instead of hanging the GPU
+            if (globaltimer_ns() - t0 > limit) { timeout = 1; break; }     // a peer is gone: fail instead of hanging the GPU
         }
     }
     __syncthreads();
@@ -1332,8 +1339,8 @@ moments_p2p_kernel(DevState* st, const double* __restrict__ part_a, int nb_a, in
         __syncwarp();
         if (k == 0) {
             info->seq = seq;
-            if (timeout) st->err = 1;
-            mstep_solve_residual(st, mom);
+            if (timeout) st->err = 1;                   // incomplete sums: the state is left as it was; the host reports the error
+            else if (st->err == 0) mstep_solve_residual(st, mom);      // (and every later step of a failed run is a no-op)
         }
     }
 }

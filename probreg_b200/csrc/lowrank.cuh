@@ -159,9 +159,8 @@ lr_scale_kernel(double* __restrict__ X, long long m, long long ld, int j, int st
 // column twice on its own (lr_orthonormalise_columnwise), with 16 launches per 16 columns instead of 96 and each finished column
 // read 4 times per PANEL instead of 4 times per COLUMN (the column-wise version moved 32 GB at M = 50k, K = 200).
 // Rank decisions (a dropped column becomes exactly zero and stays zero in every later product, like before):
-//   * nothing left after (a): norm^2 <= 1e-28 of the norm^2 the column arrived with -- the column-wise rule;
-//   * nearly dependent INSIDE its panel: Cholesky pivot <= 1e-10 of the column's own norm^2 after (a).  A direction of relative weight
-//     < 1e-5 next to its panel neighbours; G itself is only float32-accurate (cc/math_utils.cc:17-19), so nothing real is lost.
+//   * nothing left after (a): norm^2 <= 1e-28 of the norm^2 the column arrived with -- the rule of the column-wise version;
+//   * the same rule once more at (d), on what is left after the panel's own projections (lr_panel_chol_kernel).
 constexpr int LR_PANEL = 16;
 constexpr int LR_UPD_KC = 128;     // finished columns per shared-memory chunk of lr_panel_update_kernel
 
@@ -197,38 +196,51 @@ lr_panel_update_kernel(double* __restrict__ X, long long m, long long ld, int j0
     }
 }
 
-// One CTA: T = R^-1 (upper triangular, row-major [LR_PANEL][LR_PANEL]) with W = R^T R the panel's Gram matrix (row-major
-// [np][np]); n0 = the norm^2 each column arrived with (null: use W's own diagonal).  Dropped columns get a zero column in T.
+// One CTA: T (upper triangular, row-major [LR_PANEL][LR_PANEL]) such that P T has orthonormal columns, from the panel's Gram
+// matrix W (row-major [np][np]) by a Cholesky factorisation W = R^T R, T = R^-1.
+//   first = 1 (step b):  n0 = the norm^2 each column arrived with (diagonal of the arrival Gram matrix, stride n0_stride).
+//       A column with nothing left after (a) (norm^2 <= 1e-28 n0) is dropped.  A column whose pivot is lost in the cancellation
+//       (<= 1e-13 of its norm^2: it lies in the span of its panel predecessors up to ~3e-7) is still projected with the computed
+//       coefficients -- which removes the predecessors to rounding level -- but scaled by a guess and left out of the
+//       factorisation of the later columns; step (d) sees it well separated and measures what is really left.
+//       scale2[p] = the square of the factor column p was multiplied with.
+//   first = 0 (step d):  scale2 from (b) turns the diagonal of W back into the column's remaining norm^2 in arrival units; the
+//       column-wise rule (kept iff that is > 1e-28 n0) decides.  Dropped columns get a zero column in T and stay exactly zero.
 __global__ void __launch_bounds__(32)
-lr_panel_chol_kernel(const double* __restrict__ W, int np, const double* __restrict__ n0, int n0_stride, double* __restrict__ T) {
+lr_panel_chol_kernel(const double* __restrict__ W, int np, const double* __restrict__ n0, int n0_stride, int first,
+                     double* __restrict__ scale2, double* __restrict__ T) {
     __shared__ double R[LR_PANEL][LR_PANEL], Ti[LR_PANEL][LR_PANEL];
-    __shared__ int live[LR_PANEL];
+    __shared__ int live[LR_PANEL];          // 1: part of the factorisation, 2: projected and rescaled only, 0: dropped
     const int t = threadIdx.x;
     if (t == 0) {
         for (int a = 0; a < LR_PANEL; ++a)
             for (int b = 0; b < LR_PANEL; ++b) { R[a][b] = 0.0; Ti[a][b] = 0.0; }
         for (int p = 0; p < np; ++p) {
             const double wpp = W[(size_t)p * np + p];
-            const double arrived = n0 ? n0[(size_t)p * n0_stride] : wpp;
+            const double arrived = n0[(size_t)p * n0_stride];
             double piv = wpp;
             for (int q = 0; q < p; ++q) piv -= R[q][p] * R[q][p];
-            const bool ok = wpp > 1e-280 && wpp > 1e-28 * arrived && piv > 1e-10 * wpp;
-            live[p] = ok ? 1 : 0;
-            if (!ok) continue;
-            const double rpp = sqrt(piv);
+            int state;
+            if (first) state = !(wpp > 1e-280 && wpp > 1e-28 * arrived) ? 0 : (piv > 1e-13 * wpp ? 1 : 2);
+            else state = (wpp > 1e-280 && wpp / scale2[p] > 1e-28 * arrived && piv > 1e-13 * wpp) ? 1 : 0;
+            live[p] = state;
+            if (state == 0) { if (first) scale2[p] = 1.0; continue; }
+            const double rpp = state == 1 ? sqrt(piv) : sqrt(1e-20 * wpp);
             R[p][p] = rpp;
+            if (first) scale2[p] = 1.0 / (rpp * rpp);
+            if (state == 2) continue;                     // row p of R stays zero: later columns are not measured against it
             for (int b = p + 1; b < np; ++b) {
                 double v = W[(size_t)p * np + b];
                 for (int q = 0; q < p; ++q) v -= R[q][p] * R[q][b];
                 R[p][b] = v / rpp;
             }
         }
-        // T = R^-1 restricted to the live columns: back substitution column by column
+        // T = R^-1 over the kept columns: back substitution column by column (rows of dropped / rescaled-only columns are zero)
         for (int b = 0; b < np; ++b) {
             if (!live[b]) continue;
             Ti[b][b] = 1.0 / R[b][b];
             for (int a = b - 1; a >= 0; --a) {
-                if (!live[a]) continue;
+                if (live[a] != 1) continue;
                 double v = 0.0;
                 for (int q = a + 1; q <= b; ++q) v -= R[a][q] * Ti[q][b];
                 Ti[a][b] = v / R[a][a];

@@ -82,6 +82,9 @@ cudaError_t cudaStreamDestroy(cudaStream_t s);
 cudaError_t cudaStreamSynchronize(cudaStream_t s);
 cudaError_t cudaDeviceSynchronize();
 cudaError_t cudaEventCreate(cudaEvent_t* e);
+enum { cudaEventDisableTiming = 2 };
+static inline cudaError_t cudaEventCreateWithFlags(cudaEvent_t* e, unsigned) { return cudaEventCreate(e); }
+typedef struct emu_graph_exec* cudaGraphExec_t;      // never instantiated: the EM graph is a device-build feature
 cudaError_t cudaEventDestroy(cudaEvent_t e);
 cudaError_t cudaEventRecord(cudaEvent_t e, cudaStream_t s = nullptr);
 cudaError_t cudaEventSynchronize(cudaEvent_t e);

@@ -143,8 +143,11 @@ def test_parity_survives_a_mufu_like_ex2(emu_lib_path):
 
 
 def test_emulation_is_not_reachable_from_the_package(emu_lib_path):
-    """The package loads probreg_b200/libcpd_b200.so (or CPD_B200_LIB) and nothing else; the emulation lives under tests/."""
+    """The package loads probreg_b200/libcpd_b200.so (or another build of it named by CPD_B200_LIB) and nothing else; pointing
+    CPD_B200_LIB at the emulation is refused (a subprocess, so that this process's loaded library is untouched)."""
     import os
+    import subprocess
+    import sys
 
     from probreg_b200 import _cabi
 
@@ -154,4 +157,11 @@ def test_emulation_is_not_reachable_from_the_package(emu_lib_path):
     for f in os.listdir(pkg):
         if f.endswith(".py"):
             text = open(os.path.join(pkg, f)).read()
-            assert "tests/emu" not in text and "_emu" not in text and "is_emulation" not in text, f
+            assert "tests/emu" not in text and "_emu." not in text and "emu_" not in text, f       # no path to the emulation build
+    env = dict(os.environ, CPD_B200_LIB=emu_lib_path)
+    code = ("from probreg_b200 import _cabi\n"
+            "try:\n    _cabi.lib()\n    print('LOADED')\n"
+            "except _cabi.CpdError as e:\n    print('REFUSED', 'emulation' in str(e))\n")
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=env, timeout=120,
+                       cwd=os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    assert r.stdout.strip() == "REFUSED True", r.stdout + r.stderr

@@ -8,6 +8,8 @@ oracle run on the SAME approximate G = Q Bc Q^T, where only rounding separates t
 CPU tests run the library under the emulation of tests/emu; the gpu-marked ones call the real library (first hardware run: round 2,
 profiles/r2_pytest_runxfail_first.txt -- the one failure there was the iteration count of the config-5 property test, see below).
 """
+import os
+
 import numpy as np
 import pytest
 
@@ -256,6 +258,47 @@ def test_sliced_dot_products_give_the_same_basis_emulated(emulated, monkeypatch)
     np.testing.assert_allclose(qs.T.dot(qs), np.identity(24), atol=1e-12)
     np.testing.assert_allclose(qs.dot(sliced.transformation.bcore).dot(qs.T), qb.dot(base.transformation.bcore).dot(qb.T), atol=2e-6)
     assert sliced.sigma2 == pytest.approx(base.sigma2, rel=1e-6)       # the trailing columns are rounding noise: another summation order, another noise basis
+
+
+def _check_blocked_orthonormalisation(m, rank):
+    """The blocked orthonormalisation (panels of 16 columns, Cholesky inside the panel) against the column-wise one it replaced
+    (CPD_B200_LR_ORTH=columnwise), at a rank beyond the numerical rank of G so that columns get dropped and Cholesky pivots get lost:
+    same kept / dropped decision per column, orthonormal kept columns, the same G ~= Q Bc Q^T."""
+    src, tgt = _deformed_pair(m)
+    h = _cabi.Handle(3)
+    h.set_source(src)
+    h.set_target(tgt)
+    h.nonrigid_lowrank_begin(2.0, 2.0, 0.05, 0.0, rank, 1, 3)
+    qb, bb = h.nonrigid_lowrank_factors()
+    os.environ["CPD_B200_LR_ORTH"] = "columnwise"
+    try:
+        h2 = _cabi.Handle(3)
+        h2.set_source(src)
+        h2.set_target(tgt)
+        h2.nonrigid_lowrank_begin(2.0, 2.0, 0.05, 0.0, rank, 1, 3)
+        qc, bc = h2.nonrigid_lowrank_factors()
+    finally:
+        del os.environ["CPD_B200_LR_ORTH"]
+    gram = qb.T.dot(qb)
+    d = np.diag(gram)
+    assert np.all((np.abs(d - 1.0) < 1e-11) | (d == 0.0))
+    np.testing.assert_allclose(gram - np.diag(d), 0.0, atol=1e-11)
+    dc = np.diag(qc.T.dot(qc))
+    assert abs(int((d == 0).sum()) - int((dc == 0).sum())) <= 1          # a column at the 1e-14 threshold may fall either way
+    np.testing.assert_allclose(qb.dot(bb).dot(qb.T), qc.dot(bc).dot(qc.T), atol=2e-6)
+    return int((d == 0).sum())
+
+
+def test_blocked_orthonormalisation_emulated(emulated):
+    _check_blocked_orthonormalisation(300, 70)
+    _check_blocked_orthonormalisation(150, 150)                           # K = M: every direction, most of them rounding noise
+
+
+@pytest.mark.gpu
+@pytest.mark.timeout(600)
+def test_blocked_orthonormalisation_gpu():
+    _check_blocked_orthonormalisation(3000, 200)
+    _check_blocked_orthonormalisation(400, 400)
 
 
 @pytest.mark.gpu

@@ -13,6 +13,7 @@
 
 #include "lowrank.cuh"
 #include "gram_umma.cuh"
+#include "gram_i8.cuh"
 
 using namespace cpd;
 
@@ -134,7 +135,7 @@ static int full_test(long long m, int rank, int chunk, double beta, bool time_ol
         cudaEventRecord(e1);
         gu_gram_kernel<<<sms, GU_THREADS, GU_SMEM>>>(map, dPts, mpad, chunk, 0, m, n16, dPart, ldp);
         cudaEventRecord(e2);
-        gu_reduce_kernel<<<dim3((unsigned)((m + THREADS - 1) / THREADS), rank), THREADS>>>(dPart, nq, n16, ldp, rank, m, 0, mpad, dOutNew);
+        gu_reduce_kernel<<<dim3((unsigned)((m + 4 * THREADS - 1) / (4 * THREADS)), rank), THREADS>>>(dPart, nq, n16, ldp, rank, m, 0, mpad, dOutNew);
         cudaEventRecord(e3);
         CK(cudaGetLastError());
         CK(cudaDeviceSynchronize());
@@ -186,19 +187,202 @@ static int full_test(long long m, int rank, int chunk, double beta, bool time_ol
     return (en / scale < 2e-5) ? 0 : 4;
 }
 
+// ---- kind::i8 (gram_i8.cuh): exact integer results, so every comparison is for equality --------------------------------------------
+static int run_layout_i8(int n16, const std::vector<unsigned char>& A, const std::vector<signed char>& B, std::vector<int>& D) {
+    unsigned char* dA; signed char* dB; int* dD;
+    CK(cudaMalloc(&dA, 128 * 32)); CK(cudaMalloc(&dB, (size_t)n16 * 32)); CK(cudaMalloc(&dD, (size_t)128 * n16 * 4));
+    CK(cudaMemcpy(dA, A.data(), 128 * 32, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(dB, B.data(), (size_t)n16 * 32, cudaMemcpyHostToDevice));
+    CK(cudaMemset(dD, 0x7f, (size_t)128 * n16 * 4));
+    CUtensorMap map;
+    if (gi_make_map(&map, dB, 32, n16, n16) != 0) { printf("i8 tensor map encode failed\n"); return 1; }
+    CK(cudaFuncSetAttribute(gi_layout_probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 20000));
+    gi_layout_probe_kernel<<<1, 128, 20000>>>(map, dA, n16, dD);
+    CK(cudaGetLastError());
+    CK(cudaDeviceSynchronize());
+    D.resize((size_t)128 * n16);
+    CK(cudaMemcpy(D.data(), dD, D.size() * 4, cudaMemcpyDeviceToHost));
+    cudaFree(dA); cudaFree(dB); cudaFree(dD);
+    const int tc = timeout_code();
+    if (tc) { printf("i8 layout probe: wait %d timed out\n", tc); return 2; }
+    return 0;
+}
+static int layout_tests_i8() {
+    unsigned long long seed = 4242;
+    int bad = 0;
+    for (int n16 : {16, 112, 256}) {
+        std::vector<unsigned char> A(128 * 32);
+        std::vector<signed char> B((size_t)n16 * 32);
+        std::vector<int> D;
+        for (auto& v : A) v = (unsigned char)(urand(seed) * 256.0);
+        for (auto& v : B) v = (signed char)((int)(urand(seed) * 256.0) - 128);
+        const int rc = run_layout_i8(n16, A, B, D);
+        if (rc) return rc;
+        long long wrong = 0;
+        for (int r = 0; r < 128; ++r)
+            for (int n = 0; n < n16; ++n) {
+                int s = 0;
+                for (int k = 0; k < 32; ++k) s += (int)A[r * 32 + k] * (int)B[n * 32 + k];
+                wrong += s != D[(size_t)r * n16 + n];
+            }
+        printf("i8 layout n=%3d: %lld of %d entries differ from the integer reference   %s\n", n16, wrong, 128 * n16, wrong ? "MISMATCH" : "OK");
+        if (wrong) bad = 1;
+    }
+    if (bad) {
+        // decode: B = identity rows (B[n][k] = (n == k), n < 32), A[r][k] = (8 r + k) % 251: D[r][n] shows which A byte sat at (r, k = n)
+        const int n16 = 32;
+        std::vector<unsigned char> A(128 * 32);
+        std::vector<signed char> B((size_t)n16 * 32, 0);
+        std::vector<int> D;
+        for (int r = 0; r < 128; ++r) for (int k = 0; k < 32; ++k) A[r * 32 + k] = (unsigned char)((r & 7) * 32 + k);
+        for (int n = 0; n < 32; ++n) B[n * 32 + n] = 1;
+        if (run_layout_i8(n16, A, B, D) == 0) {
+            printf("decode A (identity B): D[r][n] should be 32 (r %% 8) + n; as (row %% 8, k) read:\n");
+            for (int r : {0, 1, 2, 3, 4, 5, 6, 7, 8, 12, 127}) {
+                printf("  r=%3d:", r);
+                for (int n = 0; n < 32; ++n) printf(" (%d,%d)", D[(size_t)r * n16 + n] / 32, D[(size_t)r * n16 + n] % 32);
+                printf("\n");
+            }
+        }
+        for (int r = 0; r < 128; ++r) for (int k = 0; k < 32; ++k) A[r * 32 + k] = (r % 32 == k) ? 1 : 0;
+        for (int n = 0; n < 32; ++n) for (int k = 0; k < 32; ++k) B[n * 32 + k] = (signed char)((n & 3) * 32 + k - 64);
+        if (run_layout_i8(n16, A, B, D) == 0) {
+            printf("decode B (identity-pattern A): D[r][n] should be 32 (n %% 4) + r %% 32 - 64; rows 0..7:\n");
+            for (int r = 0; r < 8; ++r) {
+                printf("  r=%3d:", r);
+                for (int n = 0; n < 32; ++n) printf(" %d", D[(size_t)r * n16 + n] + 64);
+                printf("\n");
+            }
+        }
+    }
+    return bad ? 3 : 0;
+}
+
+static int full_test_i8(long long m, int rank, double beta, bool time_old, int xkind) {
+    const long long mpad = (m + 511) / 512 * 512;
+    unsigned long long seed = 999;
+    std::vector<double> Y((size_t)m * 3), X((size_t)rank * mpad, 0.0);
+    for (long long i = 0; i < m; ++i) { Y[3 * i] = urand(seed); Y[3 * i + 1] = 0.6 * urand(seed); Y[3 * i + 2] = 0.3 * urand(seed); }
+    for (int c = 0; c < rank; ++c)
+        for (long long j = 0; j < m; ++j) {
+            double v = 2.0 * urand(seed) - 1.0;
+            if (xkind == 1) v *= exp(-12.0 * urand(seed)) * (1.0 + c);          // entries over 5 decades, columns of different scale
+            X[(size_t)c * mpad + j] = v;
+        }
+    double *dY, *dX, *dOutNew, *dOutOld, *dColmax, *dPart;
+    float4* dPts;
+    signed char* dPlanes;
+    const long long chunk = mpad < GI_MAX_CHUNK ? mpad : GI_MAX_CHUNK;
+    const int nq = (int)((mpad + chunk - 1) / chunk), ntiles = (int)((m + GI_ROWS - 1) / GI_ROWS);
+    const long long ldp = (long long)ntiles * GI_ROWS;
+    const int passes = (rank + GI_NMAX - 1) / GI_NMAX, per = (rank + passes - 1) / passes, n16max = (per + 15) / 16 * 16;
+    CK(cudaMalloc(&dY, (size_t)m * 3 * 8)); CK(cudaMalloc(&dX, (size_t)rank * mpad * 8));
+    CK(cudaMalloc(&dOutNew, (size_t)rank * mpad * 8)); CK(cudaMalloc(&dOutOld, (size_t)rank * mpad * 8));
+    CK(cudaMalloc(&dPts, (size_t)mpad * 16));
+    CK(cudaMalloc(&dPlanes, (size_t)3 * n16max * mpad));
+    CK(cudaMalloc(&dPart, (size_t)nq * n16max * ldp * 8));
+    CK(cudaMalloc(&dColmax, (size_t)(rank + 256) * 8));
+    CK(cudaMemset(dColmax, 0, (size_t)(rank + 256) * 8));
+    CK(cudaMemcpy(dY, Y.data(), (size_t)m * 3 * 8, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(dX, X.data(), (size_t)rank * mpad * 8, cudaMemcpyHostToDevice));
+    lr_pack_kernel<<<(unsigned)((mpad + THREADS - 1) / THREADS), THREADS>>>(dY, 0.0, 0.0, 0.0, m, mpad, (float)sqrt(LOG2E / (2.0 * beta)), dPts);
+    CK(cudaFuncSetAttribute(gi_gram_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GI_SMEM));
+    int sms = 148;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, 0);
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0); cudaEventCreate(&e1);
+    float t_all = 0, t_gram = 0;
+    for (int rep = 0; rep < 3; ++rep) {
+        t_gram = 0;
+        cudaEventRecord(e0);
+        gi_colmax_kernel<<<rank, THREADS>>>(dX, m, mpad, dColmax);
+        for (int c0 = 0; c0 < rank; c0 += per) {
+            const int nc = per < rank - c0 ? per : rank - c0, n16 = (nc + 15) / 16 * 16;
+            gi_split_kernel<<<dim3((unsigned)((mpad + THREADS - 1) / THREADS), n16), THREADS>>>(dX + (size_t)c0 * mpad, m, mpad, nc, n16, mpad, dColmax + c0, dPlanes);
+            CUtensorMap map;
+            if (gi_make_map(&map, dPlanes, mpad, 3 * n16, n16) != 0) { printf("i8 map encode failed\n"); return 1; }
+            cudaEvent_t g0, g1; cudaEventCreate(&g0); cudaEventCreate(&g1);
+            cudaEventRecord(g0);
+            gi_gram_kernel<<<sms, GI_THREADS, GI_SMEM>>>(map, dPts, mpad, (int)chunk, 0, m, n16, dColmax + c0, dPart, ldp);
+            cudaEventRecord(g1);
+            gi_reduce_kernel<<<dim3((unsigned)((m + THREADS - 1) / THREADS), nc), THREADS>>>(dPart, nq, n16, ldp, nc, m, 0, mpad, dOutNew + (size_t)c0 * mpad);
+            CK(cudaGetLastError());
+            CK(cudaDeviceSynchronize());
+            float tg = 0; cudaEventElapsedTime(&tg, g0, g1); t_gram += tg;
+            cudaEventDestroy(g0); cudaEventDestroy(g1);
+        }
+        cudaEventRecord(e1);
+        CK(cudaDeviceSynchronize());
+        cudaEventElapsedTime(&t_all, e0, e1);
+        const int tc = timeout_code();
+        if (tc) { printf("i8 full kernel: wait %d timed out\n", tc); return 2; }
+    }
+    printf("i8: m=%lld rank=%d (%d passes of N=%d) beta=%g xkind=%d: gram kernels %.3f ms, whole product (incl. split/reduce and host syncs) %.3f ms; "
+           "%.1f TFLOP/s useful\n", m, rank, passes, n16max, beta, xkind, t_gram, t_all, 2.0 * m * m * rank / (t_gram * 1e-3) / 1e12);
+    float t_old = 0;
+    if (time_old) {
+        cudaEventRecord(e0);
+        lr_gram_apply_kernel<<<dim3((unsigned)((m + THREADS - 1) / THREADS), (unsigned)((rank + LR_COLS - 1) / LR_COLS)), THREADS>>>(
+            dPts, m, mpad, dX, mpad, rank, dOutOld, 0, m);
+        cudaEventRecord(e1);
+        CK(cudaDeviceSynchronize());
+        cudaEventElapsedTime(&t_old, e0, e1);
+    }
+    std::vector<double> on((size_t)rank * mpad), oo((size_t)rank * mpad);
+    CK(cudaMemcpy(on.data(), dOutNew, on.size() * 8, cudaMemcpyDeviceToHost));
+    if (time_old) CK(cudaMemcpy(oo.data(), dOutOld, oo.size() * 8, cudaMemcpyDeviceToHost));
+    std::vector<float4> P(mpad);
+    CK(cudaMemcpy(P.data(), dPts, (size_t)mpad * 16, cudaMemcpyDeviceToHost));
+    const int nsample = 32;
+    double en = 0, eo = 0;      // per column: max |err| / max |value| of that column, then the max over columns
+    std::vector<double> ref((size_t)nsample * rank), colscale(rank, 0.0);
+    std::vector<long long> rowsel(nsample);
+    for (int s = 0; s < nsample; ++s) {
+        const long long i = (s == 0) ? 0 : (s == 1 ? m - 1 : (long long)(urand(seed) * m));
+        rowsel[s] = i;
+        for (int c = 0; c < rank; ++c) ref[(size_t)s * rank + c] = 0.0;
+        for (long long j = 0; j < m; ++j) {
+            const float dx = P[i].x - P[j].x, dy = P[i].y - P[j].y, dz = P[i].z - P[j].z;
+            const double g = exp2(-(double)fmaf(dz, dz, fmaf(dy, dy, dx * dx)));
+            for (int c = 0; c < rank; ++c) ref[(size_t)s * rank + c] += g * X[(size_t)c * mpad + j];
+        }
+        for (int c = 0; c < rank; ++c) colscale[c] = fmax(colscale[c], fabs(ref[(size_t)s * rank + c]));
+    }
+    for (int s = 0; s < nsample; ++s)
+        for (int c = 0; c < rank; ++c) {
+            const double r = ref[(size_t)s * rank + c];
+            en = fmax(en, fabs(on[(size_t)c * mpad + rowsel[s]] - r) / colscale[c]);
+            if (time_old) eo = fmax(eo, fabs(oo[(size_t)c * mpad + rowsel[s]] - r) / colscale[c]);
+        }
+    printf("   accuracy on %d rows, per column relative to the column's largest sampled |value|: int8 digits %.3e   CUDA-core FP32 %.3e (%.3f ms)\n",
+           nsample, en, eo, t_old);
+    cudaFree(dY); cudaFree(dX); cudaFree(dOutNew); cudaFree(dOutOld); cudaFree(dPts); cudaFree(dPlanes); cudaFree(dPart); cudaFree(dColmax);
+    return en < 2e-6 ? 0 : 4;
+}
+
 int main(int argc, char** argv) {
     const long long m = argc > 1 ? atoll(argv[1]) : 50000;
     const int rank = argc > 2 ? atoi(argv[2]) : 200;
     const int chunk = argc > 3 ? atoi(argv[3]) : 2048;
-    int rc = layout_tests();
-    printf("layout tests: %s\n", rc == 0 ? "PASS" : "FAIL");
-    if (rc == 2) return rc;                 // a wait timed out: the context is suspect
-    int rc2 = full_test(3000, 200, 512, 2.0, true);
-    if (rc2 == 2) return rc2;
-    rc2 |= full_test(5000, 37, 2048, 0.05, true);
-    rc2 |= full_test(m, rank, chunk, 2.0, true);
-    rc2 |= full_test(m, rank, 2 * chunk, 2.0, false);
-    rc2 |= full_test(m, rank, chunk / 2, 2.0, false);
-    printf("full tests: %s\n", rc2 == 0 ? "PASS" : "FAIL");
-    return rc | rc2;
+    const char* which = argc > 4 ? argv[4] : "all";
+    int rc = 0, rc2 = 0;
+    if (strcmp(which, "i8")) {
+        rc = layout_tests();
+        printf("layout tests (tf32): %s\n", rc == 0 ? "PASS" : "FAIL");
+        if (rc == 2) return rc;                 // a wait timed out: the context is suspect
+        rc2 = full_test(3000, 200, 512, 2.0, true);
+        if (rc2 == 2) return rc2;
+        rc2 |= full_test(m, rank, chunk, 2.0, true);
+        printf("full tests (tf32; 4 = accuracy above 2e-5 of the largest value, expected: FP32 TMEM accumulation truncates): %d\n", rc2);
+    }
+    int rc3 = layout_tests_i8();
+    printf("layout tests (i8): %s\n", rc3 == 0 ? "PASS" : "FAIL");
+    if (rc3 == 2) return rc3;
+    int rc4 = full_test_i8(3000, 200, 2.0, true, 0);
+    if (rc4 == 2) return rc4;
+    rc4 |= full_test_i8(5000, 37, 0.05, true, 1);
+    rc4 |= full_test_i8(20000, 230, 0.5, true, 1);
+    rc4 |= full_test_i8(m, rank, 2.0, true, 0);
+    printf("full tests (i8): %s\n", rc4 == 0 ? "PASS" : "FAIL");
+    return rc3 | rc4;
 }
