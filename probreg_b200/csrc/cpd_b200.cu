@@ -219,7 +219,7 @@ struct cpd_ctx {
     size_t lr_part_cap = 0;               // doubles in d_lr_part (slice partials of lr_inner)
     float *d_gu_planes = nullptr, *d_gu_part = nullptr;      // tcgen05 G X product: TF32 hi / lo planes of X, chunk partials
     size_t gu_planes_cap = 0, gu_part_cap = 0;
-    signed char* d_gi_planes = nullptr;                      // exact int8-digit product: digit planes of X, FP64 chunk partials, column maxima
+    unsigned char* d_gi_planes = nullptr;                      // exact int8-digit product: digit planes of X, FP64 chunk partials, column maxima
     double *d_gi_part = nullptr, *d_gi_colmax = nullptr;
     size_t gi_planes_cap = 0, gi_part_cap = 0, gi_colmax_cap = 0;
     size_t lr_out_cap = 0;

@@ -2,12 +2,13 @@
 // both operands are cut into 8-bit digits and multiplied with tcgen05.mma kind::i8 (unsigned x signed, 32-bit integer
 // accumulators in TMEM).  Integer MMAs do not round, so -- unlike the TF32 x 3 kernel of gram_umma.cuh, whose FP32 TMEM
 // accumulation truncates once per MMA (measured: a systematic shrink of ~1e-5 over a 2048-point chunk, profiles/r2_umma_*) --
-// the only errors are the two quantisations, both at the 2^-24 level of the float32 G the reference itself uses
+// the only errors are the two quantisations (2^-24 absolute on G, 2^-23 of the column maximum on X), at the level of the float32 G
+// the reference itself uses
 // (cc/math_utils.cc:17-19).  Same role as gram_umma.cuh: the products of the low-rank range finder (probreg/cpd.py:296-297 with
 // G = rbf_kernel(Y, Y, beta) of transformation.py:91-102, never stored).
 //
 // Fixed point ("Ozaki splitting" with integer digits):
-//     g_ij = round(2^24 G_ij) in [0, 2^24)         = a0 2^16 + a1 2^8 + a2,     a_s in [0, 255]        (unsigned digits)
+//     g_ij = round(2^23 G_ij) in [0, 2^23)         = a0 2^16 + a1 2^8 + a2,     a_s in [0, 255]        (unsigned digits, a0 < 128)
 //     x_cj = round(2^22 X[c][j] / max_j |X[c][j]|) = b0 2^16 + b1 2^8 + b2,     b_t in [-128, 127]     (balanced digits, |b0| <= 64)
 //     g x  = sum_{s,t} a_s b_t 2^(8 (4 - s - t)):   the products of level l = s + t share one accumulator,
 //            levels 0, 1, 2 are kept (6 MMAs per 32 points), levels 3 and 4 (< 2^-22 of the largest term) are dropped.
@@ -19,6 +20,10 @@
 // warp roles, pipeline and barriers as in gram_umma.cuh, with 32-point stages (one MMA K-step) and 8 stages of 24 KB.
 // Shared-memory operand layout: K-major, 32-byte rows, SWIZZLE_32B: row r at byte 32 r (8-row groups 256 B apart), the 16-byte
 // half h of a row at position h ^ ((r >> 2) & 1).
+// The digit planes of X are stored in global memory AS the shared-memory image of each stage (gi_split_kernel: point block jb ->
+// 3 planes x 4096 bytes, rows already swizzled), so a stage's B operand is ONE 12 KB bulk copy (cp.async.bulk, SASS UBLKCP).
+// A tensor-map box of 32-byte rows -- the first version of this kernel, and the 64-byte rows of gram_umma.cuh -- is limited by the
+// TMA unit's row rate, measured at ~4.5 cycles per box row per SM: 336 rows = 1470 cycles per stage against 360 cycles of MMAs.
 #pragma once
 #ifndef CPD_HOST_EMU
 #include "gram_umma.cuh"
@@ -32,7 +37,8 @@ constexpr int GI_STAGES = 8;
 constexpr int GI_PLANE = 4096;         // bytes reserved per digit plane of a stage (128 x 32 used for A, n16 x 32 for B)
 constexpr int GI_STAGE_BYTES = 6 * GI_PLANE;
 constexpr int GI_THREADS = 14 * 32;
-constexpr int GI_SMEM = GI_STAGES * GI_STAGE_BYTES + 1024 + 256;
+constexpr int GI_PTS_BYTES = GI_KS * 16;                  // the stage's 32 j-points (float4), staged by the same TMA producer
+constexpr int GI_SMEM = GI_STAGES * (GI_STAGE_BYTES + GI_PTS_BYTES) + 1024 + 256;
 constexpr int GI_MAX_CHUNK = 16384;
 
 __device__ __forceinline__ void gi_mma_i8(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
@@ -82,27 +88,37 @@ gi_colmax_kernel(const double* __restrict__ X, long long m, long long ld, double
         colmax[c] = v;
     }
 }
-// digit planes of the columns [c0, c0 + nc): planes[p][c][j] (p = 0, 1, 2; n16 rows per plane, ldx bytes per row), zero-padded
+// digit planes of the columns [c0, c0 + nc) as stage images: image[jb] (jb = point block of 32) = 3 planes x GI_PLANE bytes, plane p
+// holds digit p of column c (row c, 32 bytes, the two 16-byte halves swizzled like the MMA reads them).  One thread = one column x
+// 16 points = one 16-byte store per plane; rows c >= nc and points j >= m are zero.
 __global__ void __launch_bounds__(THREADS)
 gi_split_kernel(const double* __restrict__ X, long long m, long long ld, int nc, int n16, long long ldx, const double* __restrict__ colmax,
-                signed char* __restrict__ planes) {
-    const long long j = (long long)blockIdx.x * THREADS + threadIdx.x;
+                unsigned char* __restrict__ images) {
+    const long long jh = (long long)blockIdx.x * THREADS + threadIdx.x;          // 16-point group
     const int c = blockIdx.y;
-    if (j < ldx && c < n16) {
-        int b0 = 0, b1 = 0, b2 = 0;
-        if (j < m && c < nc) {
-            const double mx = colmax[c];
-            if (mx > 0.0) {
-                const int xi = (int)rint(X[(long long)c * ld + j] / mx * 4194304.0);          // |xi| <= 2^22
-                b2 = ((xi + 128) & 255) - 128;
-                const int r1 = (xi - b2) >> 8;
-                b1 = ((r1 + 128) & 255) - 128;
-                b0 = (r1 - b1) >> 8;
+    if (jh * 16 < ldx && c < n16) {
+        uint32_t w[3][4] = {{0u, 0u, 0u, 0u}, {0u, 0u, 0u, 0u}, {0u, 0u, 0u, 0u}};
+        const double mx = c < nc ? colmax[c] : 0.0;
+        if (mx > 0.0) {
+            const double inv = 4194304.0 / mx;
+#pragma unroll
+            for (int k = 0; k < 16; ++k) {
+                const long long j = jh * 16 + k;
+                if (j < m) {
+                    const int xi = (int)rint(X[(long long)c * ld + j] * inv);                 // |xi| <= 2^22
+                    const int b2 = ((xi + 128) & 255) - 128;
+                    const int r1 = (xi - b2) >> 8;
+                    const int b1 = ((r1 + 128) & 255) - 128;
+                    const int b0 = (r1 - b1) >> 8;
+                    w[0][k >> 2] |= (uint32_t)(b0 & 255) << (8 * (k & 3));
+                    w[1][k >> 2] |= (uint32_t)(b1 & 255) << (8 * (k & 3));
+                    w[2][k >> 2] |= (uint32_t)(b2 & 255) << (8 * (k & 3));
+                }
             }
         }
-        planes[(long long)c * ldx + j] = (signed char)b0;
-        planes[(long long)(n16 + c) * ldx + j] = (signed char)b1;
-        planes[(long long)(2 * n16 + c) * ldx + j] = (signed char)b2;
+        unsigned char* img = images + (jh >> 1) * (3 * GI_PLANE) + gi_row_half_offset(c, (int)(jh & 1));
+#pragma unroll
+        for (int p = 0; p < 3; ++p) *reinterpret_cast<uint4*>(img + p * GI_PLANE) = make_uint4(w[p][0], w[p][1], w[p][2], w[p][3]);
     }
 }
 // out[c][i_begin + ii] = sum over the j-chunks of part[q][c][ii] (FP64, chunk order)
@@ -119,14 +135,15 @@ gi_reduce_kernel(const double* __restrict__ part, int nq, int n16, long long ldp
 }
 
 // ---- the product -----------------------------------------------------------------------------------------------------------------
-// one column pass: bmap over the digit planes ([3 n16][ldx] bytes, box {32, n16}, 32-byte swizzle); rows [i_begin, i_end) of G;
-// part[q][c][ii] (FP64) = colmax[c] 2^-46 sum_{j in chunk q} g_ij x_cj
+// one column pass: images = the stage images of gi_split_kernel (jpad / 32 of them); rows [i_begin, i_end) of G;
+// part[q][c][ii] (FP64) = colmax[c] 2^-45 sum_{j in chunk q} g_ij x_cj
 __global__ void __launch_bounds__(GI_THREADS, 1)
-gi_gram_kernel(const __grid_constant__ CUtensorMap bmap, const float4* __restrict__ pts, long long jpad, int chunk, long long i_begin,
+gi_gram_kernel(const unsigned char* __restrict__ images, const float4* __restrict__ pts, long long jpad, int chunk, long long i_begin,
                long long i_end, int n16, const double* __restrict__ colmax, double* __restrict__ part, long long ldp) {
-    extern __shared__ unsigned char gu_smem_raw[];
-    unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(gu_smem_raw) + 1023) & ~(uintptr_t)1023);
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + GI_STAGES * GI_STAGE_BYTES);
+    extern __shared__ __align__(1024) unsigned char gu_smem_raw[];
+    unsigned char* smem = gu_smem_raw;
+    unsigned char* spts = smem + GI_STAGES * GI_STAGE_BYTES;            // [GI_STAGES][32] float4: the j-points of each stage
+    uint64_t* bars = reinterpret_cast<uint64_t*>(spts + GI_STAGES * GI_PTS_BYTES);
     uint64_t* full_a = bars;
     uint64_t* full_b = bars + GI_STAGES;
     uint64_t* empty = bars + 2 * GI_STAGES;
@@ -153,21 +170,20 @@ gi_gram_kernel(const __grid_constant__ CUtensorMap bmap, const float4* __restric
     const uint32_t tmem_base = *tmem_base_slot;
 
     if (warp == 0) {
-        // ===== TMA producer: the three digit planes of X for this stage's 32 points =====
+        // ===== TMA producer: the stage image (three digit planes of X for 32 points), one bulk copy =====
         if (lane == 0) {
-            asm volatile("prefetch.tensormap [%0];" ::"l"(&bmap) : "memory");
             uint32_t stage = 0, phase = 0;
             for (long long u = blockIdx.x; u < nunits; u += gridDim.x) {
                 const int q = (int)(u / ntiles);
                 const long long j0 = (long long)q * chunk;
                 const int nst = (int)((min((long long)chunk, jpad - j0)) / GI_KS);
+                const unsigned char* src = images + (j0 / GI_KS) * (3 * GI_PLANE);
                 for (int kb = 0; kb < nst; ++kb) {
                     gu_wait(&empty[stage], phase ^ 1, 11);
-                    unsigned char* sb = smem + stage * GI_STAGE_BYTES + 3 * GI_PLANE;
-                    mbar_expect_tx(&full_b[stage], (uint32_t)(3 * n16 * GI_KS));
-#pragma unroll
-                    for (int p = 0; p < 3; ++p)
-                        gu_tma_load_2d(sb + p * GI_PLANE, &bmap, (int)(j0 + (long long)kb * GI_KS), p * n16, &full_b[stage]);
+                    mbar_expect_tx(&full_b[stage], (uint32_t)(3 * GI_PLANE + GI_PTS_BYTES));
+                    tma_load_1d(smem + stage * GI_STAGE_BYTES + 3 * GI_PLANE, src + (long long)kb * (3 * GI_PLANE), (uint32_t)(3 * GI_PLANE),
+                                &full_b[stage]);
+                    tma_load_1d(spts + stage * GI_PTS_BYTES, pts + j0 + (long long)kb * GI_KS, (uint32_t)GI_PTS_BYTES, &full_b[stage]);
                     if (++stage == GI_STAGES) { stage = 0; phase ^= 1; }
                 }
             }
@@ -226,7 +242,7 @@ gi_gram_kernel(const __grid_constant__ CUtensorMap bmap, const float4* __restric
 #pragma unroll
                 for (int k = 0; k < 16; ++k) {
                     const double s = (double)v0[k] * 65536.0 + (double)v1[k] * 256.0 + (double)v2[k];      // exact: < 2^48
-                    dst[(long long)(c0 + k) * ldp] = s * (colmax[c0 + k] * (1.0 / 1073741824.0));          // 2^16 2^-46
+                    dst[(long long)(c0 + k) * ldp] = s * (colmax[c0 + k] * (1.0 / 536870912.0));           // 2^16 2^-45
                 }
             }
             gu_tc_fence_before();
@@ -235,7 +251,7 @@ gi_gram_kernel(const __grid_constant__ CUtensorMap bmap, const float4* __restric
             acc_phase ^= 1;
         }
     } else {
-        // ===== generators: two threads per row (16 points each); digits of round(2^24 G) into the three A planes =====
+        // ===== generators: two threads per row (16 points each); digits of round(2^23 G) into the three A planes =====
         const int g = threadIdx.x - 6 * 32, r = g & 127, hf = g >> 7;
         const uint32_t off = gi_row_half_offset(r, hf);
         uint32_t stage = 0, phase = 0;
@@ -246,15 +262,20 @@ gi_gram_kernel(const __grid_constant__ CUtensorMap bmap, const float4* __restric
             long long i = i_begin + (long long)t * GI_ROWS + r;
             if (i >= i_end) i = i_end - 1;
             const float4 a = pts[i];
-            const float4* bj = pts + j0 + hf * 16;
             for (int kb = 0; kb < nst; ++kb) {
+                // the j-points arrive with the B image (global loads here stalled the 8 generator warps on L2 latency: long-scoreboard
+                // 4.2 of 7.6 warp-cycles per issue in the first version, profiles/r2_ncu_gi_gram_v2.txt)
+                gu_wait(&full_b[stage], phase, 19);
+                const float4* bj = reinterpret_cast<const float4*>(spts + stage * GI_PTS_BYTES) + hf * 16;
+                // g = round(2^23 G) sits in the mantissa of 2^23 + 2^23 G (one FFMA; a float -> integer conversion would go through the
+                // quarter-rate XU pipe that MUFU.EX2 already loads): bytes 2, 1, 0 of the float ARE the digits a0 < 128, a1, a2
                 uint32_t gq[16];
 #pragma unroll
                 for (int jj = 0; jj < 16; ++jj) {
-                    const float4 b = __ldg(bj + kb * GI_KS + jj);
+                    const float4 b = bj[jj];
                     const float dx = a.x - b.x, dy = a.y - b.y, dz = a.z - b.z;
                     const float e = ex2(-fmaf(dz, dz, fmaf(dy, dy, dx * dx)));                 // the same float32 G as the other kernels
-                    gq[jj] = min(__float2uint_rn(e * 16777216.0f), 16777215u);
+                    gq[jj] = __float_as_uint(fmaf(fminf(e, 0.99999988f), 8388608.0f, 8388608.0f));
                 }
                 gu_wait(&empty[stage], phase ^ 1, 16);
                 unsigned char* sa = smem + stage * GI_STAGE_BYTES;
@@ -283,8 +304,8 @@ gi_gram_kernel(const __grid_constant__ CUtensorMap bmap, const float4* __restric
 // ---- layout probe: D[128][n16] (int32) = A[128][32] (u8) x B[n16][32]^T (s8), through the conventions above -------------------------
 __global__ void __launch_bounds__(128, 1)
 gi_layout_probe_kernel(const __grid_constant__ CUtensorMap bmap, const unsigned char* __restrict__ A, int n16, int* __restrict__ D) {
-    extern __shared__ unsigned char gu_smem_raw[];
-    unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(gu_smem_raw) + 1023) & ~(uintptr_t)1023);
+    extern __shared__ __align__(1024) unsigned char gu_smem_raw[];
+    unsigned char* smem = gu_smem_raw;
     unsigned char* sa = smem;
     unsigned char* sb = smem + 4096;
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 4096 + 8192);

@@ -198,9 +198,12 @@ gu_compare_kernel(const double* __restrict__ a, const double* __restrict__ b, lo
 __global__ void __launch_bounds__(GU_THREADS, 1)
 gu_gram_kernel(const __grid_constant__ CUtensorMap xmap, const float4* __restrict__ pts, long long jpad, int chunk, long long i_begin,
                long long i_end, int n16, float* __restrict__ part, long long ldp) {
-    extern __shared__ unsigned char gu_smem_raw[];
-    // 1024-byte alignment keeps the swizzle pattern of every tile anchored the way the TMA unit and the MMA unit both expect
-    unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(gu_smem_raw) + 1023) & ~(uintptr_t)1023);
+    extern __shared__ __align__(1024) unsigned char gu_smem_raw[];
+    // 1024-byte alignment (declared on the array, honoured for dynamic shared memory) keeps the swizzle pattern of every tile
+    // anchored the way the TMA unit and the MMA unit both expect.  NOT aligned by pointer arithmetic: that launders the address
+    // space and every access through the pointer becomes a generic LD/ST instead of LDS/STS (measured: the j-point loads of the
+    // int8 kernel showed up as LD.E.64 with long-scoreboard stalls, profiles/r2_ncu_gi_gram_v3_source.txt)
+    unsigned char* smem = gu_smem_raw;
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + GU_STAGES * GU_STAGE_BYTES);
     uint64_t* full_a = bars;                    // [GU_STAGES]
     uint64_t* full_b = bars + GU_STAGES;        // [GU_STAGES]
@@ -360,8 +363,8 @@ gu_gram_kernel(const __grid_constant__ CUtensorMap xmap, const float4* __restric
 // by the tensor core).  bmap: tensor map over B ([n16][16] floats), box {16, n16}, 64-byte swizzle.
 __global__ void __launch_bounds__(128, 1)
 gu_layout_probe_kernel(const __grid_constant__ CUtensorMap bmap, const float* __restrict__ A, int n16, float* __restrict__ D) {
-    extern __shared__ unsigned char gu_smem_raw[];
-    unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(gu_smem_raw) + 1023) & ~(uintptr_t)1023);
+    extern __shared__ __align__(1024) unsigned char gu_smem_raw[];
+    unsigned char* smem = gu_smem_raw;
     unsigned char* sa = smem;                              // 128 rows x 64 B
     unsigned char* sb = smem + 8192;                       // n16 rows x 64 B
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 8192 + GU_B_BYTES);

@@ -138,15 +138,13 @@ int lr_gram_rows_i8(cpd_ctx* h, const double* src, double* dst, int rank, long l
     h->launches += 1;
     for (int c0 = 0; c0 < rank; c0 += per) {
         const int nc = std::min(per, rank - c0), n16 = (nc + 15) / 16 * 16;
-        const size_t need_planes = (size_t)3 * n16 * ld, need_part = (size_t)nq * n16 * ldp;
+        const size_t need_planes = (size_t)(ld / GI_KS) * 3 * GI_PLANE, need_part = (size_t)nq * n16 * ldp;
         if (need_planes > h->gi_planes_cap) { TRY(dev_alloc(&h->d_gi_planes, need_planes)); h->gi_planes_cap = need_planes; }
         if (need_part > h->gi_part_cap) { TRY(dev_alloc(&h->d_gi_part, need_part)); h->gi_part_cap = need_part; }
-        gi_split_kernel<<<dim3(blocks_for(ld), (unsigned)n16), THREADS, 0, h->stream>>>(src + (size_t)c0 * ld, h->m, ld, nc, n16, ld,
-                                                                                     h->d_gi_colmax + c0, h->d_gi_planes);
-        CUtensorMap map;
-        if (gi_make_map(&map, h->d_gi_planes, ld, 3 * n16, n16) != 0) return fail(CPD_ERR_CUDA, "cuTensorMapEncodeTiled failed");
-        gi_gram_kernel<<<h->sm_count, GI_THREADS, GI_SMEM, h->stream>>>(map, h->d_lr_pts, ld, (int)chunk, i_lo, i_hi, n16, h->d_gi_colmax + c0,
-                                                                       h->d_gi_part, ldp);
+        gi_split_kernel<<<dim3(blocks_for(ld / 16), (unsigned)n16), THREADS, 0, h->stream>>>(src + (size_t)c0 * ld, h->m, ld, nc, n16, ld,
+                                                                                          h->d_gi_colmax + c0, h->d_gi_planes);
+        gi_gram_kernel<<<h->sm_count, GI_THREADS, GI_SMEM, h->stream>>>(h->d_gi_planes, h->d_lr_pts, ld, (int)chunk, i_lo, i_hi, n16,
+                                                                       h->d_gi_colmax + c0, h->d_gi_part, ldp);
         gi_reduce_kernel<<<dim3(blocks_for(rows), (unsigned)nc), THREADS, 0, h->stream>>>(h->d_gi_part, nq, n16, ldp, nc, rows, i_lo, ld,
                                                                                            dst + (size_t)c0 * ld);
         KCHECK();
@@ -212,16 +210,16 @@ int lr_gram_apply(cpd_ctx* h, const double* src, double* dst, int rank) {
     if (shard) TRY(allreduce(h, dst, (size_t)rank * h->mpad));
     return CPD_OK;
 }
-// out[na][nb] = A diag(wt) Bm^T over the points.  The point range is cut into as many slices as the partial buffer holds
-// (at most 64, at least 1024 points each); lr_merge_kernel adds them in slice order.
+// out[na][nb] = A diag(wt) Bm^T over the points.  The point range is cut into as many slices as the partial buffer holds (at most
+// 256, at least 256 points each): many short CTAs instead of 8 long ones per tile; lr_merge_kernel adds the slices in a fixed order.
 int lr_inner(cpd_ctx* h, const double* A, int na, long long lda, const double* Bm, int nb, long long ldb, const double* wt, int symmetrise,
              double* out) {
     const int tiles = ((na + LR_TILE - 1) / LR_TILE) * ((nb + LR_TILE - 1) / LR_TILE);
     const long long by_cap = (long long)(h->lr_part_cap / ((size_t)na * nb));
-    const int nsl = (int)std::max<long long>(1, std::min<long long>(std::min<long long>(64, by_cap), h->m / 1024));
+    const int nsl = (int)std::max<long long>(1, std::min<long long>(std::min<long long>(256, by_cap), h->m / 256));
     dim3 grid((unsigned)tiles, (unsigned)nsl);
     lr_inner_kernel<<<grid, THREADS, 0, h->stream>>>(A, na, lda, Bm, nb, ldb, wt, h->m, symmetrise, h->d_lr_part);
-    lr_merge_kernel<<<blocks_for((long long)na * nb), THREADS, 0, h->stream>>>(h->d_lr_part, nsl, na, nb, symmetrise, out);
+    lr_merge_kernel<<<blocks_for((long long)na * nb * 8), THREADS, 0, h->stream>>>(h->d_lr_part, nsl, na, nb, symmetrise, out);
     KCHECK();
     h->launches += 2;
     return CPD_OK;
@@ -232,25 +230,28 @@ int lr_orthonormalise(cpd_ctx* h, double* X, int rank) {
     if (const char* e = getenv("CPD_B200_LR_ORTH")) if (!strcmp(e, "columnwise")) return lr_orthonormalise_columnwise(h, X, rank);
     const long long m = h->m, ld = h->mpad;
     const unsigned nb = blocks_for(m);
+    const int nblk = (int)std::min<long long>(LR_GRAM_BLOCKS, (m + LR_GRAM_PTS - 1) / LR_GRAM_PTS);
     double* C = h->d_lr_panel;                              // [rank][np] projection coefficients
-    double* W0 = C + (size_t)LR_MAX_RANK * LR_PANEL;        // Gram matrix of the panel as it arrived (its diagonal: arrival norms)
-    double* W = W0 + LR_PANEL * LR_PANEL;
-    double* T = W + LR_PANEL * LR_PANEL;
-    double* scale2 = T + LR_PANEL * LR_PANEL;               // [LR_PANEL]: see lr_panel_chol_kernel
+    double* n0 = C + (size_t)LR_MAX_RANK * LR_PANEL;        // [LR_PANEL]: the norm^2 each column of the panel arrived with
+    double* scale2 = n0 + LR_PANEL;                         // [LR_PANEL]: see lr_panel_chol_kernel
+    double* T = scale2 + LR_PANEL;                          // [LR_PANEL][LR_PANEL]
+    double* gpart = T + LR_PANEL * LR_PANEL;                // [nblk][LR_PANEL][LR_PANEL] block partials of the panel's Gram matrix
     for (int j0 = 0; j0 < rank; j0 += LR_PANEL) {
         const int np = std::min(LR_PANEL, rank - j0);
         double* P = X + (size_t)j0 * ld;
-        TRY(lr_inner(h, P, np, ld, P, np, ld, nullptr, 1, W0));
+        lr_panel_gram_kernel<<<nblk, THREADS, 0, h->stream>>>(X, m, ld, j0, np, gpart);
+        lr_panel_chol_kernel<<<1, THREADS, 0, h->stream>>>(gpart, nblk, np, n0, 2, scale2, T);
+        h->launches += 2;
         for (int pass = 0; pass < 2; ++pass) {
             if (j0 > 0) {
                 TRY(lr_inner(h, X, j0, ld, P, np, ld, nullptr, 0, C));
                 lr_panel_update_kernel<<<nb, THREADS, 0, h->stream>>>(X, m, ld, j0, np, j0, C);
                 h->launches += 1;
             }
-            TRY(lr_inner(h, P, np, ld, P, np, ld, nullptr, 1, W));
-            lr_panel_chol_kernel<<<1, 32, 0, h->stream>>>(W, np, W0, np + 1, pass == 0 ? 1 : 0, scale2, T);
+            lr_panel_gram_kernel<<<nblk, THREADS, 0, h->stream>>>(X, m, ld, j0, np, gpart);
+            lr_panel_chol_kernel<<<1, THREADS, 0, h->stream>>>(gpart, nblk, np, n0, pass == 0 ? 1 : 0, scale2, T);
             lr_panel_apply_kernel<<<nb, THREADS, 0, h->stream>>>(X, m, ld, j0, np, T);
-            h->launches += 2;
+            h->launches += 3;
         }
     }
     KCHECK();
@@ -301,9 +302,10 @@ extern "C" int cpd_nonrigid_lowrank_begin(cpd_ctx* h, double beta, double lmd, d
         TRY(dev_alloc(&h->d_lr_Q, (size_t)rank * ld));
         TRY(dev_alloc(&h->d_lr_X, (size_t)rank * ld));
         TRY(dev_alloc(&h->d_lr_coef, (size_t)3 * LR_SLICES * (rank + 1)));
-        h->lr_part_cap = std::max<size_t>((size_t)LR_SLICES * rank * rank, (size_t)64 * LR_PANEL * LR_MAX_RANK / 8);
+        h->lr_part_cap = std::max<size_t>((size_t)LR_SLICES * rank * rank, (size_t)2 << 20);        // >= 16 MB of slice partials
         TRY(dev_alloc(&h->d_lr_part, h->lr_part_cap));
-        TRY(dev_alloc(&h->d_lr_panel, (size_t)LR_MAX_RANK * LR_PANEL + 3 * LR_PANEL * LR_PANEL + LR_PANEL));
+        TRY(dev_alloc(&h->d_lr_panel, (size_t)LR_MAX_RANK * LR_PANEL + 2 * LR_PANEL + LR_PANEL * LR_PANEL +
+                                          (size_t)LR_GRAM_BLOCKS * LR_PANEL * LR_PANEL));
         TRY(dev_alloc(&h->d_lr_Bc, (size_t)rank * rank));
         TRY(dev_alloc(&h->d_lr_S, (size_t)rank * rank));
         TRY(dev_alloc(&h->d_lr_R, (size_t)rank * 3));

@@ -1225,6 +1225,22 @@ __device__ inline void mstep_solve_residual(DevState* st, const double* __restri
     st->scale = scale; st->sigma2 = sigma2; st->q = q; st->n_p = Np;
 }
 
+// The M-step of the fused loop on a shared-memory copy of the state: thread 0 alone walking DevState and the moments in global
+// memory paid one L2 round trip per field (~50 dependent loads: 20 of the kernel's 33 us, profiles/r2_ncu_shard_1of8.txt).
+// All threads of the calling block must enter; `mom` may be global or shared.
+__device__ __forceinline__ void mstep_staged(DevState* st, const double* mom) {
+    __shared__ DevState sst;
+    __shared__ double smom[MOM_PAD];
+    static_assert(sizeof(DevState) % 8 == 0, "DevState is copied as 8-byte words");
+    const int nw = (int)(sizeof(DevState) / 8);
+    for (int e = threadIdx.x; e < nw; e += blockDim.x) reinterpret_cast<double*>(&sst)[e] = reinterpret_cast<const double*>(st)[e];
+    for (int e = threadIdx.x; e < MOM_PAD; e += blockDim.x) smom[e] = mom[e];
+    __syncthreads();
+    if (threadIdx.x == 0) mstep_solve_residual(&sst, smom);
+    __syncthreads();
+    if (threadIdx.x < 16) reinterpret_cast<double*>(st)[threadIdx.x] = reinterpret_cast<const double*>(&sst)[threadIdx.x];   // lin, t, scale, sigma2, q, n_p
+}
+
 // Fixed-order reduction of per-block moment partials: column k < ka of part_a, then kb columns of
 // part_b, into mom[0 .. ka+kb); the rest of mom[0..32) is zeroed.  SOLVE = 1: the same (single)
 // block then runs the residual-form M-step.  In multi-rank runs the all-reduce sits in between.
@@ -1251,14 +1267,14 @@ moments_kernel(DevState* st, const double* __restrict__ part_a, int nb_a, int ka
 #pragma unroll
         for (int i = 0; i < 8; ++i) t += sh[i][k];
         mom[k] = t;
-        if (SOLVE) {
-            __syncwarp();
-            if (k == 0) mstep_solve_residual(st, mom);
-        }
+    }
+    if (SOLVE) {
+        __syncthreads();                    // mom[] written by warp 0 is read back by the whole block (same-block global visibility)
+        mstep_staged(st, mom);
     }
 }
 __global__ void mstep_residual_kernel(DevState* st, const double* __restrict__ mom) {
-    if (threadIdx.x == 0) mstep_solve_residual(st, mom);
+    mstep_staged(st, mom);
 }
 __global__ void mstep_api_kernel(DevState* st, const double* __restrict__ mom) {
     if (threadIdx.x == 0) mstep_solve_api(st, mom);
@@ -1336,13 +1352,13 @@ moments_p2p_kernel(DevState* st, const double* __restrict__ part_a, int nb_a, in
         double t = 0.0;
         for (int r = 0; r < world; ++r) t += ld_relaxed_sys(&info->box[rank]->slots[par][r][k]);
         mom[k] = t;
-        __syncwarp();
         if (k == 0) {
             info->seq = seq;
             if (timeout) st->err = 1;                   // incomplete sums: the state is left as it was; the host reports the error
-            else if (st->err == 0) mstep_solve_residual(st, mom);      // (and every later step of a failed run is a no-op)
         }
     }
+    __syncthreads();
+    if (!timeout && st->err == 0) mstep_staged(st, mom);             // (every later step of a failed run is a no-op)
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -181,7 +181,7 @@ lr_panel_update_kernel(double* __restrict__ X, long long m, long long ld, int j0
         }
         __syncthreads();
         if (i < m) {
-#pragma unroll 4
+#pragma unroll 8
             for (int k = 0; k < kc; ++k) {
                 const double q = X[(long long)(k0 + k) * ld + i];
 #pragma unroll
@@ -196,59 +196,93 @@ lr_panel_update_kernel(double* __restrict__ X, long long m, long long ld, int j0
     }
 }
 
-// One CTA: T (upper triangular, row-major [LR_PANEL][LR_PANEL]) such that P T has orthonormal columns, from the panel's Gram
-// matrix W (row-major [np][np]) by a Cholesky factorisation W = R^T R, T = R^-1.
-//   first = 1 (step b):  n0 = the norm^2 each column arrived with (diagonal of the arrival Gram matrix, stride n0_stride).
-//       A column with nothing left after (a) (norm^2 <= 1e-28 n0) is dropped.  A column whose pivot is lost in the cancellation
-//       (<= 1e-13 of its norm^2: it lies in the span of its panel predecessors up to ~3e-7) is still projected with the computed
-//       coefficients -- which removes the predecessors to rounding level -- but scaled by a guess and left out of the
+// part[blk][a][b] = sum over the block's points of X[j0+a][i] X[j0+b][i]   (a, b < LR_PANEL; rows >= np count as zero).
+// One CTA per LR_GRAM_PTS points (grid-stride beyond that), thread (a, b): 256 threads = the 16 x 16 outputs.
+constexpr int LR_GRAM_PTS = 256;
+constexpr int LR_GRAM_BLOCKS = 1024;   // most CTAs of lr_panel_gram_kernel (beyond 262144 points they stride)
+__global__ void __launch_bounds__(THREADS)
+lr_panel_gram_kernel(const double* __restrict__ X, long long m, long long ld, int j0, int np, double* __restrict__ part) {
+    __shared__ double sp[LR_PANEL][LR_GRAM_PTS + 1];           // + 1: the 16 rows a warp reads in one step fall into distinct banks
+    const int a = threadIdx.x / LR_PANEL, b = threadIdx.x % LR_PANEL;
+    double acc = 0.0;
+    for (long long i0 = (long long)blockIdx.x * LR_GRAM_PTS; i0 < m; i0 += (long long)gridDim.x * LR_GRAM_PTS) {
+        __syncthreads();
+        for (int e = threadIdx.x; e < LR_PANEL * LR_GRAM_PTS; e += THREADS) {
+            const int r = e / LR_GRAM_PTS, ii = e % LR_GRAM_PTS;
+            sp[r][ii] = (r < np && i0 + ii < m) ? X[(long long)(j0 + r) * ld + i0 + ii] : 0.0;
+        }
+        __syncthreads();
+#pragma unroll 8
+        for (int ii = 0; ii < LR_GRAM_PTS; ++ii) acc = fma(sp[a][ii], sp[b][ii], acc);
+    }
+    part[(size_t)blockIdx.x * (LR_PANEL * LR_PANEL) + threadIdx.x] = acc;
+}
+
+// One CTA (256 threads): W = sum over blocks of part (fixed order), then T (upper triangular, row-major [LR_PANEL][LR_PANEL]) such
+// that P T has orthonormal columns, by a Cholesky factorisation W = R^T R, T = R^-1.
+//   mode 2 (arrival): only n0[p] = W[p][p] is stored -- the norm^2 each column of the panel arrived with.
+//   mode 1 (step b):  a column with nothing left after (a) (norm^2 <= 1e-28 n0) is dropped.  A column whose pivot is lost in the
+//       cancellation (<= 1e-13 of its norm^2: it lies in the span of its panel predecessors up to ~3e-7) is still projected with the
+//       computed coefficients -- which removes the predecessors to rounding level -- but scaled by a guess and left out of the
 //       factorisation of the later columns; step (d) sees it well separated and measures what is really left.
 //       scale2[p] = the square of the factor column p was multiplied with.
-//   first = 0 (step d):  scale2 from (b) turns the diagonal of W back into the column's remaining norm^2 in arrival units; the
+//   mode 0 (step d):  scale2 from (b) turns the diagonal of W back into the column's remaining norm^2 in arrival units; the
 //       column-wise rule (kept iff that is > 1e-28 n0) decides.  Dropped columns get a zero column in T and stay exactly zero.
-__global__ void __launch_bounds__(32)
-lr_panel_chol_kernel(const double* __restrict__ W, int np, const double* __restrict__ n0, int n0_stride, int first,
-                     double* __restrict__ scale2, double* __restrict__ T) {
-    __shared__ double R[LR_PANEL][LR_PANEL], Ti[LR_PANEL][LR_PANEL];
+// The factorisation is right-looking on one warp (lane = column): 16 steps of a few operations instead of one thread walking
+// ~3000 dependent FP64 operations (75 us in the first version).
+__global__ void __launch_bounds__(THREADS)
+lr_panel_chol_kernel(const double* __restrict__ part, int nblk, int np, double* __restrict__ n0, int mode, double* __restrict__ scale2,
+                     double* __restrict__ T) {
+    __shared__ double W[LR_PANEL][LR_PANEL + 1], R[LR_PANEL][LR_PANEL + 1], Ti[LR_PANEL][LR_PANEL + 1], diag0[LR_PANEL];
     __shared__ int live[LR_PANEL];          // 1: part of the factorisation, 2: projected and rescaled only, 0: dropped
-    const int t = threadIdx.x;
-    if (t == 0) {
-        for (int a = 0; a < LR_PANEL; ++a)
-            for (int b = 0; b < LR_PANEL; ++b) { R[a][b] = 0.0; Ti[a][b] = 0.0; }
+    const int t = threadIdx.x, a = t / LR_PANEL, b = t % LR_PANEL;
+    double s = 0.0;
+#pragma unroll 8
+    for (int k = 0; k < nblk; ++k) s += part[(size_t)k * (LR_PANEL * LR_PANEL) + t];
+    W[a][b] = s; R[a][b] = 0.0; Ti[a][b] = 0.0;
+    __syncthreads();
+    if (mode == 2) {
+        if (t < LR_PANEL) n0[t] = W[t][t];
+        return;
+    }
+    if (t < LR_PANEL) diag0[t] = W[t][t];
+    __syncthreads();
+    if (t < 32) {
+        const int lane = t;                 // lane = column index b of the row being formed / the Schur update
         for (int p = 0; p < np; ++p) {
-            const double wpp = W[(size_t)p * np + p];
-            const double arrived = n0[(size_t)p * n0_stride];
-            double piv = wpp;
-            for (int q = 0; q < p; ++q) piv -= R[q][p] * R[q][p];
+            const double wpp = diag0[p], piv = W[p][p], arrived = n0[p];
             int state;
-            if (first) state = !(wpp > 1e-280 && wpp > 1e-28 * arrived) ? 0 : (piv > 1e-13 * wpp ? 1 : 2);
+            if (mode == 1) state = !(wpp > 1e-280 && wpp > 1e-28 * arrived) ? 0 : (piv > 1e-13 * wpp ? 1 : 2);
             else state = (wpp > 1e-280 && wpp / scale2[p] > 1e-28 * arrived && piv > 1e-13 * wpp) ? 1 : 0;
-            live[p] = state;
-            if (state == 0) { if (first) scale2[p] = 1.0; continue; }
-            const double rpp = state == 1 ? sqrt(piv) : sqrt(1e-20 * wpp);
-            R[p][p] = rpp;
-            if (first) scale2[p] = 1.0 / (rpp * rpp);
-            if (state == 2) continue;                     // row p of R stays zero: later columns are not measured against it
-            for (int b = p + 1; b < np; ++b) {
-                double v = W[(size_t)p * np + b];
-                for (int q = 0; q < p; ++q) v -= R[q][p] * R[q][b];
-                R[p][b] = v / rpp;
+            const double rpp = state == 1 ? sqrt(piv) : (state == 2 ? sqrt(1e-20 * wpp) : 0.0);
+            if (lane == 0) {
+                live[p] = state;
+                R[p][p] = rpp;
+                if (mode == 1) scale2[p] = state ? 1.0 / (rpp * rpp) : 1.0;
             }
+            if (state == 1) {
+                if (lane > p && lane < np) R[p][lane] = W[p][lane] / rpp;
+                __syncwarp();
+                // Schur complement of the trailing block: W[a][b] -= R[p][a] R[p][b] for p < a <= b < np (lane = b)
+                if (lane > p && lane < np)
+                    for (int aa = p + 1; aa <= lane; ++aa) W[aa][lane] -= R[p][aa] * R[p][lane];
+            }
+            __syncwarp();
         }
-        // T = R^-1 over the kept columns: back substitution column by column (rows of dropped / rescaled-only columns are zero)
-        for (int b = 0; b < np; ++b) {
-            if (!live[b]) continue;
-            Ti[b][b] = 1.0 / R[b][b];
-            for (int a = b - 1; a >= 0; --a) {
-                if (live[a] != 1) continue;
+        // T = R^-1 over the kept columns: back substitution, one column per lane (rows of dropped / rescaled-only columns are zero)
+        if (lane < np && live[lane]) {
+            const int bb = lane;
+            Ti[bb][bb] = 1.0 / R[bb][bb];
+            for (int aa = bb - 1; aa >= 0; --aa) {
+                if (live[aa] != 1) continue;
                 double v = 0.0;
-                for (int q = a + 1; q <= b; ++q) v -= R[a][q] * Ti[q][b];
-                Ti[a][b] = v / R[a][a];
+                for (int q = aa + 1; q <= bb; ++q) v -= R[aa][q] * Ti[q][bb];
+                Ti[aa][bb] = v / R[aa][aa];
             }
         }
     }
     __syncthreads();
-    for (int e = t; e < LR_PANEL * LR_PANEL; e += 32) T[e] = Ti[e / LR_PANEL][e % LR_PANEL];
+    T[t] = Ti[a][b];
 }
 
 // X[j0+p][i] <- sum_{q<=p} X[j0+q][i] T[q][p]
@@ -315,23 +349,27 @@ lr_inner_kernel(const double* __restrict__ A, int na, long long lda, const doubl
             if (a < na && b < nb) dst[(size_t)a * nb + b] = acc[u][v];
         }
 }
-// out[e] = sum_slices part[s][e]  (fixed order).  symmetrise != 0 (square, mathematically symmetric result whose tiles below
-// the diagonal were not computed): diagonal tiles give (x + x^T) / 2, the others are mirrored from the upper triangle.
+// out[e] = sum_slices part[s][e]  (fixed order: 8 lanes per output take the slices l, l + 8, ..., then a fixed shuffle tree joins
+// them).  symmetrise != 0 (square, mathematically symmetric result whose tiles below the diagonal were not computed): diagonal
+// tiles give (x + x^T) / 2, the others are mirrored from the upper triangle.
 __global__ void __launch_bounds__(THREADS)
 lr_merge_kernel(const double* __restrict__ part, int nsl, int na, int nb, int symmetrise, double* __restrict__ out) {
-    const int e = blockIdx.x * THREADS + threadIdx.x;
-    if (e < na * nb) {
-        const int a = e / nb, b = e % nb;
-        const int ta = a / LR_TILE, tb = b / LR_TILE;
-        const size_t e_ab = (size_t)a * nb + b, e_ba = (size_t)b * nb + a;
-        double s = 0.0, t = 0.0;
-        for (int sl = 0; sl < nsl; ++sl) {
+    const int e = (blockIdx.x * THREADS + threadIdx.x) >> 3, l = threadIdx.x & 7;
+    const bool in = e < na * nb;
+    const int a = in ? e / nb : 0, b = in ? e % nb : 0;
+    const int ta = a / LR_TILE, tb = b / LR_TILE;
+    const size_t e_ab = (size_t)a * nb + b, e_ba = (size_t)b * nb + a;
+    double s = 0.0, t = 0.0;
+    if (in) {
+        for (int sl = l; sl < nsl; sl += 8) {
             const double* p = part + (size_t)sl * na * nb;
             if (!symmetrise || ta <= tb) s += p[e_ab];
             if (symmetrise && ta >= tb) t += p[e_ba];
         }
-        out[e] = !symmetrise ? s : (ta == tb ? 0.5 * (s + t) : (ta < tb ? s : t));
     }
+#pragma unroll
+    for (int o = 4; o > 0; o >>= 1) { s += __shfl_xor_sync(0xffffffffu, s, o); t += __shfl_xor_sync(0xffffffffu, t, o); }
+    if (in && l == 0) out[e] = !symmetrise ? s : (ta == tb ? 0.5 * (s + t) : (ta < tb ? s : t));
 }
 
 // ---- the K x K system of one M-step:  Msys = c I + Bc S  (row-major),  rhs[d][a] = sum_k Bc[a][k] R[k][d],  c = lmd sigma2 ----

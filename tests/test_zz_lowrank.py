@@ -285,7 +285,8 @@ def _check_blocked_orthonormalisation(m, rank):
     np.testing.assert_allclose(gram - np.diag(d), 0.0, atol=1e-11)
     dc = np.diag(qc.T.dot(qc))
     assert abs(int((d == 0).sum()) - int((dc == 0).sum())) <= 1          # a column at the 1e-14 threshold may fall either way
-    np.testing.assert_allclose(qb.dot(bb).dot(qb.T), qc.dot(bc).dot(qc.T), atol=2e-6)
+    # the two versions pick different bases for the directions that are float32 noise of G: entries of G ~ 1 agree to that noise
+    np.testing.assert_allclose(qb.dot(bb).dot(qb.T), qc.dot(bc).dot(qc.T), atol=5e-6)
     return int((d == 0).sum())
 
 

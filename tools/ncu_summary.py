@@ -12,7 +12,8 @@ keys = [k for k in hdr if any(s in k for s in (
     "sm__throughput.avg.pct", "dram__bytes_read.sum", "dram__bytes_write.sum", "launch__registers_per_thread",
     "launch__occupancy_limit", "sm__pipe_", "smsp__average_warp", "gpu__dram_throughput", "lts__t_bytes.sum", "smsp__cycles_active.avg",
     "l1tex__data_bank_conflicts_pipe_lsu", "smsp__warp_issue_stalled"))
-    and not any(s in k for s in ("_pred_on", ".max_rate", "peak_sustained.", "_realtime"))]
+    and not any(s in k for s in ("_pred_on", ".max_rate", "peak_sustained.", "_realtime", ".min.", ".max.", ".sum.pct", "_elapsed",
+                                 ".min ", ".max "))]
 for r in rows[2:]:
     print("=" * 100)
     for k in keys:
