@@ -221,7 +221,8 @@ struct cpd_ctx {
     size_t gu_planes_cap = 0, gu_part_cap = 0;
     unsigned char* d_gi_planes = nullptr;                      // exact int8-digit product: digit planes of X, FP64 chunk partials, column maxima
     double *d_gi_part = nullptr, *d_gi_colmax = nullptr;
-    size_t gi_planes_cap = 0, gi_part_cap = 0, gi_colmax_cap = 0;
+    size_t gi_planes_cap = 0, gi_part_cap = 0, gi_colmax_cap = 0, gi_pairs_cap = 0;
+    float4* d_gi_pairs = nullptr;                            // the scaled source points as packed pair records (generators' f32x2 maths)
     size_t lr_out_cap = 0;
     P2PMailbox* d_box = nullptr;          // this rank's mailbox (peers write into it)
     P2PInfo* d_p2p = nullptr;             // device copy of the peer table; non-null => fused P2P exchange
@@ -594,7 +595,7 @@ extern "C" void cpd_destroy(cpd_ctx* h) {
     void* nrp[] = {h->d_G, h->d_W, h->d_A, h->d_B, h->d_ts2, h->d_nrpart, h->d_ipiv, h->d_info, h->d_work};
     for (void* p : nrp) if (p) cudaFree(p);
     void* lrp[] = {h->d_lr_pts, h->d_lr_Q, h->d_lr_X, h->d_lr_coef, h->d_lr_part, h->d_lr_Bc, h->d_lr_S, h->d_lr_R, h->d_lr_sys, h->d_lr_rhs,
-                   h->d_lr_c, h->d_lr_out, h->d_lr_panel, h->d_gu_planes, h->d_gu_part, h->d_gi_planes, h->d_gi_part, h->d_gi_colmax, h->d_wgt, h->d_p1t, h->d_pxt, h->d_la, h->d_log2c};
+                   h->d_lr_c, h->d_lr_out, h->d_lr_panel, h->d_gu_planes, h->d_gu_part, h->d_gi_planes, h->d_gi_part, h->d_gi_colmax, h->d_gi_pairs, h->d_wgt, h->d_p1t, h->d_pxt, h->d_la, h->d_log2c};
     for (void* p : lrp) if (p) cudaFree(p);
     if (h->h_work) free(h->h_work);
     if (h->sol_params && g_sol.DestroyParams) g_sol.DestroyParams(h->sol_params);

@@ -134,11 +134,23 @@ gi_reduce_kernel(const double* __restrict__ part, int nq, int n16, long long ldp
     }
 }
 
+// j-points as packed pairs for the generators' f32x2 arithmetic: record k (32 bytes) = {x_2k, x_2k+1, y_2k, y_2k+1}, {z_2k, z_2k+1, 0, 0}
+__global__ void __launch_bounds__(THREADS)
+gi_pairs_kernel(const float4* __restrict__ pts, long long npairs, float4* __restrict__ rec) {
+    const long long k = (long long)blockIdx.x * THREADS + threadIdx.x;
+    if (k < npairs) {
+        const float4 p = pts[2 * k], q = pts[2 * k + 1];
+        rec[2 * k] = make_float4(p.x, q.x, p.y, q.y);
+        rec[2 * k + 1] = make_float4(p.z, q.z, 0.0f, 0.0f);
+    }
+}
+
 // ---- the product -----------------------------------------------------------------------------------------------------------------
 // one column pass: images = the stage images of gi_split_kernel (jpad / 32 of them); rows [i_begin, i_end) of G;
 // part[q][c][ii] (FP64) = colmax[c] 2^-45 sum_{j in chunk q} g_ij x_cj
 __global__ void __launch_bounds__(GI_THREADS, 1)
-gi_gram_kernel(const unsigned char* __restrict__ images, const float4* __restrict__ pts, long long jpad, int chunk, long long i_begin,
+gi_gram_kernel(const unsigned char* __restrict__ images, const float4* __restrict__ pts, const float4* __restrict__ pairs, long long jpad, int chunk,
+               long long i_begin,
                long long i_end, int n16, const double* __restrict__ colmax, double* __restrict__ part, long long ldp) {
     extern __shared__ __align__(1024) unsigned char gu_smem_raw[];
     unsigned char* smem = gu_smem_raw;
@@ -183,14 +195,14 @@ gi_gram_kernel(const unsigned char* __restrict__ images, const float4* __restric
                     mbar_expect_tx(&full_b[stage], (uint32_t)(3 * GI_PLANE + GI_PTS_BYTES));
                     tma_load_1d(smem + stage * GI_STAGE_BYTES + 3 * GI_PLANE, src + (long long)kb * (3 * GI_PLANE), (uint32_t)(3 * GI_PLANE),
                                 &full_b[stage]);
-                    tma_load_1d(spts + stage * GI_PTS_BYTES, pts + j0 + (long long)kb * GI_KS, (uint32_t)GI_PTS_BYTES, &full_b[stage]);
+                    tma_load_1d(spts + stage * GI_PTS_BYTES, pairs + j0 + (long long)kb * GI_KS, (uint32_t)GI_PTS_BYTES, &full_b[stage]);
                     if (++stage == GI_STAGES) { stage = 0; phase ^= 1; }
                 }
             }
         }
     } else if (warp == 1) {
-        // ===== MMA issuer: level l = s + t accumulates a_s x b_t =====
-        if (lane == 0) {
+        // ===== MMA issuer: level l = s + t accumulates a_s x b_t; the whole warp walks the pipeline, one elected lane issues =====
+        {
             const uint32_t idesc = gi_instr_desc(n16);
             uint32_t stage = 0, phase = 0, acc_phase = 0;
             for (long long u = blockIdx.x; u < nunits; u += gridDim.x) {
@@ -203,20 +215,23 @@ gi_gram_kernel(const unsigned char* __restrict__ images, const float4* __restric
                     gu_wait(&full_a[stage], phase, 13);
                     gu_wait(&full_b[stage], phase, 14);
                     gu_tc_fence_after();
-                    const uint32_t sa = smem_u32(smem + stage * GI_STAGE_BYTES);
+                    const uint32_t sa = smem_u32(smem) + stage * GI_STAGE_BYTES;
                     const uint32_t sb = sa + 3 * GI_PLANE;
                     const uint32_t first = kb != 0 ? 1u : 0u;
-                    uint64_t a[3], b[3];
+                    if (gu_elect_one()) {
+                        uint64_t a[3], b[3];
 #pragma unroll
-                    for (int p = 0; p < 3; ++p) { a[p] = gi_smem_desc(sa + p * GI_PLANE); b[p] = gi_smem_desc(sb + p * GI_PLANE); }
-                    gi_mma_i8(tmem_base, a[0], b[0], idesc, first);
-                    gi_mma_i8(tmem_base + (uint32_t)n16, a[0], b[1], idesc, first);
-                    gi_mma_i8(tmem_base + (uint32_t)n16, a[1], b[0], idesc, 1u);
-                    gi_mma_i8(tmem_base + (uint32_t)(2 * n16), a[0], b[2], idesc, first);
-                    gi_mma_i8(tmem_base + (uint32_t)(2 * n16), a[1], b[1], idesc, 1u);
-                    gi_mma_i8(tmem_base + (uint32_t)(2 * n16), a[2], b[0], idesc, 1u);
-                    gu_commit(&empty[stage]);
-                    if (kb == nst - 1) gu_commit(acc_full);
+                        for (int p = 0; p < 3; ++p) { a[p] = gi_smem_desc(sa + p * GI_PLANE); b[p] = gi_smem_desc(sb + p * GI_PLANE); }
+                        gi_mma_i8(tmem_base, a[0], b[0], idesc, first);
+                        gi_mma_i8(tmem_base + (uint32_t)n16, a[0], b[1], idesc, first);
+                        gi_mma_i8(tmem_base + (uint32_t)n16, a[1], b[0], idesc, 1u);
+                        gi_mma_i8(tmem_base + (uint32_t)(2 * n16), a[0], b[2], idesc, first);
+                        gi_mma_i8(tmem_base + (uint32_t)(2 * n16), a[1], b[1], idesc, 1u);
+                        gi_mma_i8(tmem_base + (uint32_t)(2 * n16), a[2], b[0], idesc, 1u);
+                        gu_commit(&empty[stage]);
+                        if (kb == nst - 1) gu_commit(acc_full);
+                    }
+                    __syncwarp();
                     if (++stage == GI_STAGES) { stage = 0; phase ^= 1; }
                 }
                 acc_phase ^= 1;
@@ -228,7 +243,7 @@ gi_gram_kernel(const unsigned char* __restrict__ images, const float4* __restric
         uint32_t acc_phase = 0;
         for (long long u = blockIdx.x; u < nunits; u += gridDim.x) {
             const int q = (int)(u / ntiles), t = (int)(u % ntiles);
-            gu_wait(acc_full, acc_phase, 15);
+            gu_wait_relaxed(acc_full, acc_phase, 15);
             gu_tc_fence_after();
             const long long ii = (long long)t * GI_ROWS + quarter * 32 + lane;
             double* dst = part + (long long)q * n16 * ldp + ii;
@@ -262,20 +277,26 @@ gi_gram_kernel(const unsigned char* __restrict__ images, const float4* __restric
             long long i = i_begin + (long long)t * GI_ROWS + r;
             if (i >= i_end) i = i_end - 1;
             const float4 a = pts[i];
+            const u64 ax2 = pack2(a.x, a.x), ay2 = pack2(a.y, a.y), az2 = pack2(a.z, a.z), magic2 = pack2(8388608.0f, 8388608.0f);
             for (int kb = 0; kb < nst; ++kb) {
                 // the j-points arrive with the B image (global loads here stalled the 8 generator warps on L2 latency: long-scoreboard
                 // 4.2 of 7.6 warp-cycles per issue in the first version, profiles/r2_ncu_gi_gram_v2.txt)
                 gu_wait(&full_b[stage], phase, 19);
-                const float4* bj = reinterpret_cast<const float4*>(spts + stage * GI_PTS_BYTES) + hf * 16;
-                // g = round(2^23 G) sits in the mantissa of 2^23 + 2^23 G (one FFMA; a float -> integer conversion would go through the
-                // quarter-rate XU pipe that MUFU.EX2 already loads): bytes 2, 1, 0 of the float ARE the digits a0 < 128, a1, a2
+                const ulonglong2* bj = reinterpret_cast<const ulonglong2*>(spts + stage * GI_PTS_BYTES) + hf * 16;     // 8 pair records
+                // g = round(2^23 G) sits in the mantissa of 2^23 + 2^23 G (one FMA; a float -> integer conversion would go through the
+                // quarter-rate XU pipe that MUFU.EX2 already loads): bytes 2, 1, 0 of the float ARE the digits a0 < 128, a1, a2.
+                // Two points per packed f32x2 instruction (the distance chain and the magic FMA), like the E-step kernels.
                 uint32_t gq[16];
 #pragma unroll
-                for (int jj = 0; jj < 16; ++jj) {
-                    const float4 b = bj[jj];
-                    const float dx = a.x - b.x, dy = a.y - b.y, dz = a.z - b.z;
-                    const float e = ex2(-fmaf(dz, dz, fmaf(dy, dy, dx * dx)));                 // the same float32 G as the other kernels
-                    gq[jj] = __float_as_uint(fmaf(fminf(e, 0.99999988f), 8388608.0f, 8388608.0f));
+                for (int pr = 0; pr < 8; ++pr) {
+                    const ulonglong2 bxy = bj[2 * pr];
+                    const u64 bz = bj[2 * pr + 1].x;
+                    const u64 dx = fsub2(ax2, bxy.x), dy = fsub2(ay2, bxy.y), dz = fsub2(az2, bz);
+                    const float2 u = unpack2(ffma2(dz, dz, ffma2(dy, dy, fmul2(dx, dx))));
+                    const u64 e = pack2(fminf(ex2(-u.x), 0.99999988f), fminf(ex2(-u.y), 0.99999988f));    // the same float32 G as the other kernels
+                    const float2 t = unpack2(ffma2(e, magic2, magic2));
+                    gq[2 * pr] = __float_as_uint(t.x);
+                    gq[2 * pr + 1] = __float_as_uint(t.y);
                 }
                 gu_wait(&empty[stage], phase ^ 1, 16);
                 unsigned char* sa = smem + stage * GI_STAGE_BYTES;

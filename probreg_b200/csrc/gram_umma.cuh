@@ -72,6 +72,46 @@ __device__ __forceinline__ void gu_wait(uint64_t* bar, uint32_t parity, int code
 #else
 __device__ __forceinline__ void gu_wait(uint64_t* bar, uint32_t parity, int) { mbar_wait(bar, parity); }
 #endif
+// a wait that is not on the critical path (the epilogue warps wait a whole work unit for acc_full): poll with a pause, so that the
+// waiting warps do not take issue slots from the generators (their spin loops were 30 % of all issued instructions)
+__device__ __forceinline__ void gu_wait_relaxed(uint64_t* bar, uint32_t parity, int code) {
+#ifdef GU_DEBUG_WAIT
+    gu_wait(bar, parity, code);
+#else
+    for (;;) {
+        uint32_t ok;
+        asm volatile(
+            "{\n"
+            ".reg .pred P1;\n"
+            "mbarrier.try_wait.parity.shared::cta.b64 P1, [%1], %2;\n"
+            "selp.u32 %0, 1, 0, P1;\n"
+            "}"
+            : "=r"(ok)
+            : "r"(smem_u32(bar)), "r"(parity)
+            : "memory");
+        if (ok) return;
+        __nanosleep(400);
+    }
+#endif
+}
+// one lane of a converged warp (elect.sync).  The MMA-issuing warp runs its loop with all 32 lanes and elects only around the
+// tcgen05 instructions: the descriptor arithmetic then stays warp-uniform and compiles to the uniform datapath.  Inside an
+// `if (lane == 0)` branch the same values are per-thread registers and every tcgen05.mma needs ~8 R2UR transfers on one thread --
+// the issue loop, not the tensor pipe, set the pace (tensor pipe 37 % active, profiles/r2_ncu_gi_gram_v5.txt).
+__device__ __forceinline__ bool gu_elect_one() {
+    uint32_t pred = 0, laneid = 0;
+    asm volatile(
+        "{\n"
+        ".reg .b32 %%rx;\n"
+        ".reg .pred %%px;\n"
+        "     elect.sync %%rx|%%px, %2;\n"
+        "@%%px mov.s32 %1, 1;\n"
+        "     mov.s32 %0, %%rx;\n"
+        "}\n"
+        : "+r"(laneid), "+r"(pred)
+        : "r"(0xFFFFFFFF));
+    return pred != 0;
+}
 __device__ __forceinline__ void gu_fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void gu_tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void gu_tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
@@ -250,8 +290,8 @@ gu_gram_kernel(const __grid_constant__ CUtensorMap xmap, const float4* __restric
             }
         }
     } else if (warp == 1) {
-        // ===== MMA issuer =====
-        if (lane == 0) {
+        // ===== MMA issuer: the whole warp walks the pipeline, one elected lane issues =====
+        {
             const uint32_t idesc = gu_instr_desc(n16);
             uint32_t stage = 0, phase = 0, acc_phase = 0;
             for (long long u = blockIdx.x; u < nunits; u += gridDim.x) {
@@ -264,24 +304,27 @@ gu_gram_kernel(const __grid_constant__ CUtensorMap xmap, const float4* __restric
                     gu_wait(&full_a[stage], phase, 3);
                     gu_wait(&full_b[stage], phase, 4);
                     gu_tc_fence_after();
-                    const uint32_t sa = smem_u32(smem + stage * GU_STAGE_BYTES);
+                    const uint32_t sa = smem_u32(smem) + stage * GU_STAGE_BYTES;
                     const uint32_t sb = sa + 2 * GU_A_BYTES;
+                    if (gu_elect_one()) {
 #pragma unroll
-                    for (int half = 0; half < 2; ++half) {
-                        const uint32_t d = tmem_base + (uint32_t)(half * n16);
+                        for (int half = 0; half < 2; ++half) {
+                            const uint32_t d = tmem_base + (uint32_t)(half * n16);
 #pragma unroll
-                        for (int kk = 0; kk < 2; ++kk) {
-                            const uint64_t a_hi = gu_smem_desc(sa + half * (128 * 64) + kk * 32);
-                            const uint64_t a_lo = gu_smem_desc(sa + GU_A_BYTES + half * (128 * 64) + kk * 32);
-                            const uint64_t b_hi = gu_smem_desc(sb + kk * 32);
-                            const uint64_t b_lo = gu_smem_desc(sb + GU_B_BYTES + kk * 32);
-                            gu_mma_tf32(d, a_lo, b_hi, idesc, (kb | kk) != 0 ? 1u : 0u);     // small terms first
-                            gu_mma_tf32(d, a_hi, b_lo, idesc, 1u);
-                            gu_mma_tf32(d, a_hi, b_hi, idesc, 1u);
+                            for (int kk = 0; kk < 2; ++kk) {
+                                const uint64_t a_hi = gu_smem_desc(sa + half * (128 * 64) + kk * 32);
+                                const uint64_t a_lo = gu_smem_desc(sa + GU_A_BYTES + half * (128 * 64) + kk * 32);
+                                const uint64_t b_hi = gu_smem_desc(sb + kk * 32);
+                                const uint64_t b_lo = gu_smem_desc(sb + GU_B_BYTES + kk * 32);
+                                gu_mma_tf32(d, a_lo, b_hi, idesc, (kb | kk) != 0 ? 1u : 0u);     // small terms first
+                                gu_mma_tf32(d, a_hi, b_lo, idesc, 1u);
+                                gu_mma_tf32(d, a_hi, b_hi, idesc, 1u);
+                            }
                         }
+                        gu_commit(&empty[stage]);                     // frees the stage once these MMAs have read it
+                        if (kb == nst - 1) gu_commit(acc_full);       // ... and tells the epilogue the unit is complete
                     }
-                    gu_commit(&empty[stage]);                     // frees the stage once these MMAs have read it
-                    if (kb == nst - 1) gu_commit(acc_full);       // ... and tells the epilogue the unit is complete
+                    __syncwarp();
                     if (++stage == GU_STAGES) { stage = 0; phase ^= 1; }
                 }
                 acc_phase ^= 1;
@@ -293,7 +336,7 @@ gu_gram_kernel(const __grid_constant__ CUtensorMap xmap, const float4* __restric
         uint32_t acc_phase = 0;
         for (long long u = blockIdx.x; u < nunits; u += gridDim.x) {
             const int q = (int)(u / ntiles), t = (int)(u % ntiles);
-            gu_wait(acc_full, acc_phase, 5);
+            gu_wait_relaxed(acc_full, acc_phase, 5);
             gu_tc_fence_after();
 #pragma unroll 1
             for (int half = 0; half < 2; ++half) {

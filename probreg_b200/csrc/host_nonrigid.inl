@@ -135,7 +135,9 @@ int lr_gram_rows_i8(cpd_ctx* h, const double* src, double* dst, int rank, long l
     if (ncm > h->gi_colmax_cap) { TRY(dev_alloc(&h->d_gi_colmax, ncm)); h->gi_colmax_cap = ncm; }
     CU(cudaMemsetAsync(h->d_gi_colmax, 0, ncm * sizeof(double), h->stream));
     gi_colmax_kernel<<<(unsigned)rank, THREADS, 0, h->stream>>>(src, h->m, ld, h->d_gi_colmax);
-    h->launches += 1;
+    if ((size_t)ld > h->gi_pairs_cap) { TRY(dev_alloc(&h->d_gi_pairs, (size_t)ld)); h->gi_pairs_cap = (size_t)ld; }
+    gi_pairs_kernel<<<blocks_for(ld / 2), THREADS, 0, h->stream>>>(h->d_lr_pts, ld / 2, h->d_gi_pairs);
+    h->launches += 2;
     for (int c0 = 0; c0 < rank; c0 += per) {
         const int nc = std::min(per, rank - c0), n16 = (nc + 15) / 16 * 16;
         const size_t need_planes = (size_t)(ld / GI_KS) * 3 * GI_PLANE, need_part = (size_t)nq * n16 * ldp;
@@ -143,7 +145,7 @@ int lr_gram_rows_i8(cpd_ctx* h, const double* src, double* dst, int rank, long l
         if (need_part > h->gi_part_cap) { TRY(dev_alloc(&h->d_gi_part, need_part)); h->gi_part_cap = need_part; }
         gi_split_kernel<<<dim3(blocks_for(ld / 16), (unsigned)n16), THREADS, 0, h->stream>>>(src + (size_t)c0 * ld, h->m, ld, nc, n16, ld,
                                                                                           h->d_gi_colmax + c0, h->d_gi_planes);
-        gi_gram_kernel<<<h->sm_count, GI_THREADS, GI_SMEM, h->stream>>>(h->d_gi_planes, h->d_lr_pts, ld, (int)chunk, i_lo, i_hi, n16,
+        gi_gram_kernel<<<h->sm_count, GI_THREADS, GI_SMEM, h->stream>>>(h->d_gi_planes, h->d_lr_pts, h->d_gi_pairs, ld, (int)chunk, i_lo, i_hi, n16,
                                                                        h->d_gi_colmax + c0, h->d_gi_part, ldp);
         gi_reduce_kernel<<<dim3(blocks_for(rows), (unsigned)nc), THREADS, 0, h->stream>>>(h->d_gi_part, nq, n16, ldp, nc, rows, i_lo, ld,
                                                                                            dst + (size_t)c0 * ld);
@@ -302,7 +304,8 @@ extern "C" int cpd_nonrigid_lowrank_begin(cpd_ctx* h, double beta, double lmd, d
         TRY(dev_alloc(&h->d_lr_Q, (size_t)rank * ld));
         TRY(dev_alloc(&h->d_lr_X, (size_t)rank * ld));
         TRY(dev_alloc(&h->d_lr_coef, (size_t)3 * LR_SLICES * (rank + 1)));
-        h->lr_part_cap = std::max<size_t>((size_t)LR_SLICES * rank * rank, (size_t)2 << 20);        // >= 16 MB of slice partials
+        h->lr_part_cap = std::max<size_t>(std::max<size_t>((size_t)LR_SLICES * rank * rank, (size_t)2 << 20),      // >= 16 MB of slice partials
+                                          (size_t)((m + LR_NARROW_PTS - 1) / LR_NARROW_PTS) * rank * 4);
         TRY(dev_alloc(&h->d_lr_part, h->lr_part_cap));
         TRY(dev_alloc(&h->d_lr_panel, (size_t)LR_MAX_RANK * LR_PANEL + 2 * LR_PANEL + LR_PANEL * LR_PANEL +
                                           (size_t)LR_GRAM_BLOCKS * LR_PANEL * LR_PANEL));
@@ -440,7 +443,15 @@ int nonrigid_solve(cpd_ctx* h) {
         const int k = h->lr_rank;
         const long long ld = h->mpad;
         TRY(lr_inner(h, h->d_lr_Q, k, ld, h->d_lr_Q, k, ld, wgt, 1, h->d_lr_S));                 // S = Q^T diag(wgt) Q
-        TRY(lr_inner(h, h->d_lr_Q, k, ld, h->d_B, 3, m, nullptr, 0, h->d_lr_R));              // R = Q^T F (F is [3][m])
+        {   // R = Q^T F (F is [3][m]): the narrow product kernel, block partials merged in a fixed order
+            const int nblk = (int)((m + LR_NARROW_PTS - 1) / LR_NARROW_PTS);
+            if ((size_t)nblk * k * 3 > h->lr_part_cap) return fail(CPD_ERR_STATE, "partial buffer too small for Q^T F");
+            lr_inner_narrow_kernel<<<dim3((unsigned)((k + 7) / 8), (unsigned)nblk), THREADS, 0, h->stream>>>(h->d_lr_Q, k, ld, h->d_B, 3, m, m,
+                                                                                                         h->d_lr_part);
+            lr_merge_kernel<<<blocks_for((long long)k * 3 * 8), THREADS, 0, h->stream>>>(h->d_lr_part, nblk, k, 3, 0, h->d_lr_R);
+            KCHECK();
+            h->launches += 2;
+        }
         lr_system_kernel<<<blocks_for((long long)k * k + 3 * k), THREADS, 0, h->stream>>>(h->d_lr_Bc, h->d_lr_S, h->d_lr_R, k,
                                                                                           &h->d_state->sigma2, h->nr_lmd, h->d_lr_sys,
                                                                                           h->d_lr_rhs, h->d_lr_c);

@@ -349,6 +349,30 @@ lr_inner_kernel(const double* __restrict__ A, int na, long long lda, const doubl
             if (a < na && b < nb) dst[(size_t)a * nb + b] = acc[u][v];
         }
 }
+// part[blk][a][d] = sum over the block's points of A[a][i] F[d][i]   for a narrow right factor (nd <= 4 rows, e.g. the three
+// coordinates of F = px - diag(p1) Y): one warp per row a, lanes over the points -- lr_inner_kernel would pad the 3 columns to a
+// 32-wide tile.  Merged by lr_merge_kernel like the other partials ([blk][na][nd]).
+constexpr int LR_NARROW_PTS = 1024;
+__global__ void __launch_bounds__(THREADS)
+lr_inner_narrow_kernel(const double* __restrict__ A, int na, long long lda, const double* __restrict__ F, int nd, long long ldf, long long m,
+                       double* __restrict__ part) {
+    const int a = blockIdx.x * (THREADS / 32) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (a >= na) return;
+    const long long i_lo = (long long)blockIdx.y * LR_NARROW_PTS, i_hi = (i_lo + LR_NARROW_PTS < m) ? i_lo + LR_NARROW_PTS : m;
+    double acc[4] = {0.0, 0.0, 0.0, 0.0};
+    for (long long i = i_lo + lane; i < i_hi; i += 32) {
+        const double q = A[(long long)a * lda + i];
+#pragma unroll
+        for (int d = 0; d < 4; ++d)
+            if (d < nd) acc[d] = fma(q, F[(long long)d * ldf + i], acc[d]);
+    }
+#pragma unroll
+    for (int d = 0; d < 4; ++d) {
+        const double v = warp_sum(acc[d]);
+        if (lane == 0 && d < nd) part[((size_t)blockIdx.y * na + a) * nd + d] = v;
+    }
+}
+
 // out[e] = sum_slices part[s][e]  (fixed order: 8 lanes per output take the slices l, l + 8, ..., then a fixed shuffle tree joins
 // them).  symmetrise != 0 (square, mathematically symmetric result whose tiles below the diagonal were not computed): diagonal
 // tiles give (x + x^T) / 2, the others are mirrored from the upper triangle.

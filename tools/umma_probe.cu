@@ -270,7 +270,7 @@ static int full_test_i8(long long m, int rank, double beta, bool time_old, int x
             X[(size_t)c * mpad + j] = v;
         }
     double *dY, *dX, *dOutNew, *dOutOld, *dColmax, *dPart;
-    float4* dPts;
+    float4 *dPts, *dPairs;
     unsigned char* dPlanes;
     const long long chunk = mpad < GI_MAX_CHUNK ? mpad : GI_MAX_CHUNK;
     const int nq = (int)((mpad + chunk - 1) / chunk), ntiles = (int)((m + GI_ROWS - 1) / GI_ROWS);
@@ -280,12 +280,14 @@ static int full_test_i8(long long m, int rank, double beta, bool time_old, int x
     CK(cudaMalloc(&dOutNew, (size_t)rank * mpad * 8)); CK(cudaMalloc(&dOutOld, (size_t)rank * mpad * 8));
     CK(cudaMalloc(&dPts, (size_t)mpad * 16));
     CK(cudaMalloc(&dPlanes, (size_t)(mpad / GI_KS) * 3 * GI_PLANE));
+    CK(cudaMalloc(&dPairs, (size_t)mpad * 16));
     CK(cudaMalloc(&dPart, (size_t)nq * n16max * ldp * 8));
     CK(cudaMalloc(&dColmax, (size_t)(rank + 256) * 8));
     CK(cudaMemset(dColmax, 0, (size_t)(rank + 256) * 8));
     CK(cudaMemcpy(dY, Y.data(), (size_t)m * 3 * 8, cudaMemcpyHostToDevice));
     CK(cudaMemcpy(dX, X.data(), (size_t)rank * mpad * 8, cudaMemcpyHostToDevice));
     lr_pack_kernel<<<(unsigned)((mpad + THREADS - 1) / THREADS), THREADS>>>(dY, 0.0, 0.0, 0.0, m, mpad, (float)sqrt(LOG2E / (2.0 * beta)), dPts);
+    gi_pairs_kernel<<<(unsigned)((mpad / 2 + THREADS - 1) / THREADS), THREADS>>>(dPts, mpad / 2, dPairs);
     CK(cudaFuncSetAttribute(gi_gram_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GI_SMEM));
     int sms = 148;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, 0);
@@ -301,7 +303,7 @@ static int full_test_i8(long long m, int rank, double beta, bool time_old, int x
             gi_split_kernel<<<dim3((unsigned)((mpad / 16 + THREADS - 1) / THREADS), n16), THREADS>>>(dX + (size_t)c0 * mpad, m, mpad, nc, n16, mpad, dColmax + c0, dPlanes);
             cudaEvent_t g0, g1; cudaEventCreate(&g0); cudaEventCreate(&g1);
             cudaEventRecord(g0);
-            gi_gram_kernel<<<sms, GI_THREADS, GI_SMEM>>>(dPlanes, dPts, mpad, (int)chunk, 0, m, n16, dColmax + c0, dPart, ldp);
+            gi_gram_kernel<<<sms, GI_THREADS, GI_SMEM>>>(dPlanes, dPts, dPairs, mpad, (int)chunk, 0, m, n16, dColmax + c0, dPart, ldp);
             cudaEventRecord(g1);
             gi_reduce_kernel<<<dim3((unsigned)((m + THREADS - 1) / THREADS), nc), THREADS>>>(dPart, nq, n16, ldp, nc, m, 0, mpad, dOutNew + (size_t)c0 * mpad);
             CK(cudaGetLastError());
