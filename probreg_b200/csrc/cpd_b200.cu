@@ -335,20 +335,14 @@ int download_cloud(cpd_ctx* h, const double* src3, long long count, double* dst)
     return CPD_OK;
 }
 
-// sums[0] = sum |p|^2, sums[1..3] = sum p   over a device count x 3 cloud (result on host)
-int cloud_sums(cpd_ctx* h, const double* d_pts, long long count, double out[4]) {
+// d_out[0] = sum |p|^2, d_out[1..3] = sum p   over a device count x 3 cloud; stays on the device (stream-ordered, no sync).
+// `part`: blocks_for(count) * 4 doubles of scratch.
+int cloud_sums_dev(cpd_ctx* h, const double* d_pts, long long count, double* part, double* d_out) {
     const unsigned nb = blocks_for(count);
-    if (h->sums_cap < (size_t)nb * 4 + 4) {
-        TRY(dev_alloc(&h->d_sums, (size_t)nb * 4 + 4));
-        h->sums_cap = (size_t)nb * 4 + 4;
-    }
-    cloud_sums_kernel<<<nb, THREADS, 0, h->stream>>>(d_pts, count, h->d_sums + 4);
-    reduce_cols_kernel<<<1, 32, 0, h->stream>>>(h->d_sums + 4, (int)nb, 4, h->d_sums);
+    cloud_sums_kernel<<<nb, THREADS, 0, h->stream>>>(d_pts, count, part);
+    reduce_cols_kernel<<<1, 32, 0, h->stream>>>(part, (int)nb, 4, d_out);
     KCHECK();
     h->launches += 2;
-    CU(cudaMemcpyAsync(h->h_pin, h->d_sums, 4 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
-    CU(cudaStreamSynchronize(h->stream));
-    for (int k = 0; k < 4; ++k) out[k] = h->h_pin[k];
     return CPD_OK;
 }
 
@@ -684,16 +678,16 @@ extern "C" int cpd_sigma2_init(cpd_ctx* h, double* sigma2) {
     if (!h || !sigma2) return fail(CPD_ERR_ARG, "null argument");
     if (!h->have_source || !h->have_target) return fail(CPD_ERR_STATE, "source and target must both be set");
     CU(cudaSetDevice(h->device));
+    // target sums (summed over the ranks on the device), source sums, ONE read-back: a single host synchronisation
     double sx[4], sy[4];
-    TRY(cloud_sums(h, h->d_xc, h->n, sx));
-    if (h->comm) {   // sum the target-side sums over ranks
-        CU(cudaMemcpyAsync(h->d_mom, sx, 4 * sizeof(double), cudaMemcpyHostToDevice, h->stream));
-        TRY(allreduce(h, h->d_mom, 4));
-        CU(cudaMemcpyAsync(h->h_pin, h->d_mom, 4 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
-        CU(cudaStreamSynchronize(h->stream));
-        for (int k = 0; k < 4; ++k) sx[k] = h->h_pin[k];
-    }
-    TRY(cloud_sums(h, h->d_yc, h->m, sy));
+    const size_t pn = (size_t)blocks_for(h->n) * 4, pm = (size_t)blocks_for(h->m) * 4;
+    if (h->sums_cap < 16 + pn + pm) { TRY(dev_alloc(&h->d_sums, 16 + pn + pm)); h->sums_cap = 16 + pn + pm; }
+    TRY(cloud_sums_dev(h, h->d_xc, h->n, h->d_sums + 16, h->d_sums));
+    if (h->comm) TRY(allreduce(h, h->d_sums, 4));
+    TRY(cloud_sums_dev(h, h->d_yc, h->m, h->d_sums + 16 + pn, h->d_sums + 4));
+    CU(cudaMemcpyAsync(h->h_pin, h->d_sums, 8 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    for (int k = 0; k < 4; ++k) { sx[k] = h->h_pin[k]; sy[k] = h->h_pin[4 + k]; }
     // move the source sums into the targets' frame: y' = y~ + (cy - cx)
     double dlt[3], d2 = 0.0, dsy = 0.0;
     for (int a = 0; a < 3; ++a) { dlt[a] = h->h_state.cy[a] - h->h_state.cx[a]; d2 += dlt[a] * dlt[a]; dsy += dlt[a] * sy[1 + a]; }

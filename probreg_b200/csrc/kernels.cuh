@@ -61,10 +61,10 @@ constexpr int RI1 = CPD_RI1, RI2 = CPD_RI2;            // i-points held in regis
 constexpr int ITILE1 = THREADS * RI1, ITILE2 = THREADS * RI2;   // i-points per CTA
 constexpr int NPAIR1 = RI1 / 2, NPAIR2 = RI2 / 2;      // i-points are processed as packed f32x2 pairs (FADD2 / FFMA2)
 #ifndef CPD_P1_STAGE
-#define CPD_P1_STAGE 256
+#define CPD_P1_STAGE 512
 #endif
 #ifndef CPD_P2_STAGE
-#define CPD_P2_STAGE 256
+#define CPD_P2_STAGE 512
 #endif
 constexpr int P1_STAGE = CPD_P1_STAGE;   // sources per TMA stage in pass 1 (32 B records -> 16 KB); a multiple of 256
 constexpr int P2_STAGE = CPD_P2_STAGE;   // targets per TMA stage in pass 2 (48 B records -> 24 KB); a multiple of 256
