@@ -1,0 +1,12 @@
+#!/bin/bash
+# round 2, call K: the round-end sequence on one GPU (tests, smoke, reference arm, bench line) on the final build
+mkdir -p gpurun_out
+timeout 1500 python -m pytest tests -m gpu -q --maxfail=20 -rfEs --tb=short > gpurun_out/pytest_k.txt 2>&1; echo "pytest exit $?" >> gpurun_out/pytest_k.txt
+tail -6 gpurun_out/pytest_k.txt
+timeout 600 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/smoke_k.txt 2>&1; echo "smoke exit $?" >> gpurun_out/smoke_k.txt; tail -4 gpurun_out/smoke_k.txt
+timeout 900 python bench.py --impl reference --steps 5 --warmup 1 > gpurun_out/bench_ref_k.json 2> gpurun_out/bench_ref_k.err
+timeout 1200 python bench.py --steps 20 --warmup 3 > gpurun_out/bench_k.json 2> gpurun_out/bench_k.err; echo "bench exit $?" >> gpurun_out/bench_k.err
+python -c "
+import json; j=json.load(open('gpurun_out/bench_k.json')); print('cfg2', j['value'], j['ms_per_step'], j['e2e']['value'], j['stage_ms'], j['roofline']['frac']); print(json.dumps(j['config']['also'])[:1500]); print(j['cpu_baseline']['value'], j['cpu_baseline']['kind'])
+r=json.load(open('gpurun_out/bench_ref_k.json')); print('ref', r['value'], r['cpu_baseline']['kind'], r['config'])"
+tail -3 gpurun_out/bench_k.err
