@@ -275,11 +275,11 @@ class NonRigidCPD(CoherentPointDrift):
         self._tf_obj = None
         self._nr_key = self._nr_src = self._nr_handle = self._nr_factors = None      # what the handle's G / factors were built for
         if not self._source is None:
-            self._tf_obj = self._tf_type(None, self._source, self._beta, self.xp)
+            self._tf_obj = self._tf_type(None, self._source, self._beta, self.xp, device=self._device)
 
     def set_source(self, source):
         super(NonRigidCPD, self).set_source(source)
-        self._tf_obj = self._tf_type(None, self._source, self._beta)
+        self._tf_obj = self._tf_type(None, self._source, self._beta, device=self._device)
 
     def maximization_step(self, target, estep_res, sigma2_p=None):
         """Non-rigid M-step (probreg/cpd.py:284-303) from a caller-supplied EstepResult, on the device
@@ -307,7 +307,7 @@ class NonRigidCPD(CoherentPointDrift):
                 h.nonrigid_lowrank_begin(self._beta, self._lmd, sigma2, 0.0, self._low_rank, self._low_rank_iters, self._low_rank_seed)
                 self._nr_factors = h.nonrigid_lowrank_factors()
                 self._tf_obj = tf.LowRankNonRigidTransformation(self._tf_obj.w, self._source, self._beta, self._nr_factors[0],
-                                                                self._nr_factors[1])
+                                                                self._nr_factors[1], device=self._device)
             else:
                 h.nonrigid_begin(self._beta, self._lmd, sigma2, 0.0)
             self._nr_key, self._nr_src, self._nr_handle = key, np.array(self._source, copy=True), h
@@ -357,14 +357,14 @@ class NonRigidCPD(CoherentPointDrift):
             h.nonrigid_restart(self._lmd, res.sigma2, w)          # same source as last time: G / the factors are still valid
             if self._low_rank:
                 self._tf_obj = tf.LowRankNonRigidTransformation(self._tf_obj.w, self._source, self._beta, self._nr_factors[0],
-                                                                self._nr_factors[1])
+                                                                self._nr_factors[1], device=self._device)
         else:
             self._nr_key = self._nr_src = None
             if self._low_rank:
                 h.nonrigid_lowrank_begin(self._beta, self._lmd, res.sigma2, w, self._low_rank, self._low_rank_iters, self._low_rank_seed)
                 self._nr_factors = h.nonrigid_lowrank_factors()
                 self._tf_obj = tf.LowRankNonRigidTransformation(self._tf_obj.w, self._source, self._beta, self._nr_factors[0],
-                                                                self._nr_factors[1])
+                                                                self._nr_factors[1], device=self._device)
             else:
                 h.nonrigid_begin(self._beta, self._lmd, res.sigma2, w)
             self._nr_key, self._nr_src, self._nr_handle = key, np.array(self._source, copy=True), h
@@ -445,7 +445,24 @@ class ConstrainedNonRigidCPD(NonRigidCPD):
         self.p1_tilde = np.zeros(m)
         self.px_tilde = np.zeros((m, dim))
         if self.idx_source is not None and self.idx_target is not None:
-            pairs = np.unique(np.c_[np.asarray(self.idx_source).ravel(), np.asarray(self.idx_target).ravel()], axis=0)
+            # the reference writes p_tilde[idx_source, idx_target] = 1 (cpd.py:368): NumPy advanced indexing -- the two index arrays
+            # broadcast against each other, negative indices count from the end, boolean masks select positions
+            n = np.asarray(target).shape[0]
+
+            def as_index(idx, size):
+                a = np.asarray(idx)
+                if a.dtype == np.bool_:
+                    if a.shape != (size,):
+                        raise IndexError("boolean index of shape %s does not match the axis of size %d" % (a.shape, size))
+                    return np.flatnonzero(a)
+                if not np.issubdtype(a.dtype, np.integer):
+                    raise IndexError("idx_source / idx_target must be integer or boolean index arrays, got %s" % a.dtype)
+                if a.size and (a.min() < -size or a.max() >= size):
+                    raise IndexError("index out of bounds for axis of size %d" % size)
+                return a.astype(np.intp) % size
+
+            isrc, itgt = np.broadcast_arrays(as_index(self.idx_source, m), as_index(self.idx_target, n))
+            pairs = np.unique(np.c_[isrc.ravel(), itgt.ravel()], axis=0)
             np.add.at(self.p1_tilde, pairs[:, 0], 1.0)
             np.add.at(self.px_tilde, pairs[:, 0], np.asarray(target, dtype=np.float64)[pairs[:, 1]])
 

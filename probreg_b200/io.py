@@ -39,6 +39,7 @@ def read_ply(path):
         if f.readline().strip() != b"ply":
             raise ValueError("%s: not a PLY file" % path)
         fmt, n_vertex, props, in_vertex = None, 0, [], False
+        before = []          # elements declared BEFORE the vertex element: (count, [(name, type) or ("list", count type, item type)])
         while True:
             line = f.readline()
             if not line:
@@ -52,13 +53,28 @@ def read_ply(path):
                 in_vertex = tok[1] == "vertex"
                 if in_vertex:
                     n_vertex = int(tok[2])
+                elif n_vertex == 0:
+                    before.append((int(tok[2]), []))
             elif tok[0] == "property" and in_vertex:
                 if tok[1] == "list":
                     raise ValueError("list properties on vertices are not supported")
                 props.append((tok[2], _PLY_TYPES[tok[1]]))
+            elif tok[0] == "property" and before and n_vertex == 0:
+                before[-1][1].append(tuple(tok[1:]))
             elif tok[0] == "end_header":
                 break
         names = [p[0] for p in props]
+        if n_vertex == 0 or not all(c in names for c in ("x", "y", "z")):
+            raise ValueError("%s: no vertex element with x, y, z properties" % path)
+        # skip whatever the file stores in front of the vertices (rare, but legal PLY)
+        for count, eprops in before:
+            if fmt == "ascii":
+                for _ in range(count):
+                    f.readline()
+            elif any(p[0] == "list" for p in eprops):
+                raise ValueError("%s: a list-valued element precedes the vertices in a binary file" % path)
+            else:
+                f.read(count * sum(np.dtype(_PLY_TYPES[p[0]]).itemsize for p in eprops))
         if fmt == "ascii":
             rows = [f.readline().split() for _ in range(n_vertex)]
             return np.array([[float(r[names.index(c)]) for c in ("x", "y", "z")] for r in rows], dtype=np.float64)

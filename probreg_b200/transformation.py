@@ -78,17 +78,18 @@ class NonRigidTransformation(Transformation):
     ``w`` or the final moved points never pays for an M x M host array.
     """
 
-    def __init__(self, w, points, beta=2.0, xp=np):
+    def __init__(self, w, points, beta=2.0, xp=np, device=0):
         super(NonRigidTransformation, self).__init__(xp)
         self._points = points
         self._beta = beta
         self._g = None
+        self._device = device            # CUDA ordinal of the registration that owns this map (extension over the reference)
         self.w = w
 
     @property
     def g(self):
-        if self._g is None:
-            self._g = mu.rbf_kernel(self._points, self._points, self._beta)
+        if self._g is None:              # built lazily, on the owner's GPU (not always GPU 0: multi-rank runs)
+            self._g = mu.rbf_kernel(self._points, self._points, self._beta, device=self._device)
         return self._g
 
     @g.setter
@@ -107,8 +108,8 @@ class LowRankNonRigidTransformation(NonRigidTransformation):
     ``g`` stays available (dense, built on first use) for code written against the reference's attribute.
     """
 
-    def __init__(self, w, points, beta, q, bcore, xp=np):
-        super(LowRankNonRigidTransformation, self).__init__(w, points, beta, xp)
+    def __init__(self, w, points, beta, q, bcore, xp=np, device=0):
+        super(LowRankNonRigidTransformation, self).__init__(w, points, beta, xp, device)
         self.q = q
         self.bcore = bcore
 

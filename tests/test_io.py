@@ -85,3 +85,21 @@ def test_example_utils_follow_the_reference_recipes():
     assert d.max() < 0.01
     fish = ex.prepare_source_and_target_nonrigid_2d(ex.reference_file("fish_source.txt"), ex.reference_file("fish_target.txt"))
     assert fish[0].shape == (91, 2) and fish[1].shape == (91, 2)
+
+
+def test_ply_with_an_element_in_front_of_the_vertices(tmp_path):
+    """Legal PLY: another element may precede `vertex`; its rows are skipped (ascii and binary)."""
+    import struct
+
+    pts = np.arange(15, dtype=np.float32).reshape(5, 3)
+    head = ("ply\nformat %s 1.0\nelement camera 2\nproperty float32 fx\nproperty int32 id\nelement vertex 5\n"
+            "property float32 x\nproperty float32 y\nproperty float32 z\nend_header\n")
+    p = tmp_path / "pre_ascii.ply"
+    p.write_text(head % "ascii" + "1.5 7\n2.5 8\n" + "\n".join(" ".join("%g" % v for v in r) for r in pts) + "\n")
+    np.testing.assert_allclose(pio.read_ply(str(p)), pts)
+    p = tmp_path / "pre_bin.ply"
+    with open(str(p), "wb") as f:
+        f.write((head % "binary_little_endian").encode())
+        f.write(struct.pack("<fi", 1.5, 7) + struct.pack("<fi", 2.5, 8))
+        f.write(pts.astype("<f4").tobytes())
+    np.testing.assert_allclose(pio.read_ply(str(p)), pts)

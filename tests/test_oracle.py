@@ -144,3 +144,37 @@ def test_bench_workload_is_the_oracles():
         a = orc.synthetic_pair(777, kind)
         b = synthetic.synthetic_pair(777, kind)
         assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1])
+
+
+def test_constrained_prior_terms_follow_numpy_indexing():
+    """ConstrainedNonRigidCPD builds p1_tilde / px_tilde of cpd.py:364-374 as a sparse gather; the reference's dense
+    `p_tilde[idx_source, idx_target] = 1` accepts anything NumPy advanced indexing accepts (broadcasting, negative indices,
+    boolean masks) -- the gather must give the same two sums.  Host-only: no device call is made by _prior_terms."""
+    from probreg_b200 import cpd
+
+    rng = np.random.default_rng(5)
+    m, n = 17, 23
+    src, tgt = rng.random((m, 3)), rng.random((n, 3))
+    mask = np.zeros(m, dtype=bool)
+    mask[[2, 5, 11]] = True
+    cases = [
+        (np.array([0, 3, 3, 9]), np.array([1, 4, 4, 20])),              # equal length, a duplicate pair
+        (np.array([0, 3, 9]), 7),                                        # scalar broadcasts
+        (np.array([-1, -17, 4]), np.array([-23, 5, -1])),                # negative indices
+        (mask, np.array([6, 7, 8])),                                     # boolean mask on the source axis
+        (np.array([[0], [1]]), np.array([[2, 3, 4]])),                   # 2-D broadcast: 2 x 3 pairs
+    ]
+    for isrc, itgt in cases:
+        obj = cpd.ConstrainedNonRigidCPD.__new__(cpd.ConstrainedNonRigidCPD)
+        obj._source, obj.idx_source, obj.idx_target = src, isrc, itgt
+        obj._prior_terms(tgt)
+        dense = np.zeros((m, n))
+        dense[isrc, itgt] = 1.0
+        np.testing.assert_allclose(obj.p1_tilde, dense.sum(axis=1))
+        np.testing.assert_allclose(obj.px_tilde, dense.dot(tgt), atol=1e-15)
+    obj.idx_source, obj.idx_target = np.array([0.5]), np.array([1])
+    with pytest.raises(IndexError):
+        obj._prior_terms(tgt)
+    obj.idx_source, obj.idx_target = np.array([m]), np.array([1])
+    with pytest.raises(IndexError):
+        obj._prior_terms(tgt)
