@@ -322,6 +322,207 @@ gi_gram_kernel(const unsigned char* __restrict__ images, const float4* __restric
     if (warp == 1) gu_tmem_dealloc(tmem_base, 512);
 }
 
+constexpr int GI_TS_STAGES = 7;                        // the A ring in TMEM: 7 x 24 columns behind the 336 accumulator columns
+constexpr int GI_TS_STAGE_BYTES = 3 * GI_PLANE;         // shared memory per stage: the B image only
+constexpr int GI_TS_SMEM = GI_TS_STAGES * (GI_TS_STAGE_BYTES + GI_PTS_BYTES) + 1024 + 256;
+__device__ __forceinline__ void gi_mma_i8_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "setp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::1.kind::i8 [%0], [%1], %2, %3, p;\n"
+        "}" ::"r"(d_tmem),
+        "r"(a_tmem), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// four consecutive 32-bit columns of this thread's TMEM lane
+__device__ __forceinline__ void gi_tmem_st4(uint32_t taddr, uint32_t w0, uint32_t w1, uint32_t w2, uint32_t w3) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1, %2, %3, %4};" ::"r"(taddr), "r"(w0), "r"(w1), "r"(w2), "r"(w3) : "memory");
+}
+
+// ---- the product, A operand in TENSOR MEMORY (tcgen05.mma ".ts" form) ---------------------------------------------------------------
+// Same algorithm, barriers and B pipeline as gi_gram_kernel; the generators write their digit rows with tcgen05.st into a ring of
+// TMEM columns (lane = row of the tile, 8 columns of 4 bytes per digit plane and stage) instead of shared memory, and the MMAs take A
+// from there.  Why: gi_gram_kernel is bound by the shared-memory port (generator STS + LDS 51 %, tensor operand reads 42 %,
+// profiles/r2_ncu_gi_gram_final.txt); this removes the 12 KB of STS and the 24 KB of A-operand reads per stage.
+// TMEM: accumulators in columns [0, 3 n16), the A ring behind 3 GI_NMAX: GI_TS_STAGES x 3 planes x 8 columns (336 + 168 = 504 <= 512).
+// A generator warp can only reach the 32 lanes of its quarter (warp id % 4): row = 32 (warp % 4) + lane, half = (warp - 6) / 4.
+// one column pass: images = the stage images of gi_split_kernel (jpad / 32 of them); rows [i_begin, i_end) of G;
+// part[q][c][ii] (FP64) = colmax[c] 2^-45 sum_{j in chunk q} g_ij x_cj
+__global__ void __launch_bounds__(GI_THREADS, 1)
+gi_gram_ts_kernel(const unsigned char* __restrict__ images, const float4* __restrict__ pts, const float4* __restrict__ pairs, long long jpad, int chunk,
+               long long i_begin,
+               long long i_end, int n16, const double* __restrict__ colmax, double* __restrict__ part, long long ldp) {
+    extern __shared__ __align__(1024) unsigned char gu_smem_raw[];
+    unsigned char* smem = gu_smem_raw;
+    unsigned char* spts = smem + GI_TS_STAGES * GI_TS_STAGE_BYTES;            // [GI_TS_STAGES][32] float4: the j-points of each stage
+    uint64_t* bars = reinterpret_cast<uint64_t*>(spts + GI_TS_STAGES * GI_PTS_BYTES);
+    uint64_t* full_a = bars;
+    uint64_t* full_b = bars + GI_TS_STAGES;
+    uint64_t* empty = bars + 2 * GI_TS_STAGES;
+    uint64_t* acc_full = bars + 3 * GI_TS_STAGES;
+    uint64_t* acc_empty = bars + 3 * GI_TS_STAGES + 1;
+    uint32_t* tmem_base_slot = reinterpret_cast<uint32_t*>(bars + 3 * GI_TS_STAGES + 2);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const long long rows = i_end - i_begin;
+    const int ntiles = (int)((rows + GI_ROWS - 1) / GI_ROWS);
+    const int nq = (int)((jpad + chunk - 1) / chunk);
+    const long long nunits = (long long)ntiles * nq;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < GI_TS_STAGES; ++s) { mbar_init(&full_a[s], 8); mbar_init(&full_b[s], 1); mbar_init(&empty[s], 1); }
+        mbar_init(acc_full, 1);
+        mbar_init(acc_empty, 4);
+        mbar_fence_init();
+    }
+    if (warp == 1) gu_tmem_alloc(tmem_base_slot, 512);
+    gu_tc_fence_before();
+    __syncthreads();
+    gu_tc_fence_after();
+    const uint32_t tmem_base = *tmem_base_slot;
+
+    if (warp == 0) {
+        // ===== TMA producer: the stage image (three digit planes of X for 32 points), one bulk copy =====
+        if (lane == 0) {
+            uint32_t stage = 0, phase = 0;
+            for (long long u = blockIdx.x; u < nunits; u += gridDim.x) {
+                const int q = (int)(u / ntiles);
+                const long long j0 = (long long)q * chunk;
+                const int nst = (int)((min((long long)chunk, jpad - j0)) / GI_KS);
+                const unsigned char* src = images + (j0 / GI_KS) * (3 * GI_PLANE);
+                for (int kb = 0; kb < nst; ++kb) {
+                    gu_wait(&empty[stage], phase ^ 1, 11);
+                    mbar_expect_tx(&full_b[stage], (uint32_t)(3 * GI_PLANE + GI_PTS_BYTES));
+                    tma_load_1d(smem + stage * GI_TS_STAGE_BYTES, src + (long long)kb * (3 * GI_PLANE), (uint32_t)(3 * GI_PLANE),
+                                &full_b[stage]);
+                    tma_load_1d(spts + stage * GI_PTS_BYTES, pairs + j0 + (long long)kb * GI_KS, (uint32_t)GI_PTS_BYTES, &full_b[stage]);
+                    if (++stage == GI_TS_STAGES) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===== MMA issuer: level l = s + t accumulates a_s x b_t; the whole warp walks the pipeline, one elected lane issues =====
+        {
+            const uint32_t idesc = gi_instr_desc(n16);
+            uint32_t stage = 0, phase = 0, acc_phase = 0;
+            for (long long u = blockIdx.x; u < nunits; u += gridDim.x) {
+                const int q = (int)(u / ntiles);
+                const long long j0 = (long long)q * chunk;
+                const int nst = (int)((min((long long)chunk, jpad - j0)) / GI_KS);
+                gu_wait(acc_empty, acc_phase ^ 1, 12);
+                gu_tc_fence_after();
+                for (int kb = 0; kb < nst; ++kb) {
+                    gu_wait(&full_a[stage], phase, 13);
+                    gu_wait(&full_b[stage], phase, 14);
+                    gu_tc_fence_after();
+                    const uint32_t sb = smem_u32(smem) + stage * GI_TS_STAGE_BYTES;
+                    const uint32_t ta = tmem_base + (uint32_t)(3 * GI_NMAX + stage * 24);       // this stage's three A planes (8 columns each)
+                    const uint32_t first = kb != 0 ? 1u : 0u;
+                    if (gu_elect_one()) {
+                        uint64_t b[3];
+#pragma unroll
+                        for (int p = 0; p < 3; ++p) b[p] = gi_smem_desc(sb + p * GI_PLANE);
+                        gi_mma_i8_ts(tmem_base, ta, b[0], idesc, first);
+                        gi_mma_i8_ts(tmem_base + (uint32_t)n16, ta, b[1], idesc, first);
+                        gi_mma_i8_ts(tmem_base + (uint32_t)n16, ta + 8, b[0], idesc, 1u);
+                        gi_mma_i8_ts(tmem_base + (uint32_t)(2 * n16), ta, b[2], idesc, first);
+                        gi_mma_i8_ts(tmem_base + (uint32_t)(2 * n16), ta + 8, b[1], idesc, 1u);
+                        gi_mma_i8_ts(tmem_base + (uint32_t)(2 * n16), ta + 16, b[0], idesc, 1u);
+                        gu_commit(&empty[stage]);
+                        if (kb == nst - 1) gu_commit(acc_full);
+                    }
+                    __syncwarp();
+                    if (++stage == GI_TS_STAGES) { stage = 0; phase ^= 1; }
+                }
+                acc_phase ^= 1;
+            }
+        }
+    } else if (warp < 6) {
+        // ===== epilogue: join the three levels in FP64 (exact), scale, store the chunk partial =====
+        const int quarter = warp & 3;
+        uint32_t acc_phase = 0;
+        for (long long u = blockIdx.x; u < nunits; u += gridDim.x) {
+            const int q = (int)(u / ntiles), t = (int)(u % ntiles);
+            gu_wait_relaxed(acc_full, acc_phase, 15);
+            gu_tc_fence_after();
+            const long long ii = (long long)t * GI_ROWS + quarter * 32 + lane;
+            double* dst = part + (long long)q * n16 * ldp + ii;
+            const uint32_t tlane = tmem_base + ((uint32_t)(quarter * 32) << 16);
+#pragma unroll 1
+            for (int c0 = 0; c0 < n16; c0 += 16) {
+                int v0[16], v1[16], v2[16];
+                gi_tmem_ld16(tlane + (uint32_t)c0, v0);
+                gi_tmem_ld16(tlane + (uint32_t)(n16 + c0), v1);
+                gi_tmem_ld16(tlane + (uint32_t)(2 * n16 + c0), v2);
+#pragma unroll
+                for (int k = 0; k < 16; ++k) {
+                    const double s = (double)v0[k] * 65536.0 + (double)v1[k] * 256.0 + (double)v2[k];      // exact: < 2^48
+                    dst[(long long)(c0 + k) * ldp] = s * (colmax[c0 + k] * (1.0 / 536870912.0));           // 2^16 2^-45
+                }
+            }
+            gu_tc_fence_before();
+            __syncwarp();
+            if (lane == 0) gu_mbar_arrive(acc_empty);
+            acc_phase ^= 1;
+        }
+    } else {
+        // ===== generators: two threads per row (16 points each); digits of round(2^23 G) into the three A planes =====
+        const int quarter = warp & 3, r = quarter * 32 + lane, hf = (warp - 6) >> 2;
+        uint32_t stage = 0, phase = 0;
+        for (long long u = blockIdx.x; u < nunits; u += gridDim.x) {
+            const int q = (int)(u / ntiles), t = (int)(u % ntiles);
+            const long long j0 = (long long)q * chunk;
+            const int nst = (int)((min((long long)chunk, jpad - j0)) / GI_KS);
+            long long i = i_begin + (long long)t * GI_ROWS + r;
+            if (i >= i_end) i = i_end - 1;
+            const float4 a = pts[i];
+            const u64 ax2 = pack2(a.x, a.x), ay2 = pack2(a.y, a.y), az2 = pack2(a.z, a.z), magic2 = pack2(8388608.0f, 8388608.0f);
+            for (int kb = 0; kb < nst; ++kb) {
+                // the j-points arrive with the B image (global loads here stalled the 8 generator warps on L2 latency: long-scoreboard
+                // 4.2 of 7.6 warp-cycles per issue in the first version, profiles/r2_ncu_gi_gram_v2.txt)
+                gu_wait(&full_b[stage], phase, 19);
+                const ulonglong2* bj = reinterpret_cast<const ulonglong2*>(spts + stage * GI_PTS_BYTES) + hf * 16;     // 8 pair records
+                // g = round(2^23 G) sits in the mantissa of 2^23 + 2^23 G (one FMA; a float -> integer conversion would go through the
+                // quarter-rate XU pipe that MUFU.EX2 already loads): bytes 2, 1, 0 of the float ARE the digits a0 < 128, a1, a2.
+                // Two points per packed f32x2 instruction (the distance chain and the magic FMA), like the E-step kernels.
+                uint32_t gq[16];
+#pragma unroll
+                for (int pr = 0; pr < 8; ++pr) {
+                    const ulonglong2 bxy = bj[2 * pr];
+                    const u64 bz = bj[2 * pr + 1].x;
+                    const u64 dx = fsub2(ax2, bxy.x), dy = fsub2(ay2, bxy.y), dz = fsub2(az2, bz);
+                    const float2 u = unpack2(ffma2(dz, dz, ffma2(dy, dy, fmul2(dx, dx))));
+                    const u64 e = pack2(fminf(ex2(-u.x), 0.99999988f), fminf(ex2(-u.y), 0.99999988f));    // the same float32 G as the other kernels
+                    const float2 t = unpack2(ffma2(e, magic2, magic2));
+                    gq[2 * pr] = __float_as_uint(t.x);
+                    gq[2 * pr + 1] = __float_as_uint(t.y);
+                }
+                gu_wait(&empty[stage], phase ^ 1, 16);
+                gu_tc_fence_after();                               // the MMAs that read this slot last have completed (tcgen05.commit)
+                const uint32_t ta = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(3 * GI_NMAX + stage * 24 + hf * 4);
+#pragma unroll
+                for (int p = 0; p < 3; ++p) {
+                    const uint32_t sel = p == 0 ? 0x0062u : (p == 1 ? 0x0051u : 0x0040u);     // byte (2 - p) of both inputs
+                    const uint32_t w0 = __byte_perm(__byte_perm(gq[0], gq[1], sel), __byte_perm(gq[2], gq[3], sel), 0x5410u);
+                    const uint32_t w1 = __byte_perm(__byte_perm(gq[4], gq[5], sel), __byte_perm(gq[6], gq[7], sel), 0x5410u);
+                    const uint32_t w2 = __byte_perm(__byte_perm(gq[8], gq[9], sel), __byte_perm(gq[10], gq[11], sel), 0x5410u);
+                    const uint32_t w3 = __byte_perm(__byte_perm(gq[12], gq[13], sel), __byte_perm(gq[14], gq[15], sel), 0x5410u);
+                    gi_tmem_st4(ta + (uint32_t)(p * 8), w0, w1, w2, w3);       // this row's 16 bytes of plane p: 4 columns
+                }
+                asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+                gu_tc_fence_before();
+                __syncwarp();
+                if (lane == 0) gu_mbar_arrive(&full_a[stage]);
+                if (++stage == GI_TS_STAGES) { stage = 0; phase ^= 1; }
+            }
+        }
+    }
+    gu_tc_fence_before();
+    __syncthreads();
+    if (warp == 1) gu_tmem_dealloc(tmem_base, 512);
+}
+
 // ---- layout probe: D[128][n16] (int32) = A[128][32] (u8) x B[n16][32]^T (s8), through the conventions above -------------------------
 __global__ void __launch_bounds__(128, 1)
 gi_layout_probe_kernel(const __grid_constant__ CUtensorMap bmap, const unsigned char* __restrict__ A, int n16, int* __restrict__ D) {
@@ -362,6 +563,50 @@ gi_layout_probe_kernel(const __grid_constant__ CUtensorMap bmap, const unsigned 
     gu_tc_fence_before();
     __syncthreads();
     if (warp == 0) gu_tmem_dealloc(tmem_base, 256);
+}
+
+// the same probe with A in tensor memory (tcgen05.st by the owning thread, ".ts" MMA)
+__global__ void __launch_bounds__(128, 1)
+gi_layout_probe_ts_kernel(const __grid_constant__ CUtensorMap bmap, const unsigned char* __restrict__ A, int n16, int* __restrict__ D) {
+    extern __shared__ __align__(1024) unsigned char gu_smem_raw[];
+    unsigned char* smem = gu_smem_raw;
+    unsigned char* sb = smem;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 8192);
+    uint32_t* slot = reinterpret_cast<uint32_t*>(bars + 2);
+    const int warp = threadIdx.x >> 5, r = threadIdx.x;
+    if (threadIdx.x == 0) { mbar_init(&bars[0], 1); mbar_init(&bars[1], 1); mbar_fence_init(); }
+    if (warp == 0) gu_tmem_alloc(slot, 512);
+    gu_tc_fence_before();
+    __syncthreads();
+    gu_tc_fence_after();
+    const uint32_t tmem_base = *slot;
+    if (threadIdx.x == 0) {
+        mbar_expect_tx(&bars[0], (uint32_t)(n16 * 32));
+        gu_tma_load_2d(sb, &bmap, 0, 0, &bars[0]);
+    }
+    const uint4 lo = *reinterpret_cast<const uint4*>(A + r * 32), hi = *reinterpret_cast<const uint4*>(A + r * 32 + 16);
+    const uint32_t ta = tmem_base + ((uint32_t)(warp * 32) << 16) + 256u;          // A in columns 256..263
+    gi_tmem_st4(ta, lo.x, lo.y, lo.z, lo.w);
+    gi_tmem_st4(ta + 4, hi.x, hi.y, hi.z, hi.w);
+    asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+    gu_tc_fence_before();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        gu_wait(&bars[0], 0, 27);
+        gu_tc_fence_after();
+        gi_mma_i8_ts(tmem_base, tmem_base + 256u, gi_smem_desc(smem_u32(sb)), gi_instr_desc(n16), 0u);
+        gu_commit(&bars[1]);
+    }
+    gu_wait(&bars[1], 0, 28);
+    gu_tc_fence_after();
+    for (int c0 = 0; c0 < n16; c0 += 16) {
+        int v[16];
+        gi_tmem_ld16(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)c0, v);
+        for (int k = 0; k < 16; ++k) D[r * n16 + c0 + k] = v[k];
+    }
+    gu_tc_fence_before();
+    __syncthreads();
+    if (warp == 0) gu_tmem_dealloc(tmem_base, 512);
 }
 
 // tensor map over byte planes: [rows][ld] bytes, box {32, box_rows}, 32-byte swizzle

@@ -119,7 +119,7 @@ int lr_gram_rows_umma(cpd_ctx* h, const double* src, double* dst, int rank, long
     return CPD_OK;
 }
 // exact integer-digit product (gram_i8.cuh): the default
-int lr_gram_rows_i8(cpd_ctx* h, const double* src, double* dst, int rank, long long i_lo, long long i_hi) {
+int lr_gram_rows_i8(cpd_ctx* h, const double* src, double* dst, int rank, long long i_lo, long long i_hi, bool a_in_tmem) {
     const long long ld = h->mpad, rows = i_hi - i_lo;
     const long long chunk = std::min<long long>(GI_MAX_CHUNK, ld);          // ld is a multiple of 512, hence of GI_KS
     const int nq = (int)((ld + chunk - 1) / chunk);
@@ -128,6 +128,7 @@ int lr_gram_rows_i8(cpd_ctx* h, const double* src, double* dst, int rank, long l
     static bool attr_set = false;
     if (!attr_set) {
         CU(cudaFuncSetAttribute(gi_gram_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GI_SMEM));
+        CU(cudaFuncSetAttribute(gi_gram_ts_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GI_TS_SMEM));
         attr_set = true;
     }
     const int passes = (rank + GI_NMAX - 1) / GI_NMAX, per = (rank + passes - 1) / passes;
@@ -145,8 +146,12 @@ int lr_gram_rows_i8(cpd_ctx* h, const double* src, double* dst, int rank, long l
         if (need_part > h->gi_part_cap) { TRY(dev_alloc(&h->d_gi_part, need_part)); h->gi_part_cap = need_part; }
         gi_split_kernel<<<dim3(blocks_for(ld / 16), (unsigned)n16), THREADS, 0, h->stream>>>(src + (size_t)c0 * ld, h->m, ld, nc, n16, ld,
                                                                                           h->d_gi_colmax + c0, h->d_gi_planes);
-        gi_gram_kernel<<<h->sm_count, GI_THREADS, GI_SMEM, h->stream>>>(h->d_gi_planes, h->d_lr_pts, h->d_gi_pairs, ld, (int)chunk, i_lo, i_hi, n16,
-                                                                       h->d_gi_colmax + c0, h->d_gi_part, ldp);
+        if (a_in_tmem)
+            gi_gram_ts_kernel<<<h->sm_count, GI_THREADS, GI_TS_SMEM, h->stream>>>(h->d_gi_planes, h->d_lr_pts, h->d_gi_pairs, ld, (int)chunk, i_lo, i_hi,
+                                                                                 n16, h->d_gi_colmax + c0, h->d_gi_part, ldp);
+        else
+            gi_gram_kernel<<<h->sm_count, GI_THREADS, GI_SMEM, h->stream>>>(h->d_gi_planes, h->d_lr_pts, h->d_gi_pairs, ld, (int)chunk, i_lo, i_hi, n16,
+                                                                           h->d_gi_colmax + c0, h->d_gi_part, ldp);
         gi_reduce_kernel<<<dim3(blocks_for(rows), (unsigned)nc), THREADS, 0, h->stream>>>(h->d_gi_part, nq, n16, ldp, nc, rows, i_lo, ld,
                                                                                            dst + (size_t)c0 * ld);
         KCHECK();
@@ -180,13 +185,13 @@ int lr_gram_apply(cpd_ctx* h, const double* src, double* dst, int rank) {
         static bool checked = false;
         if (mode < 0) {
             const char* e = getenv("CPD_B200_LR_GRAM");
-            mode = (e && !strcmp(e, "simt")) ? 1 : ((e && !strcmp(e, "tf32")) ? 2 : 0);
+            mode = (e && !strcmp(e, "simt")) ? 1 : ((e && !strcmp(e, "tf32")) ? 2 : ((e && !strcmp(e, "i8ts")) ? 3 : 0));   // 3: i8, A operand in TMEM
         }
         if (mode == 1) {
             TRY(lr_gram_rows_simt(h, src, dst, rank, i_lo, i_hi));
         } else {
             if (mode == 2) TRY(lr_gram_rows_umma(h, src, dst, rank, i_lo, i_hi));
-            else TRY(lr_gram_rows_i8(h, src, dst, rank, i_lo, i_hi));
+            else TRY(lr_gram_rows_i8(h, src, dst, rank, i_lo, i_hi, mode == 3));
             if (!checked) {
                 // first use in this process: the first rows of the first <= 16 columns once more on the CUDA cores.  A mismatch
                 // is an error (a wrong descriptor or swizzle shows as O(1) differences), never a silent change of path.

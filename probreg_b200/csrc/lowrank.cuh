@@ -314,7 +314,9 @@ __global__ void __launch_bounds__(THREADS)
 lr_inner_kernel(const double* __restrict__ A, int na, long long lda, const double* __restrict__ Bm, int nb, long long ldb,
                 const double* __restrict__ wt, long long m, int upper_only /* symmetric result: tiles below the diagonal are skipped */,
                 double* __restrict__ part /* [gridDim.y][na][nb] */) {
-    __shared__ double sa[LR_TILE][LR_CHUNK + 1], sb[LR_TILE][LR_CHUNK + 1];
+    // rows padded by 2 doubles: 16-byte aligned for the two-point LDS.128 of the inner loop, and the 16 rows a quarter-warp reads
+    // in one step fall into distinct bank quads (row stride 132 words)
+    __shared__ __align__(16) double sa[LR_TILE][LR_CHUNK + 2], sb[LR_TILE][LR_CHUNK + 2];
     const int tiles_b = (nb + LR_TILE - 1) / LR_TILE;
     const int ta0 = (blockIdx.x / tiles_b) * LR_TILE, tb0 = (blockIdx.x % tiles_b) * LR_TILE;
     if (upper_only && ta0 > tb0) return;            // the whole CTA, before any barrier; lr_merge_kernel mirrors the upper tiles
@@ -334,10 +336,15 @@ lr_inner_kernel(const double* __restrict__ A, int na, long long lda, const doubl
             sb[r][ii] = (in && tb0 + r < nb) ? Bm[(long long)(tb0 + r) * ldb + i] : 0.0;
         }
         __syncthreads();
+        // two points per shared-memory load: 4 LDS.128 feed 8 DFMA (one LDS.64 per DFMA made the loop shared-memory bound)
 #pragma unroll 8
-        for (int ii = 0; ii < LR_CHUNK; ++ii) {
-            const double a0 = sa[ty][ii], a1 = sa[ty + 16][ii], b0 = sb[tx][ii], b1 = sb[tx + 16][ii];
-            acc[0][0] += a0 * b0; acc[0][1] += a0 * b1; acc[1][0] += a1 * b0; acc[1][1] += a1 * b1;
+        for (int ii = 0; ii < LR_CHUNK; ii += 2) {
+            const double2 a0 = *reinterpret_cast<const double2*>(&sa[ty][ii]), a1 = *reinterpret_cast<const double2*>(&sa[ty + 16][ii]);
+            const double2 b0 = *reinterpret_cast<const double2*>(&sb[tx][ii]), b1 = *reinterpret_cast<const double2*>(&sb[tx + 16][ii]);
+            acc[0][0] = fma(a0.x, b0.x, acc[0][0]); acc[0][1] = fma(a0.x, b1.x, acc[0][1]);
+            acc[1][0] = fma(a1.x, b0.x, acc[1][0]); acc[1][1] = fma(a1.x, b1.x, acc[1][1]);
+            acc[0][0] = fma(a0.y, b0.y, acc[0][0]); acc[0][1] = fma(a0.y, b1.y, acc[0][1]);
+            acc[1][0] = fma(a1.y, b0.y, acc[1][0]); acc[1][1] = fma(a1.y, b1.y, acc[1][1]);
         }
     }
     double* dst = part + (size_t)slice * na * nb;

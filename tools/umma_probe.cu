@@ -188,7 +188,7 @@ static int full_test(long long m, int rank, int chunk, double beta, bool time_ol
 }
 
 // ---- kind::i8 (gram_i8.cuh): exact integer results, so every comparison is for equality --------------------------------------------
-static int run_layout_i8(int n16, const std::vector<unsigned char>& A, const std::vector<signed char>& B, std::vector<int>& D) {
+static int run_layout_i8(int n16, const std::vector<unsigned char>& A, const std::vector<signed char>& B, std::vector<int>& D, bool ts = false) {
     unsigned char* dA; signed char* dB; int* dD;
     CK(cudaMalloc(&dA, 128 * 32)); CK(cudaMalloc(&dB, (size_t)n16 * 32)); CK(cudaMalloc(&dD, (size_t)128 * n16 * 4));
     CK(cudaMemcpy(dA, A.data(), 128 * 32, cudaMemcpyHostToDevice));
@@ -197,7 +197,9 @@ static int run_layout_i8(int n16, const std::vector<unsigned char>& A, const std
     CUtensorMap map;
     if (gi_make_map(&map, dB, 32, n16, n16) != 0) { printf("i8 tensor map encode failed\n"); return 1; }
     CK(cudaFuncSetAttribute(gi_layout_probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 20000));
-    gi_layout_probe_kernel<<<1, 128, 20000>>>(map, dA, n16, dD);
+    CK(cudaFuncSetAttribute(gi_layout_probe_ts_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 20000));
+    if (ts) gi_layout_probe_ts_kernel<<<1, 128, 20000>>>(map, dA, n16, dD);
+    else gi_layout_probe_kernel<<<1, 128, 20000>>>(map, dA, n16, dD);
     CK(cudaGetLastError());
     CK(cudaDeviceSynchronize());
     D.resize((size_t)128 * n16);
@@ -207,7 +209,7 @@ static int run_layout_i8(int n16, const std::vector<unsigned char>& A, const std
     if (tc) { printf("i8 layout probe: wait %d timed out\n", tc); return 2; }
     return 0;
 }
-static int layout_tests_i8() {
+static int layout_tests_i8(bool ts = false) {
     unsigned long long seed = 4242;
     int bad = 0;
     for (int n16 : {16, 112, 256}) {
@@ -216,7 +218,7 @@ static int layout_tests_i8() {
         std::vector<int> D;
         for (auto& v : A) v = (unsigned char)(urand(seed) * 256.0);
         for (auto& v : B) v = (signed char)((int)(urand(seed) * 256.0) - 128);
-        const int rc = run_layout_i8(n16, A, B, D);
+        const int rc = run_layout_i8(n16, A, B, D, ts);
         if (rc) return rc;
         long long wrong = 0;
         for (int r = 0; r < 128; ++r)
@@ -225,7 +227,7 @@ static int layout_tests_i8() {
                 for (int k = 0; k < 32; ++k) s += (int)A[r * 32 + k] * (int)B[n * 32 + k];
                 wrong += s != D[(size_t)r * n16 + n];
             }
-        printf("i8 layout n=%3d: %lld of %d entries differ from the integer reference   %s\n", n16, wrong, 128 * n16, wrong ? "MISMATCH" : "OK");
+        printf("i8 layout%s n=%3d: %lld of %d entries differ from the integer reference   %s\n", ts ? " (A in TMEM)" : "", n16, wrong, 128 * n16, wrong ? "MISMATCH" : "OK");
         if (wrong) bad = 1;
     }
     if (bad) {
@@ -236,7 +238,7 @@ static int layout_tests_i8() {
         std::vector<int> D;
         for (int r = 0; r < 128; ++r) for (int k = 0; k < 32; ++k) A[r * 32 + k] = (unsigned char)((r & 7) * 32 + k);
         for (int n = 0; n < 32; ++n) B[n * 32 + n] = 1;
-        if (run_layout_i8(n16, A, B, D) == 0) {
+        if (run_layout_i8(n16, A, B, D, ts) == 0) {
             printf("decode A (identity B): D[r][n] should be 32 (r %% 8) + n; as (row %% 8, k) read:\n");
             for (int r : {0, 1, 2, 3, 4, 5, 6, 7, 8, 12, 127}) {
                 printf("  r=%3d:", r);
@@ -258,7 +260,7 @@ static int layout_tests_i8() {
     return bad ? 3 : 0;
 }
 
-static int full_test_i8(long long m, int rank, double beta, bool time_old, int xkind) {
+static int full_test_i8(long long m, int rank, double beta, bool time_old, int xkind, bool ts = false) {
     const long long mpad = (m + 511) / 512 * 512;
     unsigned long long seed = 999;
     std::vector<double> Y((size_t)m * 3), X((size_t)rank * mpad, 0.0);
@@ -289,6 +291,7 @@ static int full_test_i8(long long m, int rank, double beta, bool time_old, int x
     lr_pack_kernel<<<(unsigned)((mpad + THREADS - 1) / THREADS), THREADS>>>(dY, 0.0, 0.0, 0.0, m, mpad, (float)sqrt(LOG2E / (2.0 * beta)), dPts);
     gi_pairs_kernel<<<(unsigned)((mpad / 2 + THREADS - 1) / THREADS), THREADS>>>(dPts, mpad / 2, dPairs);
     CK(cudaFuncSetAttribute(gi_gram_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GI_SMEM));
+    CK(cudaFuncSetAttribute(gi_gram_ts_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GI_TS_SMEM));
     int sms = 148;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, 0);
     cudaEvent_t e0, e1;
@@ -303,7 +306,8 @@ static int full_test_i8(long long m, int rank, double beta, bool time_old, int x
             gi_split_kernel<<<dim3((unsigned)((mpad / 16 + THREADS - 1) / THREADS), n16), THREADS>>>(dX + (size_t)c0 * mpad, m, mpad, nc, n16, mpad, dColmax + c0, dPlanes);
             cudaEvent_t g0, g1; cudaEventCreate(&g0); cudaEventCreate(&g1);
             cudaEventRecord(g0);
-            gi_gram_kernel<<<sms, GI_THREADS, GI_SMEM>>>(dPlanes, dPts, dPairs, mpad, (int)chunk, 0, m, n16, dColmax + c0, dPart, ldp);
+            if (ts) gi_gram_ts_kernel<<<sms, GI_THREADS, GI_TS_SMEM>>>(dPlanes, dPts, dPairs, mpad, (int)chunk, 0, m, n16, dColmax + c0, dPart, ldp);
+            else gi_gram_kernel<<<sms, GI_THREADS, GI_SMEM>>>(dPlanes, dPts, dPairs, mpad, (int)chunk, 0, m, n16, dColmax + c0, dPart, ldp);
             cudaEventRecord(g1);
             gi_reduce_kernel<<<dim3((unsigned)((m + THREADS - 1) / THREADS), nc), THREADS>>>(dPart, nq, n16, ldp, nc, m, 0, mpad, dOutNew + (size_t)c0 * mpad);
             CK(cudaGetLastError());
@@ -317,8 +321,8 @@ static int full_test_i8(long long m, int rank, double beta, bool time_old, int x
         const int tc = timeout_code();
         if (tc) { printf("i8 full kernel: wait %d timed out\n", tc); return 2; }
     }
-    printf("i8: m=%lld rank=%d (%d passes of N=%d) beta=%g xkind=%d: gram kernels %.3f ms, whole product (incl. split/reduce and host syncs) %.3f ms; "
-           "%.1f TFLOP/s useful\n", m, rank, passes, n16max, beta, xkind, t_gram, t_all, 2.0 * m * m * rank / (t_gram * 1e-3) / 1e12);
+    printf("i8%s: m=%lld rank=%d (%d passes of N=%d) beta=%g xkind=%d: gram kernels %.3f ms, whole product (incl. split/reduce and host syncs) %.3f ms; "
+           "%.1f TFLOP/s useful\n", ts ? " (A in TMEM)" : "", m, rank, passes, n16max, beta, xkind, t_gram, t_all, 2.0 * m * m * rank / (t_gram * 1e-3) / 1e12);
     float t_old = 0;
     if (time_old) {
         cudaEventRecord(e0);
@@ -384,5 +388,16 @@ int main(int argc, char** argv) {
     rc4 |= full_test_i8(20000, 230, 0.5, true, 1);
     rc4 |= full_test_i8(m, rank, 2.0, true, 0);
     printf("full tests (i8): %s\n", rc4 == 0 ? "PASS" : "FAIL");
-    return rc3 | rc4;
+    int rc5 = layout_tests_i8(true);
+    printf("layout tests (i8, A in TMEM): %s\n", rc5 == 0 ? "PASS" : "FAIL");
+    if (rc5 == 2) return rc5;
+    int rc6 = 0;
+    if (rc5 == 0) {
+        rc6 = full_test_i8(3000, 200, 2.0, true, 0, true);
+        if (rc6 == 2) return rc6;
+        rc6 |= full_test_i8(20000, 230, 0.5, true, 1, true);
+        rc6 |= full_test_i8(m, rank, 2.0, true, 0, true);
+        printf("full tests (i8, A in TMEM): %s\n", rc6 == 0 ? "PASS" : "FAIL");
+    }
+    return rc3 | rc4 | rc5 | rc6;
 }
