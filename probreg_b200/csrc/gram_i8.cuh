@@ -15,6 +15,7 @@
 // An accumulator receives at most 3 products of magnitude < 2^15 per point: exact in int32 for chunks of up to 16384 points.
 // The epilogue joins the three levels in FP64 (exact) and applies the column scale; chunk partials are added in a fixed order.
 //
+// Two kernels: gi_gram_kernel (A operand in shared memory) and gi_gram_ts_kernel (A operand in tensor memory: the default, see below).
 // CTA = 128 rows of G x up to 112 columns (3 accumulators x 112 columns of TMEM); the columns of X are taken in passes of <= 112,
 // G is regenerated per pass (the generator needs ~2/3 of the MMA time).  Persistent over {row tile, column pass, j-chunk};
 // warp roles, pipeline and barriers as in gram_umma.cuh, with 32-point stages (one MMA K-step) and 8 stages of 24 KB.
@@ -323,6 +324,8 @@ gi_gram_kernel(const unsigned char* __restrict__ images, const float4* __restric
 }
 
 constexpr int GI_TS_STAGES = 7;                        // the A ring in TMEM: 7 x 24 columns behind the 336 accumulator columns
+constexpr int GI_TS_GEN = 16;                          // generator warps (four threads per row of the tile)
+constexpr int GI_TS_THREADS = (6 + GI_TS_GEN) * 32;
 constexpr int GI_TS_STAGE_BYTES = 3 * GI_PLANE;         // shared memory per stage: the B image only
 constexpr int GI_TS_SMEM = GI_TS_STAGES * (GI_TS_STAGE_BYTES + GI_PTS_BYTES) + 1024 + 256;
 __device__ __forceinline__ void gi_mma_i8_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
@@ -335,6 +338,9 @@ __device__ __forceinline__ void gi_mma_i8_ts(uint32_t d_tmem, uint32_t a_tmem, u
         "r"(a_tmem), "l"(bdesc), "r"(idesc), "r"(accumulate)
         : "memory");
 }
+__device__ __forceinline__ void gi_tmem_st2(uint32_t taddr, uint32_t w0, uint32_t w1) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x2.b32 [%0], {%1, %2};" ::"r"(taddr), "r"(w0), "r"(w1) : "memory");
+}
 // four consecutive 32-bit columns of this thread's TMEM lane
 __device__ __forceinline__ void gi_tmem_st4(uint32_t taddr, uint32_t w0, uint32_t w1, uint32_t w2, uint32_t w3) {
     asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1, %2, %3, %4};" ::"r"(taddr), "r"(w0), "r"(w1), "r"(w2), "r"(w3) : "memory");
@@ -346,10 +352,10 @@ __device__ __forceinline__ void gi_tmem_st4(uint32_t taddr, uint32_t w0, uint32_
 // from there.  Why: gi_gram_kernel is bound by the shared-memory port (generator STS + LDS 51 %, tensor operand reads 42 %,
 // profiles/r2_ncu_gi_gram_final.txt); this removes the 12 KB of STS and the 24 KB of A-operand reads per stage.
 // TMEM: accumulators in columns [0, 3 n16), the A ring behind 3 GI_NMAX: GI_TS_STAGES x 3 planes x 8 columns (336 + 168 = 504 <= 512).
-// A generator warp can only reach the 32 lanes of its quarter (warp id % 4): row = 32 (warp % 4) + lane, half = (warp - 6) / 4.
+// A generator warp can only reach the 32 lanes of its quarter (warp id % 4): row = 32 (warp % 4) + lane, point group = (warp - 6) / 4.
 // one column pass: images = the stage images of gi_split_kernel (jpad / 32 of them); rows [i_begin, i_end) of G;
 // part[q][c][ii] (FP64) = colmax[c] 2^-45 sum_{j in chunk q} g_ij x_cj
-__global__ void __launch_bounds__(GI_THREADS, 1)
+__global__ void __launch_bounds__(GI_TS_THREADS, 1)
 gi_gram_ts_kernel(const unsigned char* __restrict__ images, const float4* __restrict__ pts, const float4* __restrict__ pairs, long long jpad, int chunk,
                long long i_begin,
                long long i_end, int n16, const double* __restrict__ colmax, double* __restrict__ part, long long ldp) {
@@ -371,7 +377,7 @@ gi_gram_ts_kernel(const unsigned char* __restrict__ images, const float4* __rest
     const long long nunits = (long long)ntiles * nq;
 
     if (threadIdx.x == 0) {
-        for (int s = 0; s < GI_TS_STAGES; ++s) { mbar_init(&full_a[s], 8); mbar_init(&full_b[s], 1); mbar_init(&empty[s], 1); }
+        for (int s = 0; s < GI_TS_STAGES; ++s) { mbar_init(&full_a[s], GI_TS_GEN); mbar_init(&full_b[s], 1); mbar_init(&empty[s], 1); }
         mbar_init(acc_full, 1);
         mbar_init(acc_empty, 4);
         mbar_fence_init();
@@ -467,8 +473,9 @@ gi_gram_ts_kernel(const unsigned char* __restrict__ images, const float4* __rest
             acc_phase ^= 1;
         }
     } else {
-        // ===== generators: two threads per row (16 points each); digits of round(2^23 G) into the three A planes =====
-        const int quarter = warp & 3, r = quarter * 32 + lane, hf = (warp - 6) >> 2;
+        // ===== generators: FOUR threads per row (8 points each), 16 warps: four per scheduler instead of two -- the 8-warp version
+        // issued at half the peak rate with every pipe below 45 % (latency, not throughput).  Digits of round(2^23 G) -> TMEM =====
+        const int quarter = warp & 3, r = quarter * 32 + lane, part = (warp - 6) >> 2;          // part: which 8 of the stage's 32 points
         uint32_t stage = 0, phase = 0;
         for (long long u = blockIdx.x; u < nunits; u += gridDim.x) {
             const int q = (int)(u / ntiles), t = (int)(u % ntiles);
@@ -479,36 +486,31 @@ gi_gram_ts_kernel(const unsigned char* __restrict__ images, const float4* __rest
             const float4 a = pts[i];
             const u64 ax2 = pack2(a.x, a.x), ay2 = pack2(a.y, a.y), az2 = pack2(a.z, a.z), magic2 = pack2(8388608.0f, 8388608.0f);
             for (int kb = 0; kb < nst; ++kb) {
-                // the j-points arrive with the B image (global loads here stalled the 8 generator warps on L2 latency: long-scoreboard
-                // 4.2 of 7.6 warp-cycles per issue in the first version, profiles/r2_ncu_gi_gram_v2.txt)
-                gu_wait(&full_b[stage], phase, 19);
-                const ulonglong2* bj = reinterpret_cast<const ulonglong2*>(spts + stage * GI_PTS_BYTES) + hf * 16;     // 8 pair records
+                gu_wait(&full_b[stage], phase, 19);                // the j-points arrive with the B image
+                const ulonglong2* bj = reinterpret_cast<const ulonglong2*>(spts + stage * GI_PTS_BYTES) + part * 8;     // 4 pair records
                 // g = round(2^23 G) sits in the mantissa of 2^23 + 2^23 G (one FMA; a float -> integer conversion would go through the
                 // quarter-rate XU pipe that MUFU.EX2 already loads): bytes 2, 1, 0 of the float ARE the digits a0 < 128, a1, a2.
-                // Two points per packed f32x2 instruction (the distance chain and the magic FMA), like the E-step kernels.
-                uint32_t gq[16];
+                uint32_t gq[8];
 #pragma unroll
-                for (int pr = 0; pr < 8; ++pr) {
+                for (int pr = 0; pr < 4; ++pr) {
                     const ulonglong2 bxy = bj[2 * pr];
                     const u64 bz = bj[2 * pr + 1].x;
                     const u64 dx = fsub2(ax2, bxy.x), dy = fsub2(ay2, bxy.y), dz = fsub2(az2, bz);
-                    const float2 u = unpack2(ffma2(dz, dz, ffma2(dy, dy, fmul2(dx, dx))));
-                    const u64 e = pack2(fminf(ex2(-u.x), 0.99999988f), fminf(ex2(-u.y), 0.99999988f));    // the same float32 G as the other kernels
-                    const float2 t = unpack2(ffma2(e, magic2, magic2));
-                    gq[2 * pr] = __float_as_uint(t.x);
-                    gq[2 * pr + 1] = __float_as_uint(t.y);
+                    const float2 uu = unpack2(ffma2(dz, dz, ffma2(dy, dy, fmul2(dx, dx))));
+                    const u64 e = pack2(fminf(ex2(-uu.x), 0.99999988f), fminf(ex2(-uu.y), 0.99999988f));  // the same float32 G as the other kernels
+                    const float2 tt = unpack2(ffma2(e, magic2, magic2));
+                    gq[2 * pr] = __float_as_uint(tt.x);
+                    gq[2 * pr + 1] = __float_as_uint(tt.y);
                 }
                 gu_wait(&empty[stage], phase ^ 1, 16);
                 gu_tc_fence_after();                               // the MMAs that read this slot last have completed (tcgen05.commit)
-                const uint32_t ta = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(3 * GI_NMAX + stage * 24 + hf * 4);
+                const uint32_t ta = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(3 * GI_NMAX + stage * 24 + part * 2);
 #pragma unroll
                 for (int p = 0; p < 3; ++p) {
                     const uint32_t sel = p == 0 ? 0x0062u : (p == 1 ? 0x0051u : 0x0040u);     // byte (2 - p) of both inputs
                     const uint32_t w0 = __byte_perm(__byte_perm(gq[0], gq[1], sel), __byte_perm(gq[2], gq[3], sel), 0x5410u);
                     const uint32_t w1 = __byte_perm(__byte_perm(gq[4], gq[5], sel), __byte_perm(gq[6], gq[7], sel), 0x5410u);
-                    const uint32_t w2 = __byte_perm(__byte_perm(gq[8], gq[9], sel), __byte_perm(gq[10], gq[11], sel), 0x5410u);
-                    const uint32_t w3 = __byte_perm(__byte_perm(gq[12], gq[13], sel), __byte_perm(gq[14], gq[15], sel), 0x5410u);
-                    gi_tmem_st4(ta + (uint32_t)(p * 8), w0, w1, w2, w3);       // this row's 16 bytes of plane p: 4 columns
+                    gi_tmem_st2(ta + (uint32_t)(p * 8), w0, w1);       // this row's 8 bytes of plane p: 2 columns
                 }
                 asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
                 gu_tc_fence_before();

@@ -147,7 +147,7 @@ int lr_gram_rows_i8(cpd_ctx* h, const double* src, double* dst, int rank, long l
         gi_split_kernel<<<dim3(blocks_for(ld / 16), (unsigned)n16), THREADS, 0, h->stream>>>(src + (size_t)c0 * ld, h->m, ld, nc, n16, ld,
                                                                                           h->d_gi_colmax + c0, h->d_gi_planes);
         if (a_in_tmem)
-            gi_gram_ts_kernel<<<h->sm_count, GI_THREADS, GI_TS_SMEM, h->stream>>>(h->d_gi_planes, h->d_lr_pts, h->d_gi_pairs, ld, (int)chunk, i_lo, i_hi,
+            gi_gram_ts_kernel<<<h->sm_count, GI_TS_THREADS, GI_TS_SMEM, h->stream>>>(h->d_gi_planes, h->d_lr_pts, h->d_gi_pairs, ld, (int)chunk, i_lo, i_hi,
                                                                                  n16, h->d_gi_colmax + c0, h->d_gi_part, ldp);
         else
             gi_gram_kernel<<<h->sm_count, GI_THREADS, GI_SMEM, h->stream>>>(h->d_gi_planes, h->d_lr_pts, h->d_gi_pairs, ld, (int)chunk, i_lo, i_hi, n16,
@@ -179,19 +179,19 @@ int lr_gram_apply(cpd_ctx* h, const double* src, double* dst, int rank) {
 #ifdef CPD_HOST_EMU
         TRY(lr_gram_rows_simt(h, src, dst, rank, i_lo, i_hi));
 #else
-        // 0: tensor cores, exact integer digits (default); 1: CUDA cores (FP32); 2: tensor cores, TF32 x 3 (FP32 TMEM accumulation:
-        // ~1e-5 relative, measured -- kept for comparison, profiles/r2_umma_*)
+        // 0: tensor cores, exact integer digits, A operand in tensor memory (default); 3: the same with the A operand in shared memory;
+        // 1: CUDA cores (FP32); 2: tensor cores, TF32 x 3 (FP32 TMEM accumulation: ~1e-5 relative, measured -- kept for comparison)
         static int mode = -1;
         static bool checked = false;
         if (mode < 0) {
             const char* e = getenv("CPD_B200_LR_GRAM");
-            mode = (e && !strcmp(e, "simt")) ? 1 : ((e && !strcmp(e, "tf32")) ? 2 : ((e && !strcmp(e, "i8ts")) ? 3 : 0));   // 3: i8, A operand in TMEM
+            mode = (e && !strcmp(e, "simt")) ? 1 : ((e && !strcmp(e, "tf32")) ? 2 : ((e && !strcmp(e, "i8ss")) ? 3 : 0));   // 3: i8, A operand in smem
         }
         if (mode == 1) {
             TRY(lr_gram_rows_simt(h, src, dst, rank, i_lo, i_hi));
         } else {
             if (mode == 2) TRY(lr_gram_rows_umma(h, src, dst, rank, i_lo, i_hi));
-            else TRY(lr_gram_rows_i8(h, src, dst, rank, i_lo, i_hi, mode == 3));
+            else TRY(lr_gram_rows_i8(h, src, dst, rank, i_lo, i_hi, mode != 3));
             if (!checked) {
                 // first use in this process: the first rows of the first <= 16 columns once more on the CUDA cores.  A mismatch
                 // is an error (a wrong descriptor or swizzle shows as O(1) differences), never a silent change of path.

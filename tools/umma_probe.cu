@@ -306,7 +306,7 @@ static int full_test_i8(long long m, int rank, double beta, bool time_old, int x
             gi_split_kernel<<<dim3((unsigned)((mpad / 16 + THREADS - 1) / THREADS), n16), THREADS>>>(dX + (size_t)c0 * mpad, m, mpad, nc, n16, mpad, dColmax + c0, dPlanes);
             cudaEvent_t g0, g1; cudaEventCreate(&g0); cudaEventCreate(&g1);
             cudaEventRecord(g0);
-            if (ts) gi_gram_ts_kernel<<<sms, GI_THREADS, GI_TS_SMEM>>>(dPlanes, dPts, dPairs, mpad, (int)chunk, 0, m, n16, dColmax + c0, dPart, ldp);
+            if (ts) gi_gram_ts_kernel<<<sms, GI_TS_THREADS, GI_TS_SMEM>>>(dPlanes, dPts, dPairs, mpad, (int)chunk, 0, m, n16, dColmax + c0, dPart, ldp);
             else gi_gram_kernel<<<sms, GI_THREADS, GI_SMEM>>>(dPlanes, dPts, dPairs, mpad, (int)chunk, 0, m, n16, dColmax + c0, dPart, ldp);
             cudaEventRecord(g1);
             gi_reduce_kernel<<<dim3((unsigned)((m + THREADS - 1) / THREADS), nc), THREADS>>>(dPart, nq, n16, ldp, nc, m, 0, mpad, dOutNew + (size_t)c0 * mpad);
