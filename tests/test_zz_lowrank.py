@@ -364,3 +364,46 @@ def test_config5_body_at_emulation_size(emulated):
 def test_lowrank_baseline_config5_properties():
     _check_config5(6000, 50000, 200, 80)      # residual 0.26 of the applied deformation after 80 iterations (0.43 after 60:
                                                 # profiles/r2_convergence_traces.txt; the dense loop at 12k follows the same curve)
+
+
+_PRODUCT_SCRIPT = r"""
+import sys, numpy as np
+sys.path.insert(0, %r)
+from oracle import cpd_oracle as orc
+from probreg_b200 import _cabi
+src, _ = orc.synthetic_pair(%d)
+h = _cabi.Handle(3)
+h.set_source(src)
+h.set_target(src[:64] + 0.01)
+h.nonrigid_lowrank_begin(%g, 2.0, 0.05, 0.0, %d, 1, 5)
+q, b = h.nonrigid_lowrank_factors()
+np.save(sys.argv[1], q.dot(b).dot(q.T))
+"""
+
+
+@pytest.mark.gpu
+@pytest.mark.timeout(900)
+def test_every_selectable_gram_product_gives_the_same_factorisation(tmp_path):
+    """CPD_B200_LR_GRAM selects the kernel behind the G X products of the range finder: the exact integer-digit tensor-core kernels
+    (A operand in tensor memory -- the default -- or in shared memory), the TF32 x 3 tensor-core kernel, the CUDA-core kernel.  The
+    variable is read once per process, hence subprocesses.  The two integer kernels and the CUDA-core kernel agree with the float32
+    G of the reference to 1e-6 (relative, spectral norm); the TF32 kernel to the 3e-5 its truncating FP32 accumulation in TMEM
+    allows -- which is why it is not the default.  A rank of 130 takes two column passes, 1300 points 11 row tiles."""
+    import subprocess
+    import sys
+
+    from conftest import ROOT
+
+    m, rank, beta = 1300, 130, 0.6
+    src, _ = orc.synthetic_pair(m)
+    g = orc.rbf_kernel_f32(src, src, beta).astype(np.float64)
+    code = _PRODUCT_SCRIPT % (ROOT, m, beta, rank)
+    errs = {}
+    for mode in ("i8", "i8ss", "simt", "tf32"):
+        out = str(tmp_path / ("g_%s.npy" % mode))
+        r = subprocess.run([sys.executable, "-c", code, out], capture_output=True, text=True, timeout=600,
+                           env=dict(os.environ, CPD_B200_LR_GRAM=mode))
+        assert r.returncode == 0, (mode, r.stderr[-2000:])
+        errs[mode] = np.linalg.norm(np.load(out) - g, 2) / np.linalg.norm(g, 2)
+    assert errs["i8"] < 1e-6 and errs["i8ss"] < 1e-6 and errs["simt"] < 1e-6, errs
+    assert errs["tf32"] < 3e-5, errs
