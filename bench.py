@@ -435,7 +435,7 @@ def run_ours(args):
     bytes_iter = hbm_bytes_per_iter(n_local, n)
     traffic, traffic_src = None, None
     try:   # dram__bytes_read.sum + dram__bytes_write.sum per launch of the two E-step kernels, from the committed ncu capture
-        tj = json.load(open(os.path.join(ROOT, "profiles", "r1_traffic.json")))
+        tj = json.load(open(os.path.join(ROOT, "profiles", "r2_traffic.json")))
         if world == 1 and n == 100000:
             traffic = sum(k["dram_read_bytes"] + k["dram_write_bytes"] for k in tj["kernels"].values())
             traffic_src = tj["source"]

@@ -8,7 +8,7 @@
 // G = rbf_kernel(Y, Y, beta) of transformation.py:91-102, never stored).
 //
 // Fixed point ("Ozaki splitting" with integer digits):
-//     g_ij = round(2^23 G_ij) in [0, 2^23)         = a0 2^16 + a1 2^8 + a2,     a_s in [0, 255]        (unsigned digits, a0 < 128)
+//     g_ij = round(2^23 G_ij) in [0, 2^23]         = a0 2^16 + a1 2^8 + a2,     a_s in [0, 255]        (unsigned digits, a0 <= 128)
 //     x_cj = round(2^22 X[c][j] / max_j |X[c][j]|) = b0 2^16 + b1 2^8 + b2,     b_t in [-128, 127]     (balanced digits, |b0| <= 64)
 //     g x  = sum_{s,t} a_s b_t 2^(8 (4 - s - t)):   the products of level l = s + t share one accumulator,
 //            levels 0, 1, 2 are kept (6 MMAs per 32 points), levels 3 and 4 (< 2^-22 of the largest term) are dropped.
@@ -294,7 +294,7 @@ gi_gram_kernel(const unsigned char* __restrict__ images, const float4* __restric
                     const u64 bz = bj[2 * pr + 1].x;
                     const u64 dx = fsub2(ax2, bxy.x), dy = fsub2(ay2, bxy.y), dz = fsub2(az2, bz);
                     const float2 u = unpack2(ffma2(dz, dz, ffma2(dy, dy, fmul2(dx, dx))));
-                    const u64 e = pack2(fminf(ex2(-u.x), 0.99999988f), fminf(ex2(-u.y), 0.99999988f));    // the same float32 G as the other kernels
+                    const u64 e = pack2(ex2(-u.x), ex2(-u.y));    // the same float32 G as the other kernels; G = 1 gives the digits (128, 0, 0)
                     const float2 t = unpack2(ffma2(e, magic2, magic2));
                     gq[2 * pr] = __float_as_uint(t.x);
                     gq[2 * pr + 1] = __float_as_uint(t.y);
@@ -497,7 +497,7 @@ gi_gram_ts_kernel(const unsigned char* __restrict__ images, const float4* __rest
                     const u64 bz = bj[2 * pr + 1].x;
                     const u64 dx = fsub2(ax2, bxy.x), dy = fsub2(ay2, bxy.y), dz = fsub2(az2, bz);
                     const float2 uu = unpack2(ffma2(dz, dz, ffma2(dy, dy, fmul2(dx, dx))));
-                    const u64 e = pack2(fminf(ex2(-uu.x), 0.99999988f), fminf(ex2(-uu.y), 0.99999988f));  // the same float32 G as the other kernels
+                    const u64 e = pack2(ex2(-uu.x), ex2(-uu.y));  // the same float32 G as the other kernels; G = 1 gives the digits (128, 0, 0)
                     const float2 tt = unpack2(ffma2(e, magic2, magic2));
                     gq[2 * pr] = __float_as_uint(tt.x);
                     gq[2 * pr + 1] = __float_as_uint(tt.y);

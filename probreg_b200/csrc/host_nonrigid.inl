@@ -247,7 +247,7 @@ int lr_orthonormalise(cpd_ctx* h, double* X, int rank) {
         const int np = std::min(LR_PANEL, rank - j0);
         double* P = X + (size_t)j0 * ld;
         lr_panel_gram_kernel<<<nblk, THREADS, 0, h->stream>>>(X, m, ld, j0, np, gpart);
-        lr_panel_chol_kernel<<<1, THREADS, 0, h->stream>>>(gpart, nblk, np, n0, 2, scale2, T);
+        lr_panel_chol_kernel<<<1, LR_CHOL_THREADS, 0, h->stream>>>(gpart, nblk, np, n0, 2, scale2, T);
         h->launches += 2;
         for (int pass = 0; pass < 2; ++pass) {
             if (j0 > 0) {
@@ -256,7 +256,7 @@ int lr_orthonormalise(cpd_ctx* h, double* X, int rank) {
                 h->launches += 1;
             }
             lr_panel_gram_kernel<<<nblk, THREADS, 0, h->stream>>>(X, m, ld, j0, np, gpart);
-            lr_panel_chol_kernel<<<1, THREADS, 0, h->stream>>>(gpart, nblk, np, n0, pass == 0 ? 1 : 0, scale2, T);
+            lr_panel_chol_kernel<<<1, LR_CHOL_THREADS, 0, h->stream>>>(gpart, nblk, np, n0, pass == 0 ? 1 : 0, scale2, T);
             lr_panel_apply_kernel<<<nb, THREADS, 0, h->stream>>>(X, m, ld, j0, np, T);
             h->launches += 3;
         }
