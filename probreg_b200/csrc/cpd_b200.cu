@@ -170,6 +170,12 @@ struct cpd_ctx {
     DevState* d_state = nullptr;
     DevState h_state;
     double* h_pin = nullptr;   // 64 pinned doubles for small D2H reads
+    double* d_frame = nullptr;          // [2][8]: what cloud_frame_kernel derives per cloud (sources, targets)
+    double* h_stats = nullptr;          // [2][9] pinned: the clouds' statistics on their way to the host (ensure_stats)
+    cudaEvent_t stats_ev = nullptr, copy_ev = nullptr;
+    int stats_pending = 0;              // bit 0: sources, bit 1: targets
+    long long stats_count[2] = {0, 0};
+    bool origin_given = false;
     int it1 = 0, it2 = 0, j1 = 1, j2 = 1, g1 = 1, g2 = 1;   // i-tiles, max partial slots per tile, work items (= grid)
     // exact culling of far blocks (late iterations): stage bounding boxes, per-stage max offset
     float4 *d_sbox = nullptr, *d_tbox = nullptr, *d_ssub = nullptr, *d_tsub = nullptr;
@@ -300,7 +306,9 @@ WorkList build_work(int ntiles, int nstages, int slots) {
 
 // Stream-ordered, no synchronise: the state goes through a small ring of pinned staging slots (a cudaMemcpyAsync from pageable
 // memory would synchronise the stream first); a slot is re-used only after the copy that last read it has completed.
+int ensure_stats(cpd_ctx* h);
 int upload_state(cpd_ctx* h) {
+    TRY(ensure_stats(h));
     if (!h->h_state_ring) {
         CU(cudaMallocHost((void**)&h->h_state_ring, STATE_RING * sizeof(DevState)));
         for (int k = 0; k < STATE_RING; ++k) CU(cudaEventCreateWithFlags(&h->state_ev[k], cudaEventDisableTiming));
@@ -340,43 +348,31 @@ int download_cloud(cpd_ctx* h, const double* src3, long long count, double* dst)
 int cloud_sums_dev(cpd_ctx* h, const double* d_pts, long long count, double* part, double* d_out) {
     const unsigned nb = blocks_for(count);
     cloud_sums_kernel<<<nb, THREADS, 0, h->stream>>>(d_pts, count, part);
-    reduce_cols_kernel<<<1, 32, 0, h->stream>>>(part, (int)nb, 4, d_out);
+    reduce_cols_kernel<<<1, 4 * 32, 0, h->stream>>>(part, (int)nb, 4, d_out);
     KCHECK();
     h->launches += 2;
     return CPD_OK;
 }
 
-// Morton-sort a raw device cloud (count x 3): perm[k] = index (in the caller's order) of the k-th point in Z-order,
-// out[k] = raw[perm[k]] - origin.
-struct HostStats { double mean[3], lo[3], hi[3]; };
-int device_stats(cpd_ctx* h, const double* d_pts, long long n, HostStats& st) {
-    const unsigned nb = blocks_for(n);
+// A cloud's way into the library, one stream-ordered sequence without a host round trip: upload -> nine statistics (sums, minima,
+// maxima) -> frame (cloud_frame_kernel: Morton box, origin; origin and count patched into the device state) -> Morton sort ->
+// out[k] = raw[perm[k]] - origin.  The host copy of the statistics travels behind (pinned h_stats, stats_ev) and is read by
+// ensure_stats() when the host first needs the centroid or the extent.  The call returns once the upload itself has been
+// consumed (copy_ev), so the caller's buffer is free again, as before.
+int ingest_cloud(cpd_ctx* h, const double* host_pts, long long count, int is_target, long long n_global, const double* origin,
+                 int* d_perm, double* d_out) {
+    if (h->raw_cap < (size_t)count * 3) { TRY(dev_alloc(&h->d_raw, (size_t)count * 3)); h->raw_cap = (size_t)count * 3; }
+    const unsigned nb = blocks_for(count);
     if (h->sums_cap < (size_t)nb * 9 + 16) {
         TRY(dev_alloc(&h->d_sums, (size_t)nb * 9 + 16));
         h->sums_cap = (size_t)nb * 9 + 16;
     }
-    stats_kernel<<<nb, THREADS, 0, h->stream>>>(d_pts, n, h->d_sums + 16);
-    stats_fold_kernel<<<1, 288, 0, h->stream>>>(h->d_sums + 16, (int)nb, h->d_sums);
-    KCHECK();
-    h->launches += 2;
-    CU(cudaMemcpyAsync(h->h_pin + 48, h->d_sums, 9 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
-    CU(cudaStreamSynchronize(h->stream));
-    for (int a = 0; a < 3; ++a) { st.mean[a] = h->h_pin[48 + a] / (double)n; st.lo[a] = h->h_pin[51 + a]; st.hi[a] = h->h_pin[54 + a]; }
-    return CPD_OK;
-}
-int sort_cloud(cpd_ctx* h, const double* d_rawpts, long long count, const HostStats& st, const double origin[3], int* d_perm,
-               double* d_out) {
     if (h->sort_cap < (size_t)count) {
         TRY(dev_alloc(&h->d_codes, (size_t)count));
         TRY(dev_alloc(&h->d_codes_out, (size_t)count));
         TRY(dev_alloc(&h->d_idx_tmp, (size_t)count));
         h->sort_cap = (size_t)count;
     }
-    double range = 0.0;
-    for (int a = 0; a < 3; ++a) range = std::max(range, st.hi[a] - st.lo[a]);
-    const double inv = range > 0.0 ? 1.0 / range : 0.0;
-    morton_kernel<<<blocks_for(count), THREADS, 0, h->stream>>>(d_rawpts, count, st.lo[0], st.lo[1], st.lo[2], inv, h->d_codes,
-                                                                h->d_idx_tmp);
     size_t need = 0;
     CU(cub::DeviceRadixSort::SortPairs(nullptr, need, h->d_codes, h->d_codes_out, h->d_idx_tmp, d_perm, (int)count, 0, 30, h->stream));
     if (need > h->sort_tmp_cap) {
@@ -385,15 +381,45 @@ int sort_cloud(cpd_ctx* h, const double* d_rawpts, long long count, const HostSt
         CU(cudaMalloc(&h->d_sort_tmp, need));
         h->sort_tmp_cap = need;
     }
+    TRY(upload_cloud(h, host_pts, count, h->d_raw));
+    CU(cudaEventRecord(h->copy_ev, h->stream));
+    double* frame = h->d_frame + 8 * is_target;
+    stats_kernel<<<nb, THREADS, 0, h->stream>>>(h->d_raw, count, h->d_sums + 16);
+    stats_fold_kernel<<<1, 288, 0, h->stream>>>(h->d_sums + 16, (int)nb, h->d_sums);
+    cloud_frame_kernel<<<1, 32, 0, h->stream>>>(h->d_sums, count, is_target, n_global, origin != nullptr, origin ? origin[0] : 0.0,
+                                                origin ? origin[1] : 0.0, origin ? origin[2] : 0.0, h->d_state, frame);
+    CU(cudaMemcpyAsync(h->h_stats + 9 * is_target, h->d_sums, 9 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaEventRecord(h->stats_ev, h->stream));
+    h->stats_pending |= 1 << is_target;
+    h->stats_count[is_target] = count;
+    morton_frame_kernel<<<nb, THREADS, 0, h->stream>>>(h->d_raw, count, frame, h->d_codes, h->d_idx_tmp);
     CU(cub::DeviceRadixSort::SortPairs(h->d_sort_tmp, need, h->d_codes, h->d_codes_out, h->d_idx_tmp, d_perm, (int)count, 0, 30,
                                        h->stream));
-    gather3_kernel<<<blocks_for(count), THREADS, 0, h->stream>>>(d_rawpts, d_perm, count, origin[0], origin[1], origin[2], d_out);
+    gather3_frame_kernel<<<nb, THREADS, 0, h->stream>>>(h->d_raw, d_perm, count, frame, d_out);
     KCHECK();
-    h->launches += 3;
+    h->launches += 6;
+    CU(cudaEventSynchronize(h->copy_ev));
+    return CPD_OK;
+}
+
+// The host's copy of what cloud_frame_kernel derived on the device (centroid of the sources, frame origin and extent of the targets).
+// Every entry point that reads h_state.cx / cy or h->extent, or uploads the host state, calls this first.
+int ensure_stats(cpd_ctx* h) {
+    if (!h->stats_pending) return CPD_OK;
+    CU(cudaEventSynchronize(h->stats_ev));
+    if (h->stats_pending & 1)
+        for (int a = 0; a < 3; ++a) h->h_state.cy[a] = h->h_stats[a] / (double)h->stats_count[0];
+    if (h->stats_pending & 2) {
+        const double* t = h->h_stats + 9;
+        if (!h->origin_given) for (int a = 0; a < 3; ++a) h->h_state.cx[a] = t[a] / (double)h->stats_count[1];
+        h->extent = std::max(t[6] - t[3], std::max(t[7] - t[4], t[8] - t[5]));
+    }
+    h->stats_pending = 0;
     return CPD_OK;
 }
 
 int prepare(cpd_ctx* h) {
+    TRY(ensure_stats(h));
     if (h->prepared) return CPD_OK;
     if (!h->have_source || !h->have_target) return fail(CPD_ERR_STATE, "source and target must both be set");
     h->it1 = (int)((h->n + ITILE1 - 1) / ITILE1);
@@ -505,6 +531,7 @@ int read_params(cpd_ctx* h, cpd_params* out) {
     out->scale = h->h_pin[12];
     out->sigma2 = h->h_pin[13];
     // a point reaches ~13.3 sigma (2^-127); culling can only pay once that is well inside the cloud
+    TRY(ensure_stats(h));
     h->cull_active = h->extent > 0.0 && 13.3 * sqrt(out->sigma2) < 0.25 * h->extent;
     out->q = h->h_pin[14];
     out->n_p = h->h_pin[15];
@@ -564,6 +591,10 @@ extern "C" int cpd_create(cpd_ctx** out, int device, int dim, void* stream) {
     TRY(dev_alloc(&h->d_state, 1));
     TRY(dev_alloc(&h->d_mom, (size_t)MOM_PAD));
     CU(cudaMallocHost((void**)&h->h_pin, 64 * sizeof(double)));
+    TRY(dev_alloc(&h->d_frame, 16));
+    CU(cudaMallocHost((void**)&h->h_stats, 18 * sizeof(double)));
+    CU(cudaEventCreateWithFlags(&h->stats_ev, cudaEventDisableTiming));
+    CU(cudaEventCreateWithFlags(&h->copy_ev, cudaEventDisableTiming));
     CU(cudaEventCreate(&h->ev0));
     CU(cudaEventCreate(&h->ev1));
     for (int k = 0; k < 7; ++k) CU(cudaEventCreate(&h->sev[k]));
@@ -575,7 +606,7 @@ extern "C" int cpd_create(cpd_ctx** out, int device, int dim, void* stream) {
     h->h_state.lin[0] = h->h_state.lin[4] = h->h_state.lin[8] = 1.0;
     h->h_state.update_scale = 1;
     *out = h;
-    return CPD_OK;
+    return upload_state(h);          // the device state starts as a copy of the host's (cloud_frame_kernel patches single fields)
 }
 
 extern "C" void cpd_destroy(cpd_ctx* h) {
@@ -601,6 +632,10 @@ extern "C" void cpd_destroy(cpd_ctx* h) {
                     h->d_pxc, h->d_px, h->d_mom_src, h->d_mom_tgt, h->d_mom, h->d_sums, h->d_state, h->d_flush};
     for (void* p : ptrs) if (p) cudaFree(p);
     if (h->h_pin) cudaFreeHost(h->h_pin);
+    if (h->h_stats) cudaFreeHost(h->h_stats);
+    if (h->d_frame) cudaFree(h->d_frame);
+    if (h->stats_ev) cudaEventDestroy(h->stats_ev);
+    if (h->copy_ev) cudaEventDestroy(h->copy_ev);
 #ifndef CPD_HOST_EMU
     if (h->em_graph) cudaGraphExecDestroy(h->em_graph);
 #endif
@@ -633,15 +668,10 @@ extern "C" int cpd_set_source(cpd_ctx* h, const double* source, int64_t m) {
         h->prepared = false;
         h->nr_ready = false;
     }
-    if (h->raw_cap < (size_t)m * 3) { TRY(dev_alloc(&h->d_raw, (size_t)m * 3)); h->raw_cap = (size_t)m * 3; }
-    TRY(upload_cloud(h, source, m, h->d_raw));
-    HostStats st;
-    TRY(device_stats(h, h->d_raw, m, st));
-    for (int a = 0; a < 3; ++a) h->h_state.cy[a] = st.mean[a];
-    TRY(sort_cloud(h, h->d_raw, m, st, h->h_state.cy, h->d_perm_src, h->d_yc));
+    TRY(ingest_cloud(h, source, m, 0, 0, nullptr, h->d_perm_src, h->d_yc));
     h->h_state.m = m;
     h->have_source = true;
-    return upload_state(h);
+    return CPD_OK;
 }
 
 extern "C" int cpd_set_target(cpd_ctx* h, const double* target, int64_t n_local, int64_t n_global, const double* frame_origin) {
@@ -662,16 +692,14 @@ extern "C" int cpd_set_target(cpd_ctx* h, const double* target, int64_t n_local,
         h->prepared = false;
     }
     h->n_global = n_global;
-    if (h->raw_cap < (size_t)n_local * 3) { TRY(dev_alloc(&h->d_raw, (size_t)n_local * 3)); h->raw_cap = (size_t)n_local * 3; }
-    TRY(upload_cloud(h, target, n_local, h->d_raw));
-    HostStats st;
-    TRY(device_stats(h, h->d_raw, n_local, st));
-    for (int a = 0; a < 3; ++a) h->h_state.cx[a] = frame_origin ? ((a < h->dim) ? frame_origin[a] : 0.0) : st.mean[a];
-    h->extent = std::max(st.hi[0] - st.lo[0], std::max(st.hi[1] - st.lo[1], st.hi[2] - st.lo[2]));
-    TRY(sort_cloud(h, h->d_raw, n_local, st, h->h_state.cx, h->d_perm_tgt, h->d_xc));
+    double origin[3] = {0.0, 0.0, 0.0};
+    if (frame_origin) for (int a = 0; a < h->dim; ++a) origin[a] = frame_origin[a];
+    h->origin_given = frame_origin != nullptr;
+    if (h->origin_given) for (int a = 0; a < 3; ++a) h->h_state.cx[a] = origin[a];
+    TRY(ingest_cloud(h, target, n_local, 1, n_global, frame_origin ? origin : nullptr, h->d_perm_tgt, h->d_xc));
     h->h_state.n_global = n_global;
     h->have_target = true;
-    return upload_state(h);
+    return CPD_OK;
 }
 
 extern "C" int cpd_sigma2_init(cpd_ctx* h, double* sigma2) {
@@ -687,6 +715,7 @@ extern "C" int cpd_sigma2_init(cpd_ctx* h, double* sigma2) {
     TRY(cloud_sums_dev(h, h->d_yc, h->m, h->d_sums + 16 + pn, h->d_sums + 4));
     CU(cudaMemcpyAsync(h->h_pin, h->d_sums, 8 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
     CU(cudaStreamSynchronize(h->stream));
+    TRY(ensure_stats(h));
     for (int k = 0; k < 4; ++k) { sx[k] = h->h_pin[k]; sy[k] = h->h_pin[4 + k]; }
     // move the source sums into the targets' frame: y' = y~ + (cy - cx)
     double dlt[3], d2 = 0.0, dsy = 0.0;
@@ -718,6 +747,7 @@ extern "C" int cpd_set_state(cpd_ctx* h, int tf_kind, int update_scale, double w
     s.tf_kind = tf_kind;
     s.update_scale = update_scale ? 1 : 0;
     s.dim = d;
+    TRY(ensure_stats(h));
     h->cull_active = h->extent > 0.0 && 13.3 * sqrt(init->sigma2) < 0.25 * h->extent;
     h->have_state = true;
     return upload_state(h);
@@ -819,6 +849,7 @@ extern "C" int cpd_estep(cpd_ctx* h, const double* t_source, double sigma2, doub
     TRY(upload_cloud(h, t_source, h->m, h->d_raw));
     gather3_kernel<<<blocks_for(h->m), THREADS, 0, h->stream>>>(h->d_raw, h->d_perm_src, h->m, 0.0, 0.0, 0.0, h->d_ts);
     h->launches += 1;
+    TRY(ensure_stats(h));
     h->cull_active = h->extent > 0.0 && 13.3 * sqrt(sigma2) < 0.25 * h->extent;
     h->h_pin[32] = sigma2;
     h->h_pin[33] = w;
@@ -872,6 +903,7 @@ extern "C" int cpd_bcpd_estep(cpd_ctx* h, const double* t_source, double scale, 
     TRY(upload_cloud(h, t_source, m, h->d_raw));
     gather3_kernel<<<blocks_for(m), THREADS, 0, h->stream>>>(h->d_raw, h->d_perm_src, m, 0.0, 0.0, 0.0, h->d_ts);
     h->launches += 2;
+    TRY(ensure_stats(h));
     h->cull_active = h->extent > 0.0 && 13.3 * sqrt(sigma2) < 0.25 * h->extent;
     h->h_pin[32] = sigma2;
     h->h_pin[33] = w;
@@ -914,7 +946,7 @@ extern "C" int cpd_last_estep(cpd_ctx* h, double* pt1, double* p1, double* px, d
         const unsigned nb = blocks_for(h->m);
         if (h->sums_cap < (size_t)nb * 4 + 4) { TRY(dev_alloc(&h->d_sums, (size_t)nb * 4 + 4)); h->sums_cap = (size_t)nb * 4 + 4; }
         src_moments_api_kernel<<<nb, THREADS, 0, h->stream>>>((int)h->m, h->d_yc, h->d_p1, h->d_pxc, h->d_mom_src);
-        reduce_cols_kernel<<<1, 32, 0, h->stream>>>(h->d_mom_src, (int)nb, MOM_SRC, h->d_mom);
+        reduce_cols_kernel<<<1, MOM_SRC * 32, 0, h->stream>>>(h->d_mom_src, (int)nb, MOM_SRC, h->d_mom);
         KCHECK();
         h->launches += 2;
         CU(cudaMemcpyAsync(h->h_pin + 40, h->d_mom, sizeof(double), cudaMemcpyDeviceToHost, h->stream));

@@ -26,6 +26,7 @@ int nonrigid_common_begin(cpd_ctx* h, double lmd, double sigma2, double w) {
         SOLV(g_sol.SetStream(h->sol, h->stream));
         SOLV(g_sol.CreateParams(&h->sol_params));
     }
+    TRY(ensure_stats(h));
     const DevState& hs = h->h_state;
     CU(cudaMemsetAsync(h->d_W, 0, (size_t)m * 3 * sizeof(double), h->stream));                       // cpd.py:281
     h->lr_w_stale = false;
@@ -278,6 +279,7 @@ extern "C" int cpd_nonrigid_begin(cpd_ctx* h, double beta, double lmd, double si
     if (!h->d_G) TRY(dev_alloc(&h->d_G, (size_t)m * m));
     if (!h->d_A) TRY(dev_alloc(&h->d_A, (size_t)m * m));
     TRY(solver_workspace(h, m, h->d_A));
+    TRY(ensure_stats(h));
     const DevState& hs = h->h_state;
     dim3 grid((unsigned)m, blocks_for(m));
     nr_gram_kernel<<<grid, THREADS, 0, h->stream>>>(h->d_yc, hs.cy[0], hs.cy[1], hs.cy[2], m, h->dim, (float)(2.0 * beta),
@@ -324,6 +326,7 @@ extern "C" int cpd_nonrigid_lowrank_begin(cpd_ctx* h, double beta, double lmd, d
         h->lr_cap = rank;
     }
     TRY(solver_workspace(h, rank, h->d_lr_sys));
+    TRY(ensure_stats(h));
     const DevState& hs = h->h_state;
     lr_pack_kernel<<<blocks_for(ld), THREADS, 0, h->stream>>>(h->d_yc, hs.cy[0], hs.cy[1], hs.cy[2], m, ld,
                                                               (float)sqrt(LOG2E / (2.0 * beta)), h->d_lr_pts);
@@ -420,6 +423,7 @@ namespace {
 // the K x K form of lowrank.cuh.  sigma2 of the PREVIOUS iteration is read from the device state.
 int nonrigid_solve(cpd_ctx* h) {
     const long long m = h->m;
+    TRY(ensure_stats(h));
     const DevState& hs = h->h_state;
     const int nbs = (int)blocks_for(m);
     // weights and right-hand side of cpd.py:296 (with priors: cpd.py:390-396)
@@ -534,7 +538,7 @@ extern "C" int cpd_nonrigid_mstep(cpd_ctx* h, const double* pt1, const double* p
     const unsigned nb = blocks_for(std::max(m, n));
     if (h->sums_cap < (size_t)nb * 4 + 4) { TRY(dev_alloc(&h->d_sums, (size_t)nb * 4 + 4)); h->sums_cap = (size_t)nb * 4 + 4; }
     nr_traces_kernel<<<nb, THREADS, 0, h->stream>>>(h->d_state, h->d_pt1, h->d_xc, n, h->d_p1, h->d_pxc, h->d_ts2, m, h->d_sums + 4);
-    reduce_cols_kernel<<<1, 32, 0, h->stream>>>(h->d_sums + 4, (int)nb, 4, h->d_sums);
+    reduce_cols_kernel<<<1, 4 * 32, 0, h->stream>>>(h->d_sums + 4, (int)nb, 4, h->d_sums);
     KCHECK();
     if (h->comm) TRY(allreduce(h, h->d_sums, 1));            // pt1 / x are per shard; p1, px, T are global already
     nr_sigma_api_kernel<<<1, 32, 0, h->stream>>>(h->d_state, h->d_sums);
@@ -557,6 +561,7 @@ extern "C" int cpd_nonrigid_get(cpd_ctx* h, double* w_out, double* moved_out) {
     CU(cudaSetDevice(h->device));
     if (w_out) {
         if (h->lr_rank > 0 && h->lr_w_stale) {      // d_B still holds F, d_ts the moved source and d_lr_c the c of the last solve
+            TRY(ensure_stats(h));
             const DevState& hs = h->h_state;
             lr_w_kernel<<<blocks_for(h->m), THREADS, 0, h->stream>>>(h->d_B, h->prior_on ? h->d_wgt : h->d_p1, h->d_ts, h->d_yc, hs.cy[0],
                                                                      hs.cy[1], hs.cy[2], h->m, h->d_lr_c, h->d_W);

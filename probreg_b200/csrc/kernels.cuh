@@ -1390,6 +1390,31 @@ morton_kernel(const double* __restrict__ pts, long long n, double lo0, double lo
         idx[i] = (int)i;
     }
 }
+// The same two kernels taking their parameters from device memory (`frame`, written by cloud_frame_kernel): set_source / set_target
+// enqueue upload -> statistics -> frame -> Morton sort without a host round trip in between.
+__global__ void __launch_bounds__(THREADS)
+morton_frame_kernel(const double* __restrict__ pts, long long n, const double* __restrict__ frame, unsigned* __restrict__ codes,
+                    int* __restrict__ idx) {
+    const long long i = (long long)blockIdx.x * THREADS + threadIdx.x;
+    if (i < n) {
+        const double inv_range = frame[3];
+        const double q0 = (pts[3 * i] - frame[0]) * inv_range, q1 = (pts[3 * i + 1] - frame[1]) * inv_range,
+                     q2 = (pts[3 * i + 2] - frame[2]) * inv_range;
+        const unsigned a = (unsigned)fmin(fmax(q0 * 1023.0, 0.0), 1023.0), b = (unsigned)fmin(fmax(q1 * 1023.0, 0.0), 1023.0),
+                       c = (unsigned)fmin(fmax(q2 * 1023.0, 0.0), 1023.0);
+        codes[i] = spread3(a) | (spread3(b) << 1) | (spread3(c) << 2);
+        idx[i] = (int)i;
+    }
+}
+__global__ void __launch_bounds__(THREADS)
+gather3_frame_kernel(const double* __restrict__ in, const int* __restrict__ perm, long long n, const double* __restrict__ frame,
+                     double* __restrict__ out) {
+    const long long k = (long long)blockIdx.x * THREADS + threadIdx.x;
+    if (k < n) {
+        const long long j = perm[k];
+        out[3 * k] = in[3 * j] - frame[4]; out[3 * k + 1] = in[3 * j + 1] - frame[5]; out[3 * k + 2] = in[3 * j + 2] - frame[6];
+    }
+}
 // out[k] = in[perm[k]] - origin   (n x 3)
 __global__ void __launch_bounds__(THREADS)
 gather3_kernel(const double* __restrict__ in, const int* __restrict__ perm, long long n, double o0, double o1, double o2,
@@ -1467,6 +1492,25 @@ stats_fold_kernel(const double* __restrict__ part, int nb, double* __restrict__ 
     if (lane == 0) out[k] = x;
 }
 
+// From the nine statistics of a cloud (sums, minima, maxima) to its frame, on the device:
+//   frame[0..2] = lower corner, frame[3] = 1 / longest bounding-box edge (Morton quantisation), frame[4..6] = the origin the cloud is
+//   centred on (its centroid, or the caller's frame origin).  The origin and the count also go into the device state (sources: cy, m;
+//   targets: cx, n_global); the host mirror of the state catches up when it next needs them (ensure_stats in cpd_b200.cu).
+__global__ void cloud_frame_kernel(const double* __restrict__ sums9, long long count, int is_target, long long n_global, int origin_given,
+                                   double o0, double o1, double o2, DevState* __restrict__ st, double* __restrict__ frame) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    double range = 0.0;
+    for (int a = 0; a < 3; ++a) { frame[a] = sums9[3 + a]; range = fmax(range, sums9[6 + a] - sums9[3 + a]); }
+    frame[3] = range > 0.0 ? 1.0 / range : 0.0;
+    const double og[3] = {o0, o1, o2};
+    for (int a = 0; a < 3; ++a) {
+        const double o = origin_given ? og[a] : sums9[a] / (double)count;
+        frame[4 + a] = o;
+        if (is_target) st->cx[a] = o; else st->cy[a] = o;
+    }
+    if (is_target) st->n_global = n_global; else st->m = count;
+}
+
 // sums for sigma^2 initialisation: out[block][0..4) = sum |p|^2, sum p (3)
 __global__ void __launch_bounds__(THREADS)
 cloud_sums_kernel(const double* __restrict__ pts, long long n, double* __restrict__ out) {
@@ -1478,13 +1522,17 @@ cloud_sums_kernel(const double* __restrict__ pts, long long n, double* __restric
     }
     block_reduce_store<4>(v, out + (size_t)blockIdx.x * 4);
 }
-__global__ void __launch_bounds__(32)
+// out[c] = sum_b part[b][c], c < k: one warp per column (launch with k * 32 threads, k <= 32), lanes take the blocks b = lane,
+// lane + 32, ..., a fixed shuffle tree joins them -- the same order on every run.
+__global__ void __launch_bounds__(1024)
 reduce_cols_kernel(const double* __restrict__ part, int nb, int k, double* __restrict__ out) {
-    if ((int)threadIdx.x < k) {
-        double s = 0.0;
-        for (int b = 0; b < nb; ++b) s += part[(size_t)b * k + threadIdx.x];
-        out[threadIdx.x] = s;
-    }
+    const int c = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (c >= k) return;
+    double s = 0.0;
+    for (int b = lane; b < nb; b += 32) s += part[(size_t)b * k + c];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (lane == 0) out[c] = s;
 }
 
 // px = px~ + cx * p1 (un-centre for the API-facing EstepResult)

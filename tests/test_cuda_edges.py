@@ -71,6 +71,32 @@ def test_handle_reuse_with_other_sizes_and_families():
         assert res.sigma2 == pytest.approx(oref.sigma2, rel=1e-6)
 
 
+def test_same_sizes_new_data_on_one_handle_and_buffers_free_on_return():
+    """set_source / set_target enqueue upload -> statistics -> frame -> sort without a host round trip (ingest_cloud): (i) the caller's
+    buffers may be overwritten as soon as the calls return; (ii) a second pair of clouds of the SAME sizes on the same handle (same
+    work lists, same captured graph, new centroid and extent taken from the device) gives what a fresh handle gives."""
+    rng = np.random.default_rng(11)
+    h = _cabi.Handle(3)
+    for shift in (0.0, 7.5):
+        src, tgt = orc.synthetic_pair(3000)
+        src, tgt = src * (1.0 + shift) + shift, tgt * (1.0 + shift) + shift
+        bs, bt = src.copy(), tgt.copy()
+        h.set_source(bs)
+        bs[...] = rng.random(bs.shape)                   # the upload has been consumed: scribbling must not matter
+        h.set_target(bt)
+        bt[...] = rng.random(bt.shape)
+        s2 = h.sigma2_init()
+        assert s2 == pytest.approx(orc.sigma2_init_exact(src, tgt), rel=1e-11)
+        h.set_state(_cabi.TF_RIGID, True, 0.0, np.identity(3), np.zeros(3), 1.0, s2, 0.0)
+        for _ in range(3):
+            lin, t, scale, sigma2, q, n_p = h.em_step()
+        ref, _ = orc.registration(src, tgt, "rigid", maxiter=3, tol=-1.0, sigma2_0=s2)
+        assert sigma2 == pytest.approx(ref.sigma2, rel=1e-6)
+        np.testing.assert_allclose(lin, ref.params[0], atol=1e-8)
+        np.testing.assert_allclose(t, ref.params[1], atol=1e-7 * (1.0 + shift))
+    h.close()
+
+
 def test_inputs_are_not_modified_and_any_layout_is_accepted():
     src, tgt = orc.synthetic_pair(500)
     src_f = np.asfortranarray(src)                      # non C-contiguous, float32, lists: coerced like cv() (cpd.py:444)

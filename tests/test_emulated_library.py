@@ -53,6 +53,7 @@ CASES = [
     (E.test_extreme_sigma2, {"s2": 1e-9}),
     (E.test_handle_reuse_with_other_sizes_and_families, {}),
     (E.test_inputs_are_not_modified_and_any_layout_is_accepted, {}),
+    (E.test_same_sizes_new_data_on_one_handle_and_buffers_free_on_return, {}),
     (E.test_argument_errors, {}),
     (E.test_results_are_deterministic, {}),
     (E.test_gauss_transform_vs_direct, {}),
