@@ -14,7 +14,7 @@ int nonrigid_common_begin(cpd_ctx* h, double lmd, double sigma2, double w) {
         TRY(dev_alloc(&h->d_wgt, (size_t)m));
         TRY(dev_alloc(&h->d_nrpart, (size_t)blocks_for(m) * 2));
         TRY(dev_alloc(&h->d_ipiv, (size_t)m));
-        TRY(dev_alloc(&h->d_info, 1));
+        TRY(dev_alloc(&h->d_info, 2));          // [0] cuSOLVER's info, [1] the rank lr_pchol_kernel found
         if (h->d_G) { cudaFree(h->d_G); h->d_G = nullptr; }
         if (h->d_A) { cudaFree(h->d_A); h->d_A = nullptr; }
         h->nr_m = m;
@@ -42,10 +42,15 @@ int nonrigid_common_begin(cpd_ctx* h, double lmd, double sigma2, double w) {
     h->h_state.err = 0;
     return upload_state(h);
 }
+// device / host workspace of the solver, grown on demand
+int solver_workspace_bytes(cpd_ctx* h, size_t wd, size_t wh);
 // workspace of the LU of an n x n system stored at `a`
 int solver_workspace(cpd_ctx* h, long long n, double* a) {
     size_t wd = 0, wh = 0;
     SOLV(g_sol.XgetrfBuf(h->sol, h->sol_params, n, n, CUDA_R_64F_, a, n, CUDA_R_64F_, &wd, &wh));
+    return solver_workspace_bytes(h, wd, wh);
+}
+int solver_workspace_bytes(cpd_ctx* h, size_t wd, size_t wh) {
     if (wd > h->work_dev || !h->d_work) {
         if (h->d_work) cudaFree(h->d_work);
         h->d_work = nullptr;
@@ -232,6 +237,34 @@ int lr_inner(cpd_ctx* h, const double* A, int na, long long lda, const double* B
     h->launches += 2;
     return CPD_OK;
 }
+// Symmetric form of the M-step's K x K system, once per set-up:  Bc ~= L L^T (pivoted Cholesky, lr_pchol_kernel),  Qt = Q L  (into
+// d_lr_X, which the set-up no longer needs), so that G ~= Qt Qt^T and every M-step solves the symmetric positive definite
+// (c I + Qt^T diag(p1) Qt) Z = Qt^T F in one CTA (lr_spd_solve_kernel) instead of an LU of (c I + Bc S) through cuSOLVER.
+// cpd_nonrigid_lowrank_get hands out Q and Bc = L L^T (lr_llt_kernel): exactly the G of the iteration.
+int lr_spd_form(cpd_ctx* h, int rank) {
+    const long long m = h->m, ld = h->mpad;
+    lr_pchol_kernel<<<1, LR_PCHOL_THREADS, 0, h->stream>>>(h->d_lr_Bc, rank, h->d_lr_Lt, h->d_info + 1);
+    const unsigned nb = blocks_for(m);
+    for (int j0 = 0; j0 < rank; j0 += LR_PANEL)
+        lr_rotate_kernel<<<nb, THREADS, 0, h->stream>>>(h->d_lr_Q, m, ld, rank, h->d_lr_Lt, j0, std::min(LR_PANEL, rank - j0), h->d_lr_X);
+    lr_llt_kernel<<<blocks_for((long long)rank * rank), THREADS, 0, h->stream>>>(h->d_lr_Lt, rank, h->d_lr_Bc);
+    KCHECK();
+    h->launches += 2 + (rank + LR_PANEL - 1) / LR_PANEL;
+    return CPD_OK;
+}
+// out[n][n] = A diag(wt) Bm^T where the result is symmetric (S = Q^T diag(w) Q, Bc = Q^T (G Q)): 64 x 64 tiles of the lower triangle,
+// slices of >= 256 points, as many as the partial buffer holds (at most 128).
+int lr_inner_sym(cpd_ctx* h, const double* A, int n, long long lda, const double* Bm, long long ldb, const double* wt, double* out) {
+    const int nt = (n + LRS_TILE - 1) / LRS_TILE, tiles = nt * (nt + 1) / 2;
+    const long long by_cap = (long long)(h->lr_part_cap / ((size_t)n * n));
+    const int nsl = (int)std::max<long long>(1, std::min<long long>(std::min<long long>(128, by_cap), h->m / 256));
+    dim3 grid((unsigned)tiles, (unsigned)nsl);
+    lr_inner_sym_kernel<<<grid, THREADS, 0, h->stream>>>(A, n, lda, Bm, ldb, wt, h->m, h->d_lr_part);
+    lr_merge_sym_kernel<<<blocks_for((long long)n * n * 8), THREADS, 0, h->stream>>>(h->d_lr_part, nsl, n, out);
+    KCHECK();
+    h->launches += 2;
+    return CPD_OK;
+}
 // Orthonormalise the `rank` columns of X ([rank][ld]) in place: block Gram-Schmidt with re-orthogonalisation over panels of
 // LR_PANEL columns (lowrank.cuh); numerically dependent columns become exactly zero.
 int lr_orthonormalise(cpd_ctx* h, double* X, int rank) {
@@ -311,12 +344,13 @@ extern "C" int cpd_nonrigid_lowrank_begin(cpd_ctx* h, double beta, double lmd, d
         TRY(dev_alloc(&h->d_lr_Q, (size_t)rank * ld));
         TRY(dev_alloc(&h->d_lr_X, (size_t)rank * ld));
         TRY(dev_alloc(&h->d_lr_coef, (size_t)3 * LR_SLICES * (rank + 1)));
-        h->lr_part_cap = std::max<size_t>(std::max<size_t>((size_t)LR_SLICES * rank * rank, (size_t)2 << 20),      // >= 16 MB of slice partials
+        h->lr_part_cap = std::max<size_t>(std::max<size_t>((size_t)LR_SLICES * rank * rank, (size_t)4 << 20),      // >= 32 MB of slice partials
                                           (size_t)((m + LR_NARROW_PTS - 1) / LR_NARROW_PTS) * rank * 4);
         TRY(dev_alloc(&h->d_lr_part, h->lr_part_cap));
         TRY(dev_alloc(&h->d_lr_panel, (size_t)LR_MAX_RANK * LR_PANEL + 2 * LR_PANEL + LR_PANEL * LR_PANEL +
                                           (size_t)LR_GRAM_BLOCKS * LR_PANEL * LR_PANEL));
         TRY(dev_alloc(&h->d_lr_Bc, (size_t)rank * rank));
+        TRY(dev_alloc(&h->d_lr_Lt, (size_t)rank * rank));
         TRY(dev_alloc(&h->d_lr_S, (size_t)rank * rank));
         TRY(dev_alloc(&h->d_lr_R, (size_t)rank * 3));
         TRY(dev_alloc(&h->d_lr_sys, (size_t)rank * rank));
@@ -326,6 +360,7 @@ extern "C" int cpd_nonrigid_lowrank_begin(cpd_ctx* h, double beta, double lmd, d
         h->lr_cap = rank;
     }
     TRY(solver_workspace(h, rank, h->d_lr_sys));
+    CU(cudaFuncSetAttribute(lr_spd_solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lr_spd_smem_bytes(LR_SPD_MAX_RANK)));
     TRY(ensure_stats(h));
     const DevState& hs = h->h_state;
     lr_pack_kernel<<<blocks_for(ld), THREADS, 0, h->stream>>>(h->d_yc, hs.cy[0], hs.cy[1], hs.cy[2], m, ld,
@@ -360,7 +395,9 @@ extern "C" int cpd_nonrigid_lowrank_begin(cpd_ctx* h, double beta, double lmd, d
     }
     TRY(lr_gram_apply(h, h->d_lr_Q, h->d_lr_X, rank));
     tick(0);
-    TRY(lr_inner(h, h->d_lr_Q, rank, ld, h->d_lr_X, rank, ld, nullptr, 1, h->d_lr_Bc));
+    TRY(lr_inner_sym(h, h->d_lr_Q, rank, ld, h->d_lr_X, ld, nullptr, h->d_lr_Bc));
+    { const char* e = getenv("CPD_B200_LR_CORE"); h->lr_spd = rank <= LR_SPD_MAX_RANK && !(e && !strcmp(e, "lu")); }
+    if (h->lr_spd) TRY(lr_spd_form(h, rank));
     tick(2);
     if (!ev.empty()) {
         h->lr_setup_ms[0] = h->lr_setup_ms[1] = h->lr_setup_ms[2] = 0.0f;
@@ -451,25 +488,33 @@ int nonrigid_solve(cpd_ctx* h) {
     } else {
         const int k = h->lr_rank;
         const long long ld = h->mpad;
-        TRY(lr_inner(h, h->d_lr_Q, k, ld, h->d_lr_Q, k, ld, wgt, 1, h->d_lr_S));                 // S = Q^T diag(wgt) Q
+        const double* Qf = h->lr_spd ? h->d_lr_X : h->d_lr_Q;          // the factor of the iteration: Qt = Q L (lr_spd_form) or Q
+        TRY(lr_inner_sym(h, Qf, k, ld, Qf, ld, wgt, h->d_lr_S));                 // S = Q^T diag(wgt) Q
         {   // R = Q^T F (F is [3][m]): the narrow product kernel, block partials merged in a fixed order
             const int nblk = (int)((m + LR_NARROW_PTS - 1) / LR_NARROW_PTS);
             if ((size_t)nblk * k * 3 > h->lr_part_cap) return fail(CPD_ERR_STATE, "partial buffer too small for Q^T F");
-            lr_inner_narrow_kernel<<<dim3((unsigned)((k + 7) / 8), (unsigned)nblk), THREADS, 0, h->stream>>>(h->d_lr_Q, k, ld, h->d_B, 3, m, m,
+            lr_inner_narrow_kernel<<<dim3((unsigned)((k + 7) / 8), (unsigned)nblk), THREADS, 0, h->stream>>>(Qf, k, ld, h->d_B, 3, m, m,
                                                                                                          h->d_lr_part);
             lr_merge_kernel<<<blocks_for((long long)k * 3 * 8), THREADS, 0, h->stream>>>(h->d_lr_part, nblk, k, 3, 0, h->d_lr_R);
             KCHECK();
             h->launches += 2;
         }
-        lr_system_kernel<<<blocks_for((long long)k * k + 3 * k), THREADS, 0, h->stream>>>(h->d_lr_Bc, h->d_lr_S, h->d_lr_R, k,
-                                                                                          &h->d_state->sigma2, h->nr_lmd, h->d_lr_sys,
-                                                                                          h->d_lr_rhs, h->d_lr_c);
-        KCHECK();
-        SOLV(g_sol.Xgetrf(h->sol, h->sol_params, k, k, CUDA_R_64F_, h->d_lr_sys, k, h->d_ipiv, CUDA_R_64F_, h->d_work, h->work_dev,
-                          h->h_work, h->work_host, h->d_info));
-        SOLV(g_sol.Xgetrs(h->sol, h->sol_params, CUBLAS_OP_T_, k, 3, CUDA_R_64F_, h->d_lr_sys, k, h->d_ipiv, CUDA_R_64F_, h->d_lr_rhs, k,
-                          h->d_info));
-        lr_apply_kernel<<<nbs, THREADS, 0, h->stream>>>(h->d_lr_Q, m, ld, k, h->d_lr_rhs, h->d_yc, hs.cy[0], hs.cy[1], hs.cy[2], h->d_ts2);
+        if (h->lr_spd) {
+            // (c I + St) Z = Rt: symmetric positive definite, one CTA (lr_spd_solve_kernel)
+            lr_spd_solve_kernel<<<1, LR_SPD_THREADS, lr_spd_smem_bytes(k), h->stream>>>(h->d_lr_S, h->d_lr_R, k, &h->d_state->sigma2, h->nr_lmd,
+                                                                                       h->d_lr_rhs, h->d_lr_c);
+            KCHECK();
+        } else {
+            lr_system_kernel<<<blocks_for((long long)k * k + 3 * k), THREADS, 0, h->stream>>>(h->d_lr_Bc, h->d_lr_S, h->d_lr_R, k,
+                                                                                              &h->d_state->sigma2, h->nr_lmd, h->d_lr_sys,
+                                                                                              h->d_lr_rhs, h->d_lr_c);
+            KCHECK();
+            SOLV(g_sol.Xgetrf(h->sol, h->sol_params, k, k, CUDA_R_64F_, h->d_lr_sys, k, h->d_ipiv, CUDA_R_64F_, h->d_work, h->work_dev,
+                              h->h_work, h->work_host, h->d_info));
+            SOLV(g_sol.Xgetrs(h->sol, h->sol_params, CUBLAS_OP_T_, k, 3, CUDA_R_64F_, h->d_lr_sys, k, h->d_ipiv, CUDA_R_64F_, h->d_lr_rhs, k,
+                              h->d_info));
+        }
+        lr_apply_kernel<<<nbs, THREADS, 0, h->stream>>>(Qf, m, ld, k, h->d_lr_rhs, h->d_yc, hs.cy[0], hs.cy[1], hs.cy[2], h->d_ts2);
         h->lr_w_stale = true;          // W = (F - diag(wgt) Q Z) / c is formed when somebody asks for it (cpd_nonrigid_get)
         h->launches += 2;
     }

@@ -363,6 +363,93 @@ lr_inner_kernel(const double* __restrict__ A, int na, long long lda, const doubl
             if (a < na && b < nb) dst[(size_t)a * nb + b] = acc[u][v];
         }
 }
+// ---- the square, mathematically symmetric case  out = A diag(wt) Bm^T  (S = Q^T diag(w) Q of every M-step, Bc = Q^T (G Q)) --------
+// One CTA per {64 x 64 tile of the LOWER triangle (ta >= tb), i-slice}; 4 x 4 outputs per thread: two points cost 8 LDS.128 for 32
+// DFMA (12 shared-memory wavefronts against 16 cycles of the FP64 pipe per warp: FP64-bound, where the 2 x 2 tiles of
+// lr_inner_kernel are shared-memory bound by 2x).  A thread owns the CONSECUTIVE rows 4 ty .. 4 ty + 3 (a warp: 8 rows), so in the
+// last tile row -- the only one with padding, the lower triangle keeps the padded index on the row side -- whole warps have nothing
+// to do and skip the arithmetic (n = 200: rows 192..199 of 256, one warp of eight); its columns are strided (tx + 16 v), which keeps
+// the shared-memory reads conflict-free.  Partials per slice, joined by lr_merge_sym_kernel.
+constexpr int LRS_TILE = 64, LRS_CHUNK = 32;
+__global__ void __launch_bounds__(THREADS, 2)
+lr_inner_sym_kernel(const double* __restrict__ A, int n, long long lda, const double* __restrict__ Bm, long long ldb,
+                    const double* __restrict__ wt, long long m, double* __restrict__ part /* [gridDim.y][n][n], lower tiles only */) {
+    __shared__ __align__(16) double sa[LRS_TILE][LRS_CHUNK + 2], sb[LRS_TILE][LRS_CHUNK + 2];   // row stride 68 words: see above
+    int ta = 0, tb = (int)blockIdx.x;
+    while (tb > ta) { tb -= ta + 1; ++ta; }            // blockIdx.x enumerates (0,0), (1,0), (1,1), (2,0), ...
+    const int ta0 = ta * LRS_TILE, tb0 = tb * LRS_TILE;
+    const int slice = blockIdx.y, nsl = gridDim.y;
+    const long long per = (m + nsl - 1) / nsl;
+    const long long i_lo = (per * slice < m) ? per * slice : m, i_hi = (i_lo + per < m) ? i_lo + per : m;
+    const int ty = threadIdx.x >> 4, tx = threadIdx.x & 15;
+    const bool warp_has_rows = ta0 + (int)(threadIdx.x >> 5) * 8 < n;
+    double acc[4][4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u)
+#pragma unroll
+        for (int v = 0; v < 4; ++v) acc[u][v] = 0.0;
+    for (long long i0 = i_lo; i0 < i_hi; i0 += LRS_CHUNK) {
+        __syncthreads();
+        for (int e = threadIdx.x; e < LRS_TILE * LRS_CHUNK; e += THREADS) {
+            const int r = e / LRS_CHUNK, ii = e % LRS_CHUNK;
+            const long long i = i0 + ii;
+            const bool in = i < i_hi;
+            const double w = in ? (wt ? wt[i] : 1.0) : 0.0;
+            sa[r][ii] = (in && ta0 + r < n) ? w * A[(long long)(ta0 + r) * lda + i] : 0.0;
+            sb[r][ii] = (in && tb0 + r < n) ? Bm[(long long)(tb0 + r) * ldb + i] : 0.0;
+        }
+        __syncthreads();
+        if (warp_has_rows) {
+#pragma unroll 4
+            for (int ii = 0; ii < LRS_CHUNK; ii += 2) {
+                double2 a[4], b[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) a[u] = *reinterpret_cast<const double2*>(&sa[4 * ty + u][ii]);
+#pragma unroll
+                for (int v = 0; v < 4; ++v) b[v] = *reinterpret_cast<const double2*>(&sb[tx + 16 * v][ii]);
+#pragma unroll
+                for (int u = 0; u < 4; ++u)
+#pragma unroll
+                    for (int v = 0; v < 4; ++v) acc[u][v] = fma(a[u].x, b[v].x, acc[u][v]);
+#pragma unroll
+                for (int u = 0; u < 4; ++u)
+#pragma unroll
+                    for (int v = 0; v < 4; ++v) acc[u][v] = fma(a[u].y, b[v].y, acc[u][v]);
+            }
+        }
+    }
+    double* dst = part + (size_t)slice * n * n;
+#pragma unroll
+    for (int u = 0; u < 4; ++u)
+#pragma unroll
+        for (int v = 0; v < 4; ++v) {
+            const int a = ta0 + 4 * ty + u, b = tb0 + tx + 16 * v;
+            if (a < n && b < n) dst[(size_t)a * n + b] = acc[u][v];
+        }
+}
+// out[a][b] (n x n, exactly symmetric) from the slice partials of lr_inner_sym_kernel: 8 lanes per output take the slices l, l + 8,
+// ..., a fixed shuffle tree joins them; tiles above the diagonal are mirrored, diagonal tiles give (x + x^T) / 2.
+__global__ void __launch_bounds__(THREADS)
+lr_merge_sym_kernel(const double* __restrict__ part, int nsl, int n, double* __restrict__ out) {
+    const int e = (blockIdx.x * THREADS + threadIdx.x) >> 3, l = threadIdx.x & 7;
+    const bool in = e < n * n;
+    const int a = in ? e / n : 0, b = in ? e % n : 0;
+    const int ta = a / LRS_TILE, tb = b / LRS_TILE;
+    const size_t e_ab = (size_t)a * n + b, e_ba = (size_t)b * n + a;
+    double s = 0.0, t = 0.0;
+    if (in) {
+#pragma unroll 4
+        for (int sl = l; sl < nsl; sl += 8) {
+            const double* p = part + (size_t)sl * n * n;
+            if (ta >= tb) s += p[e_ab];
+            if (ta <= tb) t += p[e_ba];
+        }
+    }
+#pragma unroll
+    for (int o = 4; o > 0; o >>= 1) { s += __shfl_xor_sync(0xffffffffu, s, o); t += __shfl_xor_sync(0xffffffffu, t, o); }
+    if (in && l == 0) out[e] = ta == tb ? 0.5 * (s + t) : (ta > tb ? s : t);
+}
+
 // part[blk][a][d] = sum over the block's points of A[a][i] F[d][i]   for a narrow right factor (nd <= 4 rows, e.g. the three
 // coordinates of F = px - diag(p1) Y): one warp per row a, lanes over the points -- lr_inner_kernel would pad the 3 columns to a
 // 32-wide tile.  Merged by lr_merge_kernel like the other partials ([blk][na][nd]).
@@ -430,6 +517,271 @@ lr_system_kernel(const double* __restrict__ Bc, const double* __restrict__ S, co
         for (int k = 0; k < rank; ++k) s += Bc[(size_t)a * rank + k] * R[(size_t)k * 3 + d];
         rhs[f] = s;
     }
+}
+
+// ---- symmetric form of the K x K system: G ~= Q Bc Q^T = Qt Qt^T with Qt = Q L, Bc ~= L L^T (pivoted Cholesky, once, at set-up) -----
+// With the (non-orthonormal) factor Qt the Woodbury system of an M-step is symmetric positive definite,
+//     (c I + St) Z = Rt,      St = Qt^T diag(p1) Qt,  Rt = Qt^T F,      W = (F - diag(p1) Qt Z) / c,   T = Y + Qt Z,
+// against the unsymmetric (c I + Bc S) Z = Bc R of the orthonormal factor.  lr_spd_solve_kernel solves it in ONE CTA: the lower
+// triangle of  c I + St  with the three right-hand sides appended as rows K .. K+2 lives in shared memory (packed by rows,
+// (K+3)(K+4)/2 doubles: 166 KB at K = 200), an LDL^T factorisation runs over it right-looking with one barrier per column -- the
+// appended rows come out as the forward substitution -- then the back substitution, one barrier per column.  cuSOLVER's LU of the
+// unsymmetric form took 0.48 ms per M-step at K = 200 (getrf is a single 256-thread CTA there, plus laswp and two trsm).
+// (An eigen-decomposition of Bc would serve as well as the Cholesky factor; cusolverDnXsyevd takes 1.8 ms at K = 200 but 38 s on
+//  its first call in a process on the B200 box -- profiles/r2_syevd_probe.txt -- so the factor is computed here.)
+constexpr int LR_SPD_THREADS = 512;           // 128 registers per thread: phase 1 keeps an 8 x 8 block in registers
+constexpr int LR_SPD_B = 8;                  // columns per panel: two barriers per LR_SPD_B columns
+constexpr int LR_SPD_RG = 4;                 // rows per warp pass in the trailing update
+constexpr int LR_SPD_MAX_RANK = 228;         // (K+3)(K+4)/2 + LR_SPD_B (K+3) + K doubles <= 227 KB
+__host__ __device__ constexpr size_t lr_spd_smem_bytes(int k) {
+    return ((size_t)(k + 3) * (k + 4) / 2 + (size_t)LR_SPD_B * (k + 3) + (size_t)k) * sizeof(double);
+}
+// Blocked LDL^T (no pivoting: the matrix is c I + a positive semi-definite one).  "Unscaled" storage throughout: below the diagonal
+// a'_ik = l_ik d_k, on it d_k.  Per panel of LR_SPD_B columns at j0:
+//   phase 1, one THREAD per row i >= j0: factor the LR_SPD_B x LR_SPD_B diagonal block (every thread for itself: 36 broadcast loads,
+//            ~90 FMAs -- cheaper than a barrier) and run the row through it:  p_c = a_{i,j0+c} - sum_{c'<c} p_c' l_{c c'};  p goes
+//            back into the triangle and into the panel buffer (rows >= j0 + B: that is all they ever need from this panel);
+//   phase 2, one WARP per row i >= j0 + B, lanes over k:  a_ik -= sum_c p_ic p_kc / d_c  -- LR_SPD_B FMAs per load/store pair.
+// The right-hand sides ride along as rows K .. K+2 (phase 2 leaves them as the forward substitution).  Then L = a' / d in place and
+// one warp per right-hand side does the back substitution in registers (lane-owned entries, shuffles; no barrier).
+__global__ void __launch_bounds__(LR_SPD_THREADS, 1)
+lr_spd_solve_kernel(const double* __restrict__ S, const double* __restrict__ R /* [K][3] */, int K, const double* __restrict__ sigma2_ptr,
+                    double lmd, double* __restrict__ Zt /* [3][K] */, double* __restrict__ c_out) {
+    CPD_DYN_SMEM(smraw);
+    constexpr int B = LR_SPD_B, NW = LR_SPD_THREADS / 32;
+    double* const tri = reinterpret_cast<double*>(smraw);               // row i at i (i + 1) / 2, entries k <= i
+    const int rows = K + 3;
+    double* const pan = tri + (size_t)rows * (rows + 1) / 2;            // [B][rows]: the current panel, rows relative to j0 (column-major:
+                                                                        // consecutive rows in consecutive banks)
+    double* const dinv = pan + (size_t)B * rows;                        // [K]: 1 / d_k
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const double c = lmd * *sigma2_ptr;
+    if (tid == 0) *c_out = c;
+    for (int i = warp; i < rows; i += NW) {
+        double* row = tri + (size_t)i * (i + 1) / 2;
+        if (i < K) for (int k = lane; k <= i; k += 32) row[k] = S[(size_t)i * K + k] + (i == k ? c : 0.0);
+        else for (int k = lane; k < K; k += 32) row[k] = R[(size_t)k * 3 + (i - K)];
+    }
+    __syncthreads();
+    for (int j0 = 0; j0 < K; j0 += B) {
+        const int nb = (K - j0 < B) ? K - j0 : B;
+        // phase 1
+        if (tid < rows - j0) {
+            const int i = j0 + tid;
+            double blk[B][B], rd[B], pv[B];
+#pragma unroll
+            for (int a = 0; a < B; ++a)
+#pragma unroll
+                for (int b2 = 0; b2 <= a; ++b2) blk[a][b2] = (a < nb) ? tri[(size_t)(j0 + a) * (j0 + a + 1) / 2 + j0 + b2] : (a == b2 ? 1.0 : 0.0);
+#pragma unroll
+            for (int cc = 0; cc < B; ++cc) {
+                const double dc = blk[cc][cc];
+                rd[cc] = 1.0 / (dc > 0.0 ? dc : c);            // d >= c in exact arithmetic
+#pragma unroll
+                for (int a = cc + 1; a < B; ++a) {
+                    const double f = blk[a][cc] * rd[cc];
+#pragma unroll
+                    for (int b2 = cc + 1; b2 <= a; ++b2) blk[a][b2] -= f * blk[b2][cc];
+                }
+            }
+            double* row = tri + (size_t)i * (i + 1) / 2;
+            const int have = (tid < nb) ? tid + 1 : nb;        // rows inside the block own the columns up to their diagonal
+#pragma unroll
+            for (int cc = 0; cc < B; ++cc) {
+                double v = 0.0;
+                if (cc < have) {
+                    v = row[j0 + cc];
+#pragma unroll
+                    for (int c2 = 0; c2 < cc; ++c2) v -= pv[c2] * (blk[cc][c2] * rd[c2]);
+                    if (tid >= nb) row[j0 + cc] = v;          // the block's own rows are being read by everybody: written after the barrier
+                }
+                pv[cc] = v;
+                pan[(size_t)cc * rows + tid] = v;
+            }
+            if (tid == 0)
+#pragma unroll
+                for (int cc = 0; cc < B; ++cc) if (cc < nb) dinv[j0 + cc] = rd[cc];
+        }
+        __syncthreads();
+        if (tid < nb) {
+            double* row = tri + (size_t)(j0 + tid) * (j0 + tid + 1) / 2;
+            for (int cc = 0; cc <= tid; ++cc) row[j0 + cc] = pan[(size_t)cc * rows + tid];
+        }
+        // phase 2: rows beyond the panel, columns beyond the panel; a warp takes LR_SPD_RG consecutive rows at a time and reuses the
+        // eight panel entries of its lanes' columns for all of them (shared-memory wavefronts per FMA: 20 / 8 -> 8 / 8)
+        const int k0 = j0 + nb;
+        for (int i0 = k0 + LR_SPD_RG * warp; i0 < rows; i0 += LR_SPD_RG * NW) {
+            double pi[LR_SPD_RG][B];
+            double* row[LR_SPD_RG];
+            int kend[LR_SPD_RG];
+#pragma unroll
+            for (int q = 0; q < LR_SPD_RG; ++q) {
+                const int i = i0 + q;
+                const bool live = i < rows;
+                row[q] = tri + (size_t)(live ? i : i0) * ((live ? i : i0) + 1) / 2;
+                kend[q] = live ? (i < K ? i : K - 1) : -1;
+#pragma unroll
+                for (int cc = 0; cc < B; ++cc) pi[q][cc] = (live && cc < nb) ? pan[(size_t)cc * rows + (i - j0)] * dinv[j0 + cc] : 0.0;
+            }
+            const int kmax = kend[LR_SPD_RG - 1] >= 0 ? kend[LR_SPD_RG - 1] : (i0 + LR_SPD_RG - 1 < K ? i0 + LR_SPD_RG - 1 : K - 1);
+            for (int k = k0 + lane; k <= kmax; k += 32) {
+                double pk[B];
+#pragma unroll
+                for (int cc = 0; cc < B; ++cc) pk[cc] = pan[(size_t)cc * rows + (k - j0)];
+#pragma unroll
+                for (int q = 0; q < LR_SPD_RG; ++q) {
+                    if (k <= kend[q]) {
+                        double v = row[q][k];
+#pragma unroll
+                        for (int cc = 0; cc < B; ++cc) v = fma(-pi[q][cc], pk[cc], v);
+                        row[q][k] = v;
+                    }
+                }
+            }
+        }
+        __syncthreads();
+    }
+    // L = a' / d in place (strictly lower part of rows < K); the right-hand-side rows become y0 = D^-1 L^-1 b
+    for (int i = 1 + warp; i < rows; i += NW) {
+        double* row = tri + (size_t)i * (i + 1) / 2;
+        const int kend = i < K ? i - 1 : K - 1;
+        for (int k = lane; k <= kend; k += 32) row[k] *= dinv[k];
+    }
+    __syncthreads();
+    // back substitution  L^T x = y0: warp d owns right-hand side d; lane l holds the entries 32 t + l
+    if (warp < 3) {
+        constexpr int T = (LR_SPD_MAX_RANK + 31) / 32;
+        const double* rhs = tri + (size_t)(K + warp) * (K + warp + 1) / 2;
+        double y[T];
+#pragma unroll
+        for (int t = 0; t < T; ++t) y[t] = (32 * t + lane < K) ? rhs[32 * t + lane] : 0.0;
+#pragma unroll
+        for (int t = T - 1; t >= 0; --t) {
+#pragma unroll 1
+            for (int l = 31; l >= 0; --l) {
+                const int j = 32 * t + l;
+                if (j >= K) continue;
+                const double xj = __shfl_sync(0xffffffffu, y[t], l);
+                const double* rowj = tri + (size_t)j * (j + 1) / 2;
+#pragma unroll
+                for (int tt = 0; tt <= t; ++tt) {
+                    const int i = 32 * tt + lane;
+                    if (i < j) y[tt] = fma(-rowj[i], xj, y[tt]);
+                }
+            }
+        }
+#pragma unroll
+        for (int t = 0; t < T; ++t)
+            if (32 * t + lane < K) Zt[(size_t)warp * K + 32 * t + lane] = y[t];
+    }
+}
+
+// Pivoted (diagonal pivoting) Cholesky of the symmetric positive semi-definite core, left-looking, ONE CTA:  Bc ~= L L^T with
+//   Lt[j][i] = L_ij  (row j of Lt = column j of L, in the ORIGINAL row order: nothing is permuted, the pivot order is implicit).
+// Step j: p = argmax of the remaining diagonal d; stop when d_p <= 1e-14 of the largest diagonal entry of Bc (what is left is
+// rounding -- or the float32 noise of the G X products once K reaches into it, where the remaining Schur complement is indefinite:
+// a positive semi-definite G has no use for it); L_:j = (Bc_:p - sum_{t<j} L_:t L_pt) / sqrt(d_p); d -= L_:j^2.  A dropped column of
+// Q (zero row and column of Bc) has d = 0 and is never picked.  Columns from the stopping point on are zero.
+constexpr int LR_PCHOL_THREADS = 1024;
+__global__ void __launch_bounds__(LR_PCHOL_THREADS, 1)
+lr_pchol_kernel(const double* __restrict__ Bc, int K, double* __restrict__ Lt /* [K][K] */, int* __restrict__ rank_out) {
+    __shared__ double d[LR_MAX_RANK], lp[LR_MAX_RANK];      // remaining diagonal; row p of L (columns < j)
+    __shared__ double wv[LR_PCHOL_THREADS / 32];
+    __shared__ int wi[LR_PCHOL_THREADS / 32];
+    __shared__ int piv;
+    __shared__ double dpiv, dmax0;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    for (int i = tid; i < K; i += LR_PCHOL_THREADS) d[i] = Bc[(size_t)i * K + i];
+    for (int e = tid; e < K * K; e += LR_PCHOL_THREADS) Lt[e] = 0.0;
+    __syncthreads();
+    int rank = 0;
+    for (int j = 0; j < K; ++j) {
+        // argmax of d (ties: the smaller index), two-level
+        double bv = -1.0;
+        int bi = 0x7fffffff;
+        for (int i = tid; i < K; i += LR_PCHOL_THREADS)
+            if (d[i] > bv || (d[i] == bv && i < bi)) { bv = d[i]; bi = i; }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const double ov = __shfl_xor_sync(0xffffffffu, bv, o);
+            const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+            if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
+        }
+        if (lane == 0) { wv[warp] = bv; wi[warp] = bi; }
+        __syncthreads();
+        if (tid == 0) {
+            for (int w = 1; w < LR_PCHOL_THREADS / 32; ++w)
+                if (wv[w] > bv || (wv[w] == bv && wi[w] < bi)) { bv = wv[w]; bi = wi[w]; }
+            piv = bi; dpiv = bv;
+            if (j == 0) dmax0 = bv;
+        }
+        __syncthreads();
+        const int p = piv;
+        const double dp = dpiv;
+        if (!(dp > 1e-14 * dmax0) || !(dp > 0.0)) break;          // uniform: every thread reads the same shared values
+        for (int t = tid; t < j; t += LR_PCHOL_THREADS) lp[t] = Lt[(size_t)t * K + p];
+        __syncthreads();
+        const double rs = 1.0 / sqrt(dp);
+        // one warp per row i: dot product over the finished columns, lanes over t
+        for (int i = warp; i < K; i += LR_PCHOL_THREADS / 32) {
+            double s = 0.0;
+            for (int t = lane; t < j; t += 32) s = fma(Lt[(size_t)t * K + i], lp[t], s);
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+            if (lane == 0) {
+                // rows already used as pivots have d = 0 by construction (their residual is what rounding left): keep them at zero
+                const double l = (d[i] > 0.0 || i == p) ? (Bc[(size_t)i * K + p] - s) * rs : 0.0;
+                Lt[(size_t)j * K + i] = l;
+                const double dn = d[i] - l * l;
+                d[i] = (i == p) ? 0.0 : (dn > 0.0 ? dn : 0.0);
+            }
+        }
+        rank = j + 1;
+        __syncthreads();
+    }
+    if (tid == 0) *rank_out = rank;
+}
+// Bc <- L L^T: the core that the symmetric form really uses (Bc minus what the pivoted Cholesky left out: rounding, or the indefinite
+// float32 noise of the G X products) -- it is what cpd_nonrigid_lowrank_get hands out, so G ~= Q Bc Q^T stays exactly the iteration's G.
+__global__ void __launch_bounds__(THREADS)
+lr_llt_kernel(const double* __restrict__ Lt, int K, double* __restrict__ Bc) {
+    const int e = blockIdx.x * THREADS + threadIdx.x;
+    if (e < K * K) {
+        const int a = e / K, b = e % K;
+        const int lo = a < b ? a : b, hi = a < b ? b : a;        // one summation per unordered pair: exactly symmetric
+        double s = 0.0;
+        for (int j = 0; j < K; ++j) s = fma(Lt[(size_t)j * K + lo], Lt[(size_t)j * K + hi], s);
+        Bc[e] = s;
+    }
+}
+// out[j0 + p][i] = sum_k V[j0 + p][k] Q[k][i]: the columns of Qt = Q L, LR_PANEL at a time (V = Lt of lr_pchol_kernel)
+__global__ void __launch_bounds__(THREADS)
+lr_rotate_kernel(const double* __restrict__ Q, long long m, long long ld, int K, const double* __restrict__ V, int j0, int np,
+                 double* __restrict__ out) {
+    __shared__ double sc[LR_UPD_KC][LR_PANEL];
+    const long long i = (long long)blockIdx.x * THREADS + threadIdx.x;
+    double acc[LR_PANEL];
+#pragma unroll
+    for (int p = 0; p < LR_PANEL; ++p) acc[p] = 0.0;
+    for (int k0 = 0; k0 < K; k0 += LR_UPD_KC) {
+        const int kc = (K - k0 < LR_UPD_KC) ? K - k0 : LR_UPD_KC;
+        __syncthreads();
+        for (int e = threadIdx.x; e < kc * LR_PANEL; e += THREADS) {
+            const int k = e % kc, pp = e / kc;
+            sc[k][pp] = pp < np ? V[(size_t)(j0 + pp) * K + k0 + k] : 0.0;
+        }
+        __syncthreads();
+        if (i < m) {
+#pragma unroll 8
+            for (int k = 0; k < kc; ++k) {
+                const double q = Q[(long long)(k0 + k) * ld + i];
+#pragma unroll
+                for (int p = 0; p < LR_PANEL; ++p) acc[p] = fma(q, sc[k][p], acc[p]);
+            }
+        }
+    }
+    if (i < m)
+        for (int p = 0; p < np; ++p) out[(long long)(j0 + p) * ld + i] = acc[p];
 }
 
 // T_i = y_i + sum_k Q[k][i] Z[k]   (Z arrives as the solution layout of the LU solve: Zt[d][k])

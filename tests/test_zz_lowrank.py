@@ -327,6 +327,46 @@ def test_lowrank_misc_gpu():
     _check_misc()
 
 
+def _check_spd_core(m, rank, iters, monkeypatch, noise_level=False):
+    """By default the M-step solves the symmetric positive definite system of the factor Qt = Q L, Bc ~= L L^T (pivoted Cholesky at
+    set-up, one-CTA LDL^T per iteration); CPD_B200_LR_CORE=lu keeps the unsymmetric (c I + Bc S) Z = Bc R and its LU (also what ranks
+    above LR_SPD_MAX_RANK = 232 use).  Same Q and Bc, same registration, up to the rounding of two different solves.  `noise_level`:
+    the rank reaches into the float32 noise of the G X products (K ~ M), where Bc has eigenvalues of both signs at the 1e-7 level;
+    the Cholesky factor stops there (G is positive semi-definite), the LU keeps them -- the tolerance is then that noise."""
+    src, tgt = _deformed_pair(m)
+    spd = cpd.NonRigidCPD(src, beta=1.5, lmd=2.0, low_rank=rank)
+    rs = spd.registration(tgt, w=0.05, maxiter=iters, tol=-1.0)
+    monkeypatch.setenv("CPD_B200_LR_CORE", "lu")
+    lu = cpd.NonRigidCPD(src, beta=1.5, lmd=2.0, low_rank=rank)
+    rl = lu.registration(tgt, w=0.05, maxiter=iters, tol=-1.0)
+    monkeypatch.delenv("CPD_B200_LR_CORE")
+    ts, tl = rs.transformation, rl.transformation
+    assert np.array_equal(ts.q, tl.q)
+    # the exported core is L L^T in the default form, the raw Q^T G Q with the LU: they differ by what the Cholesky factor left out
+    np.testing.assert_allclose(ts.bcore, tl.bcore, atol=(2e-6 if noise_level else 1e-8) * np.abs(tl.bcore).max())
+    if rank <= 232:
+        assert np.linalg.eigvalsh(ts.bcore).min() > -1e-12 * np.abs(ts.bcore).max()             # positive semi-definite
+    assert rs.sigma2 == pytest.approx(rl.sigma2, rel=1e-5 if noise_level else 1e-7)
+    np.testing.assert_allclose(spd.moved_source(), lu.moved_source(), atol=1e-4 if noise_level else 1e-6)
+    np.testing.assert_allclose(ts.w, tl.w, atol=(1e-2 if noise_level else 2e-5) * max(1.0, np.abs(tl.w).max()))   # W = (...) / (lmd sigma2): the least stable output
+    np.testing.assert_allclose(ts.transform(src), spd.moved_source(), atol=1e-4 if noise_level else 1e-8)
+
+
+def test_spd_core_equals_lu_core_emulated(emulated, monkeypatch):
+    _check_spd_core(260, 36, 4, monkeypatch)
+    _check_spd_core(120, 120, 3, monkeypatch, noise_level=True)          # K = M: dropped columns, pivoted Cholesky stops early
+    _check_spd_core(300, 240, 2, monkeypatch, noise_level=True)          # above LR_SPD_MAX_RANK: both runs take the LU
+
+
+@pytest.mark.gpu
+@pytest.mark.timeout(600)
+def test_spd_core_equals_lu_core_gpu(monkeypatch):
+    _check_spd_core(3000, 40, 6, monkeypatch)
+    _check_spd_core(3000, 200, 6, monkeypatch, noise_level=True)
+    _check_spd_core(300, 300, 3, monkeypatch, noise_level=True)
+    _check_spd_core(1000, 240, 3, monkeypatch, noise_level=True)
+
+
 def _check_config5(m_cross, m_big, rank, iters):
     """BASELINE configuration 5 (N = M = 50k, K = 200): size-independent properties, and the dense device loop at a size it
     can still afford as the cross-check."""
