@@ -42,15 +42,10 @@ int nonrigid_common_begin(cpd_ctx* h, double lmd, double sigma2, double w) {
     h->h_state.err = 0;
     return upload_state(h);
 }
-// device / host workspace of the solver, grown on demand
-int solver_workspace_bytes(cpd_ctx* h, size_t wd, size_t wh);
 // workspace of the LU of an n x n system stored at `a`
 int solver_workspace(cpd_ctx* h, long long n, double* a) {
     size_t wd = 0, wh = 0;
     SOLV(g_sol.XgetrfBuf(h->sol, h->sol_params, n, n, CUDA_R_64F_, a, n, CUDA_R_64F_, &wd, &wh));
-    return solver_workspace_bytes(h, wd, wh);
-}
-int solver_workspace_bytes(cpd_ctx* h, size_t wd, size_t wh) {
     if (wd > h->work_dev || !h->d_work) {
         if (h->d_work) cudaFree(h->d_work);
         h->d_work = nullptr;
@@ -225,14 +220,13 @@ int lr_gram_apply(cpd_ctx* h, const double* src, double* dst, int rank) {
 }
 // out[na][nb] = A diag(wt) Bm^T over the points.  The point range is cut into as many slices as the partial buffer holds (at most
 // 256, at least 256 points each): many short CTAs instead of 8 long ones per tile; lr_merge_kernel adds the slices in a fixed order.
-int lr_inner(cpd_ctx* h, const double* A, int na, long long lda, const double* Bm, int nb, long long ldb, const double* wt, int symmetrise,
-             double* out) {
+int lr_inner(cpd_ctx* h, const double* A, int na, long long lda, const double* Bm, int nb, long long ldb, const double* wt, double* out) {
     const int tiles = ((na + LR_TILE - 1) / LR_TILE) * ((nb + LR_TILE - 1) / LR_TILE);
     const long long by_cap = (long long)(h->lr_part_cap / ((size_t)na * nb));
     const int nsl = (int)std::max<long long>(1, std::min<long long>(std::min<long long>(256, by_cap), h->m / 256));
     dim3 grid((unsigned)tiles, (unsigned)nsl);
-    lr_inner_kernel<<<grid, THREADS, 0, h->stream>>>(A, na, lda, Bm, nb, ldb, wt, h->m, symmetrise, h->d_lr_part);
-    lr_merge_kernel<<<blocks_for((long long)na * nb * 8), THREADS, 0, h->stream>>>(h->d_lr_part, nsl, na, nb, symmetrise, out);
+    lr_inner_kernel<<<grid, THREADS, 0, h->stream>>>(A, na, lda, Bm, nb, ldb, wt, h->m, h->d_lr_part);
+    lr_merge_kernel<<<blocks_for((long long)na * nb * 8), THREADS, 0, h->stream>>>(h->d_lr_part, nsl, na, nb, out);
     KCHECK();
     h->launches += 2;
     return CPD_OK;
@@ -285,7 +279,7 @@ int lr_orthonormalise(cpd_ctx* h, double* X, int rank) {
         h->launches += 2;
         for (int pass = 0; pass < 2; ++pass) {
             if (j0 > 0) {
-                TRY(lr_inner(h, X, j0, ld, P, np, ld, nullptr, 0, C));
+                TRY(lr_inner(h, X, j0, ld, P, np, ld, nullptr, C));
                 lr_panel_update_kernel<<<nb, THREADS, 0, h->stream>>>(X, m, ld, j0, np, j0, C);
                 h->launches += 1;
             }
@@ -495,7 +489,7 @@ int nonrigid_solve(cpd_ctx* h) {
             if ((size_t)nblk * k * 3 > h->lr_part_cap) return fail(CPD_ERR_STATE, "partial buffer too small for Q^T F");
             lr_inner_narrow_kernel<<<dim3((unsigned)((k + 7) / 8), (unsigned)nblk), THREADS, 0, h->stream>>>(Qf, k, ld, h->d_B, 3, m, m,
                                                                                                          h->d_lr_part);
-            lr_merge_kernel<<<blocks_for((long long)k * 3 * 8), THREADS, 0, h->stream>>>(h->d_lr_part, nblk, k, 3, 0, h->d_lr_R);
+            lr_merge_kernel<<<blocks_for((long long)k * 3 * 8), THREADS, 0, h->stream>>>(h->d_lr_part, nblk, k, 3, h->d_lr_R);
             KCHECK();
             h->launches += 2;
         }

@@ -319,14 +319,13 @@ lr_panel_apply_kernel(double* __restrict__ X, long long m, long long ld, int j0,
 // One CTA per {32 x 32 output tile, i-slice}; 2 x 2 outputs per thread; partial per slice, merged by lr_merge_kernel.
 __global__ void __launch_bounds__(THREADS)
 lr_inner_kernel(const double* __restrict__ A, int na, long long lda, const double* __restrict__ Bm, int nb, long long ldb,
-                const double* __restrict__ wt, long long m, int upper_only /* symmetric result: tiles below the diagonal are skipped */,
+                const double* __restrict__ wt, long long m,
                 double* __restrict__ part /* [gridDim.y][na][nb] */) {
     // rows padded by 2 doubles: 16-byte aligned for the two-point LDS.128 of the inner loop, and the 16 rows a quarter-warp reads
     // in one step fall into distinct bank quads (row stride 132 words)
     __shared__ __align__(16) double sa[LR_TILE][LR_CHUNK + 2], sb[LR_TILE][LR_CHUNK + 2];
     const int tiles_b = (nb + LR_TILE - 1) / LR_TILE;
     const int ta0 = (blockIdx.x / tiles_b) * LR_TILE, tb0 = (blockIdx.x % tiles_b) * LR_TILE;
-    if (upper_only && ta0 > tb0) return;            // the whole CTA, before any barrier; lr_merge_kernel mirrors the upper tiles
     const int slice = blockIdx.y, nsl = gridDim.y;
     const long long per = (m + nsl - 1) / nsl;
     const long long i_lo = (per * slice < m) ? per * slice : m, i_hi = (i_lo + per < m) ? i_lo + per : m;
@@ -475,27 +474,19 @@ lr_inner_narrow_kernel(const double* __restrict__ A, int na, long long lda, cons
 }
 
 // out[e] = sum_slices part[s][e]  (fixed order: 8 lanes per output take the slices l, l + 8, ..., then a fixed shuffle tree joins
-// them).  symmetrise != 0 (square, mathematically symmetric result whose tiles below the diagonal were not computed): diagonal
-// tiles give (x + x^T) / 2, the others are mirrored from the upper triangle.
+// them).  The symmetric products have their own pair (lr_inner_sym_kernel / lr_merge_sym_kernel).
 __global__ void __launch_bounds__(THREADS)
-lr_merge_kernel(const double* __restrict__ part, int nsl, int na, int nb, int symmetrise, double* __restrict__ out) {
+lr_merge_kernel(const double* __restrict__ part, int nsl, int na, int nb, double* __restrict__ out) {
     const int e = (blockIdx.x * THREADS + threadIdx.x) >> 3, l = threadIdx.x & 7;
     const bool in = e < na * nb;
-    const int a = in ? e / nb : 0, b = in ? e % nb : 0;
-    const int ta = a / LR_TILE, tb = b / LR_TILE;
-    const size_t e_ab = (size_t)a * nb + b, e_ba = (size_t)b * nb + a;
-    double s = 0.0, t = 0.0;
+    double s = 0.0;
     if (in) {
 #pragma unroll 4
-        for (int sl = l; sl < nsl; sl += 8) {
-            const double* p = part + (size_t)sl * na * nb;
-            if (!symmetrise || ta <= tb) s += p[e_ab];
-            if (symmetrise && ta >= tb) t += p[e_ba];
-        }
+        for (int sl = l; sl < nsl; sl += 8) s += part[(size_t)sl * na * nb + e];
     }
 #pragma unroll
-    for (int o = 4; o > 0; o >>= 1) { s += __shfl_xor_sync(0xffffffffu, s, o); t += __shfl_xor_sync(0xffffffffu, t, o); }
-    if (in && l == 0) out[e] = !symmetrise ? s : (ta == tb ? 0.5 * (s + t) : (ta < tb ? s : t));
+    for (int o = 4; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (in && l == 0) out[e] = s;
 }
 
 // ---- the K x K system of one M-step:  Msys = c I + Bc S  (row-major),  rhs[d][a] = sum_k Bc[a][k] R[k][d],  c = lmd sigma2 ----
