@@ -174,9 +174,10 @@ int cpd_p2p_local_handle(cpd_ctx* h, char out[64]);
 int cpd_p2p_attach(cpd_ctx* h, const char* handles, int world_size, int rank);
 int cpd_p2p_detach(cpd_ctx* h);      /* back to ncclAllReduce for the moments (e.g. when a peer could not map the mailboxes) */
 
-/* Host-only: the work list {tile, first stage, end stage, partial slot} a pass over ntiles i-tiles x nstages j-stages is
- * launched with on `slots` resident CTAs (csrc/cpd_b200.cu: build_work).  items may be NULL to query the counts.      */
-int cpd_plan_work(int ntiles, int nstages, int slots, int* items, int capacity, int* n_items, int* max_slots);
+/* Host-only: the work list {tile, first unit, end unit, partial slot} a pass over ntiles i-tiles x nunits sub-chunks of j-records is
+ * launched with on `slots` resident CTAs (csrc/cpd_b200.cu: build_work); last_tile_cost in (0, 1]: the share of the last tile's
+ * warps that hold i-points.  items may be NULL to query the counts.                                                     */
+int cpd_plan_work(int ntiles, int nunits, int slots, double last_tile_cost, int* items, int capacity, int* n_items, int* max_slots);
 
 /* -- measurement helpers (bench.py): CUDA events on the handle's stream ---------------- */
 int cpd_timer_start(cpd_ctx* h);

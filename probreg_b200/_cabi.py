@@ -65,7 +65,7 @@ _PROTOS = {
     "cpd_comm_attach": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_int]),
     "cpd_p2p_local_handle": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_char_p]),
     "cpd_p2p_attach": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_char_p, ctypes.c_int, ctypes.c_int]),
-    "cpd_plan_work": (ctypes.c_int, [ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.POINTER(ctypes.c_int), ctypes.c_int,
+    "cpd_plan_work": (ctypes.c_int, [ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_double, ctypes.POINTER(ctypes.c_int), ctypes.c_int,
                                      ctypes.POINTER(ctypes.c_int), ctypes.POINTER(ctypes.c_int)]),
     "cpd_p2p_detach": (ctypes.c_int, [ctypes.c_void_p]),
     "cpd_timer_start": (ctypes.c_int, [ctypes.c_void_p]),
@@ -365,12 +365,12 @@ def unique_id():
     return buf.raw
 
 
-def plan_work(ntiles, nstages, slots):
-    """(items (k x 4 int array: tile, first stage, end stage, slot), max partial slots per tile) -- host only."""
+def plan_work(ntiles, nunits, slots, last_tile_cost=1.0):
+    """(items (k x 4 int array: tile, first unit, end unit, slot), max partial slots per tile) -- host only."""
     n, mx = ctypes.c_int(), ctypes.c_int()
-    check(lib().cpd_plan_work(ntiles, nstages, slots, None, 0, ctypes.byref(n), ctypes.byref(mx)))
+    check(lib().cpd_plan_work(ntiles, nunits, slots, float(last_tile_cost), None, 0, ctypes.byref(n), ctypes.byref(mx)))
     buf = np.zeros((n.value, 4), dtype=np.int32)
-    check(lib().cpd_plan_work(ntiles, nstages, slots, buf.ctypes.data_as(ctypes.POINTER(ctypes.c_int)), n.value,
+    check(lib().cpd_plan_work(ntiles, nunits, slots, float(last_tile_cost), buf.ctypes.data_as(ctypes.POINTER(ctypes.c_int)), n.value,
                               ctypes.byref(n), ctypes.byref(mx)))
     return buf, mx.value
 

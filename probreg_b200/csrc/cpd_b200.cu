@@ -275,33 +275,65 @@ inline unsigned blocks_for(long long n) { return (unsigned)((n + THREADS - 1) / 
 // one stage of the optimum whatever N, M and the GPU count are.  (A finer "stream-K" cut that lets one CTA span two tiles was
 // measured 15-19 % slower: the extra live state pushes the hot loops past 128 registers.)
 struct WorkList {
-    std::vector<int4> items;        // {tile, first stage, end stage, slot within the tile}
+    std::vector<int4> items;        // {tile, first unit, end unit, slot within the tile}; a unit is a sub-chunk of SUB j-records
     std::vector<int> tile_slots;    // partial slots used per tile
     int max_slots = 1;
 };
-WorkList build_work(int ntiles, int nstages, int slots) {
+// Cut ntiles x nunits of work into CTA work items for `slots` resident CTAs.  A tile costs `nunits` (the last one, whose warps
+// beyond the end of the i-points leave the kernel at once, `last_cost` = live warps / warps per CTA of that).  Two candidates:
+//   * one wave (ntiles <= slots): every tile starts with one item; the next cut always goes to the tile whose longest item is the most
+//     expensive, until the slots are used up -- cuts land where the cost is, at the granularity of a sub-chunk (an item may begin
+//     and end inside a TMA stage; the kernels load the whole stages and skip the sub-chunks outside the item);
+//   * several waves: the same number of cuts j for every tile, j chosen by waves x (item length + item overhead).
+// `overhead`: what an item costs before its first unit (offset seeding sweep, pipeline fill), in units: half a stage.
+WorkList build_work(int ntiles, int nunits, int slots, double last_cost, double overhead) {
+    const double OVERHEAD = overhead;
     WorkList w;
+    nunits = std::max(1, nunits);
+    auto cost_of = [&](int t) { return t == ntiles - 1 ? last_cost : 1.0; };
+    auto span_of = [&](int t, int j) { return cost_of(t) * (double)((nunits + j - 1) / j) + OVERHEAD; };
+    // several waves, uniform j
     int best_j = 1;
     double best = 1e300;
-    for (int j = 1; j <= std::max(1, nstages); ++j) {
+    for (int j = 1; j <= nunits; ++j) {
         const long long items = (long long)ntiles * j;
         const double waves = ceil((double)items / slots);
-        const double span = waves * (ceil((double)nstages / j) + 0.5);
+        const double span = waves * ((double)((nunits + j - 1) / j) + OVERHEAD);
         if (span < best - 1e-9) { best = span; best_j = j; }
         if (items > 8LL * slots) break;
     }
     w.tile_slots.assign(ntiles, best_j);
-    long long spare = (long long)slots - (long long)ntiles * best_j;       // > 0 only for a single-wave launch
-    for (int t = 0; t < ntiles && spare > 0 && best_j < nstages; ++t, --spare) w.tile_slots[t] = best_j + 1;
+    if (ntiles <= slots) {
+        // one wave, cuts by cost
+        std::vector<int> cuts(ntiles, 1);
+        int used = ntiles;
+        while (used < slots) {
+            int worst = -1;
+            double wv = -1.0;
+            for (int t = 0; t < ntiles; ++t) {
+                const double v = span_of(t, cuts[t]);
+                if (cuts[t] < nunits && v > wv) { wv = v; worst = t; }
+            }
+            if (worst < 0) break;
+            ++cuts[worst];
+            ++used;
+        }
+        double span = 0.0;
+        for (int t = 0; t < ntiles; ++t) span = std::max(span, span_of(t, cuts[t]));
+        if (span <= best + 1e-9) w.tile_slots = cuts;
+    }
     for (int t = 0; t < ntiles; ++t) {
         const int j = w.tile_slots[t];
         for (int s = 0; s < j; ++s) {
-            const int a = (int)((long long)nstages * s / j), b = (int)((long long)nstages * (s + 1) / j);
+            const int a = (int)((long long)nunits * s / j), b = (int)((long long)nunits * (s + 1) / j);
             w.items.push_back(make_int4(t, a, b, s));
         }
         w.max_slots = std::max(w.max_slots, j);
     }
-    std::stable_sort(w.items.begin(), w.items.end(), [](const int4& a, const int4& b) { return (a.z - a.y) > (b.z - b.y); });
+    // longest (most expensive) first: the hardware hands CTAs out in order
+    std::stable_sort(w.items.begin(), w.items.end(), [&](const int4& a, const int4& b) {
+        return cost_of(a.x) * (a.z - a.y) > cost_of(b.x) * (b.z - b.y);
+    });
     return w;
 }
 
@@ -425,8 +457,24 @@ int prepare(cpd_ctx* h) {
     if (!h->have_source || !h->have_target) return fail(CPD_ERR_STATE, "source and target must both be set");
     h->it1 = (int)((h->n + ITILE1 - 1) / ITILE1);
     h->it2 = (int)((h->m + ITILE2 - 1) / ITILE2);
-    const WorkList w1 = build_work(h->it1, (int)(h->mpad / P1_STAGE), h->slots1);
-    const WorkList w2 = build_work(h->it2, (int)(h->npad / P2_STAGE), h->slots2);
+    // Pass 1 cuts at sub-chunks, and the warps of its last i-tile whose i-points are all padding leave the kernel at once.  What such
+    // a tile then costs was measured (1/8 and 1/4 target shards of 100k: 2 and 4 of 8 warps alive; profiles/r2_plan_sweep.txt): the
+    // best plans come from a cost of 0.6 of a full tile in BOTH cases -- not w / 8: the live warps get a larger share of the SM's
+    // pipes, but a warp on its own is latency-bound (0.45 makes the tile's few long items set the time: +10 %; 1.0 wastes the early
+    // exit: +2..4 %).  Pass 2 keeps whole stages as the unit (its kernel is the one closest to the register limit; cutting it at
+    // sub-chunks cost 1.4 % at every size).
+    const long long in_last = h->n - (long long)(h->it1 - 1) * ITILE1;
+    const int live = (int)((in_last + 32 * RI1 - 1) / (32 * RI1));          // warps of the last tile that hold i-points
+    double last_cost = live < THREADS / 32 ? std::max(0.6, live / (double)(THREADS / 32)) : 1.0;
+    if (const char* e = getenv("CPD_B200_PLAN_LAST_COST")) { const double v = atof(e); if (v > 0.0 && v <= 1.0) last_cost = v; }   // tuning
+    WorkList w1;
+    if (const char* e = getenv("CPD_B200_PLAN_UNIT"); e && !strcmp(e, "stage")) {      // tuning: items of whole stages, as pass 2
+        w1 = build_work(h->it1, (int)(h->mpad / P1_STAGE), h->slots1, last_cost, 0.5);
+        for (int4& it : w1.items) { it.y *= P1_STAGE / SUB; it.z *= P1_STAGE / SUB; }
+    } else {
+        w1 = build_work(h->it1, (int)(h->mpad / SUB), h->slots1, last_cost, 0.5 * (P1_STAGE / SUB));
+    }
+    const WorkList w2 = build_work(h->it2, (int)(h->npad / P2_STAGE), h->slots2, 1.0, 0.5);
     h->j1 = w1.max_slots; h->g1 = (int)w1.items.size();
     h->j2 = w2.max_slots; h->g2 = (int)w2.items.size();
     TRY(dev_alloc(&h->d_work1, w1.items.size()));
@@ -541,11 +589,12 @@ int read_params(cpd_ctx* h, cpd_params* out) {
 }  // namespace
 
 // Host-only view of the work list a pass would be launched with (no device needed): lets the CPU tests check that
-// every (tile, stage) is covered exactly once and how well the resident CTA slots are filled.
-extern "C" int cpd_plan_work(int ntiles, int nstages, int slots, int* items /* 4 ints each, may be NULL */, int capacity,
-                             int* n_items, int* max_slots) {
-    if (ntiles < 1 || nstages < 1 || slots < 1 || !n_items || !max_slots) return fail(CPD_ERR_ARG, "bad argument");
-    const WorkList w = build_work(ntiles, nstages, slots);
+// every (tile, unit) is covered exactly once and how well the resident CTA slots are filled.
+extern "C" int cpd_plan_work(int ntiles, int nunits, int slots, double last_tile_cost, int* items /* 4 ints each, may be NULL */,
+                             int capacity, int* n_items, int* max_slots) {
+    if (ntiles < 1 || nunits < 1 || slots < 1 || !(last_tile_cost > 0.0 && last_tile_cost <= 1.0) || !n_items || !max_slots)
+        return fail(CPD_ERR_ARG, "bad argument");
+    const WorkList w = build_work(ntiles, nunits, slots, last_tile_cost, 0.5 * (P1_STAGE / SUB));     // pass 1's units
     *n_items = (int)w.items.size();
     *max_slots = w.max_slots;
     if (items) {

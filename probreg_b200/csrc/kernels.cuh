@@ -500,9 +500,11 @@ pass1_kernel(const float4* __restrict__ ipts, int ni, const float4* __restrict__
     CPD_DYN_SMEM(smraw);
     uint64_t* full = reinterpret_cast<uint64_t*>(smraw + NSTAGE * P1_STAGE_BYTES);
     const int tid = threadIdx.x;
-    const int4 wk = work[blockIdx.x];               // {i-tile, first stage, end stage, partial slot}: see build_work()
-    const int itile = wk.x, st0 = wk.y, split = wk.w;
-    const int nst = wk.z - wk.y;
+    const int4 wk = work[blockIdx.x];               // {i-tile, first sub-chunk, end sub-chunk, partial slot}: see build_work()
+    constexpr int SPS = P1_STAGE / SUB;             // an item may begin and end inside a stage: whole stages are loaded,
+    const int itile = wk.x, split = wk.w;           // the sub-chunks outside the item are skipped
+    const int st0 = wk.y / SPS, nst = (wk.z + SPS - 1) / SPS - st0;
+    const int sc_first = wk.y - st0 * SPS, sc_last = wk.z - (st0 + nst - 1) * SPS;
     const unsigned char* jbytes = reinterpret_cast<const unsigned char*>(jrec);
     if (tid == 0) {
         for (int s = 0; s < NSTAGE; ++s) mbar_init(&full[s], 1);
@@ -515,6 +517,10 @@ pass1_kernel(const float4* __restrict__ ipts, int ni, const float4* __restrict__
             tma_load_1d(smraw + s * P1_STAGE_BYTES, jbytes + (size_t)(st0 + s) * P1_STAGE_BYTES, P1_STAGE_BYTES, &full[s]);
         }
     }
+    // A warp whose i-points are all padding (the tail of the last tile) has nothing to add: it leaves before the stage loop, whose
+    // barriers then count the remaining warps only (warp 0, the TMA issuer, always has i-points); build_work() gives such a tile
+    // correspondingly longer items.
+    if (itile * ITILE1 + (tid >> 5) * (32 * RI1) >= ni) return;
     // two packed pairs of targets per thread: pair p = targets (2p, 2p+1) of this thread
     u64 ax[NPAIR1], ay[NPAIR1], az[NPAIR1], no[NPAIR1];    // no = (-o, -o'): negated integer offsets
     double S[RI1], SU[RI1];
@@ -593,7 +599,7 @@ pass1_kernel(const float4* __restrict__ ipts, int ni, const float4* __restrict__
             skip = box_gap2(mybox, blo, bhi) - omax_w >= CULL_GAP;
         }
 #pragma unroll 1
-        for (int sc = 0; sc < (skip ? 0 : P1_STAGE / SUB); ++sc) {
+        for (int sc = (it == 0 ? sc_first : 0); sc < (skip ? 0 : (it == nst - 1 ? sc_last : SPS)); ++sc) {
             if (CULL) {
                 const int sb = (st0 + it) * (P1_STAGE / SUB) + sc;
                 if (box_gap2(mybox, ssub[2 * sb], ssub[2 * sb + 1]) - omax_w >= CULL_GAP) continue;
@@ -774,8 +780,8 @@ pass2_kernel(const float4* __restrict__ ipts, int ni, const float4* __restrict__
     CPD_DYN_SMEM(smraw);
     uint64_t* full = reinterpret_cast<uint64_t*>(smraw + NSTAGE * P2_STAGE_BYTES);
     const int tid = threadIdx.x;
-    const int4 wk = work[blockIdx.x];
-    const int itile = wk.x, st0 = wk.y, split = wk.w;
+    const int4 wk = work[blockIdx.x];               // {i-tile, first stage, end stage, partial slot}: whole stages (build_work with
+    const int itile = wk.x, st0 = wk.y, split = wk.w;   // a stage as the unit; pass 1 cuts at sub-chunks)
     const int nst = wk.z - wk.y;
     const unsigned char* jbytes = reinterpret_cast<const unsigned char*>(jrec);
     if (tid == 0) {
