@@ -59,6 +59,21 @@ def main():
     say("mstep done")
     mref = orc.mstep_rigid(src, tgt, ref)
     np.testing.assert_allclose(m.transformation.rot, mref.params[0], atol=1e-5)
+    # (4) low-rank non-rigid: the G X products are sharded over rows (integer digits on the tensor cores: the factors do not depend
+    #     on the row tiling), the K x K M-step is replicated on the all-reduced p1 / px
+    f = np.array([[1.0, 0.5, 0.0], [0.0, 1.0, 0.7], [0.3, 0.0, 1.0]])
+    bent = np.ascontiguousarray(src + 0.03 * np.sin(2 * np.pi * src.dot(f)))
+    one = cpd.NonRigidCPD(src, beta=1.5, lmd=2.0, low_rank=60, device=local)
+    r1 = one.registration(bent, w=0.05, maxiter=5, tol=-1.0)
+    many = cpd.NonRigidCPD(src, beta=1.5, lmd=2.0, low_rank=60, comm=comm)
+    rn = many.registration(bent, w=0.05, maxiter=5, tol=-1.0)
+    say("low-rank non-rigid done")
+    assert np.array_equal(rn.transformation.q, r1.transformation.q) and np.array_equal(rn.transformation.bcore, r1.transformation.bcore)
+    assert abs(rn.sigma2 - r1.sigma2) <= 1e-6 * r1.sigma2, (rn.sigma2, r1.sigma2)
+    np.testing.assert_allclose(many.moved_source(), one.moved_source(), atol=1e-6)
+    box = [None] * world
+    tdist.all_gather_object(box, (float(rn.sigma2), float(np.abs(many.moved_source()).sum())))
+    assert all(b == box[0] for b in box), "ranks disagree (low-rank)"
     tdist.barrier()
     if rank == 0:
         print("DIST_OK world=%d" % world)
