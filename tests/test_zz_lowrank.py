@@ -358,6 +358,19 @@ def test_spd_core_equals_lu_core_emulated(emulated, monkeypatch):
     _check_spd_core(300, 240, 2, monkeypatch, noise_level=True)          # above LR_SPD_MAX_RANK: both runs take the LU
 
 
+def test_spd_core_at_tiny_and_ragged_ranks_emulated(emulated, monkeypatch):
+    """Ranks below, at and just above the panel width of the blocked LDL^T (8), and one that is no multiple of it."""
+    for rank in (1, 2, 7, 8, 9, 17):
+        _check_spd_core(90, rank, 2, monkeypatch)
+
+
+@pytest.mark.gpu
+@pytest.mark.timeout(600)
+def test_spd_core_at_tiny_and_ragged_ranks_gpu(monkeypatch):
+    for rank in (1, 7, 8, 9, 63, 228):
+        _check_spd_core(1200, rank, 2, monkeypatch, noise_level=rank > 20)     # 63 of 1200 points already reaches the float32 noise
+
+
 @pytest.mark.gpu
 @pytest.mark.timeout(600)
 def test_spd_core_equals_lu_core_gpu(monkeypatch):
