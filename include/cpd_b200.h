@@ -122,8 +122,10 @@ int cpd_nonrigid_mstep(cpd_ctx* h, const double* pt1, const double* p1, const do
  * reference counterpart: the reference only has the dense solve of cpd.py:296).  Same life cycle as the dense path:
  * cpd_nonrigid_lowrank_begin instead of cpd_nonrigid_begin, then cpd_nonrigid_step / cpd_nonrigid_get.  Q comes from a
  * randomised range finder (seeded, `power_iters` subspace iterations, 2 is plenty) on products G X formed on the fly, so
- * nothing of size M x M is stored; each M-step is a K x K LU.  rank is clamped to M; rank <= 1024.
- * cpd_nonrigid_lowrank_get: the rank in use, Q (m x rank row-major, caller's point order) and Bc (rank x rank); any may be NULL. */
+ * nothing of size M x M is stored; each M-step is a K x K solve: symmetric positive definite on the factor Q L, Bc ~= L L^T, in one
+ * CTA for rank <= 228, else (or with CPD_B200_LR_CORE=lu) the LU of the unsymmetric form.  rank is clamped to M; rank <= 1024.
+ * cpd_nonrigid_lowrank_get: the rank in use, Q (m x rank row-major, caller's point order) and Bc (rank x rank, symmetric; L L^T in
+ * the default form: positive semi-definite, exactly the core the iteration uses); any may be NULL. */
 int cpd_nonrigid_lowrank_begin(cpd_ctx* h, double beta, double lmd, double sigma2, double w, int rank, int power_iters, uint64_t seed);
 int cpd_nonrigid_lowrank_get(cpd_ctx* h, int* rank_out, double* q_out, double* bcore_out);
 

@@ -12,6 +12,9 @@
 //     Z  = Bc Q^T W  solves the K x K system  (c I + Bc S) Z = Bc R,   S = Q^T diag(p1) Q,  R = Q^T F
 //     T  = Y + G W ~= Y + Q Z
 // (Woodbury written without Bc^-1, so numerically rank-deficient Q -- zero columns -- is harmless.)
+// Since round 2 the iteration runs on the factor Qt = Q L, Bc ~= L L^T, whose K x K system is symmetric positive definite and is
+// solved by one CTA (lr_spd_form in host_nonrigid.inl, lr_pchol_kernel / lr_spd_solve_kernel below); the unsymmetric system above
+// with cuSOLVER's LU remains for K > LR_SPD_MAX_RANK and as the cross-check (CPD_B200_LR_CORE=lu).
 // Parity: against the dense device path / the numpy oracle at small M (tests); at K = M the two coincide up to rounding.
 //
 // Layout: Q, X, GQ are FP64 "column-major" [K][ld]: row k holds column k of the matrix, i contiguous -- every kernel below
@@ -515,9 +518,9 @@ lr_system_kernel(const double* __restrict__ Bc, const double* __restrict__ S, co
 //     (c I + St) Z = Rt,      St = Qt^T diag(p1) Qt,  Rt = Qt^T F,      W = (F - diag(p1) Qt Z) / c,   T = Y + Qt Z,
 // against the unsymmetric (c I + Bc S) Z = Bc R of the orthonormal factor.  lr_spd_solve_kernel solves it in ONE CTA: the lower
 // triangle of  c I + St  with the three right-hand sides appended as rows K .. K+2 lives in shared memory (packed by rows,
-// (K+3)(K+4)/2 doubles: 166 KB at K = 200), an LDL^T factorisation runs over it right-looking with one barrier per column -- the
-// appended rows come out as the forward substitution -- then the back substitution, one barrier per column.  cuSOLVER's LU of the
-// unsymmetric form took 0.48 ms per M-step at K = 200 (getrf is a single 256-thread CTA there, plus laswp and two trsm).
+// (K+3)(K+4)/2 doubles: 166 KB at K = 200, plus the panel buffer), a blocked LDL^T factorisation runs over it (see the kernel) -- the
+// appended rows come out as the forward substitution -- then the back substitution in registers.  0.17 ms per M-step at K = 200;
+// cuSOLVER's LU of the unsymmetric form took 0.48 ms (getrf is a single 256-thread CTA there, plus laswp and two trsm).
 // (An eigen-decomposition of Bc would serve as well as the Cholesky factor; cusolverDnXsyevd takes 1.8 ms at K = 200 but 38 s on
 //  its first call in a process on the B200 box -- profiles/r2_syevd_probe.txt -- so the factor is computed here.)
 constexpr int LR_SPD_THREADS = 512;           // 128 registers per thread: phase 1 keeps an 8 x 8 block in registers
