@@ -47,68 +47,132 @@ def hbm_bytes_per_iter(n_local, m):
 
 
 class ClockSampler(object):
-    """nvidia-smi clocks / throttle reasons (B200_PROFILING.md recipe).  ONE poller (rank 0) for all the
-    job's GPUs, started before the warm-up so that NVML start-up (slow with 8 GPUs, and it takes driver
-    locks) does not land inside the timed region; samples taken while the GPUs are busy are kept."""
+    """SM clocks / clock-event reasons while the job runs (B200_PROFILING.md recipe).  ONE poller (rank 0) for all the job's GPUs,
+    started before the warm-up.  NVML through pynvml, polled every 5 ms from a thread (a query costs microseconds, so even a
+    140 ms timed region gets ~25 samples per GPU, and every sample has a timestamp: the median reported is over the samples that
+    fall INTO the timed region); `nvidia-smi -lms 100` as the fallback when NVML cannot be loaded -- its samples are ~10x sparser
+    and carry a utilisation averaged over the driver's own window, so there the samples since the warm-up count."""
 
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,utilization.gpu,clocks_event_reasons.hw_slowdown,"
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
+    NAMES = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
 
     def __init__(self, n_gpus):
         self.n_gpus = n_gpus
-        self.rows = []
+        self.rows = []            # (time, gpu, sm MHz, power W, set of reason names)
+        self.smax = []
         self.proc = None
+        self.nvml = None
+        self.stop_flag = False
+        self.source = None
+
+    def _physical(self):
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+        if vis:
+            try:
+                return [int(x) for x in vis.split(",")][: self.n_gpus]
+            except ValueError:
+                pass
+        return list(range(self.n_gpus))
 
     def start(self):
         try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.handles = [pynvml.nvmlDeviceGetHandleByIndex(i) for i in self._physical()]
+            self.smax = [float(pynvml.nvmlDeviceGetMaxClockInfo(hd, pynvml.NVML_CLOCK_SM)) for hd in self.handles]
+            self.nvml = pynvml
+            self.source = "nvml, 5 ms"
+            self.thread = threading.Thread(target=self._poll_nvml, daemon=True)
+            self.thread.start()
+            return
+        except Exception:
+            self.nvml = None
+        try:
             self.proc = subprocess.Popen(["nvidia-smi", "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
                                           "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.source = "nvidia-smi -lms 100"
+            self.thread = threading.Thread(target=self._read_smi, daemon=True)
             self.thread.start()
         except Exception:
             self.proc = None
 
-    def _read(self):
+    def _poll_nvml(self):
+        nv = self.nvml
+        get_reasons = getattr(nv, "nvmlDeviceGetCurrentClocksEventReasons", None) or nv.nvmlDeviceGetCurrentClocksThrottleReasons
+        bits = [(0x8, "hw_slowdown"), (0x40, "hw_thermal_slowdown"), (0x20, "sw_thermal_slowdown"), (0x4, "sw_power_cap")]
+        while not self.stop_flag:
+            for g, hd in enumerate(self.handles):
+                try:
+                    sm = float(nv.nvmlDeviceGetClockInfo(hd, nv.NVML_CLOCK_SM))
+                    mask = int(get_reasons(hd))
+                    try:
+                        pw = nv.nvmlDeviceGetPowerUsage(hd) / 1000.0
+                    except Exception:
+                        pw = None
+                    self.rows.append((time.perf_counter(), g, sm, pw, {nm for b, nm in bits if mask & b}))
+                except Exception:
+                    pass
+            time.sleep(0.005 if len(self.handles) <= 2 else 0.01)
+
+    def _read_smi(self):
+        phys = self._physical()
         for line in self.proc.stdout:
-            self.rows.append((time.perf_counter(), line.strip()))
+            f = [x.strip() for x in line.strip().split(",")]
+            if len(f) < 8:
+                continue
+            try:
+                idx = int(f[0])
+                if idx not in phys:
+                    continue
+                sm, mx = float(f[1]), float(f[2])
+                try:
+                    pw = float(f[3])
+                except ValueError:
+                    pw = None
+            except ValueError:
+                continue
+            if mx not in self.smax:
+                self.smax.append(mx)
+            self.rows.append((time.perf_counter(), phys.index(idx), sm, pw,
+                              {nm for nm, v in zip(self.NAMES, f[4:8]) if v.lower().startswith("active")}))
 
     def count(self):
         return len(self.rows)
 
-    def stop(self, t0=None, t1=None):
-        if self.proc is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        self.proc.terminate()
-        try:
-            self.proc.wait(timeout=2)
-        except Exception:
-            self.proc.kill()
-        sm, smax, reasons, power, timed = [], [], set(), [], 0
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for ts, r in self.rows:
-            f = [x.strip() for x in r.split(",")]
-            if len(f) < 9:
-                continue
+    def stop(self, t0=None, t1=None, t_load=None):
+        """t0 .. t1: the timed region; t_load: since when the GPUs have been under this job's load (end of the first warm-up)."""
+        if self.nvml is None and self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["neither NVML nor nvidia-smi available"]}
+        self.stop_flag = True
+        if self.proc is not None:
+            self.proc.terminate()
             try:
-                idx = int(f[0])
-                try:
-                    util = float(f[4])
-                except ValueError:
-                    util = 100.0                          # utilisation not reported: keep the sample
-                if idx >= self.n_gpus or util < 50.0:      # keep samples taken under load on this job's GPUs
-                    continue
-                sm.append(float(f[1])); smax.append(float(f[2])); power.append(float(f[3]))
-            except ValueError:
-                continue
-            if t0 is not None and t0 <= ts <= t1 + 0.11:
-                timed += 1
-            for nm, v in zip(names, f[5:9]):
-                if v.lower().startswith("active"):
-                    reasons.add(nm)
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(smax) if smax else None,
-                "power_w_max": max(power) if power else None, "samples_under_load": len(sm),
-                "samples_in_timed_region": timed, "reasons": sorted(reasons)}
+                self.proc.wait(timeout=2)
+            except Exception:
+                self.proc.kill()
+        else:
+            self.thread.join(timeout=1.0)
+            try:
+                self.nvml.nvmlShutdown()
+            except Exception:
+                pass
+        rows = list(self.rows)
+        slack = 0.0 if self.nvml is not None else 0.11
+        timed = [r for r in rows if t0 is not None and t0 <= r[0] <= t1 + slack]
+        loaded = [r for r in rows if t_load is None or t_load <= r[0] <= (t1 if t1 is not None else r[0]) + slack]
+        use = timed if timed else loaded
+        sm = [r[2] for r in use]
+        power = [r[3] for r in use if r[3] is not None]
+        reasons = set()
+        for r in use:
+            reasons |= r[4]
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_min_mhz": min(sm) if sm else None,
+                "sm_max_mhz": max(self.smax) if self.smax else None,
+                "power_w_max": max(power) if power else None, "samples_under_load": len(loaded),
+                "samples_in_timed_region": len(timed), "median_over": "timed region" if timed else "since the warm-up",
+                "source": self.source, "reasons": sorted(reasons)}
 
 
 def workload(points, kind="rigid"):
@@ -334,7 +398,7 @@ def run_ours(args):
     t_wall1 = time.perf_counter()
     t_wall = t_wall1 - t_wall0
     launches = h.launch_count() - launches0
-    clocks = sampler.stop(t_wall0, t_wall1) if sampler else None
+    clocks = sampler.stop(t_wall0, t_wall1, t_up) if sampler else None
     per_step = np.array([h.event_elapsed(2 * i, 2 * i + 1) for i in range(args.steps)])
     total_ms = float(per_step.sum())
     if world > 1:
@@ -579,7 +643,7 @@ def run_nonrigid(args, torch, _cabi, cpd, barrier, local_rank, world):
     h.sync()
     t_wall1 = time.perf_counter()
     launches = h.launch_count() - launches0
-    clocks = sampler.stop(t_wall0, t_wall1) if sampler else None
+    clocks = sampler.stop(t_wall0, t_wall1, t_up) if sampler else None
     per_step = np.array([h.event_elapsed(2 * i, 2 * i + 1) for i in range(args.steps)])
     ms_per_step = float(per_step.sum()) / args.steps
     h.set_profiling(True)
