@@ -109,6 +109,26 @@ def test_multi_wave_work_lists_under_emulation(emulated, monkeypatch, sms):
     np.testing.assert_allclose(es.px, ref.px, rtol=2e-5, atol=2e-5)
 
 
+@pytest.mark.parametrize("unit,last_cost", [("stage", "1.0"), ("subchunk", "1.0"), ("subchunk", "0.3"), ("stage", "0.6")])
+def test_pass1_plan_switches_under_emulation(emulated, monkeypatch, unit, last_cost):
+    """Pass 1's work plan (tuning switches of DESIGN section 4): whole stages or sub-chunks as the unit of the cuts, any cost of the
+    last tile -- items that begin and end inside a TMA stage, a last tile whose warps of padding leave the kernel at once (1300
+    targets: 276 in the second tile, 3 of its 8 warps alive).  The plan must never show in the results."""
+    from oracle import cpd_oracle as orc
+    from probreg_b200 import cpd
+
+    monkeypatch.setenv("CPD_B200_PLAN_UNIT", unit)
+    monkeypatch.setenv("CPD_B200_PLAN_LAST_COST", last_cost)
+    monkeypatch.setenv("CPD_EMU_SMS", "4")
+    rng = np.random.default_rng(5)
+    src, tgt = rng.random((2300, 3)), rng.random((1300, 3)) + 0.02
+    es = cpd.RigidCPD(src).expectation_step(src, tgt, 0.004, 0.1)
+    ref = orc.expectation_step(src, tgt, 0.004, 0.1)
+    np.testing.assert_allclose(es.pt1, ref.pt1, rtol=2e-5)
+    np.testing.assert_allclose(es.p1, ref.p1, rtol=2e-5, atol=1e-9)
+    np.testing.assert_allclose(es.px, ref.px, rtol=2e-5, atol=2e-5)
+
+
 def test_results_do_not_depend_on_the_thread_schedule(emu_lib_path):
     """Same inputs under three fiber schedules (in order, reversed, a random permutation per round): bit-identical results."""
     import os
